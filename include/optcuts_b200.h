@@ -1,0 +1,199 @@
+/*
+ * optcuts_b200.h — C-ABI of liboptcuts_b200.so: the B200 (sm_100a, fp64) implementation of
+ * OptCuts' geometry-and-topology inner loop.
+ *
+ * The reference has no FFI; its "plugin surface" is two C++ abstract classes plus the concrete
+ * Optimizer.  The entry points below are what thin C++ subclasses
+ *   CudaSymDirichletEnergy : OptCuts::Energy            (src/Energy/Energy.hpp:16-46)
+ *   CudaLinSysSolver       : OptCuts::LinSysSolver<..>  (src/LinSysSolver/LinSysSolver.hpp:22-256)
+ * and a device-resident mirror of OptCuts::Optimizer (src/Optimizer.hpp:22-143) bind to; the
+ * stubs are shown in INTEGRATION.md.  Each declaration cites the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain C, no exceptions; every call returns 0 on success or a negative ocb_status; the text of
+ *    the last error is kept per context (ocb_last_error).
+ *  - all pointers are HOST pointers owned by the caller unless the name ends in `_dev`; data is
+ *    copied synchronously (the call returns after the context's stream has drained).
+ *  - matrices are column-major exactly as Eigen hands them over (MatrixXd V: all u then all v;
+ *    MatrixXi F: |F|x3 col-major); gradient / search direction / solver vectors are interleaved
+ *    [u0 v0 u1 v1 ...] (Optimizer.cpp:666-668, SymDirichletEnergy.cpp:287).
+ *  - indices are int32, scalars IEEE fp64.  Nothing here uses tensor cores.
+ *  - one CUDA stream per context; distinct contexts may be used from distinct threads.
+ *  - ocb_create does no CUDA work beyond selecting the device lazily on first upload, so the C++
+ *    shim objects are cheap to construct (nested optimizers create thousands: SURVEY H7).
+ *
+ * System layout ("whole mesh", Scaffold.cpp:179-184): global vertex ids [0,nV) are the mesh's UV
+ * vertices; air-mesh vertex i maps to localVI2Global[i] (< nV for the first nBnd, which alias mesh
+ * boundary vertices; nV + (i - nBnd) for the rest).  nSys = 2 * (nV + nVa - nBnd) DOFs.
+ */
+#ifndef OPTCUTS_B200_H
+#define OPTCUTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ocb_ctx ocb_ctx;
+
+typedef enum {
+    OCB_OK = 0,
+    OCB_ERR_CUDA = -1,        /* a CUDA runtime call failed (text in ocb_last_error) */
+    OCB_ERR_ARG = -2,         /* bad argument / call order */
+    OCB_ERR_STATE = -3,       /* required data (mesh, uv, pattern, matrix ...) not set */
+    OCB_ERR_INVERTED = -4,    /* element with non-positive signed UV area (Optimizer.cpp:65-67) */
+    OCB_ERR_NOT_CONVERGED = -5, /* PCG hit max_it (solution is still written) */
+    OCB_ERR_BREAKDOWN = -6    /* PCG breakdown: pAp <= 0 (matrix not SPD) */
+} ocb_status;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int  ocb_create(ocb_ctx** out, int device);
+void ocb_destroy(ocb_ctx* ctx);
+const char* ocb_last_error(const ocb_ctx* ctx);
+const char* ocb_version(void);
+/* run everything of this context on an existing cudaStream_t (e.g. torch's current stream) */
+int  ocb_set_stream(ocb_ctx* ctx, void* cuda_stream);
+int  ocb_synchronize(ocb_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream (what bench.py times kernels with) */
+int  ocb_timer_start(ocb_ctx* ctx);
+int  ocb_timer_stop_ms(ocb_ctx* ctx, double* ms);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t ocb_launch_count(const ocb_ctx* ctx);
+
+/* ---- a1: rest-frame features — TriMesh::computeFeatures, TriMesh.cpp:343-398 ---------------
+ * rest8_soa (8 x nF, row k contiguous): triArea, triAreaSq, e0SqLen, e1SqLen, e0dote1,
+ * e0SqLen_div_dbAreaSq, e1SqLen_div_dbAreaSq, e0dote1_div_dbAreaSq.  Triangles with area below
+ * areaThres_AM get the equilateral surrogate (TriMesh.cpp:373-383).  scalars3 = surfaceArea,
+ * avgEdgeLen (igl::avg_edge_length), virtualRadius = sqrt(surfaceArea/pi).  Returns
+ * OCB_ERR_ARG if a triangle has zero area (the reference exits: TriMesh.cpp:368-402). */
+int ocb_rest_features(ocb_ctx* ctx, int nV, int nF, const double* V_rest_colmajor /* nV x 3 */,
+                      const int32_t* F_colmajor, double areaThres_AM,
+                      double* rest8_soa, double* scalars3);
+
+/* ---- problem data --------------------------------------------------------------------------
+ * ocb_set_mesh: TriMesh::F + features + fixedVert (TriMesh.hpp:30-68).  Call when topology changes. */
+int ocb_set_mesh(ocb_ctx* ctx, int nV, int nF, const int32_t* F_colmajor, const double* rest8_soa,
+                 double surfaceArea, const int32_t* fixed, int nFixed);
+/* ocb_set_air: Scaffold::airMesh + localVI2Global + airMesh.fixedVert (Scaffold.cpp:169-199);
+ * w_scaf_over_Fa = w_scaf / |F_air| (Optimizer.cpp:776,795,839).  nFa = 0 removes the scaffold.
+ * Call after every Scaffold rebuild (Optimizer.cpp:236-239). */
+int ocb_set_air(ocb_ctx* ctx, int nVa, int nFa, const int32_t* Fa_colmajor, const double* rest8_soa,
+                const int32_t* localVI2Global, int nBnd, const int32_t* fixedAir, int nFixedAir,
+                double w_scaf_over_Fa);
+/* UV coordinates: TriMesh::V (nV x 2) and airMesh.V (nVa x 2, NULL when no scaffold) */
+int ocb_set_uv(ocb_ctx* ctx, const double* V_colmajor, const double* Va_colmajor);
+int ocb_get_uv(ocb_ctx* ctx, double* V_colmajor, double* Va_colmajor);
+/* sizes: nV, nF, nVa, nFa, nBnd, nSys, nnz_upper (reference CSR), nnz_blocks (BSR 2x2) */
+int ocb_get_sizes(const ocb_ctx* ctx, int64_t* sizes8);
+
+/* ---- a2/a13: energy — SymDirichletEnergy::getEnergyValPerElem (SymDirichletEnergy.cpp:24-46),
+ * Energy::computeEnergyVal (Energy.cpp:35-40), Optimizer::computeEnergyVal (Optimizer.cpp:764-782).
+ * E_total = energyParam0 * E_sd + E_scaf,  E_scaf = w_scaf/|Fa| * sum_air E_t(uniform).
+ * Returns OCB_ERR_INVERTED (values still written, possibly inf/nan) if any signed area <= 0. */
+int ocb_energy(ocb_ctx* ctx, double energyParam0, double* E_total, double* E_sd, double* E_scaf);
+/* per-element values of the mesh term, w = triArea/surfaceArea or 1 (uniformWeight) */
+int ocb_energy_per_elem(ocb_ctx* ctx, int uniformWeight, double* out_nF);
+
+/* ---- a4/a13: gradient — SymDirichletEnergy::computeGradient (:258-304), Optimizer::computeGradient
+ * (Optimizer.cpp:783-797), Scaffold::augmentGradient (Scaffold.cpp:210-229).  Result (nSys,
+ * interleaved, fixed vertices zeroed) stays on the device as the solver's right-hand side; g_out
+ * may be NULL.  sqnorm = ||g||^2 (Optimizer.cpp:210). */
+int ocb_gradient(ocb_ctx* ctx, double energyParam0, double* g_out, double* sqnorm);
+
+/* ---- a10: pattern — LinSysSolver::set_pattern (LinSysSolver.hpp:37-135) on the merged adjacency
+ * (Scaffold::mergeVNeighbor / mergeFixedV, Scaffold.cpp:295-313).  adj is the vNeighbor sets in CSR
+ * form (each row ascending, as std::set iterates).  Builds the device BSR(2x2) pattern, the
+ * element->block scatter map and the reference's upper-triangular scalar CSR layout. */
+int ocb_set_pattern(ocb_ctx* ctx, int nVtot, const int32_t* adj_ptr, const int32_t* adj_idx,
+                    const int32_t* fixed, int nFixed);
+/* convenience: derive the adjacency from the element lists already uploaded (mesh + air) */
+int ocb_set_pattern_from_elements(ocb_ctx* ctx);
+
+/* ---- a5/a9/a11/a18: Hessian — SymDirichletEnergy::computeHessian (:429-549) + IglUtils::makePD
+ * (IglUtils.hpp:71-90) + addBlockToMatrix/addDiagonalToMatrix (IglUtils.cpp:361-451) +
+ * Optimizer::computeHessian (Optimizer.cpp:798-843) + Scaffold::augmentProxyMatrix
+ * (Scaffold.cpp:231-248) + LinSysSolver::update_a (LinSysSolver.hpp:138-159): element blocks are
+ * projected and scattered straight into the device matrix; no triplets exist. */
+int ocb_hessian_assemble(ocb_ctx* ctx, double energyParam0);
+/* compatibility path = Energy::computeHessian(data,&V,&I,&J,uniformWeight) of the MESH term
+ * (unscaled by energyParam0): same triplet order as the reference.  Call with V==NULL to get *n. */
+int ocb_hessian_triplets(ocb_ctx* ctx, int uniformWeight, double* V, int32_t* I, int32_t* J, int64_t* n);
+/* projected 6x6 element blocks of the mesh term (row-major 36 per triangle, w applied, unscaled) */
+int ocb_hessian_blocks(ocb_ctx* ctx, int uniformWeight, double* out_nFx36);
+/* mirrors LinSysSolver::update_a(I,J,S): zero, then accumulate triplets with i<=j */
+int ocb_update_values_triplets(ocb_ctx* ctx, int64_t nT, const int32_t* I, const int32_t* J, const double* S);
+/* reference layout read-back: 1-based upper-triangular CSR (LinSysSolver.hpp:27-29, get_ia/ja/a) */
+int ocb_download_csr(ocb_ctx* ctx, int32_t* ia, int32_t* ja, double* a);
+/* y = A x with the device matrix (fixes the reference's broken LinSysSolver::multiply, :172-187) */
+int ocb_multiply(ocb_ctx* ctx, const double* x, double* y);
+
+/* ---- a12: solve — EigenLibSolver::analyze_pattern/factorize/solve (EigenLibSolver.cpp:71-107),
+ * replaced by block-Jacobi PCG (persistent cooperative kernel).  rhs==NULL solves A x = -gradient
+ * (Optimizer.cpp:557-563) with the gradient left on the device by ocb_gradient; the solution stays
+ * on the device as the search direction; x_out may be NULL.  rel_tol <= 0 -> 1e-12, max_it <= 0 -> 20*n */
+int ocb_factorize(ocb_ctx* ctx);   /* builds the block-Jacobi preconditioner; OCB_ERR_BREAKDOWN if a diagonal block is not SPD */
+int ocb_solve(ocb_ctx* ctx, const double* rhs, double* x_out, double rel_tol, int max_it,
+              int* iters, double* rel_res);
+int ocb_get_search_dir(ocb_ctx* ctx, double* p_out);
+int ocb_set_search_dir(ocb_ctx* ctx, const double* p);
+
+/* ---- a7: step bound — SymDirichletEnergy::initStepSize (:551-610) over mesh AND air mesh
+ * (Optimizer::initStepSize, Optimizer.cpp:692-704; Scaffold::wholeSearchDir2airMesh).  searchDir
+ * NULL = the device search direction.  *alpha is in/out (start value, usually 1.0). */
+int ocb_step_bound(ocb_ctx* ctx, const double* searchDir, double* alpha);
+
+/* ---- a14: line search — Optimizer::lineSearch + stepForward (Optimizer.cpp:575-673),
+ * Scaffold::stepForward (Scaffold.cpp:282-293), TriMesh::checkInversion (TriMesh.cpp:1710-1756).
+ * Uses the device search direction; alpha0 is the starting step (already x0.99).  E_last is
+ * recomputed when a scaffold is present (Optimizer.cpp:590).  Outputs: accepted alpha, new total
+ * energy, its scaffold part, its mesh SD part (unscaled), lastEDec (scaffold change excluded,
+ * :631-634), number of halvings, stop flag (:635, honoured only if allowEDecRelTol). */
+typedef struct {
+    double alpha, E_new, E_scaf_new, E_sd_new, E_last, lastEDec;
+    int n_halvings, stopped;
+} ocb_linesearch_result;
+int ocb_line_search(ocb_ctx* ctx, double energyParam0, double E_last, double alpha0,
+                    int allowEDecRelTol, ocb_linesearch_result* out);
+/* x = x0 + alpha * p without evaluation (Optimizer::stepForward) */
+int ocb_step_forward(ocb_ctx* ctx, double alpha);
+
+/* ---- one whole Newton iteration of Optimizer::solve(1) (Optimizer.cpp:203-261, 505-573):
+ * gradient -> convergence test -> Hessian -> PCG -> step bound -> line search, device resident. */
+typedef struct {
+    double sqn_g, targetGRes, alpha, E_new, E_scaf_new, E_sd_new, lastEDec, pcg_rel_res;
+    int converged, stopped, n_halvings, pcg_iters;
+} ocb_newton_result;
+int ocb_newton_step(ocb_ctx* ctx, double energyParam0, double targetGRes, double pcg_rel_tol,
+                    int pcg_max_it, int allowEDecRelTol, ocb_newton_result* out);
+
+/* ---- a15: seam energy — TriMesh::computeSeamSparsity (TriMesh.cpp:1542-1558); returns
+ * (sum + initSeamLen) / virtualRadius in *E_se (Optimizer.cpp:709-710). */
+int ocb_seam_energy(ocb_ctx* ctx, int nCoh, const int32_t* cohE_colmajor /* nCoh x 4 */,
+                    const double* edgeLen, const int32_t* boundaryEdge, double initSeamLen,
+                    double virtualRadius, double avgEdgeLen, int triSoup, double* E_se);
+
+/* ---- a8: candidate filter score — SymDirichletEnergy::computeLocalGradient (:215-256) +
+ * computeDivGradPerVert (:108-149): per-vertex sample std-dev of incident corner gradients. */
+int ocb_divgrad_scores(ocb_ctx* ctx, double* perVert_nV);
+
+/* ---- a16/a17 (non-bijective local stencils): batched evaluation of candidate operations —
+ * TriMesh::computeLocalLDec -> computeLocalEdDec_* -> nested dense Optimizer (TriMesh.cpp:2105-2794).
+ * One thread block per stencil runs the local projected-Newton solve (dense LDLT in shared memory,
+ * relGL2Tol 1e-6, <= maxIter iterations) and returns E_init - E_final per stencil. */
+typedef struct {
+    int nStencil;
+    const int32_t* vert_ptr;   /* nStencil+1: local vertex ranges */
+    const int32_t* tri_ptr;    /* nStencil+1: local triangle ranges */
+    const double*  V_rest;     /* 3 per local vertex (x y z interleaved) */
+    const double*  UV;         /* 2 per local vertex (interleaved) */
+    const int32_t* F;          /* 3 per local triangle, LOCAL vertex ids */
+    const uint8_t* is_free;    /* per local vertex: 1 = free DOF, 0 = fixed */
+} ocb_stencil_batch;
+int ocb_eval_stencils(ocb_ctx* ctx, const ocb_stencil_batch* batch, int maxIter, double relGL2Tol,
+                      double* E_init, double* E_final, double* UV_out, int32_t* iters, int* argmax_dec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTCUTS_B200_H */
