@@ -42,7 +42,7 @@ typedef enum {
     OCB_ERR_CUDA = -1,        /* a CUDA runtime call failed (text in ocb_last_error) */
     OCB_ERR_ARG = -2,         /* bad argument / call order */
     OCB_ERR_STATE = -3,       /* required data (mesh, uv, pattern, matrix ...) not set */
-    OCB_ERR_INVERTED = -4,    /* element with non-positive signed UV area (Optimizer.cpp:65-67) */
+    OCB_ERR_INVERTED = -4,    /* element with negative signed UV area (TriMesh::checkInversion, Optimizer.cpp:65-67) */
     OCB_ERR_NOT_CONVERGED = -5, /* PCG hit max_it (solution is still written) */
     OCB_ERR_BREAKDOWN = -6    /* PCG breakdown: pAp <= 0 (matrix not SPD) */
 } ocb_status;
@@ -90,7 +90,7 @@ int ocb_get_sizes(const ocb_ctx* ctx, int64_t* sizes8);
 /* ---- a2/a13: energy — SymDirichletEnergy::getEnergyValPerElem (SymDirichletEnergy.cpp:24-46),
  * Energy::computeEnergyVal (Energy.cpp:35-40), Optimizer::computeEnergyVal (Optimizer.cpp:764-782).
  * E_total = energyParam0 * E_sd + E_scaf,  E_scaf = w_scaf/|Fa| * sum_air E_t(uniform).
- * Returns OCB_ERR_INVERTED (values still written, possibly inf/nan) if any signed area <= 0. */
+ * Returns OCB_ERR_INVERTED (values still written, possibly inf/nan) if any signed area < 0. */
 int ocb_energy(ocb_ctx* ctx, double energyParam0, double* E_total, double* E_sd, double* E_scaf);
 /* per-element values of the mesh term, w = triArea/surfaceArea or 1 (uniformWeight) */
 int ocb_energy_per_elem(ocb_ctx* ctx, int uniformWeight, double* out_nF);

@@ -1,0 +1,754 @@
+// optcuts_b200 — the C-ABI (include/optcuts_b200.h): host-side orchestration of the device kernels.
+// Mirrors, call for call, what the reference's Optimizer does around its Energy / LinSysSolver
+// plugins (Optimizer.cpp:154-201, 203-261, 505-704, 764-843); every entry point cites its
+// reference counterpart in the header.
+#include "ocb_internal.cuh"
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+namespace ocb {
+
+int set_err(ocb_ctx* c, int code, const char* what)
+{
+    if (c) c->err = what ? what : "";
+    return code;
+}
+int cuda_fail(ocb_ctx* c, cudaError_t e, const char* where)
+{
+    if (c) { c->err = std::string(where) + ": " + cudaGetErrorString(e); }
+    cudaGetLastError();
+    return OCB_ERR_CUDA;
+}
+
+int ensure_init(ocb_ctx* c)
+{
+    if (c->inited) { cudaSetDevice(c->device); return 0; }
+    OCB_CUDA(c, cudaSetDevice(c->device));
+    if (!c->stream) { OCB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    OCB_CUDA(c, cudaEventCreate(&c->ev0));
+    OCB_CUDA(c, cudaEventCreate(&c->ev1));
+    cudaDeviceProp prop;
+    OCB_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    c->numSMs = prop.multiProcessorCount;
+    OCB_CUDA(c, cudaMalloc((void**)&c->dScal, sizeof(double) * S_COUNT));
+    OCB_CUDA(c, cudaMemset(c->dScal, 0, sizeof(double) * S_COUNT));
+    OCB_CUDA(c, cudaMallocHost((void**)&c->hScal, sizeof(double) * S_COUNT));
+    OCB_CUDA(c, c->sync.reserve(64, c->stream));
+    OCB_CUDA(c, cudaMemset(c->sync.p, 0, sizeof(unsigned) * 64));
+    OCB_CUDA(c, c->partials.reserve(4096, c->stream));
+    c->inited = true;
+    return 0;
+}
+
+ElemView view_of(const ocb_ctx* c, const ElemSet& s, bool isAir, double scale, int uniform)
+{
+    ElemView v;
+    const size_t n = (size_t)s.n;
+    v.n = s.n;
+    v.v0 = s.v.p; v.v1 = s.v.p + n; v.v2 = s.v.p + 2 * n;
+    const double* r = s.rest.p;
+    v.area = r; v.areaSq = r + n; v.e0 = r + 2 * n; v.e1 = r + 3 * n; v.d = r + 4 * n;
+    v.k0 = r + 5 * n; v.k1 = r + 6 * n; v.kd = r + 7 * n;
+    v.slot = s.slot.p;
+    v.surfaceArea = isAir ? 1.0 : c->surfaceArea;
+    v.uniform = uniform;
+    v.scale = scale;
+    return v;
+}
+
+int fetch_scalars(ocb_ctx* c)
+{
+    OCB_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int upload_d(ocb_ctx* c, double* dst, const double* src, size_t n) {
+    OCB_CUDA(c, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+static int upload_i(ocb_ctx* c, int32_t* dst, const int32_t* src, size_t n) {
+    OCB_CUDA(c, cudaMemcpyAsync(dst, src, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+// (re)size the system vectors after nVtot changed, keeping the mesh part of x
+static int resize_system(ocb_ctx* c)
+{
+    const size_t n = (size_t)c->nSys();
+    OCB_CUDA(c, c->x.reserve(n, c->stream, true));
+    OCB_CUDA(c, c->x0.reserve(n, c->stream));
+    OCB_CUDA(c, c->g.reserve(n, c->stream));
+    OCB_CUDA(c, c->p.reserve(n, c->stream));
+    return 0;
+}
+
+static int upload_fixed_mask(ocb_ctx* c)
+{
+    OCB_CUDA(c, c->fixedMask.reserve((size_t)c->nVtot, c->stream));
+    c->hFixed.resize((size_t)c->nVtot, 0);
+    OCB_CUDA(c, cudaMemcpyAsync(c->fixedMask.p, c->hFixed.data(), (size_t)c->nVtot, cudaMemcpyHostToDevice, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int need(ocb_ctx* c, bool cond, const char* what) { return cond ? 0 : set_err(c, OCB_ERR_STATE, what); }
+
+}  // namespace ocb
+
+using namespace ocb;
+
+extern "C" {
+
+const char* ocb_version(void) { return "optcuts_b200 0.1 (sm_100a, fp64)"; }
+
+int ocb_create(ocb_ctx** out, int device)
+{
+    if (!out) return OCB_ERR_ARG;
+    ocb_ctx* c = new (std::nothrow) ocb_ctx();
+    if (!c) return OCB_ERR_ARG;
+    c->device = device;
+    *out = c;
+    return OCB_OK;
+}
+
+void ocb_destroy(ocb_ctx* c)
+{
+    if (!c) return;
+    if (c->inited) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        c->mesh.v.release(); c->mesh.rest.release(); c->mesh.slot.release();
+        c->air.v.release(); c->air.rest.release(); c->air.slot.release();
+        c->l2g.release(); c->fixedMask.release();
+        c->x.release(); c->x0.release(); c->g.release(); c->p.release();
+        c->pr.release(); c->pz.release(); c->pd.release(); c->pAp.release(); c->pb.release(); c->minv.release();
+        c->rowPtr.release(); c->colIdx.release(); c->val.release();
+        c->partials.release(); c->sync.release(); c->scratchD.release(); c->scratchI.release();
+        if (c->dScal) cudaFree(c->dScal);
+        if (c->hScal) cudaFreeHost(c->hScal);
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->ev1) cudaEventDestroy(c->ev1);
+        if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+
+const char* ocb_last_error(const ocb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int ocb_set_stream(ocb_ctx* c, void* s)
+{
+    if (!c) return OCB_ERR_ARG;
+    if (c->inited && c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t)s; c->own_stream = false;
+    if (!c->stream && c->inited) { OCB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    return OCB_OK;
+}
+int ocb_synchronize(ocb_ctx* c) { OCB_TRY(ensure_init(c)); OCB_CUDA(c, cudaStreamSynchronize(c->stream)); return OCB_OK; }
+int ocb_timer_start(ocb_ctx* c) { OCB_TRY(ensure_init(c)); OCB_CUDA(c, cudaEventRecord(c->ev0, c->stream)); return OCB_OK; }
+int ocb_timer_stop_ms(ocb_ctx* c, double* ms)
+{
+    OCB_TRY(ensure_init(c));
+    OCB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    OCB_CUDA(c, cudaEventSynchronize(c->ev1));
+    float f = 0.f;
+    OCB_CUDA(c, cudaEventElapsedTime(&f, c->ev0, c->ev1));
+    if (ms) *ms = f;
+    return OCB_OK;
+}
+int64_t ocb_launch_count(const ocb_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------- a1
+int ocb_rest_features(ocb_ctx* c, int nV, int nF, const double* Vrest, const int32_t* F, double thres,
+                      double* rest8, double* scalars3)
+{
+    if (!c || nV <= 0 || nF <= 0 || !Vrest || !F || !rest8) return set_err(c, OCB_ERR_ARG, "ocb_rest_features: bad argument");
+    OCB_TRY(ensure_init(c));
+    OCB_CUDA(c, c->scratchD.reserve((size_t)3 * nV + (size_t)8 * nF, c->stream));
+    OCB_CUDA(c, c->scratchI.reserve((size_t)3 * nF, c->stream));
+    double* dP = c->scratchD.p; double* dR = dP + (size_t)3 * nV;
+    OCB_TRY(upload_d(c, dP, Vrest, (size_t)3 * nV));
+    OCB_TRY(upload_i(c, c->scratchI.p, F, (size_t)3 * nF));
+    OCB_TRY(launch_rest_features(c, nV, nF, dP, c->scratchI.p, thres, dR));
+    OCB_CUDA(c, cudaMemcpyAsync(rest8, dR, sizeof(double) * 8 * (size_t)nF, cudaMemcpyDeviceToHost, c->stream));
+    OCB_TRY(fetch_scalars(c));
+    const double surf = c->hScal[S_MISC0];
+    if (scalars3) { scalars3[0] = surf; scalars3[1] = c->hScal[S_MISC1] / (3.0 * nF); scalars3[2] = std::sqrt(surf / M_PI); }
+    if (c->hScal[S_MISC2] > 0.0) return set_err(c, OCB_ERR_ARG, "mesh has a zero-area triangle (TriMesh.cpp:368-402)");
+    return OCB_OK;
+}
+
+// ------------------------------------------------------------------------------------- problem data
+static int upload_elems(ocb_ctx* c, ElemSet& S, std::vector<int32_t>& hostCopy, int n, const int32_t* F_global_soa, const double* rest8)
+{
+    S.n = n;
+    OCB_CUDA(c, S.v.reserve((size_t)3 * n + 1, c->stream));
+    OCB_CUDA(c, S.rest.reserve((size_t)8 * n + 1, c->stream));
+    if (n > 0) {
+        hostCopy.assign(F_global_soa, F_global_soa + (size_t)3 * n);
+        OCB_TRY(upload_i(c, S.v.p, hostCopy.data(), (size_t)3 * n));
+        OCB_TRY(upload_d(c, S.rest.p, rest8, (size_t)8 * n));
+    } else hostCopy.clear();
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ocb_set_mesh(ocb_ctx* c, int nV, int nF, const int32_t* F, const double* rest8, double surfaceArea,
+                 const int32_t* fixed, int nFixed)
+{
+    if (!c || nV <= 0 || nF <= 0 || !F || !rest8 || !(surfaceArea > 0.0)) return set_err(c, OCB_ERR_ARG, "ocb_set_mesh: bad argument");
+    for (size_t i = 0; i < (size_t)3 * nF; ++i) if (F[i] < 0 || F[i] >= nV) return set_err(c, OCB_ERR_ARG, "ocb_set_mesh: vertex index out of range");
+    OCB_TRY(ensure_init(c));
+    c->nV = nV; c->nF = nF; c->surfaceArea = surfaceArea;
+    // a new mesh drops the scaffold (the caller re-sends it, as the reference rebuilds it: Optimizer.cpp:483-488)
+    c->nVa = c->nFa = c->nBnd = 0; c->air.n = 0; c->hFa.clear(); c->hL2G.clear(); c->wScafOverFa = 0.0;
+    c->nVtot = nV;
+    OCB_TRY(upload_elems(c, c->mesh, c->hF, nF, F, rest8));
+    c->hFixed.assign((size_t)nV, 0);
+    for (int i = 0; i < nFixed; ++i) { if (fixed[i] < 0 || fixed[i] >= nV) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range"); c->hFixed[fixed[i]] = 1; }
+    OCB_TRY(resize_system(c));
+    OCB_TRY(upload_fixed_mask(c));
+    c->haveUV = false; c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
+    return OCB_OK;
+}
+
+int ocb_set_air(ocb_ctx* c, int nVa, int nFa, const int32_t* Fa, const double* rest8, const int32_t* l2g, int nBnd,
+                const int32_t* fixedAir, int nFixedAir, double wScafOverFa)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->nV > 0, "ocb_set_air before ocb_set_mesh"));
+    OCB_TRY(ensure_init(c));
+    if (nFa <= 0) {
+        c->nVa = c->nFa = c->nBnd = 0; c->air.n = 0; c->hFa.clear(); c->hL2G.clear(); c->wScafOverFa = 0.0;
+        c->nVtot = c->nV;
+        c->hFixed.resize((size_t)c->nV);
+    } else {
+        if (!Fa || !rest8 || !l2g || nVa <= 0 || nBnd < 0 || nBnd > nVa) return set_err(c, OCB_ERR_ARG, "ocb_set_air: bad argument");
+        const int nVtot = c->nV + nVa - nBnd;
+        for (int i = 0; i < nVa; ++i) {
+            const bool ok = (i < nBnd) ? (l2g[i] >= 0 && l2g[i] < c->nV) : (l2g[i] == c->nV + i - nBnd);
+            if (!ok) return set_err(c, OCB_ERR_ARG, "ocb_set_air: localVI2Global does not follow Scaffold.cpp:179-184");
+        }
+        std::vector<int32_t> Fg((size_t)3 * nFa);
+        for (size_t i = 0; i < (size_t)3 * nFa; ++i) {
+            if (Fa[i] < 0 || Fa[i] >= nVa) return set_err(c, OCB_ERR_ARG, "ocb_set_air: vertex index out of range");
+            Fg[i] = l2g[Fa[i]];
+        }
+        c->nVa = nVa; c->nFa = nFa; c->nBnd = nBnd; c->nVtot = nVtot; c->wScafOverFa = wScafOverFa;
+        c->hL2G.assign(l2g, l2g + nVa);
+        OCB_TRY(upload_elems(c, c->air, c->hFa, nFa, Fg.data(), rest8));
+        OCB_CUDA(c, c->l2g.reserve((size_t)nVa, c->stream));
+        OCB_TRY(upload_i(c, c->l2g.p, l2g, (size_t)nVa));
+        // fixed: keep the mesh part, reset the air part
+        c->hFixed.resize((size_t)c->nV);
+        c->hFixed.resize((size_t)nVtot, 0);
+        for (int i = 0; i < nFixedAir; ++i) {
+            if (fixedAir[i] < 0 || fixedAir[i] >= nVa) return set_err(c, OCB_ERR_ARG, "fixed air vertex out of range");
+            c->hFixed[l2g[fixedAir[i]]] = 1;
+        }
+    }
+    OCB_TRY(resize_system(c));
+    OCB_TRY(upload_fixed_mask(c));
+    c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
+    return OCB_OK;
+}
+
+int ocb_set_uv(ocb_ctx* c, const double* V, const double* Va)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->nV > 0, "ocb_set_uv before ocb_set_mesh"));
+    OCB_TRY(ensure_init(c));
+    const size_t nv = V ? 2 * (size_t)c->nV : 0, na = (Va && c->nVa > 0) ? 2 * (size_t)c->nVa : 0;
+    OCB_CUDA(c, c->scratchD.reserve(nv + na + 2, c->stream));
+    double* dV = V ? c->scratchD.p : nullptr;
+    double* dVa = na ? c->scratchD.p + nv : nullptr;
+    if (V) OCB_TRY(upload_d(c, dV, V, nv));
+    if (na) OCB_TRY(upload_d(c, dVa, Va, na));
+    OCB_TRY(launch_set_uv(c, dV, dVa));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (V) c->haveUV = true;
+    c->matrixValid = c->precondValid = false;
+    return OCB_OK;
+}
+
+int ocb_get_uv(ocb_ctx* c, double* V, double* Va)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "no UV on the device"));
+    const size_t nv = V ? 2 * (size_t)c->nV : 0, na = (Va && c->nVa > 0) ? 2 * (size_t)c->nVa : 0;
+    OCB_CUDA(c, c->scratchD.reserve(nv + na + 2, c->stream));
+    double* dV = V ? c->scratchD.p : nullptr;
+    double* dVa = na ? c->scratchD.p + nv : nullptr;
+    OCB_TRY(launch_get_uv(c, dV, dVa));
+    if (V) OCB_CUDA(c, cudaMemcpyAsync(V, dV, nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (na) OCB_CUDA(c, cudaMemcpyAsync(Va, dVa, na * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OCB_OK;
+}
+
+static int64_t nnz_upper(const ocb_ctx* c)
+{
+    // LinSysSolver::set_pattern: free vertex rows: 2*k and 2*k-1 entries with k = #block cols >= row
+    int64_t nnz = 0;
+    for (int v = 0; v < c->nVtot; ++v) {
+        if (c->hFixed[v]) { nnz += 2; continue; }
+        int k = 0;
+        for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) if (c->hColIdx[b] >= v) ++k;
+        nnz += 4 * (int64_t)k - 1;
+    }
+    return nnz;
+}
+
+int ocb_get_sizes(const ocb_ctx* c, int64_t* s)
+{
+    if (!c || !s) return OCB_ERR_ARG;
+    s[0] = c->nV; s[1] = c->nF; s[2] = c->nVa; s[3] = c->nFa; s[4] = c->nBnd; s[5] = c->nSys();
+    s[6] = c->patternValid ? nnz_upper(c) : 0; s[7] = c->patternValid ? c->nnzb : 0;
+    return OCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------- energy
+int ocb_energy(ocb_ctx* c, double p0, double* E_total, double* E_sd, double* E_scaf)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_energy: no UV"));
+    OCB_TRY(launch_energy(c, p0, false, 0.0));
+    OCB_TRY(fetch_scalars(c));
+    const double esd = c->hScal[S_E_MESH], escaf = c->nFa > 0 ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
+    if (E_sd) *E_sd = esd;
+    if (E_scaf) *E_scaf = escaf;
+    if (E_total) *E_total = p0 * esd + escaf;
+    if (c->hScal[S_N_INVERTED] > 0.0) return set_err(c, OCB_ERR_INVERTED, "element with negative signed UV area");
+    return OCB_OK;
+}
+
+int ocb_energy_per_elem(ocb_ctx* c, int uniform, double* out)
+{
+    if (!c || !out) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_energy_per_elem: no UV"));
+    OCB_CUDA(c, c->scratchD.reserve((size_t)c->nF, c->stream));
+    OCB_TRY(launch_energy_per_elem(c, uniform, c->scratchD.p));
+    OCB_CUDA(c, cudaMemcpyAsync(out, c->scratchD.p, sizeof(double) * c->nF, cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OCB_OK;
+}
+
+int ocb_gradient(ocb_ctx* c, double p0, double* g_out, double* sqnorm)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_gradient: no UV"));
+    OCB_TRY(launch_gradient(c, p0));
+    if (g_out) OCB_CUDA(c, cudaMemcpyAsync(g_out, c->g.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToHost, c->stream));
+    OCB_TRY(fetch_scalars(c));
+    if (sqnorm) *sqnorm = c->hScal[S_SQN_G];
+    return OCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ pattern
+static int install_pattern(ocb_ctx* c)
+{
+    c->nnzb = (int)c->hColIdx.size();
+    OCB_CUDA(c, c->rowPtr.reserve((size_t)c->nVtot + 1, c->stream));
+    OCB_CUDA(c, c->colIdx.reserve((size_t)c->nnzb + 1, c->stream));
+    OCB_CUDA(c, c->val.reserve(4 * (size_t)c->nnzb + 4, c->stream));
+    OCB_TRY(upload_i(c, c->rowPtr.p, c->hRowPtr.data(), (size_t)c->nVtot + 1));
+    OCB_TRY(upload_i(c, c->colIdx.p, c->hColIdx.data(), (size_t)c->nnzb));
+    OCB_TRY(upload_fixed_mask(c));
+    c->patternValid = true; c->matrixValid = c->precondValid = false;
+    return launch_build_slots(c);
+}
+
+int ocb_set_pattern(ocb_ctx* c, int nVtot, const int32_t* adjPtr, const int32_t* adjIdx, const int32_t* fixed, int nFixed)
+{
+    if (!c || !adjPtr || !adjIdx) return set_err(c, OCB_ERR_ARG, "ocb_set_pattern: bad argument");
+    OCB_TRY(ensure_init(c));
+    if (c->nV == 0) {     // solver-only use (a bare LinSysSolver): the system size comes from the adjacency
+        if (nVtot <= 0) return set_err(c, OCB_ERR_ARG, "ocb_set_pattern: empty adjacency");
+        c->nVtot = nVtot;
+        OCB_CUDA(c, c->g.reserve(2 * (size_t)nVtot, c->stream));
+        OCB_CUDA(c, c->p.reserve(2 * (size_t)nVtot, c->stream));
+    }
+    if (nVtot != c->nVtot) return set_err(c, OCB_ERR_ARG, "ocb_set_pattern: nVtot does not match mesh + air sizes");
+    c->hFixed.assign((size_t)nVtot, 0);
+    for (int i = 0; i < nFixed; ++i) { if (fixed[i] < 0 || fixed[i] >= nVtot) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range"); c->hFixed[fixed[i]] = 1; }
+    c->hRowPtr.assign((size_t)nVtot + 1, 0);
+    c->hColIdx.clear();
+    c->hColIdx.reserve((size_t)adjPtr[nVtot] + nVtot);
+    for (int v = 0; v < nVtot; ++v) {
+        if (c->hFixed[v]) { c->hColIdx.push_back(v); }
+        else {
+            bool selfDone = false;
+            for (int k = adjPtr[v]; k < adjPtr[v + 1]; ++k) {
+                const int nb = adjIdx[k];
+                if (nb < 0 || nb >= nVtot) return set_err(c, OCB_ERR_ARG, "adjacency index out of range");
+                if (k > adjPtr[v] && adjIdx[k - 1] >= nb) return set_err(c, OCB_ERR_ARG, "adjacency rows must be strictly ascending");
+                if (nb == v) continue;
+                if (!selfDone && nb > v) { c->hColIdx.push_back(v); selfDone = true; }
+                if (!c->hFixed[nb]) c->hColIdx.push_back(nb);
+            }
+            if (!selfDone) c->hColIdx.push_back(v);
+        }
+        c->hRowPtr[v + 1] = (int32_t)c->hColIdx.size();
+    }
+    return install_pattern(c);
+}
+
+int ocb_set_pattern_from_elements(ocb_ctx* c)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->nV > 0, "ocb_set_pattern_from_elements before ocb_set_mesh"));
+    OCB_TRY(ensure_init(c));
+    const int nVtot = c->nVtot;
+    c->hFixed.resize((size_t)nVtot, 0);
+    // degree upper bound (with duplicates), fill, then sort + unique every short row
+    std::vector<int32_t> cnt((size_t)nVtot + 1, 0);
+    auto count = [&](const std::vector<int32_t>& F, int n) {
+        for (int t = 0; t < n; ++t) for (int k = 0; k < 3; ++k) cnt[(size_t)F[(size_t)k * n + t] + 1] += 2;
+    };
+    count(c->hF, c->nF); count(c->hFa, c->nFa);
+    for (int v = 0; v < nVtot; ++v) cnt[v + 1] += cnt[v] + 1;       // +1: the diagonal
+    std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1), buf((size_t)cnt[nVtot]);
+    for (int v = 0; v < nVtot; ++v) buf[fill[v]++] = v;
+    auto scatter = [&](const std::vector<int32_t>& F, int n) {
+        for (int t = 0; t < n; ++t) {
+            const int a = F[t], b = F[(size_t)n + t], d = F[2 * (size_t)n + t];
+            buf[fill[a]++] = b; buf[fill[a]++] = d; buf[fill[b]++] = a; buf[fill[b]++] = d; buf[fill[d]++] = a; buf[fill[d]++] = b;
+        }
+    };
+    scatter(c->hF, c->nF); scatter(c->hFa, c->nFa);
+    c->hRowPtr.assign((size_t)nVtot + 1, 0);
+    c->hColIdx.clear(); c->hColIdx.reserve(buf.size() / 2 + nVtot);
+    for (int v = 0; v < nVtot; ++v) {
+        if (c->hFixed[v]) { c->hColIdx.push_back(v); }
+        else {
+            int32_t* b = buf.data() + cnt[v]; int32_t* e = buf.data() + fill[v];
+            std::sort(b, e);
+            e = std::unique(b, e);
+            for (int32_t* q = b; q < e; ++q) if (*q == v || !c->hFixed[*q]) c->hColIdx.push_back(*q);
+        }
+        c->hRowPtr[v + 1] = (int32_t)c->hColIdx.size();
+    }
+    return install_pattern(c);
+}
+
+// ------------------------------------------------------------------------------------------ Hessian
+int ocb_hessian_assemble(ocb_ctx* c, double p0)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_hessian_assemble: no UV"));
+    OCB_TRY(need(c, c->patternValid && c->slotsValid, "ocb_hessian_assemble: no sparsity pattern (ocb_set_pattern)"));
+    OCB_TRY(launch_hessian(c, p0));
+    c->matrixValid = true; c->precondValid = false;
+    return OCB_OK;
+}
+
+int ocb_hessian_blocks(ocb_ctx* c, int uniform, double* out)
+{
+    if (!c || !out) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_hessian_blocks: no UV"));
+    OCB_CUDA(c, c->scratchD.reserve(36 * (size_t)c->nF, c->stream));
+    OCB_TRY(launch_hessian_blocks(c, uniform, c->scratchD.p));
+    OCB_CUDA(c, cudaMemcpyAsync(out, c->scratchD.p, sizeof(double) * 36 * (size_t)c->nF, cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OCB_OK;
+}
+
+int ocb_hessian_triplets(ocb_ctx* c, int uniform, double* V, int32_t* I, int32_t* J, int64_t* n)
+{
+    if (!c || !n) return OCB_ERR_ARG;
+    // count first: dim^2 * free^2 per triangle with >=1 free vertex, + 2 per fixed vertex
+    int64_t cntT = 0;
+    const int nF = c->nF;
+    for (int t = 0; t < nF; ++t) {
+        int nf = 0;
+        for (int k = 0; k < 3; ++k) nf += c->hFixed[c->hF[(size_t)k * nF + t]] ? 0 : 1;
+        cntT += 4 * (int64_t)nf * nf;
+    }
+    int nFixedMesh = 0;
+    for (int v = 0; v < c->nV; ++v) nFixedMesh += c->hFixed[v] ? 1 : 0;
+    cntT += 2 * (int64_t)nFixedMesh;
+    *n = cntT;
+    if (!V) return OCB_OK;
+    if (!I || !J) return set_err(c, OCB_ERR_ARG, "ocb_hessian_triplets: I/J missing");
+    std::vector<double> blocks(36 * (size_t)nF);
+    OCB_TRY(ocb_hessian_blocks(c, uniform, blocks.data()));
+    int64_t w = 0;
+    for (int t = 0; t < nF; ++t) {
+        int idx[3];
+        for (int k = 0; k < 3; ++k) { idx[k] = c->hF[(size_t)k * nF + t]; if (c->hFixed[idx[k]]) idx[k] = -1; }
+        const double* B = blocks.data() + 36 * (size_t)t;
+        for (int a = 0; a < 3; ++a) {
+            if (idx[a] < 0) continue;
+            for (int b = 0; b < 3; ++b) {
+                if (idx[b] < 0) continue;
+                for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) {
+                    V[w] = B[(2 * a + i) * 6 + 2 * b + j]; I[w] = 2 * idx[a] + i; J[w] = 2 * idx[b] + j; ++w;
+                }
+            }
+        }
+    }
+    for (int v = 0; v < c->nV; ++v) if (c->hFixed[v]) for (int i = 0; i < 2; ++i) { V[w] = 1.0; I[w] = J[w] = 2 * v + i; ++w; }
+    return OCB_OK;
+}
+
+int ocb_update_values_triplets(ocb_ctx* c, int64_t nT, const int32_t* I, const int32_t* J, const double* S)
+{
+    if (!c || nT < 0 || (nT > 0 && (!I || !J || !S))) return set_err(c, OCB_ERR_ARG, "ocb_update_values_triplets: bad argument");
+    OCB_TRY(need(c, c->patternValid, "ocb_update_values_triplets: no sparsity pattern"));
+    OCB_CUDA(c, c->scratchI.reserve(2 * (size_t)nT + 2, c->stream));
+    OCB_CUDA(c, c->scratchD.reserve((size_t)nT + 1, c->stream));
+    if (nT > 0) {
+        OCB_TRY(upload_i(c, c->scratchI.p, I, (size_t)nT));
+        OCB_TRY(upload_i(c, c->scratchI.p + nT, J, (size_t)nT));
+        OCB_TRY(upload_d(c, c->scratchD.p, S, (size_t)nT));
+    }
+    OCB_TRY(launch_triplet_scatter(c, nT, c->scratchI.p, c->scratchI.p + nT, c->scratchD.p));
+    c->matrixValid = true; c->precondValid = false;
+    return OCB_OK;
+}
+
+int ocb_download_csr(ocb_ctx* c, int32_t* ia, int32_t* ja, double* a)
+{
+    if (!c || !ia || !ja || !a) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_download_csr: no matrix"));
+    std::vector<double> val(4 * (size_t)c->nnzb);
+    OCB_CUDA(c, cudaMemcpyAsync(val.data(), c->val.p, sizeof(double) * val.size(), cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    int64_t w = 0;
+    ia[0] = 1;
+    for (int v = 0; v < c->nVtot; ++v) {
+        if (c->hFixed[v]) {
+            int bdiag = -1;
+            for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) if (c->hColIdx[b] == v) bdiag = b;
+            ja[w] = 2 * v + 1; a[w] = val[4 * (size_t)bdiag]; ++w; ia[2 * v + 1] = (int32_t)(w + 1);
+            ja[w] = 2 * v + 2; a[w] = val[4 * (size_t)bdiag + 3]; ++w; ia[2 * v + 2] = (int32_t)(w + 1);
+            continue;
+        }
+        for (int r = 0; r < 2; ++r) {
+            for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) {
+                const int col = c->hColIdx[b];
+                if (col < v) continue;
+                for (int q = 0; q < 2; ++q) {
+                    if (col == v && q < r) continue;     // strict lower entry of the diagonal block
+                    ja[w] = 2 * col + q + 1; a[w] = val[4 * (size_t)b + 2 * r + q]; ++w;
+                }
+            }
+            ia[2 * v + r + 1] = (int32_t)(w + 1);
+        }
+    }
+    return OCB_OK;
+}
+
+int ocb_multiply(ocb_ctx* c, const double* x, double* y)
+{
+    if (!c || !x || !y) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_multiply: no matrix"));
+    const size_t n = c->nSys();
+    OCB_CUDA(c, c->scratchD.reserve(2 * n, c->stream));
+    OCB_TRY(upload_d(c, c->scratchD.p, x, n));
+    OCB_TRY(launch_spmv(c, c->scratchD.p, c->scratchD.p + n));
+    OCB_CUDA(c, cudaMemcpyAsync(y, c->scratchD.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OCB_OK;
+}
+
+// -------------------------------------------------------------------------------------------- solve
+int ocb_factorize(ocb_ctx* c)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_factorize: no matrix"));
+    OCB_TRY(launch_jacobi_setup(c));
+    c->precondValid = true;
+    return OCB_OK;
+}
+
+int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int max_it, int* iters, double* rel_res)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_solve: no matrix"));
+    if (!c->precondValid) OCB_TRY(ocb_factorize(c));
+    const size_t n = c->nSys();
+    if (rel_tol <= 0.0) rel_tol = 1e-12;
+    if (max_it <= 0) max_it = (int)std::min<size_t>(20 * n, 2000000);
+    const double* dRhs = c->g.p;
+    bool negate = true;
+    if (rhs) {
+        OCB_CUDA(c, c->pb.reserve(n, c->stream));
+        OCB_TRY(upload_d(c, c->pb.p, rhs, n));
+        dRhs = c->pb.p; negate = false;
+    }
+    OCB_TRY(launch_pcg(c, dRhs, negate, rel_tol, max_it));
+    if (x_out) OCB_CUDA(c, cudaMemcpyAsync(x_out, c->p.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    OCB_TRY(fetch_scalars(c));
+    if (iters) *iters = (int)c->hScal[S_PCG_ITERS];
+    if (rel_res) *rel_res = c->hScal[S_PCG_RELRES];
+    const int st = (int)c->hScal[S_PCG_STATUS];
+    if (st == 2) return set_err(c, OCB_ERR_BREAKDOWN, "PCG breakdown: d^T A d <= 0 (matrix not SPD)");
+    if (st == 1) return set_err(c, OCB_ERR_NOT_CONVERGED, "PCG reached max_it");
+    return OCB_OK;
+}
+
+int ocb_get_search_dir(ocb_ctx* c, double* p)
+{
+    if (!c || !p) return OCB_ERR_ARG;
+    OCB_CUDA(c, cudaMemcpyAsync(p, c->p.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OCB_OK;
+}
+int ocb_set_search_dir(ocb_ctx* c, const double* p)
+{
+    if (!c || !p) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->nVtot > 0, "ocb_set_search_dir before the system size is known"));
+    OCB_CUDA(c, cudaMemcpyAsync(c->p.p, p, sizeof(double) * c->nSys(), cudaMemcpyHostToDevice, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OCB_OK;
+}
+
+// ------------------------------------------------------------------------------- step bound / search
+int ocb_step_bound(ocb_ctx* c, const double* dir, double* alpha)
+{
+    if (!c || !alpha) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_step_bound: no UV"));
+    const double* dDir = c->p.p;
+    if (dir) {
+        OCB_CUDA(c, c->scratchD.reserve((size_t)c->nSys(), c->stream));
+        OCB_TRY(upload_d(c, c->scratchD.p, dir, (size_t)c->nSys()));
+        dDir = c->scratchD.p;
+    }
+    OCB_TRY(launch_step_bound(c, dDir, *alpha));
+    OCB_TRY(fetch_scalars(c));
+    *alpha = c->hScal[S_STEP_BOUND];
+    return OCB_OK;
+}
+
+int ocb_step_forward(ocb_ctx* c, double alpha)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_step_forward: no UV"));
+    OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
+    OCB_TRY(launch_step_forward(c, alpha));
+    c->matrixValid = c->precondValid = false;
+    return OCB_OK;
+}
+
+int ocb_line_search(ocb_ctx* c, double p0, double E_last, double alpha0, int allowEDecRelTol, ocb_linesearch_result* out)
+{
+    if (!c || !out) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_line_search: no UV"));
+    const bool scaf = c->nFa > 0;
+    double lastScaf = 0.0;
+    OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
+    if (scaf) {   // the scaffold changed since E_last was computed (Optimizer.cpp:588-592)
+        OCB_TRY(launch_energy(c, p0, false, 0.0));
+        OCB_TRY(fetch_scalars(c));
+        lastScaf = c->wScafOverFa * c->hScal[S_E_AIR];
+        E_last = p0 * c->hScal[S_E_MESH] + lastScaf;
+    }
+    double alpha = alpha0, E = 0.0, Escaf = 0.0, Esd = 0.0;
+    int halvings = 0, stopped = 0;
+    for (;;) {
+        OCB_TRY(launch_energy(c, p0, true, alpha));
+        OCB_TRY(fetch_scalars(c));
+        Esd = c->hScal[S_E_MESH];
+        Escaf = scaf ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
+        E = p0 * Esd + Escaf;
+        // plain decrease test (:597); the inversion guard (:615-629) follows the loop
+        if (E > E_last) {
+            alpha /= 2.0; ++halvings;
+            if (alpha == 0.0) { stopped = 1; break; }
+            continue;
+        }
+        break;
+    }
+    // inversion guard: the reference re-halves while any signed area is negative
+    while (!stopped) {
+        // S_N_INVERTED counts signed areas < 0, the test of TriMesh::checkInversion (TriMesh.cpp:1710-1734)
+        if (!(c->hScal[S_N_INVERTED] > 0.0)) break;
+        alpha /= 2.0; ++halvings;
+        if (alpha == 0.0) { stopped = 1; break; }
+        OCB_TRY(launch_energy(c, p0, true, alpha));
+        OCB_TRY(fetch_scalars(c));
+        Esd = c->hScal[S_E_MESH];
+        Escaf = scaf ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
+        E = p0 * Esd + Escaf;
+    }
+    OCB_TRY(launch_step_forward(c, alpha));
+    double eDec = E_last - E;
+    if (scaf) eDec += (-lastScaf + Escaf);
+    if (allowEDecRelTol && (eDec / E_last < 1.0e-6 * alpha) && (alpha > 1.0e-3)) stopped = 1;
+    out->alpha = alpha; out->E_new = E; out->E_scaf_new = Escaf; out->E_sd_new = Esd; out->E_last = E_last;
+    out->lastEDec = eDec; out->n_halvings = halvings; out->stopped = stopped;
+    c->matrixValid = c->precondValid = false;
+    return OCB_OK;
+}
+
+int ocb_newton_step(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_tol, int pcg_max_it,
+                    int allowEDecRelTol, ocb_newton_result* out)
+{
+    if (!c || !out) return OCB_ERR_ARG;
+    std::memset(out, 0, sizeof(*out));
+    out->targetGRes = targetGRes;
+    double sqn = 0.0;
+    OCB_TRY(ocb_gradient(c, p0, nullptr, &sqn));
+    out->sqn_g = sqn;
+    if (sqn < targetGRes) { out->converged = 1; return OCB_OK; }
+    if (!c->patternValid) OCB_TRY(ocb_set_pattern_from_elements(c));
+    OCB_TRY(ocb_hessian_assemble(c, p0));
+    OCB_TRY(ocb_factorize(c));
+    int its = 0; double rr = 0.0;
+    int rs = ocb_solve(c, nullptr, nullptr, pcg_rel_tol, pcg_max_it, &its, &rr);
+    out->pcg_iters = its; out->pcg_rel_res = rr;
+    if (rs < 0 && rs != OCB_ERR_NOT_CONVERGED) return rs;
+    double alpha = 1.0;
+    OCB_TRY(ocb_step_bound(c, nullptr, &alpha));
+    alpha *= 0.99;                                           // Optimizer.cpp:580
+    ocb_linesearch_result ls;
+    OCB_TRY(ocb_line_search(c, p0, 0.0, alpha, allowEDecRelTol, &ls));
+    out->alpha = ls.alpha; out->E_new = ls.E_new; out->E_scaf_new = ls.E_scaf_new; out->E_sd_new = ls.E_sd_new;
+    out->lastEDec = ls.lastEDec; out->n_halvings = ls.n_halvings; out->stopped = ls.stopped;
+    return rs == OCB_ERR_NOT_CONVERGED ? rs : OCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------- seam
+int ocb_seam_energy(ocb_ctx* c, int nCoh, const int32_t* cohE, const double* edgeLen, const int32_t* boundaryEdge,
+                    double initSeamLen, double virtualRadius, double avgEdgeLen, int triSoup, double* E_se)
+{
+    if (!c || !E_se || nCoh < 0) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_seam_energy: no UV"));
+    double sum = 0.0;
+    if (nCoh > 0) {
+        if (!cohE || !edgeLen || !boundaryEdge) return set_err(c, OCB_ERR_ARG, "ocb_seam_energy: bad argument");
+        // boundary rows hold -1 indices: clamp for the gather, they are skipped by the flag
+        std::vector<int32_t> coh(cohE, cohE + 4 * (size_t)nCoh);
+        for (auto& v : coh) if (v < 0) v = 0;
+        OCB_CUDA(c, c->scratchI.reserve(5 * (size_t)nCoh, c->stream));
+        OCB_CUDA(c, c->scratchD.reserve((size_t)nCoh, c->stream));
+        OCB_TRY(upload_i(c, c->scratchI.p, coh.data(), 4 * (size_t)nCoh));
+        OCB_TRY(upload_i(c, c->scratchI.p + 4 * (size_t)nCoh, boundaryEdge, (size_t)nCoh));
+        OCB_TRY(upload_d(c, c->scratchD.p, edgeLen, (size_t)nCoh));
+        OCB_TRY(launch_seam(c, nCoh, c->scratchI.p, c->scratchD.p, c->scratchI.p + 4 * (size_t)nCoh, avgEdgeLen, triSoup));
+        OCB_TRY(fetch_scalars(c));
+        sum = c->hScal[S_MISC0];
+    }
+    *E_se = (sum + initSeamLen) / virtualRadius;
+    return OCB_OK;
+}
+
+int ocb_divgrad_scores(ocb_ctx* c, double* out)
+{
+    if (!c || !out) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_divgrad_scores: no UV"));
+    OCB_CUDA(c, c->pb.reserve((size_t)c->nV, c->stream));
+    OCB_TRY(launch_divgrad(c, c->pb.p));
+    OCB_CUDA(c, cudaMemcpyAsync(out, c->pb.p, sizeof(double) * c->nV, cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OCB_OK;
+}
+
+int ocb_eval_stencils(ocb_ctx* c, const ocb_stencil_batch*, int, double, double*, double*, double*, int32_t*, int*)
+{
+    return set_err(c, OCB_ERR_STATE, "ocb_eval_stencils: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+// optcuts_b200 — per-triangle Symmetric Dirichlet math (device inline functions).
+//
+// For a triangle with rest edges e0 = P2-P1, e1 = P3-P1, rest area A, UV edges u = U2-U1,
+// v = U3-U1 and signed UV area a = (u x v)/2:
+//     R = (|v|^2 |e0|^2 + |u|^2 |e1|^2)/(4A^2) - (u.v)(e0.e1)/(2A^2)  = ||J||_F^2
+//     L = 1 + A^2/a^2                                                   = 1 + det(J)^-2
+//     E_t = w L R
+// Reference behaviour being reproduced (not its code): SymDirichletEnergy.cpp:24-46 (value),
+// :258-304 (gradient), :429-549 (Hessian), IglUtils.hpp:71-90 (makePD), :551-610 (step bound).
+#pragma once
+#ifndef OCB_ELEMENT_HOST
+#include <cuda_runtime.h>
+#endif
+
+namespace ocb {
+
+struct Vec2 { double x, y; };
+__device__ __forceinline__ Vec2 mk(double x, double y) { Vec2 r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ Vec2 operator-(Vec2 a, Vec2 b) { return mk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ Vec2 operator+(Vec2 a, Vec2 b) { return mk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ Vec2 operator*(double s, Vec2 a) { return mk(s * a.x, s * a.y); }
+__device__ __forceinline__ double dot(Vec2 a, Vec2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ double cross(Vec2 a, Vec2 b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ Vec2 perp(Vec2 a) { return mk(a.y, -a.x); }   // (x,y) -> (y,-x)
+
+__device__ __forceinline__ Vec2 ld2(const double* x, int v) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(x) + v);
+    return mk(t.x, t.y);
+}
+// position used by the line search: x0 + alpha * p with NO fma contraction, so that it is the
+// same double the CPU computes (Optimizer.cpp:666-668)
+__device__ __forceinline__ Vec2 ld2_step(const double* x0, const double* p, double alpha, int v) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(x0) + v);
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + v);
+    return mk(__dadd_rn(a.x, __dmul_rn(alpha, b.x)), __dadd_rn(a.y, __dmul_rn(alpha, b.y)));
+}
+
+// ---- value (division order as the reference's value/gradient functions) -----------------------
+__device__ __forceinline__ double sd_energy(Vec2 u, Vec2 v, double A2, double e0, double e1, double d,
+                                            double w, double& dbArea)
+{
+    dbArea = cross(u, v);
+    const double a = 0.5 * dbArea;
+    const double L = 1.0 + A2 / a / a;
+    const double R = (dot(v, v) * e0 + dot(u, u) * e1) / 4 / A2 - dot(v, u) * d / 2 / A2;
+    return w * L * R;
+}
+
+// ---- gradient w.r.t. U1,U2,U3 -----------------------------------------------------------------
+__device__ __forceinline__ void sd_gradient(Vec2 U1, Vec2 U2, Vec2 U3, double A2, double e0, double e1,
+                                            double d, double w, Vec2 g[3])
+{
+    const Vec2 u = U2 - U1, v = U3 - U1;
+    const double a = 0.5 * cross(u, v);
+    const double L = 1.0 + A2 / a / a;
+    const double R = (dot(v, v) * e0 + dot(u, u) * e1) / 4 / A2 - dot(v, u) * d / 2 / A2;
+    const double ar = A2 / a / a / a;                       // dL/dU_k = ar * perp(opposite edge of k)
+    const Vec2 n1 = perp(U3 - U2), n2 = perp(U1 - U3), n3 = perp(U2 - U1);
+    const Vec2 r1 = mk(((d - e0) * v.x + (d - e1) * u.x) / 2.0 / A2, ((d - e0) * v.y + (d - e1) * u.y) / 2.0 / A2);
+    const Vec2 r2 = mk((e1 * u.x - d * v.x) / 2.0 / A2, (e1 * u.y - d * v.y) / 2.0 / A2);
+    const Vec2 r3 = mk((e0 * v.x - d * u.x) / 2.0 / A2, (e0 * v.y - d * u.y) / 2.0 / A2);
+    // association order kept as w * ((ar*n) * R + r * L): with -fmad=false the per-element
+    // contributions are then bit-identical to the CPU reference's
+    g[0] = mk(w * ((ar * n1.x) * R + r1.x * L), w * ((ar * n1.y) * R + r1.y * L));
+    g[1] = mk(w * ((ar * n2.x) * R + r2.x * L), w * ((ar * n2.y) * R + r2.y * L));
+    g[2] = mk(w * ((ar * n3.x) * R + r3.x * L), w * ((ar * n3.y) * R + r3.y * L));
+}
+
+// ---- exact 6x6 Hessian, upper block triangle: Hb[b][i][j], b = 0:(1,1) 1:(1,2) 2:(1,3) 3:(2,2)
+// 4:(2,3) 5:(3,3); uses the precomputed k0 = |e0|^2/(2A^2), k1 = |e1|^2/(2A^2), kd = e0.e1/(2A^2)
+__device__ __forceinline__ void sd_hessian(Vec2 U1, Vec2 U2, Vec2 U3, double A2, double k0, double k1,
+                                           double kd, double w, double Hb[6][2][2])
+{
+    const Vec2 u = U2 - U1, v = U3 - U1;
+    const double a = 0.5 * cross(u, v);
+    const double ar = A2 / a / a / a;
+    const double m = 3.0 / 2.0 * ar / a;                     // d(ar)/da * (-1/2) ... coefficient of n_k n_l^T
+    const double L = 1.0 + A2 / a / a;
+    const double R = (dot(v, v) * k0 + dot(u, u) * k1) / 2. - dot(v, u) * kd;
+    Vec2 n[3], r[3];
+    n[0] = perp(U3 - U2); n[1] = perp(U1 - U3); n[2] = perp(U2 - U1);
+    r[0] = mk((kd - k0) * v.x + (kd - k1) * u.x, (kd - k0) * v.y + (kd - k1) * u.y);
+    r[1] = mk(k1 * u.x - kd * v.x, k1 * u.y - kd * v.y);
+    r[2] = mk(k0 * v.x - kd * u.x, k0 * v.y - kd * u.y);
+    // second derivative of R: c_kl * I
+    const double c[6] = {k0 + k1 - 2.0 * kd, kd - k1, kd - k0, k1, -kd, k0};
+    // derivative of perp(opp_k) w.r.t. U_l is s_kl * [[0,1],[-1,0]]
+    const double s[6] = {0.0, -1.0, 1.0, 0.0, -1.0, 0.0};
+    const int bk[6] = {0, 0, 0, 1, 1, 2}, bl[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        const Vec2 nk = n[bk[b]], nl = n[bl[b]], rk = r[bk[b]], rl = r[bl[b]];
+        const double q = ar * s[b];
+        const double cL = c[b] * L;
+        // ((R * d2L + dL_k r_l^T) + c L I) + r_k dL_l^T  — summation order of the reference's expression
+        Hb[b][0][0] = w * ((((m * nk.x) * nl.x) * R + (ar * nk.x) * rl.x + cL) + rk.x * (ar * nl.x));
+        Hb[b][0][1] = w * ((((m * nk.x) * nl.y + q) * R + (ar * nk.x) * rl.y) + rk.x * (ar * nl.y));
+        Hb[b][1][0] = w * ((((m * nk.y) * nl.x - q) * R + (ar * nk.y) * rl.x) + rk.y * (ar * nl.x));
+        Hb[b][1][1] = w * ((((m * nk.y) * nl.y) * R + (ar * nk.y) * rl.y + cL) + rk.y * (ar * nl.y));
+    }
+}
+
+// ---- symmetric 4x4 eigen-decomposition, cyclic Jacobi, everything in registers ----------------
+__device__ __forceinline__ void jacobi_rot(double A[4][4], double V[4][4], const int p, const int q)
+{
+    const double apq = A[p][q];
+    if (apq == 0.0) return;
+    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    const double c = rsqrt(t * t + 1.0), s = t * c;
+    A[p][p] -= t * apq;
+    A[q][q] += t * apq;
+    A[p][q] = A[q][p] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r != p && r != q) {
+            const double arp = A[r][p], arq = A[r][q];
+            A[r][p] = A[p][r] = c * arp - s * arq;
+            A[r][q] = A[q][r] = s * arp + c * arq;
+        }
+        const double vrp = V[r][p], vrq = V[r][q];
+        V[r][p] = c * vrp - s * vrq;
+        V[r][q] = s * vrp + c * vrq;
+    }
+}
+__device__ __forceinline__ void jacobi4(double A[4][4], double V[4][4])
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[0][3] * A[0][3] +
+                           A[1][2] * A[1][2] + A[1][3] * A[1][3] + A[2][3] * A[2][3];
+        const double dg = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2] + A[3][3] * A[3][3];
+        if (off <= 1e-33 * dg || off == 0.0) break;
+        jacobi_rot(A, V, 0, 1); jacobi_rot(A, V, 2, 3);
+        jacobi_rot(A, V, 0, 2); jacobi_rot(A, V, 1, 3);
+        jacobi_rot(A, V, 0, 3); jacobi_rot(A, V, 1, 2);
+    }
+}
+
+// ---- projection of the element Hessian onto the PSD cone ---------------------------------------
+// makePD clamps the negative eigenvalues of the 6x6 matrix in vertex space (IglUtils.hpp:71-90).
+// The exact Hessian annihilates the two UV translations, so with the fixed orthonormal basis
+// W = C (x) I2 of their complement (C = [q1 q2], q1 = (1,-1,0)/sqrt2, q2 = (1,1,-2)/sqrt6)
+//     H = W M W^T,  M = W^T H W (4x4),   PSD(H) = W PSD(M) W^T      (same eigenpairs)
+// and PSD(M) = M + sum_{lambda_i<0} |lambda_i| v_i v_i^T.  PSD blocks are left bit-untouched, like
+// the reference's early-out.  Returns the number of clamped eigenvalues.
+__device__ __forceinline__ int sd_project_psd(double Hb[6][2][2])
+{
+    const double s2 = 0.70710678118654752440, s6 = 0.40824829046386301637;
+    const double C[3][2] = {{s2, s6}, {-s2, s6}, {0.0, -2.0 * s6}};
+    double M[4][4];
+    // M_ab(i,j) = sum_kl C[k][a] C[l][b] H_kl(i,j) with H_lk = H_kl^T
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = a; b < 2; ++b)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    double acc = 0.0;
+                    acc += C[0][a] * C[0][b] * Hb[0][i][j];
+                    acc += C[0][a] * C[1][b] * Hb[1][i][j] + C[1][a] * C[0][b] * Hb[1][j][i];
+                    acc += C[0][a] * C[2][b] * Hb[2][i][j] + C[2][a] * C[0][b] * Hb[2][j][i];
+                    acc += C[1][a] * C[1][b] * Hb[3][i][j];
+                    acc += C[1][a] * C[2][b] * Hb[4][i][j] + C[2][a] * C[1][b] * Hb[4][j][i];
+                    acc += C[2][a] * C[2][b] * Hb[5][i][j];
+                    M[2 * a + i][2 * b + j] = acc;
+                }
+    // symmetrise (M11, M22 are symmetric up to rounding; M21 = M12^T)
+    M[1][0] = M[0][1] = 0.5 * (M[0][1] + M[1][0]);
+    M[3][2] = M[2][3] = 0.5 * (M[2][3] + M[3][2]);
+    M[2][0] = M[0][2]; M[2][1] = M[1][2]; M[3][0] = M[0][3]; M[3][1] = M[1][3];
+
+    // quick positive-definiteness test: LDL^T pivots
+    {
+        const double d0 = M[0][0];
+        bool pd = d0 > 0.0;
+        if (pd) {
+            const double l1 = M[0][1] / d0, l2 = M[0][2] / d0, l3 = M[0][3] / d0;
+            const double d1 = M[1][1] - l1 * M[0][1];
+            pd = d1 > 0.0;
+            if (pd) {
+                const double m12 = M[1][2] - l2 * M[0][1], m13 = M[1][3] - l3 * M[0][1];
+                const double l21 = m12 / d1, l31 = m13 / d1;
+                const double d2 = M[2][2] - l2 * M[0][2] - l21 * m12;
+                pd = d2 > 0.0;
+                if (pd) {
+                    const double m23 = M[2][3] - l3 * M[0][2] - l31 * m12;
+                    const double d3 = M[3][3] - l3 * M[0][3] - l31 * m13 - (m23 / d2) * m23;
+                    pd = d3 > 0.0;
+                }
+            }
+        }
+        if (pd) return 0;
+    }
+    double V[4][4];
+    jacobi4(M, V);
+    int clamped = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double lam = M[e][e];
+        if (lam < 0.0) {
+            ++clamped;
+            // y = W v  (6-vector as three 2-vectors)
+            double y[3][2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                y[k][0] = C[k][0] * V[0][e] + C[k][1] * V[2][e];
+                y[k][1] = C[k][0] * V[1][e] + C[k][1] * V[3][e];
+            }
+            const int bk[6] = {0, 0, 0, 1, 1, 2}, bl[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+            for (int b = 0; b < 6; ++b)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) Hb[b][i][j] -= lam * y[bk[b]][i] * y[bl[b]][j];
+        }
+    }
+    return clamped;
+}
+
+// ---- largest step keeping the signed area positive (smallest positive root of a t^2 + b t + c) ---
+__device__ __forceinline__ double sd_step_bound(Vec2 U1, Vec2 U2, Vec2 U3, Vec2 D1, Vec2 D2, Vec2 D3, double cur)
+{
+    const Vec2 u = U2 - U1, v = U3 - U1, du = D2 - D1, dv = D3 - D1;
+    const double a = cross(du, dv);
+    const double b = u.x * dv.y - u.y * dv.x + du.x * v.y - du.y * v.x;
+    const double c = cross(u, v);
+    const double delta = b * b - 4.0 * a * c;
+    double bound = cur;
+    if (a > 0.0) {
+        if (b < 0.0 && delta >= 0.0) bound = 2.0 * c / (-b + sqrt(delta));
+    } else if (a < 0.0) {
+        if (b < 0.0) bound = 2.0 * c / (-b + sqrt(delta));
+        else bound = (-b - sqrt(delta)) / 2.0 / a;
+    } else if (b < 0.0) {
+        bound = -c / b;
+    }
+    return bound < cur ? bound : cur;
+}
+
+}  // namespace ocb

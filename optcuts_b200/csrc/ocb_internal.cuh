@@ -1,0 +1,140 @@
+// optcuts_b200 — internal declarations shared by the translation units of liboptcuts_b200.so.
+// sm_100a only; fp64 everywhere; no tensor cores (nothing on this path is a dense contraction).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/optcuts_b200.h"
+
+namespace ocb {
+
+// ---------------------------------------------------------------------------------------------
+// growable device buffer
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n, cudaStream_t s, bool keep = false) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = n + n / 4 + 64;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc((void**)&q, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) {
+            e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) { cudaFree(q); return e; }
+            cudaStreamSynchronize(s);
+        }
+        if (p) cudaFree(p);
+        p = q; cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// one set of triangles (mesh or air mesh) on the device, SoA, GLOBAL vertex ids
+struct ElemSet {
+    int n = 0;
+    DevBuf<int32_t> v;      // 3 x n  (v0 | v1 | v2), stride = n
+    DevBuf<double> rest;    // 8 x n  (TriMesh.hpp:44-52 order, see optcuts_b200.h), stride = n
+    DevBuf<int32_t> slot;   // 9 x n  BSR block slot of (k,l), -1 if either vertex is fixed
+};
+
+// kernel-side view of an ElemSet
+struct ElemView {
+    int n;
+    const int32_t* v0; const int32_t* v1; const int32_t* v2;
+    const double* area; const double* areaSq; const double* e0; const double* e1; const double* d;
+    const double* k0; const double* k1; const double* kd;
+    const int32_t* slot;     // 9 x n or nullptr
+    double surfaceArea;      // normaliser; weight = uniform ? 1 : area / surfaceArea
+    int uniform;
+    double scale;            // energyParam0 (mesh) or w_scaf/|Fa| (air): applied after projection
+};
+
+enum ScalarSlot {            // layout of the device/pinned scalar block
+    S_E_MESH = 0, S_E_AIR, S_N_INVERTED, S_SQN_G, S_STEP_BOUND, S_PCG_ITERS, S_PCG_RELRES,
+    S_PCG_STATUS, S_PCG_BNORM, S_MISC0, S_MISC1, S_MISC2, S_COUNT = 16
+};
+
+}  // namespace ocb
+
+struct ocb_ctx {
+    int device = 0;
+    bool inited = false;
+    bool own_stream = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int numSMs = 148;
+
+    // sizes
+    int nV = 0, nF = 0, nVa = 0, nFa = 0, nBnd = 0, nVtot = 0;
+    double surfaceArea = 1.0, wScafOverFa = 0.0;
+    bool haveUV = false, patternValid = false, matrixValid = false, precondValid = false, slotsValid = false;
+
+    ocb::ElemSet mesh, air;
+    std::vector<int32_t> hF, hFa;            // host copies of the element lists (global ids), 3 x n SoA
+    std::vector<int32_t> hL2G;               // localVI2Global
+    std::vector<uint8_t> hFixed;             // per global vertex
+    ocb::DevBuf<int32_t> l2g;
+    ocb::DevBuf<uint8_t> fixedMask;          // nVtot
+
+    // state vectors, all nSys doubles (interleaved u,v per global vertex)
+    ocb::DevBuf<double> x, x0, g, p;
+    // PCG work vectors
+    ocb::DevBuf<double> pr, pz, pd, pAp, pb, minv;   // minv: 4 per block row
+    // BSR(2x2), full symmetric storage
+    int nnzb = 0;
+    std::vector<int32_t> hRowPtr, hColIdx;
+    ocb::DevBuf<int32_t> rowPtr, colIdx;
+    ocb::DevBuf<double> val;                 // 4 per block, row-major
+    // reductions
+    ocb::DevBuf<double> partials;            // per-block partial sums
+    ocb::DevBuf<unsigned> sync;              // tickets / grid barrier words
+    double* dScal = nullptr;                 // S_COUNT device scalars
+    double* hScal = nullptr;                 // pinned mirror
+    // scratch for uploads
+    ocb::DevBuf<double> scratchD;
+    ocb::DevBuf<int32_t> scratchI;
+    int pcgGrid = 0, pcgBlock = 0;
+
+    int nSys() const { return 2 * nVtot; }
+};
+
+namespace ocb {
+
+int set_err(ocb_ctx* c, int code, const char* what);
+int cuda_fail(ocb_ctx* c, cudaError_t e, const char* where);
+#define OCB_CUDA(c, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return ocb::cuda_fail((c), _e, #call); } while (0)
+#define OCB_TRY(call) do { int _r = (call); if (_r < 0) return _r; } while (0)
+
+int ensure_init(ocb_ctx* c);
+ElemView view_of(const ocb_ctx* c, const ElemSet& s, bool isAir, double scale, int uniform);
+int fetch_scalars(ocb_ctx* c);   // D2H of the scalar block + stream sync
+
+// launchers implemented in ocb_kernels.cu / ocb_pcg.cu
+int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha);
+int launch_energy_per_elem(ocb_ctx* c, int uniform, double* d_out);
+int launch_gradient(ocb_ctx* c, double p0);
+int launch_sqnorm(ocb_ctx* c, const double* v, int n, int slot);
+int launch_build_slots(ocb_ctx* c);
+int launch_hessian(ocb_ctx* c, double p0);
+int launch_hessian_blocks(ocb_ctx* c, int uniform, double* d_out36);
+int launch_step_bound(ocb_ctx* c, const double* d_dir, double alpha0);
+int launch_step_forward(ocb_ctx* c, double alpha);
+int launch_triplet_scatter(ocb_ctx* c, int64_t nT, const int32_t* dI, const int32_t* dJ, const double* dS);
+int launch_set_uv(ocb_ctx* c, const double* dV, const double* dVa);
+int launch_get_uv(ocb_ctx* c, double* dV, double* dVa);
+int launch_rest_features(ocb_ctx* c, int nV, int nF, const double* dVrest, const int32_t* dF, double thres, double* dRest8);
+int launch_seam(ocb_ctx* c, int nCoh, const int32_t* dCoh, const double* dLen, const int32_t* dBnd, double thresLen, int triSoup);
+int launch_divgrad(ocb_ctx* c, double* d_out);
+int launch_spmv(ocb_ctx* c, const double* dx, double* dy);
+int launch_jacobi_setup(ocb_ctx* c);
+int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it);
+
+}  // namespace ocb

@@ -1,0 +1,620 @@
+// optcuts_b200 — element kernels (energy, gradient, Hessian + PSD projection + BSR scatter, step
+// bound, line-search stepping), pattern helpers and small reductions.  sm_100a, fp64.
+// Compiled with -fmad=false so per-element values are bit-identical to the CPU reference's
+// (SSE2, no FMA) for identical inputs; sums differ only in association order.
+//
+// All of these are HBM-streaming kernels: per element they read 3 int32 vertex ids + 5 rest doubles
+// (coalesced, SoA) and gather 3 double2 UVs (L2-resident: every vertex is shared by ~6 triangles).
+// Grids are sized as a multiple of the SM count and grid-stride over the elements; reductions are
+// two-level (warp shuffle -> shared -> one partial per block -> last block sums in fixed order) and
+// therefore deterministic.
+#include "ocb_internal.cuh"
+#include "ocb_element.cuh"
+
+namespace ocb {
+
+static constexpr int kBlock = 256;
+
+static inline int grid_for(const ocb_ctx* c, long n, int perSM = 8) {
+    long g = (n + kBlock - 1) / kBlock;
+    long cap = (long)c->numSMs * perSM;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic block reduction of NV values + grid finalisation by the last block
+template <int NV, bool IS_MIN>
+__device__ __forceinline__ void reduce_finalize(double (&v)[NV], double* __restrict__ partials,
+                                                unsigned* __restrict__ ticket, double* __restrict__ out,
+                                                const int* outSlots)
+{
+    __shared__ double sm[NV][kBlock / 32];
+    __shared__ bool isLast;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, t, o);
+            t = IS_MIN ? fmin(t, other) : t + other;
+        }
+        if (lane == 0) sm[k][warp] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = sm[k][0];
+            for (int w = 1; w < kBlock / 32; ++w) t = IS_MIN ? fmin(t, sm[k][w]) : t + sm[k][w];
+            partials[(size_t)blockIdx.x * NV + k] = t;
+        }
+        __threadfence();
+        const unsigned tk = atomicAdd(ticket, 1u);
+        isLast = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    // last block: every thread sums a strided subset in fixed order, then the same tree
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = IS_MIN ? INFINITY : 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kBlock)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const double t = __ldcg(&partials[(size_t)b * NV + k]);
+            acc[k] = IS_MIN ? fmin(acc[k], t) : acc[k] + t;
+        }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, t, o);
+            t = IS_MIN ? fmin(t, other) : t + other;
+        }
+        if (lane == 0) sm[k][warp] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = sm[k][0];
+            for (int w = 1; w < kBlock / 32; ++w) t = IS_MIN ? fmin(t, sm[k][w]) : t + sm[k][w];
+            out[outSlots[k]] = t;
+        }
+        *ticket = 0u;
+    }
+}
+
+struct Slots3 { int s[3]; };
+struct Slots1 { int s[1]; };
+
+// ---------------------------------------------------------------------------------------------
+// a2/a13/a14: energy of mesh + air elements, optionally at x0 + alpha * p (line search)
+template <bool STEPPED>
+__global__ void __launch_bounds__(kBlock)
+energy_kernel(ElemView M, ElemView A, const double* __restrict__ x, const double* __restrict__ p,
+              double alpha, double* __restrict__ partials, unsigned* __restrict__ ticket,
+              double* __restrict__ scal, Slots3 slots)
+{
+    double acc[3] = {0.0, 0.0, 0.0};   // mesh sum, air sum, #elements with signed area < 0
+    const int total = M.n + A.n;
+    for (int e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock) {
+        const bool isAir = e >= M.n;
+        const ElemView& S = isAir ? A : M;
+        const int t = isAir ? e - M.n : e;
+        const int i0 = S.v0[t], i1 = S.v1[t], i2 = S.v2[t];
+        const double area = S.area[t], A2 = S.areaSq[t], e0 = S.e0[t], e1 = S.e1[t], d = S.d[t];
+        Vec2 U1, U2, U3;
+        if (STEPPED) { U1 = ld2_step(x, p, alpha, i0); U2 = ld2_step(x, p, alpha, i1); U3 = ld2_step(x, p, alpha, i2); }
+        else { U1 = ld2(x, i0); U2 = ld2(x, i1); U3 = ld2(x, i2); }
+        const double w = S.uniform ? 1.0 : area / S.surfaceArea;
+        double dbArea;
+        const double E = sd_energy(U2 - U1, U3 - U1, A2, e0, e1, d, w, dbArea);
+        acc[isAir ? 1 : 0] += E;
+        if (dbArea < 0.0) acc[2] += 1.0;
+    }
+    reduce_finalize<3, false>(acc, partials, ticket, scal, slots.s);
+}
+
+__global__ void __launch_bounds__(kBlock)
+energy_per_elem_kernel(ElemView M, const double* __restrict__ x, double* __restrict__ out)
+{
+    for (int t = blockIdx.x * kBlock + threadIdx.x; t < M.n; t += gridDim.x * kBlock) {
+        const Vec2 U1 = ld2(x, M.v0[t]), U2 = ld2(x, M.v1[t]), U3 = ld2(x, M.v2[t]);
+        const double w = M.uniform ? 1.0 : M.area[t] / M.surfaceArea;
+        double dbArea;
+        out[t] = sd_energy(U2 - U1, U3 - U1, M.areaSq[t], M.e0[t], M.e1[t], M.d[t], w, dbArea);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a4/a13: gradient, scattered with fp64 reductions in L2 (RED.ADD.F64); fixed vertices skipped
+__global__ void __launch_bounds__(kBlock)
+gradient_kernel(ElemView M, ElemView A, const double* __restrict__ x, const uint8_t* __restrict__ fixedMask,
+                double* __restrict__ g)
+{
+    const int total = M.n + A.n;
+    for (int e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock) {
+        const bool isAir = e >= M.n;
+        const ElemView& S = isAir ? A : M;
+        const int t = isAir ? e - M.n : e;
+        const int idx[3] = {S.v0[t], S.v1[t], S.v2[t]};
+        const double area = S.area[t], A2 = S.areaSq[t], e0 = S.e0[t], e1 = S.e1[t], d = S.d[t];
+        const Vec2 U1 = ld2(x, idx[0]), U2 = ld2(x, idx[1]), U3 = ld2(x, idx[2]);
+        const double w = S.uniform ? 1.0 : area / S.surfaceArea;
+        Vec2 gr[3];
+        sd_gradient(U1, U2, U3, A2, e0, e1, d, w, gr);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (fixedMask[idx[k]]) continue;
+            atomicAdd(&g[2 * idx[k]], S.scale * gr[k].x);
+            atomicAdd(&g[2 * idx[k] + 1], S.scale * gr[k].y);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+sqnorm_kernel(const double* __restrict__ v, int n, double* __restrict__ partials, unsigned* __restrict__ ticket,
+              double* __restrict__ scal, Slots1 slots)
+{
+    double acc[1] = {0.0};
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) acc[0] += v[i] * v[i];
+    reduce_finalize<1, false>(acc, partials, ticket, scal, slots.s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a10: element -> BSR block slot map.  slot[(3k+l) * n + t] = index of block (v_k, v_l) or -1.
+__global__ void __launch_bounds__(kBlock)
+build_slots_kernel(int n, const int32_t* __restrict__ v0, const int32_t* __restrict__ v1, const int32_t* __restrict__ v2,
+                   const uint8_t* __restrict__ fixedMask, const int32_t* __restrict__ rowPtr,
+                   const int32_t* __restrict__ colIdx, int32_t* __restrict__ slot, int* __restrict__ missing)
+{
+    for (int t = blockIdx.x * kBlock + threadIdx.x; t < n; t += gridDim.x * kBlock) {
+        const int idx[3] = {v0[t], v1[t], v2[t]};
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                int s = -1;
+                if (!fixedMask[idx[k]] && !fixedMask[idx[l]]) {
+                    int lo = rowPtr[idx[k]], hi = rowPtr[idx[k] + 1] - 1;
+                    const int col = idx[l];
+                    while (lo <= hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const int cm = colIdx[mid];
+                        if (cm == col) { s = mid; break; }
+                        if (cm < col) lo = mid + 1; else hi = mid - 1;
+                    }
+                    if (s < 0) atomicAdd(missing, 1);
+                }
+                slot[(size_t)(3 * k + l) * n + t] = s;
+            }
+    }
+}
+
+// identity blocks for fixed vertices (IglUtils::addDiagonalToMatrix path, SymDirichletEnergy.cpp:541-548)
+__global__ void __launch_bounds__(kBlock)
+fixed_identity_kernel(int nVtot, const uint8_t* __restrict__ fixedMask, const int32_t* __restrict__ rowPtr,
+                      const int32_t* __restrict__ colIdx, double* __restrict__ val)
+{
+    for (int v = blockIdx.x * kBlock + threadIdx.x; v < nVtot; v += gridDim.x * kBlock) {
+        if (!fixedMask[v]) continue;
+        for (int b = rowPtr[v]; b < rowPtr[v + 1]; ++b)
+            if (colIdx[b] == v) { val[4 * (size_t)b] = 1.0; val[4 * (size_t)b + 1] = 0.0; val[4 * (size_t)b + 2] = 0.0; val[4 * (size_t)b + 3] = 1.0; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a5/a9/a11/a18: per-element Hessian, PSD projection, scatter into the BSR values.
+// One thread per element; the 6 upper blocks live in registers; each of the 9 (k,l) blocks is
+// one 32-byte sector of the value array, updated with 4 fp64 reductions.
+template <bool SCATTER>
+__global__ void __launch_bounds__(kBlock)
+hessian_kernel(ElemView M, ElemView A, const double* __restrict__ x, double* __restrict__ val,
+               double* __restrict__ out36)
+{
+    const int total = M.n + (SCATTER ? A.n : 0);
+    for (int e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock) {
+        const bool isAir = e >= M.n;
+        const ElemView& S = isAir ? A : M;
+        const int t = isAir ? e - M.n : e;
+        const Vec2 U1 = ld2(x, S.v0[t]), U2 = ld2(x, S.v1[t]), U3 = ld2(x, S.v2[t]);
+        const double w = S.uniform ? 1.0 : S.area[t] / S.surfaceArea;
+        double Hb[6][2][2];
+        sd_hessian(U1, U2, U3, S.areaSq[t], S.k0[t], S.k1[t], S.kd[t], w, Hb);
+        sd_project_psd(Hb);
+        if (SCATTER) {
+            const double sc = S.scale;
+            const int bOf[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    const int s = S.slot[(size_t)(3 * k + l) * S.n + t];
+                    if (s < 0) continue;
+                    double* dst = val + 4 * (size_t)s;
+                    const int b = bOf[k][l];
+                    if (k <= l) {
+                        atomicAdd(dst + 0, sc * Hb[b][0][0]); atomicAdd(dst + 1, sc * Hb[b][0][1]);
+                        atomicAdd(dst + 2, sc * Hb[b][1][0]); atomicAdd(dst + 3, sc * Hb[b][1][1]);
+                    } else {   // transpose of the stored upper block
+                        atomicAdd(dst + 0, sc * Hb[b][0][0]); atomicAdd(dst + 1, sc * Hb[b][1][0]);
+                        atomicAdd(dst + 2, sc * Hb[b][0][1]); atomicAdd(dst + 3, sc * Hb[b][1][1]);
+                    }
+                }
+        } else {
+            // dense 6x6, row-major, for parity tests against makePD
+            double* o = out36 + 36 * (size_t)t;
+            const int bOf[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int l = 0; l < 3; ++l)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            o[(2 * k + i) * 6 + (2 * l + j)] = (k <= l) ? Hb[bOf[k][l]][i][j] : Hb[bOf[k][l]][j][i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a7: step bound (min over all mesh + air elements)
+__global__ void __launch_bounds__(kBlock)
+step_bound_kernel(ElemView M, ElemView A, const double* __restrict__ x, const double* __restrict__ dir,
+                  double alpha0, double* __restrict__ partials, unsigned* __restrict__ ticket,
+                  double* __restrict__ scal, Slots1 slots)
+{
+    double acc[1] = {alpha0};
+    const int total = M.n + A.n;
+    for (int e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock) {
+        const bool isAir = e >= M.n;
+        const ElemView& S = isAir ? A : M;
+        const int t = isAir ? e - M.n : e;
+        const int i0 = S.v0[t], i1 = S.v1[t], i2 = S.v2[t];
+        acc[0] = sd_step_bound(ld2(x, i0), ld2(x, i1), ld2(x, i2), ld2(dir, i0), ld2(dir, i1), ld2(dir, i2), acc[0]);
+    }
+    // the reference compares every bound against the running (alpha0-initialised) minimum
+    reduce_finalize<1, true>(acc, partials, ticket, scal, slots.s);
+}
+
+// a14: x = x0 + alpha p  (Optimizer::stepForward + Scaffold::stepForward)
+__global__ void __launch_bounds__(kBlock)
+step_forward_kernel(int n, const double* __restrict__ x0, const double* __restrict__ p, double alpha, double* __restrict__ x)
+{
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock)
+        x[i] = __dadd_rn(x0[i], __dmul_rn(alpha, p[i]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// LinSysSolver::update_a mirror: triplets (i<=j kept, mirrored into the full BSR)
+__global__ void __launch_bounds__(kBlock)
+triplet_scatter_kernel(long nT, const int32_t* __restrict__ I, const int32_t* __restrict__ J, const double* __restrict__ S,
+                       const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, double* __restrict__ val,
+                       int* __restrict__ missing)
+{
+    for (long k = blockIdx.x * (long)kBlock + threadIdx.x; k < nT; k += (long)gridDim.x * kBlock) {
+        const int i = I[k], j = J[k];
+        if (i > j) continue;
+        const int bi = i >> 1, bj = j >> 1, ri = i & 1, rj = j & 1;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int row = pass ? bj : bi, col = pass ? bi : bj, rr = pass ? rj : ri, cc = pass ? ri : rj;
+            if (pass && i == j) break;     // diagonal scalar entry: once
+            int lo = rowPtr[row], hi = rowPtr[row + 1] - 1, s = -1;
+            while (lo <= hi) {
+                const int mid = (lo + hi) >> 1, cm = colIdx[mid];
+                if (cm == col) { s = mid; break; }
+                if (cm < col) lo = mid + 1; else hi = mid - 1;
+            }
+            if (s < 0) { atomicAdd(missing, 1); continue; }
+            atomicAdd(&val[4 * (size_t)s + 2 * rr + cc], S[k]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// UV layout conversion: Eigen column-major (all u, then all v) <-> interleaved system vector
+__global__ void __launch_bounds__(kBlock)
+set_uv_kernel(int nV, const double* __restrict__ V, int nVa, int nBnd, const double* __restrict__ Va, double* __restrict__ x)
+{
+    const int total = (V ? nV : 0) + (Va ? (nVa - nBnd) : 0);
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < total; i += gridDim.x * kBlock) {
+        int k = i;
+        if (V) {
+            if (k < nV) { x[2 * k] = V[k]; x[2 * k + 1] = V[nV + k]; continue; }
+            k -= nV;
+        }
+        const int a = nBnd + k;   // interior air vertex
+        x[2 * (nV + k)] = Va[a]; x[2 * (nV + k) + 1] = Va[nVa + a];
+    }
+}
+__global__ void __launch_bounds__(kBlock)
+get_uv_kernel(int nV, double* __restrict__ V, int nVa, const int32_t* __restrict__ l2g, double* __restrict__ Va, const double* __restrict__ x)
+{
+    const int total = (V ? nV : 0) + (Va ? nVa : 0);
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < total; i += gridDim.x * kBlock) {
+        int k = i;
+        if (V) {
+            if (k < nV) { V[k] = x[2 * k]; V[nV + k] = x[2 * k + 1]; continue; }
+            k -= nV;
+        }
+        const int gidx = l2g[k];
+        Va[k] = x[2 * gidx]; Va[nVa + k] = x[2 * gidx + 1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a1: rest-frame features (TriMesh::computeFeatures arithmetic, TriMesh.cpp:355-398)
+__global__ void __launch_bounds__(kBlock)
+rest_features_kernel(int nV, int nF, const double* __restrict__ P, const int32_t* __restrict__ F, double thres,
+                     double* __restrict__ rest8, double* __restrict__ partials, unsigned* __restrict__ ticket,
+                     double* __restrict__ scal, Slots3 slots)
+{
+    double acc[3] = {0.0, 0.0, 0.0};   // surface area, sum of edge lengths, #zero-area triangles
+    const double sqrt3 = sqrt(3.0);
+    for (int t = blockIdx.x * kBlock + threadIdx.x; t < nF; t += gridDim.x * kBlock) {
+        const int i0 = F[t], i1 = F[nF + t], i2 = F[2 * nF + t];
+        const double ax = P[i1] - P[i0], ay = P[nV + i1] - P[nV + i0], az = P[2 * nV + i1] - P[2 * nV + i0];
+        const double bx = P[i2] - P[i0], by = P[nV + i2] - P[nV + i0], bz = P[2 * nV + i2] - P[2 * nV + i0];
+        const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+        double area = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+        if (area == 0.0) acc[2] += 1.0;
+        double A2, e0, e1, d, k0, k1, kd;
+        if (area < thres) {
+            area = thres; A2 = thres * thres;
+            e0 = e1 = 4.0 / sqrt3 * thres; d = e0 / 2.0;
+            k0 = k1 = 2.0 / sqrt3 / thres; kd = k0 / 2.0;
+        } else {
+            A2 = area * area;
+            e0 = ax * ax + ay * ay + az * az; e1 = bx * bx + by * by + bz * bz; d = ax * bx + ay * by + az * bz;
+            k0 = e0 / 2. / A2; k1 = e1 / 2. / A2; kd = d / 2. / A2;
+        }
+        acc[0] += area;
+        // igl::avg_edge_length: mean over the 3|F| triangle edges
+        const double ex = bx - ax, ey = by - ay, ez = bz - az;
+        acc[1] += sqrt(ax * ax + ay * ay + az * az) + sqrt(bx * bx + by * by + bz * bz) + sqrt(ex * ex + ey * ey + ez * ez);
+        rest8[t] = area; rest8[(size_t)nF + t] = A2; rest8[2 * (size_t)nF + t] = e0; rest8[3 * (size_t)nF + t] = e1;
+        rest8[4 * (size_t)nF + t] = d; rest8[5 * (size_t)nF + t] = k0; rest8[6 * (size_t)nF + t] = k1; rest8[7 * (size_t)nF + t] = kd;
+    }
+    reduce_finalize<3, false>(acc, partials, ticket, scal, slots.s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a15: seam length (TriMesh::computeSeamSparsity)
+__global__ void __launch_bounds__(kBlock)
+seam_kernel(int nCoh, const int32_t* __restrict__ coh, const double* __restrict__ len, const int32_t* __restrict__ bnd,
+            const double* __restrict__ x, double avgEdgeLen, int triSoup,
+            double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ scal, Slots1 slots)
+{
+    double acc[1] = {0.0};
+    const double thres = 1.0e-2;
+    for (int c = blockIdx.x * kBlock + threadIdx.x; c < nCoh; c += gridDim.x * kBlock) {
+        if (bnd[c]) continue;
+        bool take = !triSoup;
+        if (!take) {
+            const Vec2 a = ld2(x, coh[c]) - ld2(x, coh[2 * nCoh + c]);
+            const Vec2 b = ld2(x, coh[nCoh + c]) - ld2(x, coh[3 * nCoh + c]);
+            take = (sqrt(dot(a, a)) / avgEdgeLen > thres) || (sqrt(dot(b, b)) / avgEdgeLen > thres);
+        }
+        if (take) acc[0] += len[c];
+    }
+    reduce_finalize<1, false>(acc, partials, ticket, scal, slots.s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8: per-vertex std-dev of incident corner gradients (mesh term, area weights)
+// pass 1: sum of corner gradients + incidence count; pass 2: squared deviations; pass 3: sqrt
+__global__ void __launch_bounds__(kBlock)
+divgrad_pass_kernel(ElemView M, const double* __restrict__ x, int pass, double* __restrict__ sum /*2 per vertex*/,
+                    double* __restrict__ cnt, double* __restrict__ dev)
+{
+    for (int t = blockIdx.x * kBlock + threadIdx.x; t < M.n; t += gridDim.x * kBlock) {
+        const int idx[3] = {M.v0[t], M.v1[t], M.v2[t]};
+        const Vec2 U1 = ld2(x, idx[0]), U2 = ld2(x, idx[1]), U3 = ld2(x, idx[2]);
+        const double w = M.area[t] / M.surfaceArea;
+        Vec2 gr[3];
+        sd_gradient(U1, U2, U3, M.areaSq[t], M.e0[t], M.e1[t], M.d[t], w, gr);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (pass == 0) {
+                atomicAdd(&sum[2 * idx[k]], gr[k].x); atomicAdd(&sum[2 * idx[k] + 1], gr[k].y);
+                atomicAdd(&cnt[idx[k]], 1.0);
+            } else {
+                const double n = cnt[idx[k]];
+                const double dx = gr[k].x - sum[2 * idx[k]] / n, dy = gr[k].y - sum[2 * idx[k] + 1] / n;
+                atomicAdd(&dev[idx[k]], dx * dx + dy * dy);
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(kBlock)
+divgrad_final_kernel(int nV, const double* __restrict__ cnt, const double* __restrict__ dev, double* __restrict__ out)
+{
+    for (int v = blockIdx.x * kBlock + threadIdx.x; v < nV; v += gridDim.x * kBlock) {
+        const double n = cnt[v];
+        out[v] = (n == 1.0 || n == 0.0) ? 0.0 : sqrt(dev[v] / (n - 1.0));
+    }
+}
+
+// =============================================================================================
+// launchers
+#define KCHECK(c) do { (c)->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return cuda_fail((c), _e, __func__); } while (0)
+
+static int ensure_reduce_bufs(ocb_ctx* c, int grid, int nv) {
+    OCB_CUDA(c, c->partials.reserve((size_t)grid * nv + 64, c->stream));
+    return 0;
+}
+
+int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha)
+{
+    const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
+    const int grid = grid_for(c, (long)M.n + A.n);
+    OCB_TRY(ensure_reduce_bufs(c, grid, 3));
+    Slots3 sl; sl.s[0] = S_E_MESH; sl.s[1] = S_E_AIR; sl.s[2] = S_N_INVERTED;
+    if (stepped) energy_kernel<true><<<grid, kBlock, 0, c->stream>>>(M, A, c->x0.p, c->p.p, alpha, c->partials.p, c->sync.p, c->dScal, sl);
+    else energy_kernel<false><<<grid, kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, 0.0, c->partials.p, c->sync.p, c->dScal, sl);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_energy_per_elem(ocb_ctx* c, int uniform, double* d_out)
+{
+    const ElemView M = view_of(c, c->mesh, false, 1.0, uniform);
+    energy_per_elem_kernel<<<grid_for(c, M.n), kBlock, 0, c->stream>>>(M, c->x.p, d_out);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_sqnorm(ocb_ctx* c, const double* v, int n, int slot)
+{
+    const int grid = grid_for(c, n, 4);
+    OCB_TRY(ensure_reduce_bufs(c, grid, 1));
+    Slots1 sl; sl.s[0] = slot;
+    sqnorm_kernel<<<grid, kBlock, 0, c->stream>>>(v, n, c->partials.p, c->sync.p, c->dScal, sl);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_gradient(ocb_ctx* c, double p0)
+{
+    const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
+    OCB_CUDA(c, cudaMemsetAsync(c->g.p, 0, sizeof(double) * c->nSys(), c->stream));
+    gradient_kernel<<<grid_for(c, (long)M.n + A.n), kBlock, 0, c->stream>>>(M, A, c->x.p, c->fixedMask.p, c->g.p);
+    KCHECK(c);
+    return launch_sqnorm(c, c->g.p, c->nSys(), S_SQN_G);
+}
+
+int launch_build_slots(ocb_ctx* c)
+{
+    int* missing = reinterpret_cast<int*>(c->sync.p + 8);
+    OCB_CUDA(c, cudaMemsetAsync(missing, 0, sizeof(int), c->stream));
+    for (int which = 0; which < 2; ++which) {
+        ElemSet& S = which ? c->air : c->mesh;
+        if (S.n == 0) continue;
+        OCB_CUDA(c, S.slot.reserve((size_t)9 * S.n, c->stream));
+        build_slots_kernel<<<grid_for(c, S.n), kBlock, 0, c->stream>>>(S.n, S.v.p, S.v.p + S.n, S.v.p + 2 * (size_t)S.n,
+                                                                      c->fixedMask.p, c->rowPtr.p, c->colIdx.p, S.slot.p, missing);
+        KCHECK(c);
+    }
+    int hMissing = 0;
+    OCB_CUDA(c, cudaMemcpyAsync(&hMissing, missing, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (hMissing) return set_err(c, OCB_ERR_STATE, "pattern does not cover every element edge (adjacency inconsistent with the element lists)");
+    c->slotsValid = true;
+    return 0;
+}
+
+int launch_hessian(ocb_ctx* c, double p0)
+{
+    const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
+    OCB_CUDA(c, cudaMemsetAsync(c->val.p, 0, sizeof(double) * 4 * (size_t)c->nnzb, c->stream));
+    fixed_identity_kernel<<<grid_for(c, c->nVtot, 4), kBlock, 0, c->stream>>>(c->nVtot, c->fixedMask.p, c->rowPtr.p, c->colIdx.p, c->val.p);
+    KCHECK(c);
+    hessian_kernel<true><<<grid_for(c, (long)M.n + A.n), kBlock, 0, c->stream>>>(M, A, c->x.p, c->val.p, nullptr);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_hessian_blocks(ocb_ctx* c, int uniform, double* d_out36)
+{
+    const ElemView M = view_of(c, c->mesh, false, 1.0, uniform);
+    ElemView A = M; A.n = 0;
+    hessian_kernel<false><<<grid_for(c, M.n), kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, d_out36);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_step_bound(ocb_ctx* c, const double* d_dir, double alpha0)
+{
+    const ElemView M = view_of(c, c->mesh, false, 1.0, 0), A = view_of(c, c->air, true, 1.0, 1);
+    const int grid = grid_for(c, (long)M.n + A.n);
+    OCB_TRY(ensure_reduce_bufs(c, grid, 1));
+    Slots1 sl; sl.s[0] = S_STEP_BOUND;
+    step_bound_kernel<<<grid, kBlock, 0, c->stream>>>(M, A, c->x.p, d_dir, alpha0, c->partials.p, c->sync.p, c->dScal, sl);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_step_forward(ocb_ctx* c, double alpha)
+{
+    step_forward_kernel<<<grid_for(c, c->nSys(), 4), kBlock, 0, c->stream>>>(c->nSys(), c->x0.p, c->p.p, alpha, c->x.p);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_triplet_scatter(ocb_ctx* c, int64_t nT, const int32_t* dI, const int32_t* dJ, const double* dS)
+{
+    int* missing = reinterpret_cast<int*>(c->sync.p + 8);
+    OCB_CUDA(c, cudaMemsetAsync(missing, 0, sizeof(int), c->stream));
+    OCB_CUDA(c, cudaMemsetAsync(c->val.p, 0, sizeof(double) * 4 * (size_t)c->nnzb, c->stream));
+    if (nT > 0) {
+        triplet_scatter_kernel<<<grid_for(c, nT), kBlock, 0, c->stream>>>((long)nT, dI, dJ, dS, c->rowPtr.p, c->colIdx.p, c->val.p, missing);
+        KCHECK(c);
+    }
+    int hMissing = 0;
+    OCB_CUDA(c, cudaMemcpyAsync(&hMissing, missing, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (hMissing) return set_err(c, OCB_ERR_ARG, "triplet outside the sparsity pattern");
+    return 0;
+}
+
+int launch_set_uv(ocb_ctx* c, const double* dV, const double* dVa)
+{
+    const int total = (dV ? c->nV : 0) + (dVa ? (c->nVa - c->nBnd) : 0);
+    if (total <= 0) return 0;
+    set_uv_kernel<<<grid_for(c, total, 4), kBlock, 0, c->stream>>>(c->nV, dV, c->nVa, c->nBnd, dVa, c->x.p);
+    KCHECK(c);
+    return 0;
+}
+int launch_get_uv(ocb_ctx* c, double* dV, double* dVa)
+{
+    const int total = (dV ? c->nV : 0) + (dVa ? c->nVa : 0);
+    if (total <= 0) return 0;
+    get_uv_kernel<<<grid_for(c, total, 4), kBlock, 0, c->stream>>>(c->nV, dV, c->nVa, c->l2g.p, dVa, c->x.p);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_rest_features(ocb_ctx* c, int nV, int nF, const double* dVrest, const int32_t* dF, double thres, double* dRest8)
+{
+    const int grid = grid_for(c, nF);
+    OCB_TRY(ensure_reduce_bufs(c, grid, 3));
+    Slots3 sl; sl.s[0] = S_MISC0; sl.s[1] = S_MISC1; sl.s[2] = S_MISC2;
+    rest_features_kernel<<<grid, kBlock, 0, c->stream>>>(nV, nF, dVrest, dF, thres, dRest8, c->partials.p, c->sync.p, c->dScal, sl);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_seam(ocb_ctx* c, int nCoh, const int32_t* dCoh, const double* dLen, const int32_t* dBnd, double avgEdgeLen, int triSoup)
+{
+    const int grid = grid_for(c, nCoh, 1);
+    OCB_TRY(ensure_reduce_bufs(c, grid, 1));
+    Slots1 sl; sl.s[0] = S_MISC0;
+    seam_kernel<<<grid, kBlock, 0, c->stream>>>(nCoh, dCoh, dLen, dBnd, c->x.p, avgEdgeLen, triSoup, c->partials.p, c->sync.p, c->dScal, sl);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_divgrad(ocb_ctx* c, double* d_out)
+{
+    const ElemView M = view_of(c, c->mesh, false, 1.0, 0);
+    const size_t nV = c->nV;
+    OCB_CUDA(c, c->scratchD.reserve(4 * nV, c->stream));
+    double* sum = c->scratchD.p; double* cnt = sum + 2 * nV; double* dev = cnt + nV;
+    OCB_CUDA(c, cudaMemsetAsync(sum, 0, sizeof(double) * 4 * nV, c->stream));
+    const int grid = grid_for(c, M.n);
+    divgrad_pass_kernel<<<grid, kBlock, 0, c->stream>>>(M, c->x.p, 0, sum, cnt, dev); KCHECK(c);
+    divgrad_pass_kernel<<<grid, kBlock, 0, c->stream>>>(M, c->x.p, 1, sum, cnt, dev); KCHECK(c);
+    divgrad_final_kernel<<<grid_for(c, c->nV, 4), kBlock, 0, c->stream>>>(c->nV, cnt, dev, d_out); KCHECK(c);
+    return 0;
+}
+
+}  // namespace ocb

@@ -260,6 +260,28 @@ void ref_opt_get_triplets(void* h, int32_t* I, int32_t* J, double* V) {
 void ref_opt_recompute_gradient(void* h) { OptProbe* p = ((OptHandle*)h)->opt; p->computeGradient(p->result, p->scaffold, p->gradient); }
 double ref_opt_recompute_energy(void* h) { OptProbe* p = ((OptHandle*)h)->opt; double e; p->computeEnergyVal(p->result, p->scaffold, e); return e; }
 
+
+// ---------------------------------------------------------------- Scaffold (air mesh) from a mesh
+// OptCuts::Scaffold(mesh) — boundary loops + bbox ring + Triangle (Scaffold.cpp:27-208); host-side work
+// of the caller that the parity tests need in order to free-run with bijectivity on.
+void* ref_scaffold_create(void* meshH) { TriMesh* m = (TriMesh*)meshH; return new Scaffold(*m); }
+void ref_scaffold_destroy(void* h) { delete (Scaffold*)h; }
+// sizes: nVa, nFa, nBnd, nFixedAir, wholeMeshSize
+void ref_scaffold_sizes(void* h, long* out) {
+    Scaffold* s = (Scaffold*)h;
+    out[0] = s->airMesh.V.rows(); out[1] = s->airMesh.F.rows(); out[2] = s->bnd.size();
+    out[3] = (long)s->airMesh.fixedVert.size(); out[4] = s->wholeMeshSize;
+}
+void ref_scaffold_get(void* h, double* Va, int32_t* Fa, int32_t* bnd, double* rest8, double* scalars, int32_t* fixedAir, double* areaThres) {
+    Scaffold* s = (Scaffold*)h; const TriMesh& am = s->airMesh;
+    std::memcpy(Va, am.V.data(), sizeof(double) * am.V.size());
+    std::memcpy(Fa, am.F.data(), sizeof(int32_t) * am.F.size());
+    std::memcpy(bnd, s->bnd.data(), sizeof(int32_t) * s->bnd.size());
+    ref_mesh_features((void*)&am, rest8, scalars);
+    int k = 0; for (int v : am.fixedVert) fixedAir[k++] = v;
+    *areaThres = am.areaThres_AM;
+}
+
 // ---------------------------------------------------------------- timers (main.cpp:357-361 order)
 void ref_timers_reset(void) { for (int i = 0; i < 4; ++i) timer.reset(i); for (int i = 0; i < 9; ++i) timer_step.reset(i); }
 void ref_timers_get(double* t4, double* step9) { for (int i = 0; i < 4; ++i) t4[i] = timer.timing(i); for (int i = 0; i < 9; ++i) step9[i] = timer_step.timing(i); }

@@ -75,6 +75,12 @@ def lib():
         L.ref_opt_recompute_gradient.argtypes = [C.c_void_p]
         L.ref_opt_recompute_energy.argtypes = [C.c_void_p]
         L.ref_opt_recompute_energy.restype = C.c_double
+        L.ref_scaffold_create.restype = C.c_void_p
+        L.ref_scaffold_create.argtypes = [C.c_void_p]
+        L.ref_scaffold_destroy.argtypes = [C.c_void_p]
+        L.ref_scaffold_destroy.restype = None
+        L.ref_scaffold_sizes.argtypes = [C.c_void_p, _l]
+        L.ref_scaffold_get.argtypes = [C.c_void_p, _d, _i, _i, _d, _d, _i, _d]
         L.ref_timers_get.argtypes = [_d, _d]
         L.ref_set_output_folder.argtypes = [C.c_char_p]
         _lib = L
@@ -184,6 +190,26 @@ class RefMesh:
         out = np.zeros(self.nV)
         lib().ref_sd_divgrad(self.h, _pd(out))
         return out
+
+
+def build_scaffold(mesh):
+    """OptCuts::Scaffold(mesh) (Scaffold.cpp:27-208): returns the air mesh as plain arrays."""
+    L = lib()
+    h = L.ref_scaffold_create(mesh.h)
+    sz = np.zeros(5, dtype=np.int64)
+    L.ref_scaffold_sizes(h, sz.ctypes.data_as(_l))
+    nVa, nFa, nB, nFx = int(sz[0]), int(sz[1]), int(sz[2]), int(sz[3])
+    Va = np.zeros((nVa, 2), order="F")
+    Fa = np.zeros((nFa, 3), np.int32, order="F")
+    bnd = np.zeros(nB, np.int32)
+    rest8 = np.zeros((8, nFa))
+    sc = np.zeros(3)
+    fx = np.zeros(nFx, np.int32)
+    thr = C.c_double()
+    L.ref_scaffold_get(h, _pd(Va), _pi(Fa), _pi(bnd), _pd(rest8), _pd(sc), _pi(fx), C.byref(thr))
+    L.ref_scaffold_destroy(h)
+    return dict(V=Va, F=Fa, bnd=bnd, rest8=rest8, fixed=fx, areaThres_AM=thr.value, wholeMeshSize=int(sz[4]),
+                surfaceArea=sc[0], avgEdgeLen=sc[1])
 
 
 def make_pd6(M):

@@ -1,0 +1,67 @@
+// TEST HARNESS (CPU): compiles the PRODUCT's device-inline element math (optcuts_b200/csrc/ocb_element.cuh)
+// for the host so its formulas can be checked against the oracle without a GPU.  Built by
+// tests/test_element_math_host.py into a scratch directory; never shipped, never imported by the package.
+#include <cmath>
+#include <cstdint>
+#define __device__
+#define __forceinline__ inline
+#define __ldg(p) (*(p))
+struct double2 { double x, y; };
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+using std::sqrt; using std::fabs; using std::copysign;
+#define OCB_ELEMENT_HOST 1
+#include "../../optcuts_b200/csrc/ocb_element.cuh"
+
+using namespace ocb;
+extern "C" {
+// F: nF x 3 col-major; UV: nV x 2 col-major; rest8: 8 x nF
+void host_energy(int nV, int nF, const int32_t* F, const double* UV, const double* rest8, double surf, int uniform, double* out)
+{
+    for (int t = 0; t < nF; ++t) {
+        const int i0 = F[t], i1 = F[nF + t], i2 = F[2 * nF + t];
+        const Vec2 U1 = mk(UV[i0], UV[nV + i0]), U2 = mk(UV[i1], UV[nV + i1]), U3 = mk(UV[i2], UV[nV + i2]);
+        const double w = uniform ? 1.0 : rest8[t] / surf;
+        double db;
+        out[t] = sd_energy(U2 - U1, U3 - U1, rest8[nF + t], rest8[2 * nF + t], rest8[3 * nF + t], rest8[4 * nF + t], w, db);
+    }
+}
+void host_gradient_corners(int nV, int nF, const int32_t* F, const double* UV, const double* rest8, double surf, int uniform, double* out /*nF x 6*/)
+{
+    for (int t = 0; t < nF; ++t) {
+        const int i0 = F[t], i1 = F[nF + t], i2 = F[2 * nF + t];
+        const Vec2 U1 = mk(UV[i0], UV[nV + i0]), U2 = mk(UV[i1], UV[nV + i1]), U3 = mk(UV[i2], UV[nV + i2]);
+        const double w = uniform ? 1.0 : rest8[t] / surf;
+        Vec2 g[3];
+        sd_gradient(U1, U2, U3, rest8[nF + t], rest8[2 * nF + t], rest8[3 * nF + t], rest8[4 * nF + t], w, g);
+        for (int k = 0; k < 3; ++k) { out[6 * t + 2 * k] = g[k].x; out[6 * t + 2 * k + 1] = g[k].y; }
+    }
+}
+void host_hessian_blocks(int nV, int nF, const int32_t* F, const double* UV, const double* rest8, double surf, int uniform, int project,
+                         double* out /*nF x 36 row-major*/, int* clamped)
+{
+    const int bOf[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    for (int t = 0; t < nF; ++t) {
+        const int i0 = F[t], i1 = F[nF + t], i2 = F[2 * nF + t];
+        const Vec2 U1 = mk(UV[i0], UV[nV + i0]), U2 = mk(UV[i1], UV[nV + i1]), U3 = mk(UV[i2], UV[nV + i2]);
+        const double w = uniform ? 1.0 : rest8[t] / surf;
+        double Hb[6][2][2];
+        sd_hessian(U1, U2, U3, rest8[nF + t], rest8[5 * nF + t], rest8[6 * nF + t], rest8[7 * nF + t], w, Hb);
+        int c = project ? sd_project_psd(Hb) : 0;
+        if (clamped) clamped[t] = c;
+        for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j)
+            out[36 * t + (2 * k + i) * 6 + 2 * l + j] = (k <= l) ? Hb[bOf[k][l]][i][j] : Hb[bOf[k][l]][j][i];
+    }
+}
+double host_step_bound(int nV, int nF, const int32_t* F, const double* UV, const double* dir /*interleaved*/, double alpha0)
+{
+    double cur = alpha0;
+    for (int t = 0; t < nF; ++t) {
+        const int i0 = F[t], i1 = F[nF + t], i2 = F[2 * nF + t];
+        cur = sd_step_bound(mk(UV[i0], UV[nV + i0]), mk(UV[i1], UV[nV + i1]), mk(UV[i2], UV[nV + i2]),
+                            mk(dir[2 * i0], dir[2 * i0 + 1]), mk(dir[2 * i1], dir[2 * i1 + 1]), mk(dir[2 * i2], dir[2 * i2 + 1]), cur);
+    }
+    return cur;
+}
+}
