@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — Newton iterations / s of the OptCuts geometry step on B200 (BASELINE.json's metric).
+
+A "step" is ONE Newton iteration of Optimizer::solve(1) (Optimizer.cpp:203-261, 505-673): gradient ->
+convergence test -> element Hessians + PSD projection + scatter into the BSR matrix -> linear solve ->
+step bound -> line search, on mesh + air-mesh (scaffold) elements, everything fp64.
+
+Workloads (config.workload):
+  bimba10k   (default; BASELINE.json configs[1]) bimba_i_f10000, lambda 0.025, bijectivity on: the
+             iteration is replayed from two reference states recorded from the reference run
+             (tests/golden: it=1 = Tutte start, it=100 = 37 seam edges), alternating between them.
+  bimba_x4 / bimba_x10   (configs[2]) the it=1 state subdivided 4x4 / 10x10 per triangle: 159 984 /
+             999 900 faces, no scaffold (the air mesh is the host program's Triangle call).
+
+`value`  = steps / device time with the state resident in HBM (UV restored from a device snapshot);
+`e2e`    = the same through the C-ABI with HOST buffers: every step uploads the UVs (pinned host memory),
+           runs the iteration and downloads the new UVs + the result scalars.
+`--impl reference` times the reference's own CPU implementation of the same step
+(oracle/_ref/liboptcuts_ref.so = unmodified OptCuts::Optimizer with Eigen SimplicialLDLT, TBB shim on all
+host cores) from the same states: wall time of solve(1) minus the reference's own "scaffolding" timer.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden", "bimba_cfg2_states.npz")
+
+# algorithmic HBM bytes per unit of work (restated in DESIGN.md §4)
+BYTES_PER_FACE = {"energy": 60.0, "gradient": 68.0, "step_bound": 28.0, "hessian_psd_scatter": 172.0}
+PCG_BYTES_PER_FACE_PER_ITER = 228.0
+
+
+def load_states(workload):
+    g = np.load(GOLDEN)
+    p0 = float(g["energyParam0"])
+
+    def st(tag, rt):
+        return dict(V_rest=g[tag + "V_rest"], F=g[tag + "F"], UV=g[tag + "V"], fixed=g[tag + "fixedVert"],
+                    rest8=g[rt + "rest8"], surfaceArea=float(g[rt + "surfaceArea"]), targetGRes=float(g[rt + "targetGRes"]),
+                    air=dict(V=g[tag + "air_V"], F=g[tag + "air_F"], l2g=g[tag + "air_localVI2Global"],
+                             nBnd=len(g[tag + "air_bnd"]), rest8=g[rt + "air_rest8"], fixed=g[rt + "air_fixed"]),
+                    w_scaf=float(g[rt + "w_scaf"]), cohE=g[tag + "cohE"])
+    if workload == "bimba10k":
+        return [st("s1_", "r1_"), st("s100_", "r100_")], p0
+    n = {"bimba_x4": 4, "bimba_x10": 10}[workload]
+    from optcuts_b200 import synth
+    s = st("s1_", "r1_")
+    Vr, F, UV = synth.subdivide(s["V_rest"], s["F"], s["UV"], n)
+    return [dict(V_rest=Vr, F=F, UV=UV, fixed=np.array([0], np.int32), rest8=None, surfaceArea=None,
+                 targetGRes=s["targetGRes"], air=None, w_scaf=0.0, cohE=np.zeros((0, 4), np.int32))], p0
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                c = [x.strip() for x in ln.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def setup_context(ob, dev, s, p0):
+    ctx = ob.Context(dev)
+    import torch
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    if s["rest8"] is None:
+        s["rest8"], sc = ctx.rest_features(s["V_rest"], s["F"])
+        s["surfaceArea"] = sc["surfaceArea"]
+    ctx.set_mesh(s["UV"].shape[0], s["F"], s["rest8"], s["surfaceArea"], s["fixed"])
+    ctx.set_uv(s["UV"])
+    a = s["air"]
+    if a is not None:
+        ctx.set_air(a["F"], a["rest8"], a["l2g"], a["nBnd"], a["fixed"], s["w_scaf"] / a["F"].shape[0])
+        ctx.set_uv(None, a["V"])
+    ctx.set_pattern_from_elements()
+    ctx.save_uv()
+    return ctx
+
+
+def run_ours(args):
+    import torch
+    import optcuts_b200 as ob
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    states, p0 = load_states(args.workload)
+    ctxs = [setup_context(ob, local, s, p0) for s in states]
+    pcg_tol, pcg_max = args.pcg_tol, args.pcg_max_it
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def step_resident(i):
+        c, s = ctxs[i % len(ctxs)], states[i % len(ctxs)]
+        c.restore_uv()
+        return c.newton_step(p0, s["targetGRes"], pcg_tol, pcg_max)
+
+    # pinned host staging for the e2e leg
+    pinned = []
+    for s in states:
+        nV = s["UV"].shape[0]
+        hV = torch.empty((2, nV), dtype=torch.float64).pin_memory()
+        hV.numpy()[:] = np.asfortranarray(s["UV"]).T
+        hVa = None
+        if s["air"] is not None:
+            hVa = torch.empty((2, s["air"]["V"].shape[0]), dtype=torch.float64).pin_memory()
+            hVa.numpy()[:] = np.asfortranarray(s["air"]["V"]).T
+        hOut = torch.empty((2, nV), dtype=torch.float64).pin_memory()
+        pinned.append((hV, hVa, hOut))
+
+    import ctypes as C
+    _d = C.POINTER(C.c_double)
+
+    def step_e2e(i):
+        k = i % len(ctxs)
+        c, s = ctxs[k], states[k]
+        hV, hVa, hOut = pinned[k]
+        L, h = c._L, c._h
+        c._chk(L.ocb_set_uv(h, C.cast(hV.data_ptr(), _d), C.cast(hVa.data_ptr(), _d) if hVa is not None else None))
+        r = c.newton_step(p0, s["targetGRes"], pcg_tol, pcg_max)
+        c._chk(L.ocb_get_uv(h, C.cast(hOut.data_ptr(), _d), None))
+        return r
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, K, W, profile=False):
+        for i in range(W):
+            fn(i)
+        for c in ctxs:
+            c.profile_enable(profile)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        l0 = sum(c.launch_count() for c in ctxs)
+        res = []
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
+            ev[i][0].record()
+            res.append(fn(i))
+            ev[i][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        launches = sum(c.launch_count() for c in ctxs) - l0
+        return ms, wall, launches, res
+
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, wall, launches, res = timed(step_resident, K, W, profile=True)
+    prof = {}
+    for c in ctxs:
+        for name, (pms, cnt) in c.profile_get().items():
+            a = prof.setdefault(name, [0.0, 0])
+            a[0] += pms; a[1] += cnt
+        c.profile_enable(False)
+    ms_e2e, wall_e2e, _, res_e2e = timed(step_e2e, K, W)
+    clocks = sampler.stop()
+
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    value = world * K / (ms * 1e-3)
+    e2e_value = world * K / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel class, from the live per-class CUDA-event profile
+    faces = np.mean([s["F"].shape[0] + (s["air"]["F"].shape[0] if s["air"] is not None else 0) for s in states])
+    total_prof = sum(v[0] for v in prof.values()) or 1.0
+    dom = max(prof, key=lambda k: prof[k][0])
+    pcg_iters = float(np.mean([r["pcg_iters"] for r in res]))
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+
+    def kernel_line(name):
+        pms, cnt = prof[name]
+        if cnt == 0:
+            return None
+        per_launch_ms = pms / cnt
+        if name == "pcg":
+            bytes_per_launch = PCG_BYTES_PER_FACE_PER_ITER * faces * pcg_iters
+        elif name in BYTES_PER_FACE:
+            bytes_per_launch = BYTES_PER_FACE[name] * faces
+        else:
+            return dict(ms_per_launch=per_launch_ms, launches=cnt, share=pms / total_prof)
+        gbs = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+        return dict(ms_per_launch=per_launch_ms, launches=cnt, share=pms / total_prof, alg_bytes=bytes_per_launch,
+                    achieved_gbs=gbs, frac=gbs / peak)
+    kernels = {k: kernel_line(k) for k in prof if prof[k][1] > 0}
+    d = kernels[dom]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": d.get("achieved_gbs"), "peak": peak, "peak_source": peak_src,
+                "unit": "GB/s", "frac": d.get("frac"), "traffic": traffic,
+                "note": "algorithmic bytes = %.0f B/face/CG-iteration x faces x CG iterations per launch" % PCG_BYTES_PER_FACE_PER_ITER
+                if dom == "pcg" else "algorithmic bytes per face x faces"}
+
+    h2d = int(np.mean([16 * (s["UV"].shape[0] + (s["air"]["V"].shape[0] if s["air"] is not None else 0)) for s in states]))
+    d2h = int(np.mean([16 * s["UV"].shape[0] for s in states])) + 16 * 8
+    line = {
+        "metric": "newton_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "reference states of bimba_i_f10000 (recorded from the reference run, tests/golden)" if args.workload == "bimba10k"
+                else "synthetic: bimba Tutte state subdivided",
+        "config": {"workload": args.workload, "faces": int(states[0]["F"].shape[0]), "states": len(states),
+                   "air_faces": [int(s["air"]["F"].shape[0]) if s["air"] is not None else 0 for s in states],
+                   "pcg_rel_tol": pcg_tol, "pcg_iters_mean": pcg_iters, "l2": "flushed between timed iterations (256 MB memset)",
+                   "parallelism": "independent meshes per GPU, no collective"},
+        "e2e": {"value": e2e_value, "unit": "it/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "E_new": [res[i]["E_new"] for i in range(min(len(states), len(res)))],
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, budget_s=20.0)
+        print(json.dumps(line))
+    for c in ctxs:
+        c.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------- reference arm
+def ref_step_times(args, n_steps, budget_s):
+    """Times Optimizer::solve(1) of the UNMODIFIED reference (oracle/_ref) from the workload's states."""
+    from oracle import refapi
+    states, p0 = load_states(args.workload)
+    kind = "reference"
+    if not refapi.available():
+        raise RuntimeError("oracle/_ref/liboptcuts_ref.so is missing (built by `make -C oracle ref` where /root/reference exists)")
+    out_dir = tempfile.mkdtemp(prefix="ocb_ref_")
+    refapi.set_output_folder(out_dir + "/")
+    times, t_begin = [], time.perf_counter()
+    i = 0
+    # the reference chats on stdout per iteration (Optimizer.cpp:212,582,612,642): keep the JSON line clean
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        return _ref_loop(refapi, states, p0, n_steps, budget_s, times, t_begin, i), kind
+    finally:
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd); os.close(devnull)
+
+
+def _ref_loop(refapi, states, p0, n_steps, budget_s, times, t_begin, i):
+    while len(times) < n_steps and (time.perf_counter() - t_begin < budget_s or len(times) < 1):
+        s = states[i % len(states)]
+        i += 1
+        m = refapi.RefMesh(s["V_rest"], s["F"], s["UV"], cohE=s["cohE"] if len(s["cohE"]) else None)
+        opt = refapi.RefOptimizer(m, p0, scaffolding=s["air"] is not None, mute=False)     # precompute(): untimed
+        refapi.timers_reset()
+        t0 = time.perf_counter()
+        opt.solve(1)
+        dt = time.perf_counter() - t0
+        t4, _ = refapi.timers()
+        times.append(dt - t4["scaffolding"])
+        opt.close(); m.close()
+    return times
+
+
+def cpu_baseline(args, budget_s):
+    try:
+        times, kind = ref_step_times(args, n_steps=64, budget_s=budget_s)
+    except Exception as e:   # noqa: BLE001
+        return {"unavailable": str(e)}
+    return {"value": len(times) / sum(times), "unit": "it/s", "cores": os.cpu_count(), "kind": kind,
+            "ms_per_step": 1e3 * sum(times) / len(times),
+            "sample": "%d Newton iterations of the unmodified reference (Optimizer::solve(1), Eigen SimplicialLDLT, TBB shim on all cores) "
+                      "from the same states; wall time minus the reference's own scaffolding timer" % len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    K, W = args.steps, max(args.warmup, 1)
+    per_step_budget = 150.0
+    try:
+        times, kind = ref_step_times(args, n_steps=K + W, budget_s=per_step_budget)
+    except Exception as e:   # noqa: BLE001
+        print(json.dumps({"impl": "reference", "unavailable": str(e)}))
+        return
+    t = times[W:] if len(times) > W else times
+    v = len(t) / sum(t)
+    states, _ = load_states(args.workload)
+    print(json.dumps({
+        "impl": "reference", "metric": "newton_iters_per_s", "value": v, "unit": "it/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+        "steps": len(t), "warmup": W, "ms_per_step": 1e3 * sum(t) / len(t), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "same states as the GPU arm",
+        "config": {"workload": args.workload, "faces": int(states[0]["F"].shape[0]), "states": len(states)},
+        "cpu_baseline": {"value": v, "unit": "it/s", "cores": os.cpu_count(), "kind": kind,
+                         "sample": "%d timed Newton iterations (Optimizer::solve(1) minus its scaffolding timer), rank 0 only" % len(t)},
+        "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bimba10k", choices=["bimba10k", "bimba_x4", "bimba_x10"])
+    ap.add_argument("--pcg-tol", type=float, default=1e-12)
+    ap.add_argument("--pcg-max-it", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

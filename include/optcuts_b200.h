@@ -61,6 +61,14 @@ int  ocb_timer_stop_ms(ocb_ctx* ctx, double* ms);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t ocb_launch_count(const ocb_ctx* ctx);
 
+/* per-kernel-class CUDA-event profile on the context's stream (bench.py's roofline object): when enabled,
+ * every launch is bracketed by events; ocb_profile_get returns accumulated ms and launch counts per class
+ * (ocb_profile_classes() entries, names from ocb_profile_name). */
+int ocb_profile_enable(ocb_ctx* ctx, int on);
+int ocb_profile_get(ocb_ctx* ctx, double* ms, int64_t* counts);
+const char* ocb_profile_name(int kernel_class);
+int ocb_profile_classes(void);
+
 /* ---- a1: rest-frame features — TriMesh::computeFeatures, TriMesh.cpp:343-398 ---------------
  * rest8_soa (8 x nF, row k contiguous): triArea, triAreaSq, e0SqLen, e1SqLen, e0dote1,
  * e0SqLen_div_dbAreaSq, e1SqLen_div_dbAreaSq, e0dote1_div_dbAreaSq.  Triangles with area below
@@ -84,6 +92,10 @@ int ocb_set_air(ocb_ctx* ctx, int nVa, int nFa, const int32_t* Fa_colmajor, cons
 /* UV coordinates: TriMesh::V (nV x 2) and airMesh.V (nVa x 2, NULL when no scaffold) */
 int ocb_set_uv(ocb_ctx* ctx, const double* V_colmajor, const double* Va_colmajor);
 int ocb_get_uv(ocb_ctx* ctx, double* V_colmajor, double* Va_colmajor);
+/* device-side snapshot / rollback of the UV state (what the reference does with whole-TriMesh copies:
+ * data_findExtrema = result, Optimizer.cpp:381,452; triSoup_bestFeasible + setConfig, main.cpp:711-723) */
+int ocb_save_uv(ocb_ctx* ctx);
+int ocb_restore_uv(ocb_ctx* ctx);
 /* sizes: nV, nF, nVa, nFa, nBnd, nSys, nnz_upper (reference CSR), nnz_blocks (BSR 2x2) */
 int ocb_get_sizes(const ocb_ctx* ctx, int64_t* sizes8);
 

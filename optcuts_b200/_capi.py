@@ -60,6 +60,12 @@ _SIGS = [
     ("ocb_timer_start", C.c_int, [C.c_void_p]),
     ("ocb_timer_stop_ms", C.c_int, [C.c_void_p, _d]),
     ("ocb_launch_count", C.c_int64, [C.c_void_p]),
+    ("ocb_profile_enable", C.c_int, [C.c_void_p, C.c_int]),
+    ("ocb_profile_get", C.c_int, [C.c_void_p, _d, _i64]),
+    ("ocb_profile_name", C.c_char_p, [C.c_int]),
+    ("ocb_profile_classes", C.c_int, []),
+    ("ocb_save_uv", C.c_int, [C.c_void_p]),
+    ("ocb_restore_uv", C.c_int, [C.c_void_p]),
     ("ocb_rest_features", C.c_int, [C.c_void_p, C.c_int, C.c_int, _d, _i, C.c_double, _d, _d]),
     ("ocb_set_mesh", C.c_int, [C.c_void_p, C.c_int, C.c_int, _i, _d, C.c_double, _i, C.c_int]),
     ("ocb_set_air", C.c_int, [C.c_void_p, C.c_int, C.c_int, _i, _d, _i, C.c_int, _i, C.c_int, C.c_double]),
@@ -173,6 +179,21 @@ class Context:
 
     def launch_count(self):
         return int(self._L.ocb_launch_count(self._h))
+
+    def profile_enable(self, on=True):
+        self._chk(self._L.ocb_profile_enable(self._h, int(on)))
+
+    def profile_get(self):
+        n = self._L.ocb_profile_classes()
+        ms, cnt = np.zeros(n), np.zeros(n, np.int64)
+        self._chk(self._L.ocb_profile_get(self._h, _pd(ms), cnt.ctypes.data_as(_i64)))
+        return {self._L.ocb_profile_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}
+
+    def save_uv(self):
+        self._chk(self._L.ocb_save_uv(self._h))
+
+    def restore_uv(self):
+        self._chk(self._L.ocb_restore_uv(self._h))
 
     def sizes(self):
         s = np.zeros(8, np.int64)

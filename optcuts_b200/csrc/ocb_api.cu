@@ -21,6 +21,38 @@ int cuda_fail(ocb_ctx* c, cudaError_t e, const char* where)
     return OCB_ERR_CUDA;
 }
 
+static cudaEvent_t prof_event(ocb_ctx* c)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->profPool.empty()) { e = c->profPool.back(); c->profPool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+ProfScope::ProfScope(ocb_ctx* ctx, int k) : c(ctx), cls(k)
+{
+    if (!c->prof) return;
+    a = prof_event(c); b = prof_event(c);
+    cudaEventRecord(a, c->stream);
+}
+ProfScope::~ProfScope()
+{
+    if (!a) return;
+    cudaEventRecord(b, c->stream);
+    ocb_ctx::ProfRec r; r.cls = cls; r.a = a; r.b = b;
+    c->profRecs.push_back(r);
+}
+static void prof_collect(ocb_ctx* c)
+{
+    if (c->profRecs.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& r : c->profRecs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->profMs[r.cls] += ms; c->profCnt[r.cls]++; }
+        c->profPool.push_back(r.a); c->profPool.push_back(r.b);
+    }
+    c->profRecs.clear();
+}
+
 int ensure_init(ocb_ctx* c)
 {
     if (c->inited) { cudaSetDevice(c->device); return 0; }
@@ -126,6 +158,9 @@ void ocb_destroy(ocb_ctx* c)
         c->pr.release(); c->pz.release(); c->pd.release(); c->pAp.release(); c->pb.release(); c->minv.release();
         c->rowPtr.release(); c->colIdx.release(); c->val.release();
         c->partials.release(); c->sync.release(); c->scratchD.release(); c->scratchI.release();
+        c->xSaved.release();
+        prof_collect(c);
+        for (auto e : c->profPool) cudaEventDestroy(e);
         if (c->dScal) cudaFree(c->dScal);
         if (c->hScal) cudaFreeHost(c->hScal);
         if (c->ev0) cudaEventDestroy(c->ev0);
@@ -158,6 +193,30 @@ int ocb_timer_stop_ms(ocb_ctx* c, double* ms)
     return OCB_OK;
 }
 int64_t ocb_launch_count(const ocb_ctx* c) { return c ? c->launches : 0; }
+
+int ocb_profile_enable(ocb_ctx* c, int on)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));
+    prof_collect(c);
+    c->prof = on != 0;
+    for (int k = 0; k < K_COUNT; ++k) { c->profMs[k] = 0.0; c->profCnt[k] = 0; }
+    return OCB_OK;
+}
+int ocb_profile_get(ocb_ctx* c, double* ms, int64_t* counts)
+{
+    if (!c || !ms || !counts) return OCB_ERR_ARG;
+    prof_collect(c);
+    for (int k = 0; k < K_COUNT; ++k) { ms[k] = c->profMs[k]; counts[k] = c->profCnt[k]; }
+    return OCB_OK;
+}
+const char* ocb_profile_name(int k)
+{
+    static const char* names[K_COUNT] = {"energy", "gradient", "hessian_psd_scatter", "pcg", "step_bound", "step_forward",
+                                         "jacobi_setup", "spmv", "rest_features", "pattern_slots", "misc", "stencil_newton"};
+    return (k >= 0 && k < K_COUNT) ? names[k] : "";
+}
+int ocb_profile_classes(void) { return K_COUNT; }
 
 // ------------------------------------------------------------------------------------------- a1
 int ocb_rest_features(ocb_ctx* c, int nV, int nF, const double* Vrest, const int32_t* F, double thres,
@@ -284,6 +343,24 @@ int ocb_get_uv(ocb_ctx* c, double* V, double* Va)
     if (V) OCB_CUDA(c, cudaMemcpyAsync(V, dV, nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (na) OCB_CUDA(c, cudaMemcpyAsync(Va, dVa, na * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OCB_OK;
+}
+
+int ocb_save_uv(ocb_ctx* c)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_save_uv: no UV on the device"));
+    OCB_CUDA(c, c->xSaved.reserve((size_t)c->nSys(), c->stream));
+    OCB_CUDA(c, cudaMemcpyAsync(c->xSaved.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
+    c->xSavedN = c->nSys();
+    return OCB_OK;
+}
+int ocb_restore_uv(ocb_ctx* c)
+{
+    if (!c) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->xSavedN == c->nSys() && c->xSavedN > 0, "ocb_restore_uv: no snapshot of this system size"));
+    OCB_CUDA(c, cudaMemcpyAsync(c->x.p, c->xSaved.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
+    c->matrixValid = c->precondValid = false;
     return OCB_OK;
 }
 

@@ -55,6 +55,12 @@ struct ElemView {
     double scale;            // energyParam0 (mesh) or w_scaf/|Fa| (air): applied after projection
 };
 
+// kernel classes for the optional per-kernel CUDA-event profile (ocb_profile_*)
+enum KernelClass {
+    K_ENERGY = 0, K_GRADIENT, K_HESSIAN, K_PCG, K_STEP_BOUND, K_STEP_FORWARD, K_JACOBI_SETUP, K_SPMV,
+    K_FEATURES, K_PATTERN, K_MISC, K_STENCILS, K_COUNT
+};
+
 enum ScalarSlot {            // layout of the device/pinned scalar block
     S_E_MESH = 0, S_E_AIR, S_N_INVERTED, S_SQN_G, S_STEP_BOUND, S_PCG_ITERS, S_PCG_RELRES,
     S_PCG_STATUS, S_PCG_BNORM, S_MISC0, S_MISC1, S_MISC2, S_COUNT = 16
@@ -102,6 +108,16 @@ struct ocb_ctx {
     ocb::DevBuf<double> scratchD;
     ocb::DevBuf<int32_t> scratchI;
     int pcgGrid = 0, pcgBlock = 0;
+    ocb::DevBuf<double> xSaved;              // ocb_save_uv / ocb_restore_uv snapshot
+    int xSavedN = 0;
+
+    // per-kernel-class event profile
+    bool prof = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> profRecs;
+    std::vector<cudaEvent_t> profPool;
+    double profMs[ocb::K_COUNT] = {0};
+    int64_t profCnt[ocb::K_COUNT] = {0};
 
     int nSys() const { return 2 * nVtot; }
 };
@@ -114,6 +130,12 @@ int cuda_fail(ocb_ctx* c, cudaError_t e, const char* where);
 #define OCB_TRY(call) do { int _r = (call); if (_r < 0) return _r; } while (0)
 
 int ensure_init(ocb_ctx* c);
+// RAII: brackets the launches of one kernel class with CUDA events when profiling is enabled
+struct ProfScope {
+    ocb_ctx* c; int cls; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(ocb_ctx* ctx, int k);
+    ~ProfScope();
+};
 ElemView view_of(const ocb_ctx* c, const ElemSet& s, bool isAir, double scale, int uniform);
 int fetch_scalars(ocb_ctx* c);   // D2H of the scalar block + stream sync
 

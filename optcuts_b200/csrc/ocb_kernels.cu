@@ -455,6 +455,7 @@ static int ensure_reduce_bufs(ocb_ctx* c, int grid, int nv) {
 
 int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha)
 {
+    ProfScope prof(c, K_ENERGY);
     const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
     const int grid = grid_for(c, (long)M.n + A.n);
     OCB_TRY(ensure_reduce_bufs(c, grid, 3));
@@ -467,6 +468,7 @@ int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha)
 
 int launch_energy_per_elem(ocb_ctx* c, int uniform, double* d_out)
 {
+    ProfScope prof(c, K_ENERGY);
     const ElemView M = view_of(c, c->mesh, false, 1.0, uniform);
     energy_per_elem_kernel<<<grid_for(c, M.n), kBlock, 0, c->stream>>>(M, c->x.p, d_out);
     KCHECK(c);
@@ -485,6 +487,7 @@ int launch_sqnorm(ocb_ctx* c, const double* v, int n, int slot)
 
 int launch_gradient(ocb_ctx* c, double p0)
 {
+    ProfScope prof(c, K_GRADIENT);
     const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
     OCB_CUDA(c, cudaMemsetAsync(c->g.p, 0, sizeof(double) * c->nSys(), c->stream));
     gradient_kernel<<<grid_for(c, (long)M.n + A.n), kBlock, 0, c->stream>>>(M, A, c->x.p, c->fixedMask.p, c->g.p);
@@ -514,6 +517,7 @@ int launch_build_slots(ocb_ctx* c)
 
 int launch_hessian(ocb_ctx* c, double p0)
 {
+    ProfScope prof(c, K_HESSIAN);
     const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
     OCB_CUDA(c, cudaMemsetAsync(c->val.p, 0, sizeof(double) * 4 * (size_t)c->nnzb, c->stream));
     fixed_identity_kernel<<<grid_for(c, c->nVtot, 4), kBlock, 0, c->stream>>>(c->nVtot, c->fixedMask.p, c->rowPtr.p, c->colIdx.p, c->val.p);
@@ -525,6 +529,7 @@ int launch_hessian(ocb_ctx* c, double p0)
 
 int launch_hessian_blocks(ocb_ctx* c, int uniform, double* d_out36)
 {
+    ProfScope prof(c, K_HESSIAN);
     const ElemView M = view_of(c, c->mesh, false, 1.0, uniform);
     ElemView A = M; A.n = 0;
     hessian_kernel<false><<<grid_for(c, M.n), kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, d_out36);
@@ -534,6 +539,7 @@ int launch_hessian_blocks(ocb_ctx* c, int uniform, double* d_out36)
 
 int launch_step_bound(ocb_ctx* c, const double* d_dir, double alpha0)
 {
+    ProfScope prof(c, K_STEP_BOUND);
     const ElemView M = view_of(c, c->mesh, false, 1.0, 0), A = view_of(c, c->air, true, 1.0, 1);
     const int grid = grid_for(c, (long)M.n + A.n);
     OCB_TRY(ensure_reduce_bufs(c, grid, 1));
@@ -545,6 +551,7 @@ int launch_step_bound(ocb_ctx* c, const double* d_dir, double alpha0)
 
 int launch_step_forward(ocb_ctx* c, double alpha)
 {
+    ProfScope prof(c, K_STEP_FORWARD);
     step_forward_kernel<<<grid_for(c, c->nSys(), 4), kBlock, 0, c->stream>>>(c->nSys(), c->x0.p, c->p.p, alpha, c->x.p);
     KCHECK(c);
     return 0;
@@ -568,6 +575,7 @@ int launch_triplet_scatter(ocb_ctx* c, int64_t nT, const int32_t* dI, const int3
 
 int launch_set_uv(ocb_ctx* c, const double* dV, const double* dVa)
 {
+    ProfScope prof(c, K_MISC);
     const int total = (dV ? c->nV : 0) + (dVa ? (c->nVa - c->nBnd) : 0);
     if (total <= 0) return 0;
     set_uv_kernel<<<grid_for(c, total, 4), kBlock, 0, c->stream>>>(c->nV, dV, c->nVa, c->nBnd, dVa, c->x.p);
@@ -576,6 +584,7 @@ int launch_set_uv(ocb_ctx* c, const double* dV, const double* dVa)
 }
 int launch_get_uv(ocb_ctx* c, double* dV, double* dVa)
 {
+    ProfScope prof(c, K_MISC);
     const int total = (dV ? c->nV : 0) + (dVa ? c->nVa : 0);
     if (total <= 0) return 0;
     get_uv_kernel<<<grid_for(c, total, 4), kBlock, 0, c->stream>>>(c->nV, dV, c->nVa, c->l2g.p, dVa, c->x.p);
@@ -585,6 +594,7 @@ int launch_get_uv(ocb_ctx* c, double* dV, double* dVa)
 
 int launch_rest_features(ocb_ctx* c, int nV, int nF, const double* dVrest, const int32_t* dF, double thres, double* dRest8)
 {
+    ProfScope prof(c, K_FEATURES);
     const int grid = grid_for(c, nF);
     OCB_TRY(ensure_reduce_bufs(c, grid, 3));
     Slots3 sl; sl.s[0] = S_MISC0; sl.s[1] = S_MISC1; sl.s[2] = S_MISC2;
@@ -595,6 +605,7 @@ int launch_rest_features(ocb_ctx* c, int nV, int nF, const double* dVrest, const
 
 int launch_seam(ocb_ctx* c, int nCoh, const int32_t* dCoh, const double* dLen, const int32_t* dBnd, double avgEdgeLen, int triSoup)
 {
+    ProfScope prof(c, K_MISC);
     const int grid = grid_for(c, nCoh, 1);
     OCB_TRY(ensure_reduce_bufs(c, grid, 1));
     Slots1 sl; sl.s[0] = S_MISC0;
@@ -605,6 +616,7 @@ int launch_seam(ocb_ctx* c, int nCoh, const int32_t* dCoh, const double* dLen, c
 
 int launch_divgrad(ocb_ctx* c, double* d_out)
 {
+    ProfScope prof(c, K_MISC);
     const ElemView M = view_of(c, c->mesh, false, 1.0, 0);
     const size_t nV = c->nV;
     OCB_CUDA(c, c->scratchD.reserve(4 * nV, c->stream));

@@ -276,6 +276,7 @@ static int pcg_grid(ocb_ctx* c)
 
 int launch_spmv(ocb_ctx* c, const double* dx, double* dy)
 {
+    ProfScope prof(c, K_SPMV);
     PcgParams P = make_params(c);
     spmv_kernel<<<pcg_grid(c), kPcgBlock, 0, c->stream>>>(P, dx, dy);
     KCHECK(c);
@@ -288,8 +289,11 @@ int launch_jacobi_setup(ocb_ctx* c)
     OCB_CUDA(c, cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
     OCB_CUDA(c, c->minv.reserve(4 * (size_t)c->nVtot, c->stream));
     int grid = (c->nVtot + 255) / 256; if (grid > c->numSMs * 8) grid = c->numSMs * 8; if (grid < 1) grid = 1;
-    jacobi_setup_kernel<<<grid, 256, 0, c->stream>>>(c->nVtot, c->rowPtr.p, c->colIdx.p, c->val.p, c->minv.p, bad);
-    KCHECK(c);
+    {
+        ProfScope prof(c, K_JACOBI_SETUP);
+        jacobi_setup_kernel<<<grid, 256, 0, c->stream>>>(c->nVtot, c->rowPtr.p, c->colIdx.p, c->val.p, c->minv.p, bad);
+        KCHECK(c);
+    }
     int hBad = 0;
     OCB_CUDA(c, cudaMemcpyAsync(&hBad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -299,6 +303,7 @@ int launch_jacobi_setup(ocb_ctx* c)
 
 int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it)
 {
+    ProfScope prof(c, K_PCG);
     const size_t n = c->nSys();
     OCB_CUDA(c, c->pr.reserve(n, c->stream)); OCB_CUDA(c, c->pz.reserve(n, c->stream));
     OCB_CUDA(c, c->pd.reserve(n, c->stream)); OCB_CUDA(c, c->pAp.reserve(n, c->stream));

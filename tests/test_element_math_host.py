@@ -1,0 +1,113 @@
+"""The PRODUCT's device-inline element math (optcuts_b200/csrc/ocb_element.cuh) compiled for the host
+(tests/harness/element_host.cpp) and checked against the oracle, so formula regressions are caught
+without a GPU.  The harness is test-only; it is never shipped or imported by the package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from conftest import ROOT, relerr
+from test_oracle_vs_reference import random_mesh
+
+_d, _i = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    out = tmp_path_factory.mktemp("harness") / "libelement_host.so"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-o", str(out),
+                           os.path.join(ROOT, "tests", "harness", "element_host.cpp")])
+    L = C.CDLL(str(out))
+    L.host_step_bound.restype = C.c_double
+    return L
+
+
+def _args(F, UV, rest8):
+    F, UV, rest8 = np.asfortranarray(F, np.int32), np.asfortranarray(UV, np.float64), np.ascontiguousarray(rest8)
+    return F, UV, rest8, (UV.shape[0], F.shape[0], F.ctypes.data_as(_i), UV.ctypes.data_as(_d), rest8.ctypes.data_as(_d))
+
+
+def test_energy_and_gradient_bit_exact(host, port, state):
+    F, UV, rest8, a = _args(state.F, state.UV, state.rest8)
+    out = np.zeros(state.nF)
+    host.host_energy(*a, C.c_double(state.surfaceArea), 0, out.ctypes.data_as(_d))
+    assert np.array_equal(out, port.energy_per_elem(F, UV, rest8, state.surfaceArea))
+    gc = np.zeros((state.nF, 6))
+    host.host_gradient_corners(*a, C.c_double(state.surfaceArea), 0, gc.ctypes.data_as(_d))
+    g = np.zeros(2 * state.nV)
+    for k in range(3):
+        np.add.at(g, 2 * F[:, k], gc[:, 2 * k])
+        np.add.at(g, 2 * F[:, k] + 1, gc[:, 2 * k + 1])
+    g[2 * state.fixed] = 0
+    g[2 * state.fixed + 1] = 0
+    assert relerr(g, port.gradient(F, UV, rest8, state.surfaceArea, fixed=state.fixed)) < 1e-14
+
+
+def test_hessian_projection_matches_makePD(host, port, state):
+    """closed-form 4x4 projection in the translation-free basis == eigen-clamp of the 6x6"""
+    F, UV, rest8, a = _args(state.F, state.UV, state.rest8)
+    for project in (0, 1):
+        H = np.zeros((state.nF, 36))
+        cl = np.zeros(state.nF, np.int32)
+        host.host_hessian_blocks(*a, C.c_double(state.surfaceArea), 0, project, H.ctypes.data_as(_d), cl.ctypes.data_as(_i))
+        Hp = port.hessian_blocks(F, UV, rest8, state.surfaceArea, False, bool(project)).reshape(state.nF, 36)
+        scale = np.abs(Hp).max(axis=1)
+        assert np.max(np.abs(H - Hp).max(axis=1) / scale) < 5e-13
+    if state.tag == "s1_":
+        assert (cl > 0).sum() > 100          # the Tutte start has many indefinite element Hessians
+
+
+def test_isometric_known_answer(host):
+    """SymDirichletEnergy::checkEnergyVal (SymDirichletEnergy.cpp:612-645): isometry => E_t = 4 w, zero gradient,
+    PSD Hessian with a 3-dimensional null space (2 translations + rotation)."""
+    V_rest, F, _ = random_mesh(11, n=5, flat=True)
+    UV = V_rest[:, :2].copy()
+    from oracle import portapi
+    rest8, sc, _ = portapi.rest_features(V_rest, F)
+    F, UV, rest8, a = _args(F, UV, rest8)
+    nF = F.shape[0]
+    out = np.zeros(nF)
+    host.host_energy(*a, C.c_double(sc["surfaceArea"]), 0, out.ctypes.data_as(_d))
+    assert np.max(np.abs(out - 4.0 * rest8[0] / sc["surfaceArea"])) < 1e-14
+    gc = np.zeros((nF, 6))
+    host.host_gradient_corners(*a, C.c_double(sc["surfaceArea"]), 1, gc.ctypes.data_as(_d))
+    assert np.max(np.abs(gc)) < 1e-12
+    H = np.zeros((nF, 36))
+    host.host_hessian_blocks(*a, C.c_double(1.0), 1, 1, H.ctypes.data_as(_d), None)
+    for t in range(nF):
+        ev = np.linalg.eigvalsh(H[t].reshape(6, 6))
+        assert ev[0] > -1e-10 and np.sum(np.abs(ev) < 1e-9 * ev[-1]) == 3
+
+
+def test_finite_difference_gradient_and_hessian(host, port):
+    """Energy::checkGradient / checkHessian logic (Energy.cpp:42-147) on the unprojected blocks."""
+    V_rest, F, UV = random_mesh(12, n=4)
+    rest8, sc, _ = port.rest_features(V_rest, F)
+    F, UV, rest8, a = _args(F, UV, rest8)
+    nF, nV = F.shape[0], UV.shape[0]
+    surf = sc["surfaceArea"]
+    gc = np.zeros((nF, 6)); H = np.zeros((nF, 36))
+    host.host_gradient_corners(*a, C.c_double(surf), 0, gc.ctypes.data_as(_d))
+    host.host_hessian_blocks(*a, C.c_double(surf), 0, 0, H.ctypes.data_as(_d), None)
+    h = 1e-6
+    for t in (0, 7, nF - 1):
+        for k in range(3):
+            for c in range(2):
+                def at(delta):
+                    U2 = UV.copy(order="F"); U2[F[t, k], c] += delta
+                    e = port.energy_per_elem(F, U2, rest8, surf)[t]
+                    g2 = np.zeros((nF, 6))
+                    F2, U2, r2, a2 = _args(F, U2, rest8)
+                    host.host_gradient_corners(*a2, C.c_double(surf), 0, g2.ctypes.data_as(_d))
+                    return e, g2[t]
+                ep, gp = at(h); em, gm = at(-h)
+                assert abs((ep - em) / (2 * h) - gc[t, 2 * k + c]) < 1e-6 * max(1.0, abs(gc[t]).max())
+                assert np.max(np.abs((gp - gm) / (2 * h) - H[t].reshape(6, 6)[2 * k + c])) < 1e-5 * max(1.0, np.abs(H[t]).max())
+
+
+def test_step_bound_bit_exact(host, port, state):
+    F, UV, rest8, a = _args(state.F, state.UV, state.rest8)
+    p = np.ascontiguousarray(state.r("searchDir")[:2 * state.nV])
+    got = host.host_step_bound(state.nV, state.nF, F.ctypes.data_as(_i), UV.ctypes.data_as(_d), p.ctypes.data_as(_d), C.c_double(1.0))
+    assert got == port.init_step_size(F, UV, p, 1.0)

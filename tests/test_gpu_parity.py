@@ -1,0 +1,332 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (optcuts_b200._capi -> liboptcuts_b200.so),
+against the oracle on the same inputs and against the golden vectors recorded from the reference.
+
+Tolerances (stated per test): per-element values bit-exact where the kernel mirrors the reference's
+operation order (energy, rest features, step bound); sums / scatters to rounding (1e-13..1e-12, the
+association order differs); solver-dependent quantities to north_star's 1e-9 relative."""
+import numpy as np
+import pytest
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------- a1
+def test_rest_features(ctx, port, state):
+    r8, sc = ctx.rest_features(state.V_rest, state.F)
+    assert np.array_equal(r8, state.rest8)                                       # bit-exact
+    assert abs(sc["surfaceArea"] - state.surfaceArea) <= 1e-13 * state.surfaceArea
+    assert abs(sc["avgEdgeLen"] - state.avgEdgeLen) <= 1e-13 * state.avgEdgeLen
+    a = state.air
+    V3 = np.hstack([a["V"], np.zeros((len(a["V"]), 1))])
+    r8a, _ = ctx.rest_features(V3, a["F"], a["areaThres_AM"])
+    assert np.array_equal(r8a, a["rest8"])                                       # incl. the degenerate-triangle clamp
+
+
+def test_rest_features_zero_area_is_an_error(ctx):
+    import optcuts_b200 as ob
+    V = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [0, 1, 0]], dtype=float)
+    F = np.array([[0, 1, 2], [0, 1, 3]], dtype=np.int32)
+    with pytest.raises(ob.OcbError) as e:
+        ctx.rest_features(V, F)
+    assert e.value.code == -2                                                    # reference: exit(-1), TriMesh.cpp:368-402
+
+
+# ------------------------------------------------------------------------------------- a2 / a13
+def test_energy(ctx, port, state):
+    state.upload(ctx)
+    per = ctx.energy_per_elem()
+    assert np.array_equal(per, port.energy_per_elem(state.F, state.UV, state.rest8, state.surfaceArea))   # bit-exact
+    et, esd, escaf = ctx.energy(state.p0)
+    assert abs(esd - float(state.r("E_sd_last"))) <= 1e-13 * esd
+    assert abs(escaf - float(state.r("E_scaf_last"))) <= 1e-13 * escaf
+    assert abs(et - float(state.r("E_last"))) <= 1e-13 * et
+
+
+def test_energy_is_deterministic(ctx, state1):
+    state1.upload(ctx)
+    vals = {ctx.energy(state1.p0) for _ in range(5)}
+    assert len(vals) == 1
+
+
+def test_inverted_element_is_reported(ctx, state1):
+    import optcuts_b200 as ob
+    state1.upload(ctx, with_air=False)
+    UV = state1.UV.copy(order="F")
+    t = state1.F[17]
+    UV[t[0]] = UV[t[1]] + UV[t[2]] - UV[t[0]]          # reflect one corner across the opposite edge
+    ctx.set_uv(UV)
+    with pytest.raises(ob.OcbError) as e:
+        ctx.energy(state1.p0)
+    assert e.value.code == -4
+    ctx.set_uv(state1.UV)
+
+
+# ------------------------------------------------------------------------------------- a4 / a13
+def test_gradient(ctx, state):
+    state.upload(ctx)
+    g, sq = ctx.gradient(state.p0)
+    assert relerr(g, state.r("gradient")) < 1e-13
+    assert abs(sq - float(state.r("sqn_g"))) <= 1e-12 * sq
+    assert np.all(g[2 * state.fixed] == 0) and np.all(g[2 * state.fixed + 1] == 0)
+
+
+# ------------------------------------------------------------------- a5 / a9 / a10 / a11 / a18
+def test_hessian_blocks_vs_makePD(ctx, port, state):
+    state.upload(ctx, with_air=False)
+    H = ctx.hessian_blocks().reshape(state.nF, 36)
+    Hp = port.hessian_blocks(state.F, state.UV, state.rest8, state.surfaceArea).reshape(state.nF, 36)
+    assert np.max(np.abs(H - Hp).max(axis=1) / np.abs(Hp).max(axis=1)) < 5e-13
+    ev = np.linalg.eigvalsh(H.reshape(-1, 6, 6)[::37])
+    assert ev.min() > -1e-9 * np.abs(ev).max()
+
+
+def test_hessian_triplets_same_stream_as_reference(ctx, port, state1):
+    s = state1
+    s.upload(ctx, with_air=False)
+    I, J, V = ctx.hessian_triplets()
+    pI, pJ, pV = port.hessian_triplets(s.F, s.UV, s.rest8, s.surfaceArea, fixed=s.fixed)
+    assert np.array_equal(I, pI) and np.array_equal(J, pJ)                       # same order as addBlockToMatrix
+    assert np.max(np.abs(V - pV)) <= 1e-12 * np.max(np.abs(pV))
+
+
+def test_assembled_matrix_equals_reference_csr(ctx, state1):
+    """pattern from adjacency + fused projection/scatter == the reference's LinSysSolver ia/ja/a."""
+    from test_oracle_golden import _merged_adjacency
+    s = state1
+    s.upload(ctx)
+    (ptr, idx), nVtot = _merged_adjacency(s)
+    ctx.set_pattern(ptr, idx, s.fixed)
+    ctx.hessian_assemble(s.p0)
+    ia, ja, a = ctx.download_csr()
+    assert np.array_equal(ia, s.r("ia") + 1) and np.array_equal(ja, s.r("ja") + 1)
+    assert np.max(np.abs(a - s.r("a"))) <= 1e-11 * np.max(np.abs(s.r("a")))
+    # the derived pattern is the same one
+    ctx.set_pattern_from_elements()
+    ctx.hessian_assemble(s.p0)
+    ia2, ja2, a2 = ctx.download_csr()
+    assert np.array_equal(ia, ia2) and np.array_equal(ja, ja2)
+    assert np.max(np.abs(a - a2)) <= 1e-13 * np.max(np.abs(a))
+
+
+def test_assembled_matrix_state100(ctx, state100):
+    s = state100
+    s.upload(ctx)
+    ctx.set_pattern_from_elements()
+    ctx.hessian_assemble(s.p0)
+    ia, ja, a = ctx.download_csr()
+    assert abs(a.sum() - float(s.r("a_sum"))) <= 1e-5 * abs(float(s.r("a_sum")))
+    assert abs(np.abs(a).sum() - float(s.r("a_abs_sum"))) <= 1e-9 * float(s.r("a_abs_sum"))
+
+
+def test_update_values_triplets_mirrors_update_a(ctx, port, state1):
+    from test_oracle_golden import _merged_adjacency
+    s = state1
+    s.upload(ctx)
+    (ptr, idx), _ = _merged_adjacency(s)
+    ctx.set_pattern(ptr, idx, s.fixed)
+    pI, pJ, pV = port.hessian_triplets(s.F, s.UV, s.rest8, s.surfaceArea, fixed=s.fixed)
+    ctx.update_values_triplets(pI, pJ, pV)
+    ia, ja, a = ctx.download_csr()
+    pa, miss = port.update_a(ia, ja, pI, pJ, pV)
+    assert miss == 0 and np.max(np.abs(a - pa)) <= 1e-13 * np.max(np.abs(pa))
+    import optcuts_b200 as ob
+    with pytest.raises(ob.OcbError):                                             # entry outside the pattern
+        ctx.update_values_triplets([0], [2 * (s.nV - 1)], [1.0])
+
+
+def test_multiply(ctx, state1):
+    s = state1
+    s.upload(ctx)
+    ctx.set_pattern_from_elements()
+    ctx.hessian_assemble(s.p0)
+    ia, ja, a = ctx.download_csr()
+    n = len(ia) - 1
+    import scipy.sparse as sp
+    U = sp.csr_matrix((a, ja - 1, ia - 1), shape=(n, n))
+    A = U + sp.triu(U, 1).T
+    x = np.random.default_rng(0).standard_normal(n)
+    assert relerr(ctx.multiply(x), A @ x) < 1e-13
+
+
+# ------------------------------------------------------------------------------------------- a12
+def test_pcg_search_direction(ctx, state):
+    s = state
+    s.upload(ctx)
+    ctx.set_pattern_from_elements()
+    g, _ = ctx.gradient(s.p0)
+    ctx.hessian_assemble(s.p0)
+    ctx.factorize()
+    p, info = ctx.solve(None, 1e-12)
+    assert info["status"] == 0 and info["rel_res"] <= 1e-12
+    ref_p = s.r("searchDir")
+    assert np.linalg.norm(p - ref_p) <= 1e-8 * np.linalg.norm(ref_p)             # vs SimplicialLDLT
+    assert np.linalg.norm(ctx.multiply(p) + g) <= 1e-11 * np.linalg.norm(g)      # true residual
+    p2, _ = ctx.solve(None, 1e-12)
+    assert np.array_equal(p, p2)                                                 # deterministic reductions
+
+
+def test_linsys_solver_surface(ctx, port, state1):
+    """CudaLinSysSolver used the way Optimizer uses EigenLibSolver (Optimizer.cpp:173-183, 524-563)."""
+    import optcuts_b200 as ob
+    from test_oracle_golden import _merged_adjacency
+    s = state1
+    (ptr, idx), nVtot = _merged_adjacency(s)
+    sol = ob.CudaLinSysSolver(ctx=ob.Context(0))
+    sol.set_type(1, 2)
+    sol.set_pattern((ptr, idx), s.fixed)
+    ia, ja, a = s.r("ia") + 1, s.r("ja") + 1, s.r("a")
+    rows = np.repeat(np.arange(len(ia) - 1), np.diff(ia))
+    sol.update_a(rows, ja - 1, a)
+    sol.analyze_pattern()
+    assert sol.factorize()
+    x = sol.solve(-s.r("gradient"))
+    assert sol.getNumRows() == 2 * nVtot and sol.getNumNonzeros() == len(ja)
+    assert np.linalg.norm(x - s.r("searchDir")) <= 1e-8 * np.linalg.norm(s.r("searchDir"))
+    assert abs(sol.coeffMtr(0, 0) - 1.0) < 1e-15                                 # fixed vertex: identity diagonal
+    sol.ctx.close()
+
+
+def test_not_spd_is_a_status_not_a_crash(ctx, state1):
+    import optcuts_b200 as ob
+    sol = ob.CudaLinSysSolver(ctx=ob.Context(0))
+    ptr, idx = np.array([0, 1, 2], np.int32), np.array([1, 0], np.int32)
+    sol.set_pattern((ptr, idx), [])
+    sol.update_a([0, 1, 2, 3], [0, 1, 2, 3], [1.0, -1.0, 1.0, 1.0])
+    with pytest.raises(ob.OcbError) as e:
+        sol.factorize()
+    assert e.value.code == -6
+    sol.ctx.close()
+
+
+# -------------------------------------------------------------------------------------- a7 / a14
+def test_step_bound_and_line_search(ctx, port, state):
+    s = state
+    s.upload(ctx)
+    p = s.r("searchDir")
+    ctx.set_search_dir(p)
+    alpha = ctx.step_bound(None, 1.0)
+    a = s.air
+    l2g = a["localVI2Global"]
+    pa = np.stack([p[2 * l2g], p[2 * l2g + 1]], axis=1).ravel()
+    want = port.init_step_size(a["F"], a["V"], pa, port.init_step_size(s.F, s.UV, p[:2 * s.nV], 1.0))
+    assert alpha == want                                                         # bit-exact: min is order-independent
+    assert abs(0.99 * alpha - float(s.r("alpha"))) <= 1e-15
+    ls = ctx.line_search(s.p0, 0.0, 0.99 * alpha)
+    assert ls["n_halvings"] == 0 and ls["alpha"] == float(s.r("alpha"))
+    for k in ("E_new", "E_sd_new", "E_scaf_new"):
+        assert abs(ls[k] - float(s.r(k))) <= 1e-13 * abs(float(s.r(k)))
+    assert abs(ls["lastEDec"] - float(s.r("lastEDec"))) <= 1e-10 * abs(float(s.r("lastEDec")))
+    assert np.max(np.abs(ctx.get_uv() - s.next_uv())) <= 1e-15
+
+
+def test_line_search_halves_on_energy_increase(ctx, state100):
+    s = state100
+    s.upload(ctx)
+    ctx.set_search_dir(-3.0 * s.r("searchDir"))        # ascent direction: must back off until E stops increasing
+    a0 = 0.99 * ctx.step_bound(None, 1.0)
+    ls = ctx.line_search(s.p0, 0.0, a0, allowEDecRelTol=False)
+    assert ls["n_halvings"] > 0 and ls["E_new"] <= ls["E_last"] and ls["alpha"] == a0 / 2 ** ls["n_halvings"]
+
+
+# ------------------------------------------------------------------------ whole Newton iteration
+def test_newton_step_matches_reference_iteration(ctx, state):
+    """teacher-forced: upload reference state k, one device-resident iteration, compare with state k+1"""
+    s = state
+    s.upload(ctx)
+    r = ctx.newton_step(s.p0, float(s.r("targetGRes")))
+    assert not r["converged"] and r["pcg_rel_res"] <= 1e-12
+    assert abs(r["sqn_g"] - float(s.r("sqn_g"))) <= 1e-12 * r["sqn_g"]
+    assert abs(r["alpha"] - float(s.r("alpha"))) <= 1e-9 * float(s.r("alpha"))
+    for k in ("E_new", "E_sd_new", "E_scaf_new"):
+        assert abs(r[k] - float(s.r(k))) <= 1e-9 * abs(float(s.r(k)))           # north_star: 1e-9 relative
+    assert np.max(np.abs(ctx.get_uv() - s.next_uv())) <= 1e-9 * np.max(np.abs(s.next_uv()))
+
+
+def test_optimizer_free_run_with_reference_scaffold(ctx, ref, state1):
+    """Optimizer mirror free-running 6 iterations with the scaffold re-triangulated every iteration by the
+    reference's own Scaffold (host-side work of the caller) tracks the reference trace to 1e-9."""
+    import os
+    import optcuts_b200 as ob
+    from conftest import GOLDEN
+    s = state1
+    trace = [dict(kv.split("=") for kv in ln.split()) for ln in open(os.path.join(GOLDEN, "bimba_cfg2_trace.txt"))]
+    c2 = ob.Context(0)
+    mesh = ob.TriMesh(s.V_rest, s.F, s.UV, ctx=c2)
+
+    def builder(m):
+        rm = ref.RefMesh(m.V_rest, m.F, m.V)
+        sc = ref.build_scaffold(rm)
+        rm.close()
+        return ob.scaffold.Scaffold(sc["V"], sc["F"], sc["bnd"], m.nV, fixedAir=sc["fixed"], rest8=sc["rest8"])
+
+    opt = ob.Optimizer(mesh, energyParams=(s.p0,), scaffolding=True, scaffold_builder=builder, ctx=c2)
+    opt.precompute()
+    assert abs(opt.lastEnergyVal - float(s.r("E_last"))) <= 1e-13 * opt.lastEnergyVal
+    for it in range(6):
+        opt.solve(1)
+        want = trace[it + 1]
+        assert abs(opt.getLastEnergyVal() - float(want["E"])) <= 1e-9 * float(want["E"]), it
+        assert abs(opt.getLastEnergyVal(True) - float(want["Enoscaf"])) <= 1e-9 * float(want["Enoscaf"]), it
+        assert opt.getScaffold().F.shape[0] == int(want["amF"])
+    c2.close()
+
+
+# ------------------------------------------------------------------------------------- a15 / a8
+def test_seam_energy(ctx, state100):
+    s = state100
+    s.upload(ctx, with_air=False)
+    for soup, key in ((False, "seam_sparsity"), (True, "seam_sparsity_soup")):
+        e = ctx.seam_energy(s.cohE, s.r("edgeLen"), s.r("boundaryEdge"), 0.0, s.virtualRadius, s.avgEdgeLen, soup)
+        assert abs(e * s.virtualRadius - float(s.r(key))) <= 1e-13 * float(s.r(key))
+    assert ctx.seam_energy(np.zeros((0, 4), np.int32), [], [], 0.5, 2.0, 1.0, False) == 0.25     # empty cohE
+
+
+def test_divgrad_scores(ctx, state):
+    state.upload(ctx, with_air=False)
+    d = ctx.divgrad_scores()
+    assert relerr(d, state.r("divgrad")) < 1e-12
+
+
+# ----------------------------------------------------------------- Energy-plugin mirror surface
+def test_energy_plugin_surface(ctx, port, state1):
+    import optcuts_b200 as ob
+    s = state1
+    mesh = ob.TriMesh(s.V_rest, s.F, s.UV, ctx=ctx)
+    SD = ob.SymDirichletEnergy(ctx=ctx)
+    assert abs(SD.computeEnergyVal(mesh) - float(s.r("E_sd_last"))) <= 1e-13 * float(s.r("E_sd_last"))
+    assert np.array_equal(SD.getEnergyValPerElem(mesh), s.r("energy_per_elem"))
+    assert SD.getEnergyValByElemID(mesh, 5) == s.r("energy_per_elem")[5]
+    g = SD.computeGradient(mesh)
+    assert relerr(g, port.gradient(s.F, s.UV, s.rest8, s.surfaceArea, fixed=s.fixed)) < 1e-13
+    assert abs(SD.checkEnergyVal(mesh)) < 1e-12
+    # uniform weights (the scaffold flavour, Optimizer.cpp:775)
+    e_u = SD.computeEnergyVal(mesh, uniformWeight=True)
+    assert abs(e_u - port.energy(s.F, s.UV, s.rest8, 1.0, uniform=True)) <= 1e-12 * e_u
+
+
+# ------------------------------------------------------------- full-size, size-independent checks
+@pytest.mark.parametrize("n", [4, 10])
+def test_large_mesh_properties(ctx, port, state1, n):
+    """BASELINE.json sizes (160k / 1M faces): subdivision keeps the area-weighted energy; the gradient is
+    orthogonal to translations and to the infinitesimal rotation; A is symmetric; PCG reduces the residual."""
+    from optcuts_b200 import synth
+    s = state1
+    Vr, F, UV = synth.subdivide(s.V_rest, s.F, s.UV, n)
+    r8, sc = ctx.rest_features(Vr, F)
+    ctx.set_mesh(len(UV), F, r8, sc["surfaceArea"], [])
+    ctx.set_uv(UV)
+    et, esd, _ = ctx.energy(1.0)
+    assert abs(esd - float(s.r("E_sd_last"))) <= 1e-10 * esd
+    g, sq = ctx.gradient(1.0)
+    gx, gy = g[0::2], g[1::2]
+    scale = np.abs(g).sum()
+    assert abs(gx.sum()) < 1e-11 * scale and abs(gy.sum()) < 1e-11 * scale
+    assert abs(np.dot(gx, -UV[:, 1]) + np.dot(gy, UV[:, 0])) < 1e-10 * scale * np.abs(UV).max()
+    ctx.set_pattern_from_elements()
+    ctx.hessian_assemble(1.0)
+    rng = np.random.default_rng(1)
+    x, y = rng.standard_normal(len(g)), rng.standard_normal(len(g))
+    Ax, Ay = ctx.multiply(x), ctx.multiply(y)
+    assert abs(np.dot(y, Ax) - np.dot(x, Ay)) <= 1e-10 * abs(np.dot(y, Ax))
+    assert np.dot(x, Ax) > 0
