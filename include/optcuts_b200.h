@@ -158,7 +158,7 @@ int ocb_step_bound(ocb_ctx* ctx, const double* searchDir, double* alpha);
 /* ---- a14: line search — Optimizer::lineSearch + stepForward (Optimizer.cpp:575-673),
  * Scaffold::stepForward (Scaffold.cpp:282-293), TriMesh::checkInversion (TriMesh.cpp:1710-1756).
  * Uses the device search direction; alpha0 is the starting step (already x0.99).  E_last is
- * recomputed when a scaffold is present (Optimizer.cpp:590).  Outputs: accepted alpha, new total
+ * recomputed when a scaffold is present (Optimizer.cpp:590) or when E_last <= 0 is passed.  Outputs: accepted alpha, new total
  * energy, its scaffold part, its mesh SD part (unscaled), lastEDec (scaffold change excluded,
  * :631-634), number of halvings, stop flag (:635, honoured only if allowEDecRelTol). */
 typedef struct {

@@ -12,6 +12,7 @@ from .trimesh import TriMesh  # noqa: F401
 from .energy import SymDirichletEnergy  # noqa: F401
 from .linsys import CudaLinSysSolver  # noqa: F401
 from .optimizer import Optimizer  # noqa: F401
+from . import scaffold, synth  # noqa: F401
 
 __all__ = ["Context", "OcbError", "TriMesh", "SymDirichletEnergy", "CudaLinSysSolver", "Optimizer",
            "lib_path", "load_library"]

@@ -155,7 +155,7 @@ void ocb_destroy(ocb_ctx* c)
         c->air.v.release(); c->air.rest.release(); c->air.slot.release();
         c->l2g.release(); c->fixedMask.release();
         c->x.release(); c->x0.release(); c->g.release(); c->p.release();
-        c->pr.release(); c->pz.release(); c->pd.release(); c->pAp.release(); c->pb.release(); c->minv.release();
+        c->pr.release(); c->pz.release(); c->pd.release(); c->pd2.release(); c->pAp.release(); c->pb.release(); c->minv.release();
         c->rowPtr.release(); c->colIdx.release(); c->val.release();
         c->partials.release(); c->sync.release(); c->scratchD.release(); c->scratchI.release();
         c->xSaved.release();
@@ -304,7 +304,7 @@ int ocb_set_air(ocb_ctx* c, int nVa, int nFa, const int32_t* Fa, const double* r
         c->hFixed.resize((size_t)nVtot, 0);
         for (int i = 0; i < nFixedAir; ++i) {
             if (fixedAir[i] < 0 || fixedAir[i] >= nVa) return set_err(c, OCB_ERR_ARG, "fixed air vertex out of range");
-            c->hFixed[l2g[fixedAir[i]]] = 1;
+            c->hFixed[l2g[fixedAir[i]]] |= 2;
         }
     }
     OCB_TRY(resize_system(c));
@@ -448,7 +448,10 @@ int ocb_set_pattern(ocb_ctx* c, int nVtot, const int32_t* adjPtr, const int32_t*
     }
     if (nVtot != c->nVtot) return set_err(c, OCB_ERR_ARG, "ocb_set_pattern: nVtot does not match mesh + air sizes");
     c->hFixed.assign((size_t)nVtot, 0);
-    for (int i = 0; i < nFixed; ++i) { if (fixed[i] < 0 || fixed[i] >= nVtot) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range"); c->hFixed[fixed[i]] = 1; }
+    for (int i = 0; i < nFixed; ++i) {
+        if (fixed[i] < 0 || fixed[i] >= nVtot) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range");
+        c->hFixed[fixed[i]] = (c->nV > 0 && fixed[i] >= c->nV) ? 2 : 1;     // merged set (Scaffold::mergeFixedV): air-only ids follow the mesh's
+    }
     c->hRowPtr.assign((size_t)nVtot + 1, 0);
     c->hColIdx.clear();
     c->hColIdx.reserve((size_t)adjPtr[nVtot] + nVtot);
@@ -716,10 +719,12 @@ int ocb_line_search(ocb_ctx* c, double p0, double E_last, double alpha0, int all
     const bool scaf = c->nFa > 0;
     double lastScaf = 0.0;
     OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
-    if (scaf) {   // the scaffold changed since E_last was computed (Optimizer.cpp:588-592)
+    // the scaffold changed since E_last was computed (Optimizer.cpp:588-592); E_last <= 0 asks for a fresh
+    // evaluation (the Symmetric Dirichlet energy is >= 4 * energyParam0 > 0)
+    if (scaf || !(E_last > 0.0)) {
         OCB_TRY(launch_energy(c, p0, false, 0.0));
         OCB_TRY(fetch_scalars(c));
-        lastScaf = c->wScafOverFa * c->hScal[S_E_AIR];
+        lastScaf = scaf ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
         E_last = p0 * c->hScal[S_E_MESH] + lastScaf;
     }
     double alpha = alpha0, E = 0.0, Escaf = 0.0, Esd = 0.0;

@@ -93,7 +93,7 @@ struct ocb_ctx {
     // state vectors, all nSys doubles (interleaved u,v per global vertex)
     ocb::DevBuf<double> x, x0, g, p;
     // PCG work vectors
-    ocb::DevBuf<double> pr, pz, pd, pAp, pb, minv;   // minv: 4 per block row
+    ocb::DevBuf<double> pr, pz, pd, pd2, pAp, pb, minv;   // minv: 4 per block row
     // BSR(2x2), full symmetric storage
     int nnzb = 0;
     std::vector<int32_t> hRowPtr, hColIdx;
@@ -108,6 +108,7 @@ struct ocb_ctx {
     ocb::DevBuf<double> scratchD;
     ocb::DevBuf<int32_t> scratchI;
     int pcgGrid = 0, pcgBlock = 0;
+    size_t pcgSmemAttr = 0;
     ocb::DevBuf<double> xSaved;              // ocb_save_uv / ocb_restore_uv snapshot
     int xSavedN = 0;
 

@@ -201,12 +201,17 @@ build_slots_kernel(int n, const int32_t* __restrict__ v0, const int32_t* __restr
 // identity blocks for fixed vertices (IglUtils::addDiagonalToMatrix path, SymDirichletEnergy.cpp:541-548)
 __global__ void __launch_bounds__(kBlock)
 fixed_identity_kernel(int nVtot, const uint8_t* __restrict__ fixedMask, const int32_t* __restrict__ rowPtr,
-                      const int32_t* __restrict__ colIdx, double* __restrict__ val)
+                      const int32_t* __restrict__ colIdx, double* __restrict__ val, double scaleMesh, double scaleAir)
 {
+    // the identity triplets are scaled like every other triplet of their term: energyParams[e] for the mesh
+    // term (Optimizer.cpp:821-832), w_scaf/|Fa| for the air mesh (Scaffold.cpp:231-248).  mask bit 0 = fixed
+    // by the mesh, bit 1 = fixed by the air mesh.
     for (int v = blockIdx.x * kBlock + threadIdx.x; v < nVtot; v += gridDim.x * kBlock) {
-        if (!fixedMask[v]) continue;
+        const unsigned m = fixedMask[v];
+        if (!m) continue;
+        const double dgn = ((m & 1u) ? scaleMesh : 0.0) + ((m & 2u) ? scaleAir : 0.0);
         for (int b = rowPtr[v]; b < rowPtr[v + 1]; ++b)
-            if (colIdx[b] == v) { val[4 * (size_t)b] = 1.0; val[4 * (size_t)b + 1] = 0.0; val[4 * (size_t)b + 2] = 0.0; val[4 * (size_t)b + 3] = 1.0; }
+            if (colIdx[b] == v) { val[4 * (size_t)b] = dgn; val[4 * (size_t)b + 1] = 0.0; val[4 * (size_t)b + 2] = 0.0; val[4 * (size_t)b + 3] = dgn; }
     }
 }
 
@@ -520,7 +525,7 @@ int launch_hessian(ocb_ctx* c, double p0)
     ProfScope prof(c, K_HESSIAN);
     const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
     OCB_CUDA(c, cudaMemsetAsync(c->val.p, 0, sizeof(double) * 4 * (size_t)c->nnzb, c->stream));
-    fixed_identity_kernel<<<grid_for(c, c->nVtot, 4), kBlock, 0, c->stream>>>(c->nVtot, c->fixedMask.p, c->rowPtr.p, c->colIdx.p, c->val.p);
+    fixed_identity_kernel<<<grid_for(c, c->nVtot, 4), kBlock, 0, c->stream>>>(c->nVtot, c->fixedMask.p, c->rowPtr.p, c->colIdx.p, c->val.p, p0, c->wScafOverFa);
     KCHECK(c);
     hessian_kernel<true><<<grid_for(c, (long)M.n + A.n), kBlock, 0, c->stream>>>(M, A, c->x.p, c->val.p, nullptr);
     KCHECK(c);

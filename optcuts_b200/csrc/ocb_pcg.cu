@@ -14,94 +14,23 @@
 // vectors (d, Ap, x, r, z, minv) 144+48 = ~480 B  -> ~228 B per mesh face.
 #include "ocb_internal.cuh"
 #include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdlib>
 
 namespace ocb {
 
-static constexpr int kPcgBlock = 512;
+static constexpr int kPcgBlock = 1024;
 
 struct PcgParams {
     int nRows;                 // block rows (= global vertices)
     const int32_t* rowPtr; const int32_t* colIdx; const double* val; const double* minv;
     const double* rhs; int negate;
-    double* x; double* r; double* z; double* d; double* Ap;
-    double* partials;          // 3 x gridDim (double buffered by phase: 2 sets)
-    unsigned* bar;             // [0] arrival counter, [1] generation
+    double* x; double* r; double* z; double* d; double* d2; double* Ap;
+    double* partials;          // 2 x gridDim SyncSlots (64 B each), double buffered by epoch parity
     double* scal;              // device scalar block
     double relTol; int maxIt;
+    int maxBlkPerCta;          // SMEM mode: capacity of the per-CTA block arrays
 };
-
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nBlocks)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        volatile unsigned* gen = bar + 1;
-        const unsigned g = *gen;
-        __threadfence();
-        const unsigned t = atomicAdd(bar, 1u);
-        if (t == nBlocks - 1) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            while (*gen == g) { __nanosleep(20); }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-// all CTAs sum the published partials in the same order
-template <int NV>
-__device__ __forceinline__ void gather_partials(const double* partials, int nBlocks, double (&out)[NV])
-{
-    __shared__ double sm[NV][kPcgBlock / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    for (int b = threadIdx.x; b < nBlocks; b += kPcgBlock)
-#pragma unroll
-        for (int k = 0; k < NV; ++k) acc[k] += __ldcg(&partials[(size_t)b * NV + k]);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double t = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) sm[k][warp] = t;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double t = 0.0;
-        for (int w = 0; w < kPcgBlock / 32; ++w) t += sm[k][w];
-        out[k] = t;
-    }
-    __syncthreads();
-}
-
-template <int NV>
-__device__ __forceinline__ void publish_partials(double (&v)[NV], double* partials)
-{
-    __shared__ double sm[NV][kPcgBlock / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double t = v[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) sm[k][warp] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double t = 0.0;
-            for (int w = 0; w < kPcgBlock / 32; ++w) t += sm[k][w];
-            partials[(size_t)blockIdx.x * NV + k] = t;
-        }
-    }
-    __syncthreads();
-}
 
 // y[rows of this CTA] = A * v ; returns this thread's share of v . y.
 // v may have been written by other CTAs before the last grid barrier: plain (coherent) loads, no
@@ -136,82 +65,297 @@ __device__ __forceinline__ double spmv_rows(const PcgParams& P, int rowBeg, int 
     return dotAcc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// grid-wide all-reduce that doubles as the grid barrier.  No atomics and no second round trip: every
+// CTA publishes each partial as ONE 16-byte packet {value, epoch} in its own slot (after a gpu-scope
+// fence that makes the CTA's vector stores visible first); warp 0 of every CTA polls all packets with
+// relaxed 16-byte loads -- the load that sees the epoch also carries the value -- and sums them in
+// the same fixed order, so every CTA gets bitwise identical results.  Slots are double-buffered by
+// epoch parity: a CTA can publish epoch e+2 only after every CTA has published e+1, i.e. after every
+// CTA has finished reading epoch e.  Cross-CTA vectors are read through L2 (__ldcg) afterwards, so no
+// L1 invalidation (acquire) is needed anywhere.
+struct __align__(16) SyncPacket { double v; unsigned long long epoch; };
+static constexpr int kSyncVals = 2;                         // packets per CTA slot
+struct __align__(64) SyncSlot { SyncPacket p[kSyncVals]; unsigned long long pad[4]; };
+
+__device__ __forceinline__ SyncPacket ld_packet(const SyncPacket* p)
+{
+    SyncPacket r;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(*reinterpret_cast<unsigned long long*>(&r.v)), "=l"(r.epoch) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_packet(SyncPacket* p, double v, unsigned long long epoch)
+{
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(__double_as_longlong(v)), "l"(epoch) : "memory");
+}
+
+template <int NV>
+__device__ __forceinline__ void grid_allreduce(SyncSlot* slots, int nB, unsigned long long epoch, double (&loc)[NV], double (&out)[NV])
+{
+    static_assert(NV <= kSyncVals, "slot too small");
+    __shared__ double sm[NV][kPcgBlock / 32];
+    __shared__ double bc[NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = loc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) sm[k][warp] = t;
+    }
+    __syncthreads();                       // orders every thread's vector stores before the fence below
+    if (warp == 0) {
+        SyncSlot* base = slots + (size_t)(epoch & 1ull) * nB;
+        double t[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            t[k] = lane < kPcgBlock / 32 ? sm[k][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+        }
+        if (lane == 0) {
+            __threadfence();               // cumulative: the whole CTA's stores are visible before the packets
+#pragma unroll
+            for (int k = 0; k < NV; ++k) st_packet(&base[blockIdx.x].p[k], t[k], epoch);
+        }
+        double acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        for (int b = lane; b < nB; b += 32) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                SyncPacket q = ld_packet(&base[b].p[k]);
+                while (q.epoch < epoch) q = ld_packet(&base[b].p[k]);
+                acc[k] += q.v;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            if (lane == 0) bc[k] = acc[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) out[k] = bc[k];
+    __syncthreads();                       // sm / bc may be rewritten by the next call
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-resident slice (SMEM mode): when a CTA's rows fit in shared memory (<= ~200 KB: up to ~170k faces
+// over 148 CTAs) the matrix slice and all own-row vectors live there for the whole solve, so that an
+// iteration touches global memory only for the halo gathers (z, d of neighbour rows), the two vectors
+// neighbours read (z, d) and the sync packets.  Otherwise (GLOBAL mode) the slice is streamed from L2/HBM.
+struct Slice {
+    int32_t* rowPtr;   // nLoc + 1, block offsets relative to the CTA's first block
+    int32_t* col;      // nBlk
+    double2* val2;     // 2 * nBlk  (row-major 2x2 blocks as two double2)
+    double2* x; double2* r; double2* Ap; double2* z; double2* d;   // nLoc each
+    double4* minv;     // nLoc
+};
+__host__ __device__ inline size_t slice_bytes(int nLoc, int nBlk)
+{
+    size_t b = 0;
+    b += (((size_t)(nLoc + 1) * 4 + 15) / 16) * 16;
+    b += (((size_t)nBlk * 4 + 15) / 16) * 16;
+    b += (size_t)nBlk * 32;
+    b += (size_t)nLoc * 16 * 5;
+    b += (size_t)nLoc * 32;
+    return b;
+}
+__device__ __forceinline__ Slice carve(unsigned char* base, int nLoc, int nBlk)
+{
+    Slice S; size_t o = 0;
+    S.rowPtr = reinterpret_cast<int32_t*>(base + o); o += (((size_t)(nLoc + 1) * 4 + 15) / 16) * 16;
+    S.col = reinterpret_cast<int32_t*>(base + o);    o += (((size_t)nBlk * 4 + 15) / 16) * 16;
+    S.val2 = reinterpret_cast<double2*>(base + o);   o += (size_t)nBlk * 32;
+    S.x = reinterpret_cast<double2*>(base + o);      o += (size_t)nLoc * 16;
+    S.r = reinterpret_cast<double2*>(base + o);      o += (size_t)nLoc * 16;
+    S.Ap = reinterpret_cast<double2*>(base + o);     o += (size_t)nLoc * 16;
+    S.z = reinterpret_cast<double2*>(base + o);      o += (size_t)nLoc * 16;
+    S.d = reinterpret_cast<double2*>(base + o);      o += (size_t)nLoc * 16;
+    S.minv = reinterpret_cast<double4*>(base + o);
+    return S;
+}
+
+// Ap[own rows] = A * d_new with d_new = z + beta * d_old evaluated on the fly for the gathered columns
+// (so no barrier is needed between the direction update and the SpMV); writes d_new for the own rows
+// into the other direction buffer.  z and d_old of other CTAs were written before the last grid sync:
+// they are read through L2 (__ldcg), never through the non-coherent L1.
+// Mapping: 16 lanes per block row (lane pair = one 2x2 block, even lane its top row, odd lane its bottom
+// row), kUnroll row pairs per warp in flight so that every lane has several independent 16-byte loads
+// outstanding (HBM needs ~26 KB in flight per SM).
+static constexpr int kUnroll = 2;
+template <bool SMEM>
+__device__ __forceinline__ double spmv_fused(const PcgParams& P, const Slice& S, int rowBeg, int rowEnd, const double* z,
+                                             const double* dOld, double* dNew, double beta)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & 15, kblk = sub >> 1, half = sub & 1;
+    const double2* __restrict__ gval2 = reinterpret_cast<const double2*>(P.val);
+    const double2* z2 = reinterpret_cast<const double2*>(z);
+    const double2* d2 = reinterpret_cast<const double2*>(dOld);
+    double dotAcc = 0.0;
+    for (int rowBase = rowBeg + warp * 2 * kUnroll; rowBase < rowEnd; rowBase += (kPcgBlock / 32) * 2 * kUnroll) {
+        int row[kUnroll], b0[kUnroll], end[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            row[u] = rowBase + 2 * u + (lane >> 4);
+            const bool active = row[u] < rowEnd;
+            if (SMEM) {
+                b0[u] = (active ? S.rowPtr[row[u] - rowBeg] : 0) + kblk;
+                end[u] = active ? S.rowPtr[row[u] - rowBeg + 1] : 0;
+            } else {
+                b0[u] = (active ? __ldg(P.rowPtr + row[u]) : 0) + kblk;
+                end[u] = active ? __ldg(P.rowPtr + row[u] + 1) : 0;
+            }
+        }
+        int col[kUnroll]; double2 a[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const bool has = b0[u] < end[u];
+            if (SMEM) {
+                col[u] = has ? S.col[b0[u]] : -1;
+                a[u] = has ? S.val2[2 * b0[u] + half] : make_double2(0.0, 0.0);
+            } else {
+                col[u] = has ? __ldg(P.colIdx + b0[u]) : -1;
+                a[u] = has ? __ldg(gval2 + 2 * (size_t)b0[u] + half) : make_double2(0.0, 0.0);
+            }
+        }
+        double2 zz[kUnroll], dd[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            zz[u] = col[u] >= 0 ? __ldcg(z2 + col[u]) : make_double2(0.0, 0.0);
+            dd[u] = col[u] >= 0 ? __ldcg(d2 + col[u]) : make_double2(0.0, 0.0);
+        }
+        double acc[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            acc[u] = a[u].x * (zz[u].x + beta * dd[u].x) + a[u].y * (zz[u].y + beta * dd[u].y);
+            for (int b = b0[u] + 8; b < end[u]; b += 8) {          // rows with more than 8 blocks (rare)
+                const int c = SMEM ? S.col[b] : __ldg(P.colIdx + b);
+                const double2 av = SMEM ? S.val2[2 * b + half] : __ldg(gval2 + 2 * (size_t)b + half);
+                const double2 zv = __ldcg(z2 + c), dv = __ldcg(d2 + c);
+                acc[u] += av.x * (zv.x + beta * dv.x) + av.y * (zv.y + beta * dv.y);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            double t = acc[u];
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            if (row[u] < rowEnd && sub < 2) {
+                double dn;
+                if (SMEM) {
+                    const int lr = row[u] - rowBeg;
+                    double* zs = reinterpret_cast<double*>(S.z); double* ds = reinterpret_cast<double*>(S.d);
+                    dn = zs[2 * lr + half] + beta * ds[2 * lr + half];
+                    ds[2 * lr + half] = dn;
+                    reinterpret_cast<double*>(S.Ap)[2 * lr + half] = t;
+                } else {
+                    dn = __ldcg(z + 2 * (size_t)row[u] + half) + beta * __ldcg(dOld + 2 * (size_t)row[u] + half);
+                    P.Ap[2 * (size_t)row[u] + half] = t;
+                }
+                dNew[2 * (size_t)row[u] + half] = dn;
+                dotAcc += t * dn;
+            }
+        }
+    }
+    return dotAcc;
+}
+
+template <bool SMEM>
 __global__ void __launch_bounds__(kPcgBlock, 1)
 pcg_kernel(PcgParams P)
 {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
     const int nB = gridDim.x;
     const int rowsPer = (P.nRows + nB - 1) / nB;
     const int rowBeg = min(P.nRows, (int)blockIdx.x * rowsPer), rowEnd = min(P.nRows, rowBeg + rowsPer);
-    const int sBeg = 2 * rowBeg, sEnd = 2 * rowEnd;
-    double* part0 = P.partials;                 // two partial buffers, alternated between barriers
-    double* part1 = P.partials + 3 * (size_t)nB;
+    const int nLoc = rowEnd - rowBeg;
+    SyncSlot* slots = reinterpret_cast<SyncSlot*>(P.partials);
+    double* dBuf[2] = {P.d, P.d2};
+    unsigned long long epoch = 0;
+    Slice S = {};
+    if (SMEM) {
+        const int blkBeg = nLoc > 0 ? P.rowPtr[rowBeg] : 0, blkEnd = nLoc > 0 ? P.rowPtr[rowEnd] : 0;
+        S = carve(smemRaw, rowsPer, P.maxBlkPerCta);
+        for (int i = threadIdx.x; i <= nLoc; i += kPcgBlock) S.rowPtr[i] = P.rowPtr[rowBeg + i] - blkBeg;
+        for (int i = threadIdx.x; i < blkEnd - blkBeg; i += kPcgBlock) S.col[i] = P.colIdx[blkBeg + i];
+        const double2* gv = reinterpret_cast<const double2*>(P.val) + 2 * (size_t)blkBeg;
+        for (int i = threadIdx.x; i < 2 * (blkEnd - blkBeg); i += kPcgBlock) S.val2[i] = gv[i];
+    }
 
-    // ---- init: x = 0, r = b, z = Minv r, d = z ; rz = r.z, bb = b.b
-    double loc[3] = {0.0, 0.0, 0.0};
+    // ---- init: x = 0, r = b, z = Minv r, d = 0 ; rz = r.z, bb = b.b
+    double loc[2] = {0.0, 0.0}, red[2];
     for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
         const double b0 = P.negate ? -P.rhs[2 * row] : P.rhs[2 * row];
         const double b1 = P.negate ? -P.rhs[2 * row + 1] : P.rhs[2 * row + 1];
-        const double m00 = P.minv[4 * (size_t)row], m01 = P.minv[4 * (size_t)row + 1], m11 = P.minv[4 * (size_t)row + 3];
-        const double z0 = m00 * b0 + m01 * b1, z1 = m01 * b0 + m11 * b1;
-        P.x[2 * row] = 0.0; P.x[2 * row + 1] = 0.0;
-        P.r[2 * row] = b0; P.r[2 * row + 1] = b1;
-        P.z[2 * row] = z0; P.z[2 * row + 1] = z1;
-        P.d[2 * row] = z0; P.d[2 * row + 1] = z1;
-        loc[0] += b0 * z0 + b1 * z1;
+        const double4 m = reinterpret_cast<const double4*>(P.minv)[row];
+        double2 zz; zz.x = m.x * b0 + m.y * b1; zz.y = m.y * b0 + m.w * b1;
+        if (SMEM) {
+            const int lr = row - rowBeg;
+            S.x[lr] = make_double2(0.0, 0.0); S.r[lr] = make_double2(b0, b1); S.z[lr] = zz; S.d[lr] = make_double2(0.0, 0.0);
+            S.minv[lr] = m;
+        } else {
+            reinterpret_cast<double2*>(P.x)[row] = make_double2(0.0, 0.0);
+            reinterpret_cast<double2*>(P.r)[row] = make_double2(b0, b1);
+        }
+        reinterpret_cast<double2*>(P.z)[row] = zz;
+        reinterpret_cast<double2*>(P.d)[row] = make_double2(0.0, 0.0);
+        reinterpret_cast<double2*>(P.d2)[row] = make_double2(0.0, 0.0);
+        loc[0] += b0 * zz.x + b1 * zz.y;
         loc[1] += b0 * b0 + b1 * b1;
     }
-    publish_partials<3>(loc, part0);
-    grid_barrier(P.bar, nB);
-    double red[3];
-    gather_partials<3>(part0, nB, red);
+    grid_allreduce<2>(slots, nB, ++epoch, loc, red);
     double rz = red[0];
     const double bb = red[1];
     const double tol2 = P.relTol * P.relTol * bb;
-    double rr = bb;
-    int it = 0, status = 0;
-    if (bb == 0.0) { status = 0; }
-    else {
-        for (it = 0; it < P.maxIt; ) {
-            // ---- phase A: Ap = A d ; pAp
-            loc[0] = spmv_rows(P, rowBeg, rowEnd, P.d, P.Ap); loc[1] = 0.0; loc[2] = 0.0;
-            publish_partials<3>(loc, part1);
-            grid_barrier(P.bar, nB);
-            gather_partials<3>(part1, nB, red);
-            const double dAd = red[0];
+    double rr = bb, beta = 0.0;
+    int it = 0, status = 0, cur = 0;
+    if (bb > 0.0) {
+        for (;;) {
+            // ---- phase A: d_new = z + beta d_old (fused) ; Ap = A d_new ; pAp
+            double* dNew = dBuf[cur ^ 1];
+            double la[1] = {spmv_fused<SMEM>(P, S, rowBeg, rowEnd, P.z, dBuf[cur], dNew, beta)}, ra[1];
+            grid_allreduce<1>(slots, nB, ++epoch, la, ra);
+            const double dAd = ra[0];
             if (!(dAd > 0.0)) { status = 2; break; }
             const double alpha = rz / dAd;
-            // ---- phase B: x += alpha d ; r -= alpha Ap ; z = Minv r ; rz', rr
-            loc[0] = 0.0; loc[1] = 0.0; loc[2] = 0.0;
+            // ---- phase B (own rows only): x += alpha d ; r -= alpha Ap ; z = Minv r ; rz', rr
+            loc[0] = 0.0; loc[1] = 0.0;
             for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
-                const double2 dd = reinterpret_cast<const double2*>(P.d)[row];
-                const double2 ap = reinterpret_cast<const double2*>(P.Ap)[row];
-                double2 xx = reinterpret_cast<double2*>(P.x)[row];
-                double2 r2 = reinterpret_cast<double2*>(P.r)[row];
+                const int lr = row - rowBeg;
+                const double2 dd = SMEM ? S.d[lr] : reinterpret_cast<const double2*>(dNew)[row];
+                const double2 ap = SMEM ? S.Ap[lr] : reinterpret_cast<const double2*>(P.Ap)[row];
+                double2 xx = SMEM ? S.x[lr] : reinterpret_cast<double2*>(P.x)[row];
+                double2 r2 = SMEM ? S.r[lr] : reinterpret_cast<double2*>(P.r)[row];
                 xx.x += alpha * dd.x; xx.y += alpha * dd.y;
                 r2.x -= alpha * ap.x; r2.y -= alpha * ap.y;
-                const double4 m = reinterpret_cast<const double4*>(P.minv)[row];
+                const double4 m = SMEM ? S.minv[lr] : reinterpret_cast<const double4*>(P.minv)[row];
                 double2 zz; zz.x = m.x * r2.x + m.y * r2.y; zz.y = m.y * r2.x + m.w * r2.y;
-                reinterpret_cast<double2*>(P.x)[row] = xx;
-                reinterpret_cast<double2*>(P.r)[row] = r2;
+                if (SMEM) { S.x[lr] = xx; S.r[lr] = r2; S.z[lr] = zz; }
+                else { reinterpret_cast<double2*>(P.x)[row] = xx; reinterpret_cast<double2*>(P.r)[row] = r2; }
                 reinterpret_cast<double2*>(P.z)[row] = zz;
                 loc[0] += r2.x * zz.x + r2.y * zz.y;
                 loc[1] += r2.x * r2.x + r2.y * r2.y;
             }
-            publish_partials<3>(loc, part0);
-            grid_barrier(P.bar, nB);
-            gather_partials<3>(part0, nB, red);
+            grid_allreduce<2>(slots, nB, ++epoch, loc, red);
             const double rzNew = red[0];
             rr = red[1];
             ++it;
+            cur ^= 1;
             if (rr <= tol2) { status = 0; break; }
             if (it >= P.maxIt) { status = 1; break; }
-            const double beta = rzNew / rz;
+            beta = rzNew / rz;
             rz = rzNew;
-            // ---- phase C: d = z + beta d
-            for (int i = sBeg + threadIdx.x; i < sEnd; i += kPcgBlock) P.d[i] = P.z[i] + beta * P.d[i];
-            grid_barrier(P.bar, nB);
         }
-        if (it >= P.maxIt && status == 0 && rr > tol2) status = 1;
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) reinterpret_cast<double2*>(P.x)[row] = S.x[row - rowBeg];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.scal[S_PCG_ITERS] = (double)it;
@@ -253,32 +397,56 @@ static PcgParams make_params(ocb_ctx* c)
 {
     PcgParams P;
     P.nRows = c->nVtot; P.rowPtr = c->rowPtr.p; P.colIdx = c->colIdx.p; P.val = c->val.p; P.minv = c->minv.p;
-    P.rhs = nullptr; P.negate = 0; P.x = c->p.p; P.r = c->pr.p; P.z = c->pz.p; P.d = c->pd.p; P.Ap = c->pAp.p;
-    P.partials = c->partials.p; P.bar = c->sync.p + 16; P.scal = c->dScal; P.relTol = 1e-12; P.maxIt = 1;
+    P.rhs = nullptr; P.negate = 0; P.x = c->p.p; P.r = c->pr.p; P.z = c->pz.p; P.d = c->pd.p; P.d2 = c->pd2.p; P.Ap = c->pAp.p;
+    P.partials = c->partials.p; P.scal = c->dScal; P.relTol = 1e-12; P.maxIt = 1;
     return P;
 }
 
-static int pcg_grid(ocb_ctx* c)
+// grid for the stand-alone SpMV
+static int spmv_grid(ocb_ctx* c)
 {
-    if (c->pcgGrid == 0) {
-        int perSM = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, pcg_kernel, kPcgBlock, 0);
-        if (perSM < 1) perSM = 1;
-        if (perSM > 2) perSM = 2;
-        c->pcgGrid = c->numSMs * perSM;
-    }
-    // small systems: do not spread 2 rows per warp thinner than one warp-iteration per CTA
     const int rowsPerCtaPass = (kPcgBlock / 32) * 2;
     int need = (c->nVtot + rowsPerCtaPass - 1) / rowsPerCtaPass;
-    int g = c->pcgGrid < need ? c->pcgGrid : need;
+    int g = c->numSMs < need ? c->numSMs : need;
     return g < 1 ? 1 : g;
+}
+
+// Partition of the block rows over the persistent CTAs.  Small systems: few, fat CTAs (the grid-wide
+// all-reduce costs ~0.9 us at 16 CTAs and ~3 us at 148) with the slice resident in shared memory;
+// large systems: one CTA per SM, slice streamed from L2/HBM.
+struct PcgPlan { int grid; bool smem; int maxBlk; size_t smemBytes; };
+static PcgPlan pcg_plan(ocb_ctx* c)
+{
+    static const int targetRows = []() { const char* e = getenv("OCB_PCG_ROWS_PER_CTA"); int v = e ? atoi(e) : 256; return v < 32 ? 32 : v; }();
+    static const bool allowSmem = []() { const char* e = getenv("OCB_PCG_NO_SMEM"); return !(e && atoi(e)); }();
+    const size_t limit = 200 * 1024;
+    PcgPlan pl; pl.smem = false; pl.maxBlk = 0; pl.smemBytes = 0;
+    const int n = c->nVtot;
+    int g = (n + targetRows - 1) / targetRows;
+    if (g > c->numSMs) g = c->numSMs;
+    if (g < 1) g = 1;
+    for (; allowSmem; ) {
+        const int rowsPer = (n + g - 1) / g;
+        int maxBlk = 0;
+        for (int b = 0; b < g; ++b) {
+            const int r0 = std::min(n, b * rowsPer), r1 = std::min(n, r0 + rowsPer);
+            maxBlk = std::max(maxBlk, c->hRowPtr[r1] - c->hRowPtr[r0]);
+        }
+        const size_t bytes = slice_bytes(rowsPer, maxBlk);
+        if (bytes <= limit) { pl.smem = true; pl.maxBlk = maxBlk; pl.smemBytes = bytes; break; }
+        if (g >= c->numSMs) break;
+        g = std::min(c->numSMs, g + (g + 3) / 4);
+    }
+    if (!pl.smem) g = c->numSMs;
+    pl.grid = g;
+    return pl;
 }
 
 int launch_spmv(ocb_ctx* c, const double* dx, double* dy)
 {
     ProfScope prof(c, K_SPMV);
     PcgParams P = make_params(c);
-    spmv_kernel<<<pcg_grid(c), kPcgBlock, 0, c->stream>>>(P, dx, dy);
+    spmv_kernel<<<spmv_grid(c), kPcgBlock, 0, c->stream>>>(P, dx, dy);
     KCHECK(c);
     return 0;
 }
@@ -307,14 +475,25 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     const size_t n = c->nSys();
     OCB_CUDA(c, c->pr.reserve(n, c->stream)); OCB_CUDA(c, c->pz.reserve(n, c->stream));
     OCB_CUDA(c, c->pd.reserve(n, c->stream)); OCB_CUDA(c, c->pAp.reserve(n, c->stream));
+    OCB_CUDA(c, c->pd2.reserve(n, c->stream));
     OCB_CUDA(c, c->p.reserve(n, c->stream));
-    const int grid = pcg_grid(c);
-    OCB_CUDA(c, c->partials.reserve((size_t)grid * 6 + 64, c->stream));
+    const PcgPlan pl = pcg_plan(c);
+    const int grid = pl.grid;
+    const size_t slotDoubles = 2 * (size_t)grid * (sizeof(SyncSlot) / sizeof(double));
+    OCB_CUDA(c, c->partials.reserve(slotDoubles + 64, c->stream));
     PcgParams P = make_params(c);
-    P.rhs = d_rhs; P.negate = negate_rhs ? 1 : 0; P.relTol = rel_tol; P.maxIt = max_it;
-    OCB_CUDA(c, cudaMemsetAsync(c->sync.p + 16, 0, 2 * sizeof(unsigned), c->stream));
+    P.rhs = d_rhs; P.negate = negate_rhs ? 1 : 0; P.relTol = rel_tol; P.maxIt = max_it; P.maxBlkPerCta = pl.maxBlk;
+    OCB_CUDA(c, cudaMemsetAsync(c->partials.p, 0, slotDoubles * sizeof(double), c->stream));
     void* args[] = {&P};
-    OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(grid), dim3(kPcgBlock), args, 0, c->stream));
+    if (pl.smem) {
+        if (pl.smemBytes > c->pcgSmemAttr) {
+            OCB_CUDA(c, cudaFuncSetAttribute(pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+            c->pcgSmemAttr = 200 * 1024;
+        }
+        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel<true>, dim3(grid), dim3(kPcgBlock), args, pl.smemBytes, c->stream));
+    } else {
+        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel<false>, dim3(grid), dim3(kPcgBlock), args, 0, c->stream));
+    }
     c->launches++;
     return 0;
 }

@@ -183,7 +183,7 @@ def test_linsys_solver_surface(ctx, port, state1):
     x = sol.solve(-s.r("gradient"))
     assert sol.getNumRows() == 2 * nVtot and sol.getNumNonzeros() == len(ja)
     assert np.linalg.norm(x - s.r("searchDir")) <= 1e-8 * np.linalg.norm(s.r("searchDir"))
-    assert abs(sol.coeffMtr(0, 0) - 1.0) < 1e-15                                 # fixed vertex: identity diagonal
+    assert sol.coeffMtr(0, 0) == a[0] == s.p0                                    # fixed vertex: energyParam0 * identity
     sol.ctx.close()
 
 
@@ -213,7 +213,8 @@ def test_step_bound_and_line_search(ctx, port, state):
     assert alpha == want                                                         # bit-exact: min is order-independent
     assert abs(0.99 * alpha - float(s.r("alpha"))) <= 1e-15
     ls = ctx.line_search(s.p0, 0.0, 0.99 * alpha)
-    assert ls["n_halvings"] == 0 and ls["alpha"] == float(s.r("alpha"))
+    # the golden alpha was recovered from (x1 - x0) / p, hence the last-digit slack
+    assert ls["n_halvings"] == 0 and abs(ls["alpha"] - float(s.r("alpha"))) <= 1e-14
     for k in ("E_new", "E_sd_new", "E_scaf_new"):
         assert abs(ls[k] - float(s.r(k))) <= 1e-13 * abs(float(s.r(k)))
     assert abs(ls["lastEDec"] - float(s.r("lastEDec"))) <= 1e-10 * abs(float(s.r("lastEDec")))
@@ -295,8 +296,9 @@ def test_energy_plugin_surface(ctx, port, state1):
     mesh = ob.TriMesh(s.V_rest, s.F, s.UV, ctx=ctx)
     SD = ob.SymDirichletEnergy(ctx=ctx)
     assert abs(SD.computeEnergyVal(mesh) - float(s.r("E_sd_last"))) <= 1e-13 * float(s.r("E_sd_last"))
-    assert np.array_equal(SD.getEnergyValPerElem(mesh), s.r("energy_per_elem"))
-    assert SD.getEnergyValByElemID(mesh, 5) == s.r("energy_per_elem")[5]
+    # surfaceArea comes from a parallel device reduction here (last-bit different from the serial sum): 1e-14
+    assert relerr(SD.getEnergyValPerElem(mesh), s.r("energy_per_elem")) < 1e-14
+    assert abs(SD.getEnergyValByElemID(mesh, 5) - s.r("energy_per_elem")[5]) <= 1e-14 * s.r("energy_per_elem")[5]
     g = SD.computeGradient(mesh)
     assert relerr(g, port.gradient(s.F, s.UV, s.rest8, s.surfaceArea, fixed=s.fixed)) < 1e-13
     assert abs(SD.checkEnergyVal(mesh)) < 1e-12
