@@ -109,6 +109,7 @@ struct ocb_ctx {
     ocb::DevBuf<int32_t> scratchI;
     int pcgGrid = 0, pcgBlock = 0;
     size_t pcgSmemAttr = 0;
+    int clusterOk = -1;                      // -1 unknown, 0 a 16-CTA cluster cannot be scheduled, 1 ok
     ocb::DevBuf<double> xSaved;              // ocb_save_uv / ocb_restore_uv snapshot
     int xSavedN = 0;
 

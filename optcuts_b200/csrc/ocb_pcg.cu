@@ -30,6 +30,7 @@ struct PcgParams {
     double* scal;              // device scalar block
     double relTol; int maxIt;
     int maxBlkPerCta;          // SMEM mode: capacity of the per-CTA block arrays
+    long long* dbg;            // optional: per-phase clock64 totals of CTA 0 (OCB_PCG_DEBUG=1)
 };
 
 // y[rows of this CTA] = A * v ; returns this thread's share of v . y.
@@ -76,6 +77,8 @@ __device__ __forceinline__ double spmv_rows(const PcgParams& P, int rowBeg, int 
 // L1 invalidation (acquire) is needed anywhere.
 struct __align__(16) SyncPacket { double v; unsigned long long epoch; };
 static constexpr int kSyncVals = 2;                         // packets per CTA slot
+static constexpr int kPacketMaxCtas = 4096;                 // above this: counter barrier + one read pass (measured: no gain at 148 CTAs,
+                                                            // the wait is skew between CTAs, not the mechanism -- kept for larger grids)
 struct __align__(64) SyncSlot { SyncPacket p[kSyncVals]; unsigned long long pad[4]; };
 
 __device__ __forceinline__ SyncPacket ld_packet(const SyncPacket* p)
@@ -104,8 +107,36 @@ __device__ __forceinline__ void grid_allreduce(SyncSlot* slots, int nB, unsigned
         if (lane == 0) sm[k][warp] = t;
     }
     __syncthreads();                       // orders every thread's vector stores before the fence below
-    if (warp == 0) {
-        SyncSlot* base = slots + (size_t)(epoch & 1ull) * nB;
+    SyncSlot* base = slots + (size_t)(epoch & 1ull) * nB;
+    if (nB > kPacketMaxCtas) {
+        // many CTAs: all-to-all packet polling costs O(nB^2) L2 requests (measured 3-6 us at 148 CTAs); instead
+        // store the partial, cross ONE counter barrier (1.2 us flat, tools/micro/sync_bench.cu) and read all
+        // partials once, in the same fixed order everywhere.
+        if (warp == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                double t = lane < kPcgBlock / 32 ? sm[k][lane] : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) base[blockIdx.x].p[k].v = t;
+            }
+        }
+        cooperative_groups::this_grid().sync();
+        if (warp == 0) {
+            double acc[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+            for (int b = lane; b < nB; b += 32)
+#pragma unroll
+                for (int k = 0; k < NV; ++k) acc[k] += __ldcg(&base[b].p[k].v);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+                if (lane == 0) bc[k] = acc[k];
+            }
+        }
+    } else if (warp == 0) {
         double t[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
@@ -140,6 +171,51 @@ __device__ __forceinline__ void grid_allreduce(SyncSlot* slots, int nB, unsigned
 #pragma unroll
     for (int k = 0; k < NV; ++k) out[k] = bc[k];
     __syncthreads();                       // sm / bc may be rewritten by the next call
+}
+
+// ---------------------------------------------------------------------------------------------
+// CLUSTER mode (small systems, <= ~17k faces): the whole solve runs in ONE thread-block cluster of 16 CTAs
+// (16 SMs, slices resident in their shared memory).  The all-reduce then needs no global memory at all:
+// every CTA drops its partial into every peer's shared memory through DSMEM and the hardware cluster
+// barrier (arrive.release / wait.acquire, which also orders the global z/d stores) replaces the polled
+// packets: ~0.3 us instead of ~1-3 us.
+static constexpr int kClusterSize = 16;
+template <int NV>
+__device__ __forceinline__ void cluster_allreduce(double (*part)[kSyncVals][kClusterSize], unsigned long long epoch, double (&loc)[NV], double (&out)[NV])
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double sm[NV][kPcgBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = loc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) sm[k][warp] = t;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned rank = cluster.block_rank();
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = lane < kPcgBlock / 32 ? sm[k][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane < kClusterSize) {          // lane l writes this CTA's partial into peer l's buffer
+                double* remote = cluster.map_shared_rank(&part[epoch & 1ull][k][rank], lane);
+                *remote = t;
+            }
+        }
+    }
+    cluster.sync();                              // release/acquire at cluster scope
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < kClusterSize; ++r) t += part[epoch & 1ull][k][r];
+        out[k] = t;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -266,10 +342,15 @@ __device__ __forceinline__ double spmv_fused(const PcgParams& P, const Slice& S,
     return dotAcc;
 }
 
-template <bool SMEM>
+// MODE 0: slice streamed from global, grid-wide packet all-reduce; 1: slice in shared memory, packets;
+// 2: slice in shared memory, one 16-CTA cluster, DSMEM all-reduce
+template <int MODE>
 __global__ void __launch_bounds__(kPcgBlock, 1)
 pcg_kernel(PcgParams P)
 {
+    constexpr bool SMEM = MODE >= 1;
+    __shared__ double clusterPart[2][kSyncVals][kClusterSize];
+#define ALLREDUCE(NV, loc, out) do { ++epoch; if (MODE == 2) cluster_allreduce<NV>(clusterPart, epoch, loc, out); else grid_allreduce<NV>(slots, nB, epoch, loc, out); } while (0)
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int nB = gridDim.x;
     const int rowsPer = (P.nRows + nB - 1) / nB;
@@ -309,7 +390,7 @@ pcg_kernel(PcgParams P)
         loc[0] += b0 * zz.x + b1 * zz.y;
         loc[1] += b0 * b0 + b1 * b1;
     }
-    grid_allreduce<2>(slots, nB, ++epoch, loc, red);
+    ALLREDUCE(2, loc, red);
     double rz = red[0];
     const double bb = red[1];
     const double tol2 = P.relTol * P.relTol * bb;
@@ -319,8 +400,12 @@ pcg_kernel(PcgParams P)
         for (;;) {
             // ---- phase A: d_new = z + beta d_old (fused) ; Ap = A d_new ; pAp
             double* dNew = dBuf[cur ^ 1];
+            long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+            if (P.dbg) t0 = clock64();
             double la[1] = {spmv_fused<SMEM>(P, S, rowBeg, rowEnd, P.z, dBuf[cur], dNew, beta)}, ra[1];
-            grid_allreduce<1>(slots, nB, ++epoch, la, ra);
+            if (P.dbg) { __syncthreads(); t1 = clock64(); }
+            ALLREDUCE(1, la, ra);
+            if (P.dbg) t2 = clock64();
             const double dAd = ra[0];
             if (!(dAd > 0.0)) { status = 2; break; }
             const double alpha = rz / dAd;
@@ -342,7 +427,11 @@ pcg_kernel(PcgParams P)
                 loc[0] += r2.x * zz.x + r2.y * zz.y;
                 loc[1] += r2.x * r2.x + r2.y * r2.y;
             }
-            grid_allreduce<2>(slots, nB, ++epoch, loc, red);
+            if (P.dbg) { __syncthreads(); t3 = clock64(); }
+            ALLREDUCE(2, loc, red);
+            if (P.dbg && threadIdx.x == 0 && blockIdx.x == 0) {
+                P.dbg[0] += t1 - t0; P.dbg[1] += t2 - t1; P.dbg[2] += t3 - t2; P.dbg[3] += clock64() - t3; P.dbg[4] += 1;
+            }
             const double rzNew = red[0];
             rr = red[1];
             ++it;
@@ -363,6 +452,7 @@ pcg_kernel(PcgParams P)
         P.scal[S_PCG_STATUS] = (double)status;
         P.scal[S_PCG_BNORM] = sqrt(bb);
     }
+#undef ALLREDUCE
 }
 
 // stand-alone y = A x (ocb_multiply; also used by tests)
@@ -398,7 +488,7 @@ static PcgParams make_params(ocb_ctx* c)
     PcgParams P;
     P.nRows = c->nVtot; P.rowPtr = c->rowPtr.p; P.colIdx = c->colIdx.p; P.val = c->val.p; P.minv = c->minv.p;
     P.rhs = nullptr; P.negate = 0; P.x = c->p.p; P.r = c->pr.p; P.z = c->pz.p; P.d = c->pd.p; P.d2 = c->pd2.p; P.Ap = c->pAp.p;
-    P.partials = c->partials.p; P.scal = c->dScal; P.relTol = 1e-12; P.maxIt = 1;
+    P.partials = c->partials.p; P.scal = c->dScal; P.relTol = 1e-12; P.maxIt = 1; P.maxBlkPerCta = 0; P.dbg = nullptr;
     return P;
 }
 
@@ -414,14 +504,44 @@ static int spmv_grid(ocb_ctx* c)
 // Partition of the block rows over the persistent CTAs.  Small systems: few, fat CTAs (the grid-wide
 // all-reduce costs ~0.9 us at 16 CTAs and ~3 us at 148) with the slice resident in shared memory;
 // large systems: one CTA per SM, slice streamed from L2/HBM.
-struct PcgPlan { int grid; bool smem; int maxBlk; size_t smemBytes; };
+struct PcgPlan { int grid; bool smem; bool cluster; int maxBlk; size_t smemBytes; };
 static PcgPlan pcg_plan(ocb_ctx* c)
 {
     static const int targetRows = []() { const char* e = getenv("OCB_PCG_ROWS_PER_CTA"); int v = e ? atoi(e) : 256; return v < 32 ? 32 : v; }();
     static const bool allowSmem = []() { const char* e = getenv("OCB_PCG_NO_SMEM"); return !(e && atoi(e)); }();
     const size_t limit = 200 * 1024;
-    PcgPlan pl; pl.smem = false; pl.maxBlk = 0; pl.smemBytes = 0;
+    static const bool allowCluster = []() { const char* e = getenv("OCB_PCG_NO_CLUSTER"); return !(e && atoi(e)); }();
+    PcgPlan pl; pl.smem = false; pl.cluster = false; pl.maxBlk = 0; pl.smemBytes = 0;
     const int n = c->nVtot;
+    auto slice_need = [&](int g, int& maxBlk) {
+        const int rowsPer = (n + g - 1) / g;
+        maxBlk = 0;
+        for (int b = 0; b < g; ++b) {
+            const int r0 = std::min(n, b * rowsPer), r1 = std::min(n, r0 + rowsPer);
+            maxBlk = std::max(maxBlk, c->hRowPtr[r1] - c->hRowPtr[r0]);
+        }
+        return slice_bytes(rowsPer, maxBlk);
+    };
+    if (allowSmem && allowCluster && c->clusterOk != 0) {      // one 16-CTA cluster if every slice fits
+        int maxBlk = 0;
+        const size_t bytes = slice_need(kClusterSize, maxBlk);
+        if (bytes <= limit) {
+            if (c->clusterOk < 0) {                           // probe once: can such a cluster be scheduled?
+                cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+                cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(kClusterSize); cfg.blockDim = dim3(kPcgBlock); cfg.dynamicSmemBytes = limit;
+                cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int nClusters = 0;
+                cudaError_t e = cudaOccupancyMaxActiveClusters(&nClusters, pcg_kernel<2>, &cfg);
+                c->clusterOk = (e == cudaSuccess && nClusters >= 1) ? 1 : 0;
+                cudaGetLastError();
+            }
+            if (c->clusterOk == 1) { pl.smem = true; pl.cluster = true; pl.maxBlk = maxBlk; pl.smemBytes = bytes; pl.grid = kClusterSize; return pl; }
+        }
+    }
     int g = (n + targetRows - 1) / targetRows;
     if (g > c->numSMs) g = c->numSMs;
     if (g < 1) g = 1;
@@ -484,17 +604,36 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     PcgParams P = make_params(c);
     P.rhs = d_rhs; P.negate = negate_rhs ? 1 : 0; P.relTol = rel_tol; P.maxIt = max_it; P.maxBlkPerCta = pl.maxBlk;
     OCB_CUDA(c, cudaMemsetAsync(c->partials.p, 0, slotDoubles * sizeof(double), c->stream));
+    static const bool dbgOn = []() { const char* e = getenv("OCB_PCG_DEBUG"); return e && atoi(e); }();
+    long long* dDbg = nullptr;
+    if (dbgOn) { cudaMalloc((void**)&dDbg, 8 * sizeof(long long)); cudaMemset(dDbg, 0, 8 * sizeof(long long)); P.dbg = dDbg; }
     void* args[] = {&P};
-    if (pl.smem) {
+    if (pl.cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPcgBlock); cfg.dynamicSmemBytes = pl.smemBytes; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        OCB_CUDA(c, cudaLaunchKernelEx(&cfg, pcg_kernel<2>, P));
+    } else if (pl.smem) {
         if (pl.smemBytes > c->pcgSmemAttr) {
-            OCB_CUDA(c, cudaFuncSetAttribute(pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+            OCB_CUDA(c, cudaFuncSetAttribute(pcg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
             c->pcgSmemAttr = 200 * 1024;
         }
-        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel<true>, dim3(grid), dim3(kPcgBlock), args, pl.smemBytes, c->stream));
+        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel<1>, dim3(grid), dim3(kPcgBlock), args, pl.smemBytes, c->stream));
     } else {
-        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel<false>, dim3(grid), dim3(kPcgBlock), args, 0, c->stream));
+        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel<0>, dim3(grid), dim3(kPcgBlock), args, 0, c->stream));
     }
     c->launches++;
+    if (dbgOn) {
+        long long h[8];
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpy(h, dDbg, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(dDbg);
+        const double n = h[4] > 0 ? (double)h[4] : 1.0;
+        fprintf(stderr, "[ocb pcg] mode %s grid %d iters %lld  cycles/iter: spmv %.0f  sync1 %.0f  update %.0f  sync2 %.0f\n",
+                pl.cluster ? "cluster" : (pl.smem ? "smem" : "global"), grid, h[4], h[0] / n, h[1] / n, h[2] / n, h[3] / n);
+    }
     return 0;
 }
 
