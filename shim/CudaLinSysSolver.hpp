@@ -1,0 +1,113 @@
+// CudaLinSysSolver — OptCuts::LinSysSolver subclass over the optcuts_b200 C-ABI (include/optcuts_b200.h).
+//
+// Drop-in for OptCuts::EigenLibSolver (src/LinSysSolver/EigenLibSolver.{hpp,cpp}): same virtuals, called by
+// the UNMODIFIED OptCuts::Optimizer exactly as before (Optimizer.cpp:173-183, 522-544, 563):
+//     set_type -> set_pattern(vNeighbor, fixedVert) -> update_a(I,J,S) -> analyze_pattern -> factorize -> solve
+// The sparse LDL^T is replaced by the device block-Jacobi PCG; the std::map-based pattern/assembly of the
+// base class (LinSysSolver.hpp:37-159) is replaced by the device BSR pattern + triplet scatter.
+//
+// Constructing the object does no CUDA work (ocb_create is lazy): the reference creates one solver per
+// Optimizer, including thousands of nested dense-mode optimizers that never call it.
+// Errors: the C-ABI returns status codes; they are turned into std::runtime_error, which is what the
+// reference's call sites catch (Optimizer.cpp:181-189, 538-554: dump the matrix, exit(-1)).
+#ifndef CudaLinSysSolver_hpp
+#define CudaLinSysSolver_hpp
+
+#include "LinSysSolver.hpp"
+#include "optcuts_b200.h"
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace OptCuts {
+
+template <typename vectorTypeI, typename vectorTypeS>
+class CudaLinSysSolver : public LinSysSolver<vectorTypeI, vectorTypeS>
+{
+    typedef LinSysSolver<vectorTypeI, vectorTypeS> Base;
+
+protected:
+    ocb_ctx* ctx;
+    double relTol;
+    int maxIter, lastIters;
+    double lastRelRes;
+
+    void check(int rc, const char* what) const {
+        if (rc == OCB_ERR_NOT_CONVERGED) return;      // the solution is still written; Optimizer's line search decides
+        if (rc < 0) throw std::runtime_error(std::string(what) + ": " + ocb_last_error(ctx));
+    }
+
+public:
+    CudaLinSysSolver(void) : ctx(NULL), relTol(1.0e-12), maxIter(0), lastIters(0), lastRelRes(0.0) {
+        if (ocb_create(&ctx, 0) != OCB_OK) throw std::runtime_error("ocb_create failed");
+        Base::numRows = 0;
+    }
+    ~CudaLinSysSolver(void) { ocb_destroy(ctx); }
+
+    void set_type(int threadAmt, int _mtype, bool is_upper_half = false) {}   // SPD only, like EigenLibSolver::set_type
+
+    // LinSysSolver::set_pattern (LinSysSolver.hpp:37-135): the vNeighbor sets go over as CSR, ascending like std::set
+    void set_pattern(const std::vector<std::set<int>>& vNeighbor, const std::set<int>& fixedVert) {
+        const int nV = static_cast<int>(vNeighbor.size());
+        Base::numRows = nV * DIM;
+        std::vector<int32_t> ptr(nV + 1, 0), idx, fixed(fixedVert.begin(), fixedVert.end());
+        size_t tot = 0;
+        for (const auto& s : vNeighbor) tot += s.size();
+        idx.reserve(tot);
+        for (int v = 0; v < nV; ++v) {
+            for (int nb : vNeighbor[v]) idx.push_back(nb);
+            ptr[v + 1] = static_cast<int32_t>(idx.size());
+        }
+        check(ocb_set_pattern(ctx, nV, ptr.data(), idx.data(), fixed.data(), static_cast<int>(fixed.size())), "ocb_set_pattern");
+    }
+    void set_pattern(const Eigen::SparseMatrix<double>& mtr) {     // only used by the dense/SparseLU side paths of the reference
+        throw std::runtime_error("CudaLinSysSolver::set_pattern(SparseMatrix) is not on the hot path");
+    }
+
+    // LinSysSolver::update_a (LinSysSolver.hpp:138-159): zero, accumulate triplets with i <= j
+    void update_a(const vectorTypeI& II, const vectorTypeI& JJ, const vectorTypeS& SS) {
+        check(ocb_update_values_triplets(ctx, static_cast<int64_t>(SS.size()), II.data(), JJ.data(), SS.data()), "ocb_update_values_triplets");
+    }
+
+    void analyze_pattern(void) {}                                   // nothing symbolic for PCG
+
+    bool factorize(void) {                                          // EigenLibSolver::factorize: false / throw on a non-SPD matrix
+        const int rc = ocb_factorize(ctx);
+        if (rc == OCB_ERR_BREAKDOWN) return false;
+        check(rc, "ocb_factorize");
+        return true;
+    }
+
+    void solve(Eigen::VectorXd& rhs, Eigen::VectorXd& result) {
+        result.resize(rhs.size());
+        check(ocb_solve(ctx, rhs.data(), result.data(), relTol, maxIter, &lastIters, &lastRelRes), "ocb_solve");
+    }
+
+    void multiply(const Eigen::VectorXd& x, Eigen::VectorXd& Ax) {
+        Ax.resize(x.size());
+        check(ocb_multiply(ctx, x.data(), Ax.data()), "ocb_multiply");
+    }
+
+    // read-back in the reference layout (1-based upper-triangular CSR)
+    void download(void) {
+        int64_t sz[8];
+        ocb_get_sizes(ctx, sz);
+        Base::ia.resize(sz[5] + 1); Base::ja.resize(sz[6]); Base::a.resize(sz[6]);
+        check(ocb_download_csr(ctx, Base::ia.data(), Base::ja.data(), Base::a.data()), "ocb_download_csr");
+    }
+    double coeffMtr(int rowI, int colI) const {
+        if (rowI > colI) std::swap(rowI, colI);
+        const_cast<CudaLinSysSolver*>(this)->download();
+        for (int k = Base::ia[rowI] - 1; k < Base::ia[rowI + 1] - 1; ++k) if (Base::ja[k] - 1 == colI) return Base::a[k];
+        return 0.0;
+    }
+    int getNumNonzeros(void) const { int64_t sz[8]; ocb_get_sizes(ctx, sz); return static_cast<int>(sz[6]); }
+
+    void setTolerance(double tol, int maxIt) { relTol = tol; maxIter = maxIt; }
+    int lastIterations(void) const { return lastIters; }
+    double lastRelativeResidual(void) const { return lastRelRes; }
+};
+
+}  // namespace OptCuts
+#endif

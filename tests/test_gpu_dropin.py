@@ -1,0 +1,72 @@
+"""The drop-in boundary inside the REAL host program: the reference's own main.cpp / Optimizer.cpp / TriMesh.cpp /
+Scaffold.cpp (compiled from /root/reference by shim/Makefile, travelling as a prebuilt) with
+  * CudaLinSysSolver   in place of EigenLibSolver  (through the reference's compile-time solver switch) and
+  * CudaSymDirichletEnergy registered in place of SymDirichletEnergy (main.cpp:1570),
+both thin C++ subclasses over the C-ABI, run on the GPU and compared with the reference's trace."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, ROOT
+from objfixture import write_obj
+
+pytestmark = pytest.mark.gpu
+CUDA_PROBE = os.path.join(ROOT, "shim", "_build", "OptCuts_cuda_probe")
+CUDA_BIN = os.path.join(ROOT, "shim", "_build", "OptCuts_cuda")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "OptCuts_bin")
+ARGS = ["0.025", "1", "2", "4.1", "1", "0", "t"]          # BASELINE.json configs[1]
+
+
+def parse_trace(path):
+    return [dict(kv.split("=") for kv in ln.split()) for ln in open(path) if ln.strip()]
+
+
+@pytest.fixture(scope="module")
+def obj(tmp_path_factory, golden):
+    d = tmp_path_factory.mktemp("dropin")
+    p = str(d / "bimba_s1.obj")
+    write_obj(p, golden["s1_V_rest"], golden["s1_F"], golden["s1_V"])
+    return p
+
+
+def test_newton_iterations_inside_reference_host(obj, tmp_path):
+    if not os.path.exists(CUDA_PROBE):
+        pytest.skip("shim/_build/OptCuts_cuda_probe not built (make -C shim needs the reference headers)")
+    n = 10
+    env = dict(os.environ, ORACLE_TRACE=str(tmp_path / "trace.txt"), ORACLE_MAX_ITERS=str(n))
+    r = subprocess.run([CUDA_PROBE, "100", obj] + ARGS, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = parse_trace(tmp_path / "trace.txt")
+    # the fixture is the reference's state after iteration 1: iteration k here == iteration k+1 of the golden trace
+    # (the unmodified reference started from the same OBJ reproduces that trace bit for bit)
+    want = parse_trace(os.path.join(GOLDEN, "bimba_cfg2_trace.txt"))[1:]
+    assert len(got) == n
+    for k in range(n):
+        tol = 1e-9 if k < 3 else 1e-6        # see test_optimizer_free_run_with_reference_scaffold
+        for key in ("E", "Enoscaf"):
+            assert abs(float(got[k][key]) - float(want[k][key])) <= tol * float(want[k][key]), (k, key, got[k], want[k])
+        for key in ("F", "V", "amF", "amV", "bnd", "cohE"):
+            assert got[k][key] == want[k][key], (k, key)
+
+
+@pytest.mark.slow
+def test_whole_run_matches_reference(obj, tmp_path):
+    """configs[1] to convergence (geometry + topology steps, ~170 Newton iterations) with the CUDA plugins vs the
+    unmodified reference, both started from the same OBJ: same iteration counts and final E_SD / E_se to 1e-6."""
+    if not (os.path.exists(CUDA_BIN) and os.path.exists(REF_BIN)):
+        pytest.skip("prebuilt binaries missing")
+    out = {}
+    for name, exe in (("cuda", CUDA_BIN), ("ref", REF_BIN)):
+        d = tmp_path / name
+        d.mkdir()
+        r = subprocess.run([exe, "100", obj] + ARGS, cwd=d, capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        folder = os.listdir(d / "output")[0]
+        info = open(d / "output" / folder / "info.txt").read().split("\n")
+        out[name] = dict(iters=[int(v) for v in info[1].split()[:2]], E=[float(v) for v in info[3].split()],
+                         timers=info[2])
+    print("reference:", out["ref"], "\ncuda:", out["cuda"])
+    assert out["cuda"]["iters"] == out["ref"]["iters"]
+    for a, b in zip(out["cuda"]["E"], out["ref"]["E"]):
+        assert abs(a - b) <= 1e-6 * abs(b)
