@@ -13,8 +13,9 @@ Workloads (config.workload):
              999 900 faces, no scaffold (the air mesh is the host program's Triangle call).
 
 `value`  = steps / device time with the state resident in HBM (UV restored from a device snapshot);
-`e2e`    = the same through the C-ABI with HOST buffers: every step uploads the UVs (pinned host memory),
-           runs the iteration and downloads the new UVs + the result scalars.
+`e2e`    = the same through the C-ABI with HOST buffers: every step uploads the UVs (pinned host memory) and, with
+           bijectivity on, the air mesh + rebuilds the sparsity pattern (as the host program must after every
+           scaffold re-triangulation), runs the iteration and downloads the new UVs + the result scalars.
 `--impl reference` times the reference's own CPU implementation of the same step
 (oracle/_ref/liboptcuts_ref.so = unmodified OptCuts::Optimizer with Eigen SimplicialLDLT, TBB shim on all
 host cores) from the same states: wall time of solve(1) minus the reference's own "scaffolding" timer.
@@ -168,7 +169,14 @@ def run_ours(args):
         c, s = ctxs[k], states[k]
         hV, hVa, hOut = pinned[k]
         L, h = c._L, c._h
+        a = s["air"]
+        if a is not None:
+            # what the host program does every Newton iteration with bijectivity on (Optimizer.cpp:236-239, 522-530):
+            # hand over the freshly triangulated air mesh and rebuild the sparsity pattern
+            c.set_air(a["F"], a["rest8"], a["l2g"], a["nBnd"], a["fixed"], s["w_scaf"] / a["F"].shape[0])
         c._chk(L.ocb_set_uv(h, C.cast(hV.data_ptr(), _d), C.cast(hVa.data_ptr(), _d) if hVa is not None else None))
+        if a is not None:
+            c.set_pattern_from_elements()
         r = c.newton_step(p0, s["targetGRes"], pcg_tol, pcg_max)
         c._chk(L.ocb_get_uv(h, C.cast(hOut.data_ptr(), _d), None))
         return r
@@ -255,7 +263,10 @@ def run_ours(args):
                 "note": "algorithmic bytes = %.0f B/face/CG-iteration x faces x CG iterations per launch" % PCG_BYTES_PER_FACE_PER_ITER
                 if dom == "pcg" else "algorithmic bytes per face x faces"}
 
-    h2d = int(np.mean([16 * (s["UV"].shape[0] + (s["air"]["V"].shape[0] if s["air"] is not None else 0)) for s in states]))
+    def air_bytes(s):
+        a = s["air"]
+        return 0 if a is None else a["F"].nbytes + a["rest8"].nbytes + a["l2g"].nbytes + 16 * a["V"].shape[0]
+    h2d = int(np.mean([16 * s["UV"].shape[0] + air_bytes(s) for s in states]))
     d2h = int(np.mean([16 * s["UV"].shape[0] for s in states])) + 16 * 8
     line = {
         "metric": "newton_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -356,18 +367,126 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ------------------------------------------------------------------------------------------ batch leg
+def run_batch(args):
+    """BASELINE.json configs[3]: the 71-mesh benchmark sharded as independent meshes over the ranks (LPT on the
+    face count, no collective on the data path).  The benchmark OBJs cannot travel, so every mesh is a synthetic
+    disk with the benchmark mesh's face count; each gets `--batch-iters` free-running Newton iterations.
+    One "step" = the whole batch; value = Newton iterations of all meshes / max-over-ranks time (strong scaling)."""
+    import torch
+    from optcuts_b200 import batch
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    items = batch.benchmark71()
+    shards = batch.lpt_partition([batch.cost_model(it[1]) for it in items], world)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import refapi
+        import ctypes
+        t_tot, n_it, done = 0.0, 0, 0
+        sys.stdout.flush(); saved = os.dup(1); dn = os.open(os.devnull, os.O_WRONLY); os.dup2(dn, 1)
+        try:
+            for k in sorted(range(len(items)), key=lambda i: items[i][1])[::7][:10]:       # bounded sample: 10 meshes across the size range
+                V_rest, F, UV = batch.synthetic_disk(items[k][1], seed=k)
+                m = refapi.RefMesh(V_rest, F, UV)
+                opt = refapi.RefOptimizer(m, 0.975, scaffolding=False, mute=True)
+                t0 = time.perf_counter()
+                for _ in range(args.batch_iters):
+                    if opt.solve(1):
+                        break
+                    n_it += 1
+                t_tot += time.perf_counter() - t0
+                done += 1
+                opt.close(); m.close()
+        finally:
+            os.dup2(saved, 1); os.close(saved); os.close(dn)
+        v = n_it / t_tot
+        print(json.dumps({"impl": "reference", "metric": "newton_iters_per_s", "value": v, "unit": "it/s", "n_gpus": world, "steps": 1, "warmup": 0,
+                          "ms_per_step": 1e3 * t_tot, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic disks with the benchmark face counts", "config": {"workload": "batch71", "sampled_meshes": done},
+                          "cpu_baseline": {"value": v, "unit": "it/s", "cores": os.cpu_count(), "kind": "reference",
+                                           "sample": "%d of the 71 meshes (every 7th by size), %d Newton iterations each, one mesh at a time" % (done, args.batch_iters)},
+                          "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import optcuts_b200 as ob
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    meshes = {k: batch.synthetic_disk(items[k][1], seed=k) for k in shards[rank]}
+
+    def one_pass():
+        n_it, h2d, d2h, launches = 0, 0, 0, 0
+        for k, (V_rest, F, UV) in meshes.items():
+            ctx = ob.Context(local)
+            mesh = ob.TriMesh(V_rest, F, UV, ctx=ctx)
+            opt = ob.Optimizer(mesh, energyParams=(0.975,), ctx=ctx)
+            opt.precompute()
+            for _ in range(args.batch_iters):
+                if opt.solve(1):
+                    break
+                n_it += 1
+            res = opt.getResult()
+            h2d += V_rest.nbytes + F.nbytes + UV.nbytes
+            d2h += res.V.nbytes
+            launches += ctx.launch_count()
+            ctx.close()
+        return n_it, h2d, d2h, launches
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(); torch.cuda.synchronize()
+    one_pass()                                   # warm-up (library load, allocator)
+    sampler = ClockSampler(local); sampler.start()
+    K = max(1, min(args.steps, 3))
+    barrier(); t0 = time.perf_counter()
+    tot = [one_pass() for _ in range(K)]
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    n_it = sum(t[0] for t in tot) / K
+    vals = torch.tensor([dt / K, float(n_it)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        tmax = vals[:1].clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        nsum = vals[1:].clone(); dist.all_reduce(nsum, op=dist.ReduceOp.SUM)
+        tstep, ntot = float(tmax[0]), float(nsum[0])
+    else:
+        tstep, ntot = float(vals[0]), float(vals[1])
+    if rank == 0:
+        v = ntot / tstep
+        print(json.dumps({"metric": "newton_iters_per_s", "value": v, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": 1,
+                          "ms_per_step": 1e3 * tstep, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic disks with the face counts of the reference's 71 benchmark meshes",
+                          "config": {"workload": "batch71", "meshes": 71, "newton_iters_per_mesh": args.batch_iters, "total_newton_iters": ntot,
+                                     "parallelism": "LPT shard of independent meshes per GPU, no collective", "l2": "inputs re-uploaded per mesh",
+                                     "timing": "wall clock around the whole batch (host work included), max over ranks"},
+                          "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": tot[0][1], "d2h_bytes_per_step": tot[0][2]},
+                          "gpu_launches": int(sum(t[3] for t in tot)), "clocks": clocks,
+                          "batch_wall_s": tstep}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bimba10k", choices=["bimba10k", "bimba_x4", "bimba_x10"])
+    ap.add_argument("--workload", default="bimba10k", choices=["bimba10k", "bimba_x4", "bimba_x10", "batch71"])
+    ap.add_argument("--batch-iters", type=int, default=25, help="batch71: Newton iterations per mesh")
     ap.add_argument("--pcg-tol", type=float, default=1e-12)
     ap.add_argument("--pcg-max-it", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "batch71":
+        run_batch(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -1,0 +1,73 @@
+"""Batch partitioning for the multi-GPU path: a single mesh is one coupled sparse system, so
+multi-GPU work = independent meshes per GPU, no data-path collective.  The reference's batch unit is one
+process per mesh, run serially (batch.py:11-14); here the meshes of a batch are assigned to the ranks by
+longest-processing-time-first on the face count, every rank runs its shard on its own GPU, and the only
+cross-process step is gathering the per-mesh result rows.
+"""
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def benchmark71():
+    """(name, faces, vertices) of the reference's 71-mesh benchmark set (metadata only)."""
+    rows = []
+    for ln in open(os.path.join(_HERE, "data", "benchmark71.txt")):
+        if ln.startswith("#") or not ln.strip():
+            continue
+        name, f, v = ln.split()
+        rows.append((name, int(f), int(v)))
+    return rows
+
+
+def lpt_partition(costs, world):
+    """Greedy LPT: items sorted by cost descending go to the currently least-loaded rank.
+    Returns a list of index lists, one per rank; deterministic (ties by index)."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0.0] * world
+    shards = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        shards[r].append(i)
+        load[r] += costs[i]
+    return shards
+
+
+def cost_model(faces):
+    """Relative cost of one mesh: Newton iterations scale ~ faces^0.5, each costs ~ faces (PCG iterations ~ faces^0.5)."""
+    return float(faces) ** 1.5
+
+
+def run_sharded(items, work, rank, world, gather=None):
+    """Runs work(item) for this rank's shard and gathers {index: result} over all ranks.
+    `gather` is torch.distributed.all_gather_object-like (None: single process)."""
+    shards = lpt_partition([cost_model(it[1]) for it in items], world)
+    mine = {i: work(items[i]) for i in shards[rank]}
+    if gather is None or world == 1:
+        return mine, shards
+    parts = [None] * world
+    gather(parts, mine)
+    merged = {}
+    for p in parts:
+        merged.update(p)
+    return merged, shards
+
+
+def synthetic_disk(faces, seed=0):
+    """A synthetic open triangle mesh with ~`faces` triangles: a jittered grid lifted onto a bumpy surface, with
+    a distorted but inversion-free initial UV (stands in for the benchmark meshes, which cannot travel)."""
+    n = max(3, int(round(np.sqrt(faces / 2.0))) + 1)
+    rng = np.random.default_rng(seed)
+    xs, ys = np.meshgrid(np.arange(n, dtype=float), np.arange(n, dtype=float), indexing="ij")
+    P = np.stack([xs.ravel(), ys.ravel()], axis=1)
+    P += 0.2 * rng.uniform(-1, 1, P.shape)
+    V_rest = np.column_stack([P, 0.15 * n * np.sin(3.0 * P[:, 0] / n) * np.cos(2.0 * P[:, 1] / n)])
+    idx = np.arange(n * n).reshape(n, n)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel(), idx[:-1, 1:].ravel()
+    F = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)]).astype(np.int32)
+    # radial squeeze towards the centre (Tutte-like area distortion), orientation preserving
+    C = P - P.mean(axis=0)
+    r = np.linalg.norm(C, axis=1) / (0.75 * n) + 1e-9
+    UV = C * (0.3 + 0.7 * r[:, None] ** 2)
+    return V_rest, F, UV

@@ -125,6 +125,63 @@ static int upload_fixed_mask(ocb_ctx* c)
     return 0;
 }
 
+// Locality order of the mesh vertices (breadth-first over the vertex adjacency, Cuthill-McKee style): rows that
+// are coupled end up close in memory, so (i) a CTA's contiguous row range of the solver is a compact patch whose
+// halo is small, and (ii) the UV gathers of the element kernels hit the same sectors.  The caller never sees it:
+// every vertex-indexed array is converted at the C-ABI boundary.  OCB_NO_REORDER=1 keeps the caller's order.
+static void compute_order(ocb_ctx* c, int nV, int nF, const int32_t* F)
+{
+    static const bool off = []() { const char* e = getenv("OCB_NO_REORDER"); return e && atoi(e); }();
+    c->hPerm.assign((size_t)nV, 0);
+    if (off) { for (int v = 0; v < nV; ++v) c->hPerm[v] = v; return; }
+    std::vector<int32_t> ptr((size_t)nV + 1, 0);
+    for (int t = 0; t < nF; ++t) for (int k = 0; k < 3; ++k) ptr[(size_t)F[(size_t)k * nF + t] + 1] += 2;
+    for (int v = 0; v < nV; ++v) ptr[v + 1] += ptr[v];
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1), adj((size_t)ptr[nV]);
+    for (int t = 0; t < nF; ++t) {
+        const int a = F[t], b = F[(size_t)nF + t], d = F[2 * (size_t)nF + t];
+        adj[fill[a]++] = b; adj[fill[a]++] = d; adj[fill[b]++] = a; adj[fill[b]++] = d; adj[fill[d]++] = a; adj[fill[d]++] = b;
+    }
+    std::vector<int32_t> order; order.reserve((size_t)nV);
+    std::vector<uint8_t> seen((size_t)nV, 0);
+    for (int s0 = 0; s0 < nV; ++s0) {
+        if (seen[s0]) continue;
+        seen[s0] = 1; order.push_back(s0);
+        for (size_t head = order.size() - 1; head < order.size(); ++head) {
+            const int v = order[head];
+            for (int k = ptr[v]; k < ptr[v + 1]; ++k) { const int u = adj[k]; if (!seen[u]) { seen[u] = 1; order.push_back(u); } }
+        }
+    }
+    for (int i = 0; i < nV; ++i) c->hPerm[order[i]] = i;
+}
+static int upload_perm(ocb_ctx* c)
+{
+    c->hPerm.resize((size_t)c->nVtot);
+    for (int v = c->nV; v < c->nVtot; ++v) c->hPerm[v] = v;          // air interior vertices keep nV + k
+    c->hInv.assign((size_t)c->nVtot, 0);
+    for (int v = 0; v < c->nVtot; ++v) c->hInv[c->hPerm[v]] = v;
+    OCB_CUDA(c, c->perm.reserve((size_t)c->nVtot + 1, c->stream));
+    OCB_CUDA(c, cudaMemcpyAsync(c->perm.p, c->hPerm.data(), sizeof(int32_t) * c->nVtot, cudaMemcpyHostToDevice, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+// system vector: caller order on the host <-> internal order on the device
+static int vec_to_device(ocb_ctx* c, double* dst_internal, const double* host_user)
+{
+    const size_t n = (size_t)c->nSys();
+    OCB_CUDA(c, c->scratchV.reserve(n, c->stream));
+    OCB_CUDA(c, cudaMemcpyAsync(c->scratchV.p, host_user, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return launch_permute_vec(c, c->scratchV.p, dst_internal, true);
+}
+static int vec_to_host(ocb_ctx* c, double* host_user, const double* src_internal)
+{
+    const size_t n = (size_t)c->nSys();
+    OCB_CUDA(c, c->scratchV.reserve(n, c->stream));
+    OCB_TRY(launch_permute_vec(c, src_internal, c->scratchV.p, false));
+    OCB_CUDA(c, cudaMemcpyAsync(host_user, c->scratchV.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
 static int need(ocb_ctx* c, bool cond, const char* what) { return cond ? 0 : set_err(c, OCB_ERR_STATE, what); }
 
 }  // namespace ocb
@@ -153,7 +210,7 @@ void ocb_destroy(ocb_ctx* c)
         cudaStreamSynchronize(c->stream);
         c->mesh.v.release(); c->mesh.rest.release(); c->mesh.slot.release();
         c->air.v.release(); c->air.rest.release(); c->air.slot.release();
-        c->l2g.release(); c->fixedMask.release();
+        c->l2g.release(); c->fixedMask.release(); c->perm.release(); c->scratchV.release();
         c->x.release(); c->x0.release(); c->g.release(); c->p.release();
         c->pr.release(); c->pz.release(); c->pd.release(); c->pd2.release(); c->pAp.release(); c->pb.release(); c->minv.release();
         c->rowPtr.release(); c->colIdx.release(); c->val.release();
@@ -263,9 +320,16 @@ int ocb_set_mesh(ocb_ctx* c, int nV, int nF, const int32_t* F, const double* res
     // a new mesh drops the scaffold (the caller re-sends it, as the reference rebuilds it: Optimizer.cpp:483-488)
     c->nVa = c->nFa = c->nBnd = 0; c->air.n = 0; c->hFa.clear(); c->hL2G.clear(); c->wScafOverFa = 0.0;
     c->nVtot = nV;
-    OCB_TRY(upload_elems(c, c->mesh, c->hF, nF, F, rest8));
+    c->hFuser.assign(F, F + (size_t)3 * nF);
+    compute_order(c, nV, nF, F);
+    OCB_TRY(upload_perm(c));
+    {
+        std::vector<int32_t> Fi((size_t)3 * nF);
+        for (size_t i = 0; i < Fi.size(); ++i) Fi[i] = c->hPerm[F[i]];
+        OCB_TRY(upload_elems(c, c->mesh, c->hF, nF, Fi.data(), rest8));
+    }
     c->hFixed.assign((size_t)nV, 0);
-    for (int i = 0; i < nFixed; ++i) { if (fixed[i] < 0 || fixed[i] >= nV) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range"); c->hFixed[fixed[i]] = 1; }
+    for (int i = 0; i < nFixed; ++i) { if (fixed[i] < 0 || fixed[i] >= nV) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range"); c->hFixed[c->hPerm[fixed[i]]] = 1; }
     OCB_TRY(resize_system(c));
     OCB_TRY(upload_fixed_mask(c));
     c->haveUV = false; c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
@@ -282,6 +346,7 @@ int ocb_set_air(ocb_ctx* c, int nVa, int nFa, const int32_t* Fa, const double* r
         c->nVa = c->nFa = c->nBnd = 0; c->air.n = 0; c->hFa.clear(); c->hL2G.clear(); c->wScafOverFa = 0.0;
         c->nVtot = c->nV;
         c->hFixed.resize((size_t)c->nV);
+        OCB_TRY(upload_perm(c));
     } else {
         if (!Fa || !rest8 || !l2g || nVa <= 0 || nBnd < 0 || nBnd > nVa) return set_err(c, OCB_ERR_ARG, "ocb_set_air: bad argument");
         const int nVtot = c->nV + nVa - nBnd;
@@ -289,22 +354,24 @@ int ocb_set_air(ocb_ctx* c, int nVa, int nFa, const int32_t* Fa, const double* r
             const bool ok = (i < nBnd) ? (l2g[i] >= 0 && l2g[i] < c->nV) : (l2g[i] == c->nV + i - nBnd);
             if (!ok) return set_err(c, OCB_ERR_ARG, "ocb_set_air: localVI2Global does not follow Scaffold.cpp:179-184");
         }
+        c->hL2G.resize((size_t)nVa);                      // air-local id -> INTERNAL global id
+        for (int i = 0; i < nVa; ++i) c->hL2G[i] = i < nBnd ? c->hPerm[l2g[i]] : l2g[i];
         std::vector<int32_t> Fg((size_t)3 * nFa);
         for (size_t i = 0; i < (size_t)3 * nFa; ++i) {
             if (Fa[i] < 0 || Fa[i] >= nVa) return set_err(c, OCB_ERR_ARG, "ocb_set_air: vertex index out of range");
-            Fg[i] = l2g[Fa[i]];
+            Fg[i] = c->hL2G[Fa[i]];
         }
         c->nVa = nVa; c->nFa = nFa; c->nBnd = nBnd; c->nVtot = nVtot; c->wScafOverFa = wScafOverFa;
-        c->hL2G.assign(l2g, l2g + nVa);
+        OCB_TRY(upload_perm(c));
         OCB_TRY(upload_elems(c, c->air, c->hFa, nFa, Fg.data(), rest8));
         OCB_CUDA(c, c->l2g.reserve((size_t)nVa, c->stream));
-        OCB_TRY(upload_i(c, c->l2g.p, l2g, (size_t)nVa));
+        OCB_TRY(upload_i(c, c->l2g.p, c->hL2G.data(), (size_t)nVa));
         // fixed: keep the mesh part, reset the air part
         c->hFixed.resize((size_t)c->nV);
         c->hFixed.resize((size_t)nVtot, 0);
         for (int i = 0; i < nFixedAir; ++i) {
             if (fixedAir[i] < 0 || fixedAir[i] >= nVa) return set_err(c, OCB_ERR_ARG, "fixed air vertex out of range");
-            c->hFixed[l2g[fixedAir[i]]] |= 2;
+            c->hFixed[c->hL2G[fixedAir[i]]] |= 2;
         }
     }
     OCB_TRY(resize_system(c));
@@ -416,7 +483,7 @@ int ocb_gradient(ocb_ctx* c, double p0, double* g_out, double* sqnorm)
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->haveUV, "ocb_gradient: no UV"));
     OCB_TRY(launch_gradient(c, p0));
-    if (g_out) OCB_CUDA(c, cudaMemcpyAsync(g_out, c->g.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToHost, c->stream));
+    if (g_out) OCB_TRY(vec_to_host(c, g_out, c->g.p));
     OCB_TRY(fetch_scalars(c));
     if (sqnorm) *sqnorm = c->hScal[S_SQN_G];
     return OCB_OK;
@@ -447,29 +514,58 @@ int ocb_set_pattern(ocb_ctx* c, int nVtot, const int32_t* adjPtr, const int32_t*
         OCB_CUDA(c, c->p.reserve(2 * (size_t)nVtot, c->stream));
     }
     if (nVtot != c->nVtot) return set_err(c, OCB_ERR_ARG, "ocb_set_pattern: nVtot does not match mesh + air sizes");
+    if (c->nV == 0) {                                     // solver-only use: locality order straight from the adjacency
+        static const bool off = []() { const char* e = getenv("OCB_NO_REORDER"); return e && atoi(e); }();
+        c->hPerm.assign((size_t)nVtot, 0);
+        if (off) { for (int v = 0; v < nVtot; ++v) c->hPerm[v] = v; }
+        else {
+            std::vector<int32_t> order; order.reserve((size_t)nVtot);
+            std::vector<uint8_t> seen((size_t)nVtot, 0);
+            for (int s0 = 0; s0 < nVtot; ++s0) {
+                if (seen[s0]) continue;
+                seen[s0] = 1; order.push_back(s0);
+                for (size_t head = order.size() - 1; head < order.size(); ++head) {
+                    const int v = order[head];
+                    for (int k = adjPtr[v]; k < adjPtr[v + 1]; ++k) {
+                        const int u = adjIdx[k];
+                        if (u >= 0 && u < nVtot && !seen[u]) { seen[u] = 1; order.push_back(u); }
+                    }
+                }
+            }
+            for (int i = 0; i < nVtot; ++i) c->hPerm[order[i]] = i;
+        }
+        c->nV = nVtot;                                    // upload_perm keeps ids >= nV fixed: none here
+        const int rc = upload_perm(c);
+        c->nV = 0;
+        if (rc < 0) return rc;
+    }
     c->hFixed.assign((size_t)nVtot, 0);
     for (int i = 0; i < nFixed; ++i) {
         if (fixed[i] < 0 || fixed[i] >= nVtot) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range");
-        c->hFixed[fixed[i]] = (c->nV > 0 && fixed[i] >= c->nV) ? 2 : 1;     // merged set (Scaffold::mergeFixedV): air-only ids follow the mesh's
+        c->hFixed[c->hPerm[fixed[i]]] = (c->nV > 0 && fixed[i] >= c->nV) ? 2 : 1;     // merged set (Scaffold::mergeFixedV): air-only ids follow the mesh's
     }
     c->hRowPtr.assign((size_t)nVtot + 1, 0);
     c->hColIdx.clear();
     c->hColIdx.reserve((size_t)adjPtr[nVtot] + nVtot);
-    for (int v = 0; v < nVtot; ++v) {
-        if (c->hFixed[v]) { c->hColIdx.push_back(v); }
+    std::vector<int32_t> rowBuf;
+    for (int vi = 0; vi < nVtot; ++vi) {                  // vi: internal row, v: the caller's vertex
+        const int v = c->hInv[vi];
+        if (c->hFixed[vi]) { c->hColIdx.push_back(vi); }
         else {
-            bool selfDone = false;
+            rowBuf.clear();
+            rowBuf.push_back(vi);
             for (int k = adjPtr[v]; k < adjPtr[v + 1]; ++k) {
                 const int nb = adjIdx[k];
                 if (nb < 0 || nb >= nVtot) return set_err(c, OCB_ERR_ARG, "adjacency index out of range");
                 if (k > adjPtr[v] && adjIdx[k - 1] >= nb) return set_err(c, OCB_ERR_ARG, "adjacency rows must be strictly ascending");
                 if (nb == v) continue;
-                if (!selfDone && nb > v) { c->hColIdx.push_back(v); selfDone = true; }
-                if (!c->hFixed[nb]) c->hColIdx.push_back(nb);
+                const int ni = c->hPerm[nb];
+                if (!c->hFixed[ni]) rowBuf.push_back(ni);
             }
-            if (!selfDone) c->hColIdx.push_back(v);
+            std::sort(rowBuf.begin(), rowBuf.end());
+            c->hColIdx.insert(c->hColIdx.end(), rowBuf.begin(), rowBuf.end());
         }
-        c->hRowPtr[v + 1] = (int32_t)c->hColIdx.size();
+        c->hRowPtr[vi + 1] = (int32_t)c->hColIdx.size();
     }
     return install_pattern(c);
 }
@@ -542,11 +638,11 @@ int ocb_hessian_triplets(ocb_ctx* c, int uniform, double* V, int32_t* I, int32_t
     const int nF = c->nF;
     for (int t = 0; t < nF; ++t) {
         int nf = 0;
-        for (int k = 0; k < 3; ++k) nf += c->hFixed[c->hF[(size_t)k * nF + t]] ? 0 : 1;
+        for (int k = 0; k < 3; ++k) nf += c->hFixed[c->hF[(size_t)k * nF + t]] ? 0 : 1;     // hF: internal ids, like hFixed
         cntT += 4 * (int64_t)nf * nf;
     }
     int nFixedMesh = 0;
-    for (int v = 0; v < c->nV; ++v) nFixedMesh += c->hFixed[v] ? 1 : 0;
+    for (int v = 0; v < c->nV; ++v) nFixedMesh += c->hFixed[c->hPerm[v]] ? 1 : 0;
     cntT += 2 * (int64_t)nFixedMesh;
     *n = cntT;
     if (!V) return OCB_OK;
@@ -556,7 +652,7 @@ int ocb_hessian_triplets(ocb_ctx* c, int uniform, double* V, int32_t* I, int32_t
     int64_t w = 0;
     for (int t = 0; t < nF; ++t) {
         int idx[3];
-        for (int k = 0; k < 3; ++k) { idx[k] = c->hF[(size_t)k * nF + t]; if (c->hFixed[idx[k]]) idx[k] = -1; }
+        for (int k = 0; k < 3; ++k) { idx[k] = c->hFuser[(size_t)k * nF + t]; if (c->hFixed[c->hPerm[idx[k]]]) idx[k] = -1; }   // triplets carry the caller's ids
         const double* B = blocks.data() + 36 * (size_t)t;
         for (int a = 0; a < 3; ++a) {
             if (idx[a] < 0) continue;
@@ -568,7 +664,7 @@ int ocb_hessian_triplets(ocb_ctx* c, int uniform, double* V, int32_t* I, int32_t
             }
         }
     }
-    for (int v = 0; v < c->nV; ++v) if (c->hFixed[v]) for (int i = 0; i < 2; ++i) { V[w] = 1.0; I[w] = J[w] = 2 * v + i; ++w; }
+    for (int v = 0; v < c->nV; ++v) if (c->hFixed[c->hPerm[v]]) for (int i = 0; i < 2; ++i) { V[w] = 1.0; I[w] = J[w] = 2 * v + i; ++w; }
     return OCB_OK;
 }
 
@@ -597,21 +693,27 @@ int ocb_download_csr(ocb_ctx* c, int32_t* ia, int32_t* ja, double* a)
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     int64_t w = 0;
     ia[0] = 1;
-    for (int v = 0; v < c->nVtot; ++v) {
-        if (c->hFixed[v]) {
+    std::vector<std::pair<int32_t, int32_t>> row;         // (caller column id, block slot)
+    for (int v = 0; v < c->nVtot; ++v) {                  // v: the caller's vertex, vi its internal row
+        const int vi = c->hPerm[v];
+        if (c->hFixed[vi]) {
             int bdiag = -1;
-            for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) if (c->hColIdx[b] == v) bdiag = b;
+            for (int b = c->hRowPtr[vi]; b < c->hRowPtr[vi + 1]; ++b) if (c->hColIdx[b] == vi) bdiag = b;
             ja[w] = 2 * v + 1; a[w] = val[4 * (size_t)bdiag]; ++w; ia[2 * v + 1] = (int32_t)(w + 1);
             ja[w] = 2 * v + 2; a[w] = val[4 * (size_t)bdiag + 3]; ++w; ia[2 * v + 2] = (int32_t)(w + 1);
             continue;
         }
+        row.clear();
+        for (int b = c->hRowPtr[vi]; b < c->hRowPtr[vi + 1]; ++b) {
+            const int col = c->hInv[c->hColIdx[b]];
+            if (col >= v) row.push_back(std::make_pair((int32_t)col, (int32_t)b));
+        }
+        std::sort(row.begin(), row.end());
         for (int r = 0; r < 2; ++r) {
-            for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) {
-                const int col = c->hColIdx[b];
-                if (col < v) continue;
+            for (const auto& cb : row) {
                 for (int q = 0; q < 2; ++q) {
-                    if (col == v && q < r) continue;     // strict lower entry of the diagonal block
-                    ja[w] = 2 * col + q + 1; a[w] = val[4 * (size_t)b + 2 * r + q]; ++w;
+                    if (cb.first == v && q < r) continue;     // strict lower entry of the diagonal block
+                    ja[w] = 2 * cb.first + q + 1; a[w] = val[4 * (size_t)cb.second + 2 * r + q]; ++w;
                 }
             }
             ia[2 * v + r + 1] = (int32_t)(w + 1);
@@ -626,9 +728,9 @@ int ocb_multiply(ocb_ctx* c, const double* x, double* y)
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_multiply: no matrix"));
     const size_t n = c->nSys();
     OCB_CUDA(c, c->scratchD.reserve(2 * n, c->stream));
-    OCB_TRY(upload_d(c, c->scratchD.p, x, n));
+    OCB_TRY(vec_to_device(c, c->scratchD.p, x));
     OCB_TRY(launch_spmv(c, c->scratchD.p, c->scratchD.p + n));
-    OCB_CUDA(c, cudaMemcpyAsync(y, c->scratchD.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    OCB_TRY(vec_to_host(c, y, c->scratchD.p + n));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     return OCB_OK;
 }
@@ -655,11 +757,11 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
     bool negate = true;
     if (rhs) {
         OCB_CUDA(c, c->pb.reserve(n, c->stream));
-        OCB_TRY(upload_d(c, c->pb.p, rhs, n));
+        OCB_TRY(vec_to_device(c, c->pb.p, rhs));
         dRhs = c->pb.p; negate = false;
     }
     OCB_TRY(launch_pcg(c, dRhs, negate, rel_tol, max_it));
-    if (x_out) OCB_CUDA(c, cudaMemcpyAsync(x_out, c->p.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (x_out) OCB_TRY(vec_to_host(c, x_out, c->p.p));
     OCB_TRY(fetch_scalars(c));
     if (iters) *iters = (int)c->hScal[S_PCG_ITERS];
     if (rel_res) *rel_res = c->hScal[S_PCG_RELRES];
@@ -672,7 +774,7 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
 int ocb_get_search_dir(ocb_ctx* c, double* p)
 {
     if (!c || !p) return OCB_ERR_ARG;
-    OCB_CUDA(c, cudaMemcpyAsync(p, c->p.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToHost, c->stream));
+    OCB_TRY(vec_to_host(c, p, c->p.p));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     return OCB_OK;
 }
@@ -680,7 +782,7 @@ int ocb_set_search_dir(ocb_ctx* c, const double* p)
 {
     if (!c || !p) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->nVtot > 0, "ocb_set_search_dir before the system size is known"));
-    OCB_CUDA(c, cudaMemcpyAsync(c->p.p, p, sizeof(double) * c->nSys(), cudaMemcpyHostToDevice, c->stream));
+    OCB_TRY(vec_to_device(c, c->p.p, p));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     return OCB_OK;
 }
@@ -693,7 +795,7 @@ int ocb_step_bound(ocb_ctx* c, const double* dir, double* alpha)
     const double* dDir = c->p.p;
     if (dir) {
         OCB_CUDA(c, c->scratchD.reserve((size_t)c->nSys(), c->stream));
-        OCB_TRY(upload_d(c, c->scratchD.p, dir, (size_t)c->nSys()));
+        OCB_TRY(vec_to_device(c, c->scratchD.p, dir));
         dDir = c->scratchD.p;
     }
     OCB_TRY(launch_step_bound(c, dDir, *alpha));
@@ -803,7 +905,7 @@ int ocb_seam_energy(ocb_ctx* c, int nCoh, const int32_t* cohE, const double* edg
         if (!cohE || !edgeLen || !boundaryEdge) return set_err(c, OCB_ERR_ARG, "ocb_seam_energy: bad argument");
         // boundary rows hold -1 indices: clamp for the gather, they are skipped by the flag
         std::vector<int32_t> coh(cohE, cohE + 4 * (size_t)nCoh);
-        for (auto& v : coh) if (v < 0) v = 0;
+        for (auto& v : coh) v = v < 0 ? 0 : c->hPerm[v];
         OCB_CUDA(c, c->scratchI.reserve(5 * (size_t)nCoh, c->stream));
         OCB_CUDA(c, c->scratchD.reserve((size_t)nCoh, c->stream));
         OCB_TRY(upload_i(c, c->scratchI.p, coh.data(), 4 * (size_t)nCoh));
@@ -821,9 +923,10 @@ int ocb_divgrad_scores(ocb_ctx* c, double* out)
 {
     if (!c || !out) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->haveUV, "ocb_divgrad_scores: no UV"));
-    OCB_CUDA(c, c->pb.reserve((size_t)c->nV, c->stream));
+    OCB_CUDA(c, c->pb.reserve(2 * (size_t)c->nV, c->stream));
     OCB_TRY(launch_divgrad(c, c->pb.p));
-    OCB_CUDA(c, cudaMemcpyAsync(out, c->pb.p, sizeof(double) * c->nV, cudaMemcpyDeviceToHost, c->stream));
+    OCB_TRY(launch_permute_scalar(c, c->nV, c->pb.p, c->pb.p + c->nV));
+    OCB_CUDA(c, cudaMemcpyAsync(out, c->pb.p + c->nV, sizeof(double) * c->nV, cudaMemcpyDeviceToHost, c->stream));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     return OCB_OK;
 }

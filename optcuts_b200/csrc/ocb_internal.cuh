@@ -84,7 +84,10 @@ struct ocb_ctx {
     bool haveUV = false, patternValid = false, matrixValid = false, precondValid = false, slotsValid = false;
 
     ocb::ElemSet mesh, air;
-    std::vector<int32_t> hF, hFa;            // host copies of the element lists (global ids), 3 x n SoA
+    std::vector<int32_t> hF, hFa;            // host copies of the element lists (INTERNAL global ids), 3 x n SoA
+    std::vector<int32_t> hFuser;             // mesh element list in the caller's vertex numbering
+    std::vector<int32_t> hPerm, hInv;        // caller vertex id -> internal id (locality order) and back; size nVtot
+    ocb::DevBuf<int32_t> perm;
     std::vector<int32_t> hL2G;               // localVI2Global
     std::vector<uint8_t> hFixed;             // per global vertex
     ocb::DevBuf<int32_t> l2g;
@@ -105,7 +108,7 @@ struct ocb_ctx {
     double* dScal = nullptr;                 // S_COUNT device scalars
     double* hScal = nullptr;                 // pinned mirror
     // scratch for uploads
-    ocb::DevBuf<double> scratchD;
+    ocb::DevBuf<double> scratchD, scratchV;
     ocb::DevBuf<int32_t> scratchI;
     int pcgGrid = 0, pcgBlock = 0;
     size_t pcgSmemAttr = 0;
@@ -154,6 +157,8 @@ int launch_step_forward(ocb_ctx* c, double alpha);
 int launch_triplet_scatter(ocb_ctx* c, int64_t nT, const int32_t* dI, const int32_t* dJ, const double* dS);
 int launch_set_uv(ocb_ctx* c, const double* dV, const double* dVa);
 int launch_get_uv(ocb_ctx* c, double* dV, double* dVa);
+int launch_permute_vec(ocb_ctx* c, const double* in, double* out, bool toInternal);
+int launch_permute_scalar(ocb_ctx* c, int n, const double* in, double* out);
 int launch_rest_features(ocb_ctx* c, int nV, int nF, const double* dVrest, const int32_t* dF, double thres, double* dRest8);
 int launch_seam(ocb_ctx* c, int nCoh, const int32_t* dCoh, const double* dLen, const int32_t* dBnd, double thresLen, int triSoup);
 int launch_divgrad(ocb_ctx* c, double* d_out);

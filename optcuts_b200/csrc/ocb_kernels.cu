@@ -303,12 +303,12 @@ step_forward_kernel(int n, const double* __restrict__ x0, const double* __restri
 __global__ void __launch_bounds__(kBlock)
 triplet_scatter_kernel(long nT, const int32_t* __restrict__ I, const int32_t* __restrict__ J, const double* __restrict__ S,
                        const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, double* __restrict__ val,
-                       int* __restrict__ missing)
+                       int* __restrict__ missing, const int32_t* __restrict__ perm)
 {
     for (long k = blockIdx.x * (long)kBlock + threadIdx.x; k < nT; k += (long)gridDim.x * kBlock) {
         const int i = I[k], j = J[k];
-        if (i > j) continue;
-        const int bi = i >> 1, bj = j >> 1, ri = i & 1, rj = j & 1;
+        if (i > j) continue;                    // the reference keeps the upper triangle of the CALLER's numbering
+        const int bi = perm[i >> 1], bj = perm[j >> 1], ri = i & 1, rj = j & 1;
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
             const int row = pass ? bj : bi, col = pass ? bi : bj, rr = pass ? rj : ri, cc = pass ? ri : rj;
@@ -328,13 +328,15 @@ triplet_scatter_kernel(long nT, const int32_t* __restrict__ I, const int32_t* __
 // ---------------------------------------------------------------------------------------------
 // UV layout conversion: Eigen column-major (all u, then all v) <-> interleaved system vector
 __global__ void __launch_bounds__(kBlock)
-set_uv_kernel(int nV, const double* __restrict__ V, int nVa, int nBnd, const double* __restrict__ Va, double* __restrict__ x)
+set_uv_kernel(int nV, const double* __restrict__ V, int nVa, int nBnd, const double* __restrict__ Va, double* __restrict__ x,
+              const int32_t* __restrict__ perm)
 {
+    // perm: user vertex id -> internal (locality-ordered) id; air interior vertices keep nV + k
     const int total = (V ? nV : 0) + (Va ? (nVa - nBnd) : 0);
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < total; i += gridDim.x * kBlock) {
         int k = i;
         if (V) {
-            if (k < nV) { x[2 * k] = V[k]; x[2 * k + 1] = V[nV + k]; continue; }
+            if (k < nV) { const int q = perm[k]; x[2 * q] = V[k]; x[2 * q + 1] = V[nV + k]; continue; }
             k -= nV;
         }
         const int a = nBnd + k;   // interior air vertex
@@ -342,18 +344,36 @@ set_uv_kernel(int nV, const double* __restrict__ V, int nVa, int nBnd, const dou
     }
 }
 __global__ void __launch_bounds__(kBlock)
-get_uv_kernel(int nV, double* __restrict__ V, int nVa, const int32_t* __restrict__ l2g, double* __restrict__ Va, const double* __restrict__ x)
+get_uv_kernel(int nV, double* __restrict__ V, int nVa, const int32_t* __restrict__ l2g, double* __restrict__ Va, const double* __restrict__ x,
+              const int32_t* __restrict__ perm)
 {
     const int total = (V ? nV : 0) + (Va ? nVa : 0);
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < total; i += gridDim.x * kBlock) {
         int k = i;
         if (V) {
-            if (k < nV) { V[k] = x[2 * k]; V[nV + k] = x[2 * k + 1]; continue; }
+            if (k < nV) { const int q = perm[k]; V[k] = x[2 * q]; V[nV + k] = x[2 * q + 1]; continue; }
             k -= nV;
         }
         const int gidx = l2g[k];
         Va[k] = x[2 * gidx]; Va[nVa + k] = x[2 * gidx + 1];
     }
+}
+
+// system vectors cross the API in the caller's vertex order; on the device they live in the internal order
+__global__ void __launch_bounds__(kBlock)
+permute_vec_kernel(int nVtot, const int32_t* __restrict__ perm, const double* __restrict__ in, double* __restrict__ out, int toInternal)
+{
+    const double2* in2 = reinterpret_cast<const double2*>(in);
+    double2* out2 = reinterpret_cast<double2*>(out);
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < nVtot; k += gridDim.x * kBlock) {
+        const int q = perm[k];
+        if (toInternal) out2[q] = in2[k]; else out2[k] = in2[q];
+    }
+}
+__global__ void __launch_bounds__(kBlock)
+permute_scalar_kernel(int n, const int32_t* __restrict__ perm, const double* __restrict__ in, double* __restrict__ out)
+{
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < n; k += gridDim.x * kBlock) out[k] = in[perm[k]];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -568,7 +588,7 @@ int launch_triplet_scatter(ocb_ctx* c, int64_t nT, const int32_t* dI, const int3
     OCB_CUDA(c, cudaMemsetAsync(missing, 0, sizeof(int), c->stream));
     OCB_CUDA(c, cudaMemsetAsync(c->val.p, 0, sizeof(double) * 4 * (size_t)c->nnzb, c->stream));
     if (nT > 0) {
-        triplet_scatter_kernel<<<grid_for(c, nT), kBlock, 0, c->stream>>>((long)nT, dI, dJ, dS, c->rowPtr.p, c->colIdx.p, c->val.p, missing);
+        triplet_scatter_kernel<<<grid_for(c, nT), kBlock, 0, c->stream>>>((long)nT, dI, dJ, dS, c->rowPtr.p, c->colIdx.p, c->val.p, missing, c->perm.p);
         KCHECK(c);
     }
     int hMissing = 0;
@@ -583,7 +603,7 @@ int launch_set_uv(ocb_ctx* c, const double* dV, const double* dVa)
     ProfScope prof(c, K_MISC);
     const int total = (dV ? c->nV : 0) + (dVa ? (c->nVa - c->nBnd) : 0);
     if (total <= 0) return 0;
-    set_uv_kernel<<<grid_for(c, total, 4), kBlock, 0, c->stream>>>(c->nV, dV, c->nVa, c->nBnd, dVa, c->x.p);
+    set_uv_kernel<<<grid_for(c, total, 4), kBlock, 0, c->stream>>>(c->nV, dV, c->nVa, c->nBnd, dVa, c->x.p, c->perm.p);
     KCHECK(c);
     return 0;
 }
@@ -592,7 +612,21 @@ int launch_get_uv(ocb_ctx* c, double* dV, double* dVa)
     ProfScope prof(c, K_MISC);
     const int total = (dV ? c->nV : 0) + (dVa ? c->nVa : 0);
     if (total <= 0) return 0;
-    get_uv_kernel<<<grid_for(c, total, 4), kBlock, 0, c->stream>>>(c->nV, dV, c->nVa, c->l2g.p, dVa, c->x.p);
+    get_uv_kernel<<<grid_for(c, total, 4), kBlock, 0, c->stream>>>(c->nV, dV, c->nVa, c->l2g.p, dVa, c->x.p, c->perm.p);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_permute_vec(ocb_ctx* c, const double* in, double* out, bool toInternal)
+{
+    ProfScope prof(c, K_MISC);
+    permute_vec_kernel<<<grid_for(c, c->nVtot, 4), kBlock, 0, c->stream>>>(c->nVtot, c->perm.p, in, out, toInternal ? 1 : 0);
+    KCHECK(c);
+    return 0;
+}
+int launch_permute_scalar(ocb_ctx* c, int n, const double* in, double* out)
+{
+    permute_scalar_kernel<<<grid_for(c, n, 4), kBlock, 0, c->stream>>>(n, c->perm.p, in, out);
     KCHECK(c);
     return 0;
 }

@@ -1,14 +1,16 @@
 #!/bin/bash
 mkdir -p gpurun_out
 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
+tail -12 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 for w in bimba10k bimba_x4 bimba_x10; do
-python bench.py --workload $w --steps 6 --warmup 3 --pcg-max-it 60000 --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
+OCB_PCG_DEBUG=1 python bench.py --workload $w --steps 4 --warmup 3 --pcg-max-it 60000 --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
+tail -1 gpurun_out/bench_$w.err
 python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_$w.json"))
 print("$w", "it/s", round(d["value"],3), "ms", round(d["ms_per_step"],3), "e2e ms", round(d["e2e"]["ms_per_step"],3), "pcg iters", d["config"]["pcg_iters_mean"], "E", d["E_new"])
-for k,v in d["kernels"].items(): print("   ", k, {a:(round(b,5) if isinstance(b,float) else b) for a,b in v.items()})
+for k,v in d["kernels"].items():
+    if k in ("energy","gradient","hessian_psd_scatter","pcg","step_bound"): print("   ", k, {a:(round(b,5) if isinstance(b,float) else b) for a,b in v.items()})
 PY
 done
