@@ -224,35 +224,81 @@ __device__ __forceinline__ void cluster_allreduce(double (*part)[kSyncVals][kClu
 // iteration touches global memory only for the halo gathers (z, d of neighbour rows), the two vectors
 // neighbours read (z, d) and the sync packets.  Otherwise (GLOBAL mode) the slice is streamed from L2/HBM.
 struct Slice {
-    int32_t* rowPtr;   // nLoc + 1, block offsets relative to the CTA's first block
-    int32_t* col;      // nBlk
-    double2* val2;     // 2 * nBlk  (row-major 2x2 blocks as two double2)
-    double2* x; double2* r; double2* Ap; double2* z; double2* d;   // nLoc each
+    // ELL layout, slot-major: entry (k, r) at k * nLoc + r, so that consecutive threads (rows) touch consecutive
+    // words: conflict-free shared-memory reads with ONE thread per scalar row and no shuffles
+    int32_t* len;      // nLoc: blocks of the row held in the slice (<= W; longer rows continue in the global BSR)
+    int32_t* col;      // W * nLoc
+    double2* val2;     // W * nLoc * 2  (entry (k, r): [top row, bottom row] of the 2x2 block)
+    double2* x; double2* r; double2* Ap; double2* z; double2* d[2];   // nLoc each; d is double-buffered like the global copy
     double4* minv;     // nLoc
+    int W, nLoc;
 };
-__host__ __device__ inline size_t slice_bytes(int nLoc, int nBlk)
+__host__ __device__ inline size_t slice_bytes(int nLoc, int W)
 {
     size_t b = 0;
-    b += (((size_t)(nLoc + 1) * 4 + 15) / 16) * 16;
-    b += (((size_t)nBlk * 4 + 15) / 16) * 16;
-    b += (size_t)nBlk * 32;
-    b += (size_t)nLoc * 16 * 5;
+    b += (((size_t)nLoc * 4 + 15) / 16) * 16;
+    b += (((size_t)W * nLoc * 4 + 15) / 16) * 16;
+    b += (size_t)W * nLoc * 32;
+    b += (size_t)nLoc * 16 * 6;
     b += (size_t)nLoc * 32;
     return b;
 }
-__device__ __forceinline__ Slice carve(unsigned char* base, int nLoc, int nBlk)
+__device__ __forceinline__ Slice carve(unsigned char* base, int nLoc, int W)
 {
     Slice S; size_t o = 0;
-    S.rowPtr = reinterpret_cast<int32_t*>(base + o); o += (((size_t)(nLoc + 1) * 4 + 15) / 16) * 16;
-    S.col = reinterpret_cast<int32_t*>(base + o);    o += (((size_t)nBlk * 4 + 15) / 16) * 16;
-    S.val2 = reinterpret_cast<double2*>(base + o);   o += (size_t)nBlk * 32;
+    S.W = W; S.nLoc = nLoc;
+    S.len = reinterpret_cast<int32_t*>(base + o);    o += (((size_t)nLoc * 4 + 15) / 16) * 16;
+    S.col = reinterpret_cast<int32_t*>(base + o);    o += (((size_t)W * nLoc * 4 + 15) / 16) * 16;
+    S.val2 = reinterpret_cast<double2*>(base + o);   o += (size_t)W * nLoc * 32;
     S.x = reinterpret_cast<double2*>(base + o);      o += (size_t)nLoc * 16;
     S.r = reinterpret_cast<double2*>(base + o);      o += (size_t)nLoc * 16;
     S.Ap = reinterpret_cast<double2*>(base + o);     o += (size_t)nLoc * 16;
     S.z = reinterpret_cast<double2*>(base + o);      o += (size_t)nLoc * 16;
-    S.d = reinterpret_cast<double2*>(base + o);      o += (size_t)nLoc * 16;
+    S.d[0] = reinterpret_cast<double2*>(base + o);   o += (size_t)nLoc * 16;
+    S.d[1] = reinterpret_cast<double2*>(base + o);   o += (size_t)nLoc * 16;
     S.minv = reinterpret_cast<double4*>(base + o);
     return S;
+}
+
+// SMEM-mode SpMV with the fused direction update: one thread per SCALAR row (thread pair = block row), the row's
+// blocks walked serially out of the ELL slice.  ~14 instructions per block and no shuffles: the 16-lanes-per-row
+// mapping of the streaming path below costs ~10x more issue slots, which is what bounds a solve that runs on few SMs.
+__device__ __forceinline__ double spmv_fused_ell(const PcgParams& P, const Slice& S, int rowBeg, int rowEnd, const double* z,
+                                                 const double* dOld, double* dNew, double beta,
+                                                 const double2* __restrict__ sdOld, double2* __restrict__ sdNew)
+{
+    const double2* z2 = reinterpret_cast<const double2*>(z);
+    const double2* d2 = reinterpret_cast<const double2*>(dOld);
+    const double2* __restrict__ gval2 = reinterpret_cast<const double2*>(P.val);
+    const int nLoc = rowEnd - rowBeg, half = threadIdx.x & 1;
+    double dotAcc = 0.0;
+    for (int lr = threadIdx.x >> 1; lr < nLoc; lr += kPcgBlock / 2) {
+        const int len = S.len[lr];
+        double acc = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < len; ++k) {
+            const int c = S.col[k * S.nLoc + lr];
+            const double2 a = S.val2[2 * (k * S.nLoc + lr) + half];
+            double2 zz, dd;
+            if (c >= rowBeg && c < rowEnd) { zz = S.z[c - rowBeg]; dd = sdOld[c - rowBeg]; }     // own range: no global traffic
+            else { zz = __ldcg(z2 + c); dd = __ldcg(d2 + c); }
+            acc += a.x * (zz.x + beta * dd.x) + a.y * (zz.y + beta * dd.y);
+        }
+        const int row = rowBeg + lr;
+        const int gEnd = __ldg(P.rowPtr + row + 1);
+        for (int b = __ldg(P.rowPtr + row) + len; b < gEnd; ++b) {       // rows longer than the slice width (rare)
+            const int c = __ldg(P.colIdx + b);
+            const double2 a = __ldg(gval2 + 2 * (size_t)b + half);
+            const double2 zz = __ldcg(z2 + c), dd = __ldcg(d2 + c);
+            acc += a.x * (zz.x + beta * dd.x) + a.y * (zz.y + beta * dd.y);
+        }
+        const double dn = reinterpret_cast<const double*>(S.z)[2 * lr + half] + beta * reinterpret_cast<const double*>(sdOld)[2 * lr + half];
+        reinterpret_cast<double*>(sdNew)[2 * lr + half] = dn;
+        reinterpret_cast<double*>(S.Ap)[2 * lr + half] = acc;
+        dNew[2 * (size_t)row + half] = dn;
+        dotAcc += acc * dn;
+    }
+    return dotAcc;
 }
 
 // Ap[own rows] = A * d_new with d_new = z + beta * d_old evaluated on the fly for the gathered columns
@@ -263,8 +309,7 @@ __device__ __forceinline__ Slice carve(unsigned char* base, int nLoc, int nBlk)
 // row), kUnroll row pairs per warp in flight so that every lane has several independent 16-byte loads
 // outstanding (HBM needs ~26 KB in flight per SM).
 static constexpr int kUnroll = 2;
-template <bool SMEM>
-__device__ __forceinline__ double spmv_fused(const PcgParams& P, const Slice& S, int rowBeg, int rowEnd, const double* z,
+__device__ __forceinline__ double spmv_fused(const PcgParams& P, int rowBeg, int rowEnd, const double* z,
                                              const double* dOld, double* dNew, double beta)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -279,25 +324,15 @@ __device__ __forceinline__ double spmv_fused(const PcgParams& P, const Slice& S,
         for (int u = 0; u < kUnroll; ++u) {
             row[u] = rowBase + 2 * u + (lane >> 4);
             const bool active = row[u] < rowEnd;
-            if (SMEM) {
-                b0[u] = (active ? S.rowPtr[row[u] - rowBeg] : 0) + kblk;
-                end[u] = active ? S.rowPtr[row[u] - rowBeg + 1] : 0;
-            } else {
-                b0[u] = (active ? __ldg(P.rowPtr + row[u]) : 0) + kblk;
-                end[u] = active ? __ldg(P.rowPtr + row[u] + 1) : 0;
-            }
+            b0[u] = (active ? __ldg(P.rowPtr + row[u]) : 0) + kblk;
+            end[u] = active ? __ldg(P.rowPtr + row[u] + 1) : 0;
         }
         int col[kUnroll]; double2 a[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const bool has = b0[u] < end[u];
-            if (SMEM) {
-                col[u] = has ? S.col[b0[u]] : -1;
-                a[u] = has ? S.val2[2 * b0[u] + half] : make_double2(0.0, 0.0);
-            } else {
-                col[u] = has ? __ldg(P.colIdx + b0[u]) : -1;
-                a[u] = has ? __ldg(gval2 + 2 * (size_t)b0[u] + half) : make_double2(0.0, 0.0);
-            }
+            col[u] = has ? __ldg(P.colIdx + b0[u]) : -1;
+            a[u] = has ? __ldg(gval2 + 2 * (size_t)b0[u] + half) : make_double2(0.0, 0.0);
         }
         double2 zz[kUnroll], dd[kUnroll];
 #pragma unroll
@@ -310,8 +345,8 @@ __device__ __forceinline__ double spmv_fused(const PcgParams& P, const Slice& S,
         for (int u = 0; u < kUnroll; ++u) {
             acc[u] = a[u].x * (zz[u].x + beta * dd[u].x) + a[u].y * (zz[u].y + beta * dd[u].y);
             for (int b = b0[u] + 8; b < end[u]; b += 8) {          // rows with more than 8 blocks (rare)
-                const int c = SMEM ? S.col[b] : __ldg(P.colIdx + b);
-                const double2 av = SMEM ? S.val2[2 * b + half] : __ldg(gval2 + 2 * (size_t)b + half);
+                const int c = __ldg(P.colIdx + b);
+                const double2 av = __ldg(gval2 + 2 * (size_t)b + half);
                 const double2 zv = __ldcg(z2 + c), dv = __ldcg(d2 + c);
                 acc[u] += av.x * (zv.x + beta * dv.x) + av.y * (zv.y + beta * dv.y);
             }
@@ -323,17 +358,8 @@ __device__ __forceinline__ double spmv_fused(const PcgParams& P, const Slice& S,
             t += __shfl_xor_sync(0xffffffffu, t, 4);
             t += __shfl_xor_sync(0xffffffffu, t, 8);
             if (row[u] < rowEnd && sub < 2) {
-                double dn;
-                if (SMEM) {
-                    const int lr = row[u] - rowBeg;
-                    double* zs = reinterpret_cast<double*>(S.z); double* ds = reinterpret_cast<double*>(S.d);
-                    dn = zs[2 * lr + half] + beta * ds[2 * lr + half];
-                    ds[2 * lr + half] = dn;
-                    reinterpret_cast<double*>(S.Ap)[2 * lr + half] = t;
-                } else {
-                    dn = __ldcg(z + 2 * (size_t)row[u] + half) + beta * __ldcg(dOld + 2 * (size_t)row[u] + half);
-                    P.Ap[2 * (size_t)row[u] + half] = t;
-                }
+                const double dn = __ldcg(z + 2 * (size_t)row[u] + half) + beta * __ldcg(dOld + 2 * (size_t)row[u] + half);
+                P.Ap[2 * (size_t)row[u] + half] = t;
                 dNew[2 * (size_t)row[u] + half] = dn;
                 dotAcc += t * dn;
             }
@@ -357,16 +383,19 @@ pcg_kernel(PcgParams P)
     const int rowBeg = min(P.nRows, (int)blockIdx.x * rowsPer), rowEnd = min(P.nRows, rowBeg + rowsPer);
     const int nLoc = rowEnd - rowBeg;
     SyncSlot* slots = reinterpret_cast<SyncSlot*>(P.partials);
-    double* dBuf[2] = {P.d, P.d2};
     unsigned long long epoch = 0;
     Slice S = {};
     if (SMEM) {
-        const int blkBeg = nLoc > 0 ? P.rowPtr[rowBeg] : 0, blkEnd = nLoc > 0 ? P.rowPtr[rowEnd] : 0;
-        S = carve(smemRaw, rowsPer, P.maxBlkPerCta);
-        for (int i = threadIdx.x; i <= nLoc; i += kPcgBlock) S.rowPtr[i] = P.rowPtr[rowBeg + i] - blkBeg;
-        for (int i = threadIdx.x; i < blkEnd - blkBeg; i += kPcgBlock) S.col[i] = P.colIdx[blkBeg + i];
-        const double2* gv = reinterpret_cast<const double2*>(P.val) + 2 * (size_t)blkBeg;
-        for (int i = threadIdx.x; i < 2 * (blkEnd - blkBeg); i += kPcgBlock) S.val2[i] = gv[i];
+        S = carve(smemRaw, rowsPer, P.maxBlkPerCta);          // maxBlkPerCta carries the ELL width W here
+        const double2* gv = reinterpret_cast<const double2*>(P.val);
+        for (int lr = threadIdx.x >> 1; lr < nLoc; lr += kPcgBlock / 2) {
+            const int b0 = P.rowPtr[rowBeg + lr], len = min(S.W, P.rowPtr[rowBeg + lr + 1] - b0), half = threadIdx.x & 1;
+            if (half == 0) S.len[lr] = len;
+            for (int k = 0; k < len; ++k) {
+                if (half == 0) S.col[k * S.nLoc + lr] = P.colIdx[b0 + k];
+                S.val2[2 * (k * S.nLoc + lr) + half] = gv[2 * (size_t)(b0 + k) + half];
+            }
+        }
     }
 
     // ---- init: x = 0, r = b, z = Minv r, d = 0 ; rz = r.z, bb = b.b
@@ -378,7 +407,8 @@ pcg_kernel(PcgParams P)
         double2 zz; zz.x = m.x * b0 + m.y * b1; zz.y = m.y * b0 + m.w * b1;
         if (SMEM) {
             const int lr = row - rowBeg;
-            S.x[lr] = make_double2(0.0, 0.0); S.r[lr] = make_double2(b0, b1); S.z[lr] = zz; S.d[lr] = make_double2(0.0, 0.0);
+            S.x[lr] = make_double2(0.0, 0.0); S.r[lr] = make_double2(b0, b1); S.z[lr] = zz;
+            S.d[0][lr] = make_double2(0.0, 0.0); S.d[1][lr] = make_double2(0.0, 0.0);
             S.minv[lr] = m;
         } else {
             reinterpret_cast<double2*>(P.x)[row] = make_double2(0.0, 0.0);
@@ -399,10 +429,14 @@ pcg_kernel(PcgParams P)
     if (bb > 0.0) {
         for (;;) {
             // ---- phase A: d_new = z + beta d_old (fused) ; Ap = A d_new ; pAp
-            double* dNew = dBuf[cur ^ 1];
+            double* dNew = cur ? P.d : P.d2;
             long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
             if (P.dbg) t0 = clock64();
-            double la[1] = {spmv_fused<SMEM>(P, S, rowBeg, rowEnd, P.z, dBuf[cur], dNew, beta)}, ra[1];
+            double2* sdOld = cur ? S.d[1] : S.d[0];
+            double2* sdNew = cur ? S.d[0] : S.d[1];
+            double* dOldG = cur ? P.d2 : P.d;
+            double la[1] = {SMEM ? spmv_fused_ell(P, S, rowBeg, rowEnd, P.z, dOldG, dNew, beta, sdOld, sdNew)
+                                 : spmv_fused(P, rowBeg, rowEnd, P.z, dOldG, dNew, beta)}, ra[1];
             if (P.dbg) { __syncthreads(); t1 = clock64(); }
             ALLREDUCE(1, la, ra);
             if (P.dbg) t2 = clock64();
@@ -413,7 +447,7 @@ pcg_kernel(PcgParams P)
             loc[0] = 0.0; loc[1] = 0.0;
             for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
                 const int lr = row - rowBeg;
-                const double2 dd = SMEM ? S.d[lr] : reinterpret_cast<const double2*>(dNew)[row];
+                const double2 dd = SMEM ? sdNew[lr] : reinterpret_cast<const double2*>(dNew)[row];
                 const double2 ap = SMEM ? S.Ap[lr] : reinterpret_cast<const double2*>(P.Ap)[row];
                 double2 xx = SMEM ? S.x[lr] : reinterpret_cast<double2*>(P.x)[row];
                 double2 r2 = SMEM ? S.r[lr] : reinterpret_cast<double2*>(P.r)[row];
@@ -513,14 +547,12 @@ static PcgPlan pcg_plan(ocb_ctx* c)
     static const bool allowCluster = []() { const char* e = getenv("OCB_PCG_NO_CLUSTER"); return !(e && atoi(e)); }();
     PcgPlan pl; pl.smem = false; pl.cluster = false; pl.maxBlk = 0; pl.smemBytes = 0;
     const int n = c->nVtot;
-    auto slice_need = [&](int g, int& maxBlk) {
-        const int rowsPer = (n + g - 1) / g;
-        maxBlk = 0;
-        for (int b = 0; b < g; ++b) {
-            const int r0 = std::min(n, b * rowsPer), r1 = std::min(n, r0 + rowsPer);
-            maxBlk = std::max(maxBlk, c->hRowPtr[r1] - c->hRowPtr[r0]);
-        }
-        return slice_bytes(rowsPer, maxBlk);
+    int maxLen = 1;
+    for (int v = 0; v < n; ++v) maxLen = std::max(maxLen, c->hRowPtr[v + 1] - c->hRowPtr[v]);
+    const int ellW = std::min(maxLen, 12);                  // longer rows (valence > 11) continue in the global BSR
+    auto slice_need = [&](int g, int& W) {
+        W = ellW;
+        return slice_bytes((n + g - 1) / g, ellW);
     };
     if (allowSmem && allowCluster && c->clusterOk != 0) {      // one 16-CTA cluster if every slice fits
         int maxBlk = 0;
@@ -546,13 +578,8 @@ static PcgPlan pcg_plan(ocb_ctx* c)
     if (g > c->numSMs) g = c->numSMs;
     if (g < 1) g = 1;
     for (; allowSmem; ) {
-        const int rowsPer = (n + g - 1) / g;
         int maxBlk = 0;
-        for (int b = 0; b < g; ++b) {
-            const int r0 = std::min(n, b * rowsPer), r1 = std::min(n, r0 + rowsPer);
-            maxBlk = std::max(maxBlk, c->hRowPtr[r1] - c->hRowPtr[r0]);
-        }
-        const size_t bytes = slice_bytes(rowsPer, maxBlk);
+        const size_t bytes = slice_need(g, maxBlk);
         if (bytes <= limit) { pl.smem = true; pl.maxBlk = maxBlk; pl.smemBytes = bytes; break; }
         if (g >= c->numSMs) break;
         g = std::min(c->numSMs, g + (g + 3) / 4);
