@@ -191,8 +191,15 @@ int ocb_divgrad_scores(ocb_ctx* ctx, double* perVert_nV);
 
 /* ---- a16/a17 (non-bijective local stencils): batched evaluation of candidate operations —
  * TriMesh::computeLocalLDec -> computeLocalEdDec_* -> nested dense Optimizer (TriMesh.cpp:2105-2794).
- * One thread block per stencil runs the local projected-Newton solve (dense LDLT in shared memory,
- * relGL2Tol 1e-6, <= maxIter iterations) and returns E_init - E_final per stencil. */
+ * The caller builds the local meshes exactly as the reference does (local TriMesh after the local split /
+ * merge, 1-2 free vertices, TriMesh.cpp:2270-2300, 2330) and packs them into a ragged batch; one thread
+ * block per stencil runs Optimizer::precompute + setRelGL2Tol(relGL2Tol) + solve(maxIter) (dense LDL^T in
+ * shared memory, energyParams = {1}, weights = local area fractions) and returns E_init and E_final of the
+ * local energy (the caller forms eDec = (initE - E_final) * A_local / A_total, TriMesh.cpp:2380-2381).
+ * score[i] = score_scale[i] * (E_init[i] - E_final[i]) + score_offset[i] (NULL: 1 and 0), e.g.
+ * (1 - lambda) * A_local/A_total and -lambda * seInc (TriMesh.cpp:2184-2186); *argmax = first maximum of
+ * score (TriMesh.cpp:726-731).  Limits: 64 local vertices, 96 triangles, 16 free vertices per stencil
+ * (status -2 beyond); status -4 = inverted input. */
 typedef struct {
     int nStencil;
     const int32_t* vert_ptr;   /* nStencil+1: local vertex ranges */
@@ -201,9 +208,12 @@ typedef struct {
     const double*  UV;         /* 2 per local vertex (interleaved) */
     const int32_t* F;          /* 3 per local triangle, LOCAL vertex ids */
     const uint8_t* is_free;    /* per local vertex: 1 = free DOF, 0 = fixed */
+    const double*  score_scale;   /* nStencil or NULL */
+    const double*  score_offset;  /* nStencil or NULL */
 } ocb_stencil_batch;
 int ocb_eval_stencils(ocb_ctx* ctx, const ocb_stencil_batch* batch, int maxIter, double relGL2Tol,
-                      double* E_init, double* E_final, double* UV_out, int32_t* iters, int* argmax_dec);
+                      double* E_init, double* E_final, double* UV_out, int32_t* iters, double* score,
+                      int32_t* status, int* argmax);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,7 @@ class NewtonResult(C.Structure):
 
 class StencilBatch(C.Structure):
     _fields_ = [("nStencil", C.c_int), ("vert_ptr", _i), ("tri_ptr", _i), ("V_rest", _d), ("UV", _d),
-                ("F", _i), ("is_free", _u8)]
+                ("F", _i), ("is_free", _u8), ("score_scale", _d), ("score_offset", _d)]
 
 
 def lib_path():
@@ -93,7 +93,7 @@ _SIGS = [
     ("ocb_newton_step", C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(NewtonResult)]),
     ("ocb_seam_energy", C.c_int, [C.c_void_p, C.c_int, _i, _d, _i, C.c_double, C.c_double, C.c_double, C.c_int, _d]),
     ("ocb_divgrad_scores", C.c_int, [C.c_void_p, _d]),
-    ("ocb_eval_stencils", C.c_int, [C.c_void_p, C.POINTER(StencilBatch), C.c_int, C.c_double, _d, _d, _d, _i, C.POINTER(C.c_int)]),
+    ("ocb_eval_stencils", C.c_int, [C.c_void_p, C.POINTER(StencilBatch), C.c_int, C.c_double, _d, _d, _d, _i, _d, _i, C.POINTER(C.c_int)]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
 
@@ -343,6 +343,26 @@ class Context:
                                           _pi(_i32(np.asarray(boundaryEdge).ravel())), float(initSeamLen),
                                           float(virtualRadius), float(avgEdgeLen), int(triSoup), C.byref(e)))
         return e.value
+
+    def eval_stencils(self, stencils, maxIter=100, relGL2Tol=1e-6, score_scale=None, score_offset=None):
+        """stencils: list of (V_rest (nv,3), UV (nv,2), F (nt,3) local ids, is_free (nv,) bool).  Returns a dict of arrays."""
+        nS = len(stencils)
+        vp = np.zeros(nS + 1, np.int32); tp = np.zeros(nS + 1, np.int32)
+        for k, (Vr, UV, F, fr) in enumerate(stencils):
+            vp[k + 1] = vp[k] + len(Vr); tp[k + 1] = tp[k] + len(F)
+        Vr = np.ascontiguousarray(np.concatenate([np.asarray(s[0], np.float64).reshape(-1, 3) for s in stencils]) if nS else np.zeros((0, 3)))
+        UV = np.ascontiguousarray(np.concatenate([np.asarray(s[1], np.float64).reshape(-1, 2) for s in stencils]) if nS else np.zeros((0, 2)))
+        F = np.ascontiguousarray(np.concatenate([np.asarray(s[2], np.int32).reshape(-1, 3) for s in stencils]) if nS else np.zeros((0, 3), np.int32))
+        fr = np.ascontiguousarray(np.concatenate([np.asarray(s[3]).astype(np.uint8).ravel() for s in stencils]) if nS else np.zeros(0, np.uint8))
+        sc = None if score_scale is None else _f64(np.asarray(score_scale, np.float64).ravel())
+        so = None if score_offset is None else _f64(np.asarray(score_offset, np.float64).ravel())
+        b = StencilBatch(nS, _pi(vp), _pi(tp), _pd(Vr), _pd(UV), _pi(F), fr.ctypes.data_as(_u8), _pd(sc), _pd(so))
+        E0, E1, UVo = np.zeros(nS), np.zeros(nS), np.zeros_like(UV)
+        it, st, score = np.zeros(nS, np.int32), np.zeros(nS, np.int32), np.zeros(nS)
+        arg = C.c_int(-1)
+        self._chk(self._L.ocb_eval_stencils(self._h, C.byref(b), int(maxIter), float(relGL2Tol), _pd(E0), _pd(E1), _pd(UVo), _pi(it),
+                                            _pd(score), _pi(st), C.byref(arg)))
+        return dict(E_init=E0, E_final=E1, UV=[UVo[vp[k]:vp[k + 1]] for k in range(nS)], iters=it, status=st, score=score, argmax=arg.value)
 
     def divgrad_scores(self):
         out = np.zeros(self.sizes()["nV"])

@@ -210,7 +210,7 @@ void ocb_destroy(ocb_ctx* c)
         cudaStreamSynchronize(c->stream);
         c->mesh.v.release(); c->mesh.rest.release(); c->mesh.slot.release();
         c->air.v.release(); c->air.rest.release(); c->air.slot.release();
-        c->l2g.release(); c->fixedMask.release(); c->perm.release(); c->scratchV.release();
+        c->l2g.release(); c->fixedMask.release(); c->perm.release(); c->scratchV.release(); c->stD.release(); c->stI.release();
         c->x.release(); c->x0.release(); c->g.release(); c->p.release();
         c->pr.release(); c->pz.release(); c->pd.release(); c->pd2.release(); c->pAp.release(); c->pb.release(); c->minv.release();
         c->rowPtr.release(); c->colIdx.release(); c->val.release();
@@ -931,9 +931,54 @@ int ocb_divgrad_scores(ocb_ctx* c, double* out)
     return OCB_OK;
 }
 
-int ocb_eval_stencils(ocb_ctx* c, const ocb_stencil_batch*, int, double, double*, double*, double*, int32_t*, int*)
+int ocb_eval_stencils(ocb_ctx* c, const ocb_stencil_batch* B, int maxIter, double relGL2Tol, double* E_init, double* E_final,
+                      double* UV_out, int32_t* iters, double* score, int32_t* status, int* argmax)
 {
-    return set_err(c, OCB_ERR_STATE, "ocb_eval_stencils: not built yet");
+    if (!c || !B || B->nStencil < 0) return set_err(c, OCB_ERR_ARG, "ocb_eval_stencils: bad argument");
+    if (argmax) *argmax = -1;
+    if (B->nStencil == 0) return OCB_OK;
+    if (!B->vert_ptr || !B->tri_ptr || !B->V_rest || !B->UV || !B->F || !B->is_free) return set_err(c, OCB_ERR_ARG, "ocb_eval_stencils: bad argument");
+    OCB_TRY(ensure_init(c));
+    const int nS = B->nStencil;
+    const size_t nV = (size_t)B->vert_ptr[nS], nT = (size_t)B->tri_ptr[nS];
+    for (int s = 0; s < nS; ++s) if (B->vert_ptr[s + 1] < B->vert_ptr[s] || B->tri_ptr[s + 1] < B->tri_ptr[s]) return set_err(c, OCB_ERR_ARG, "ocb_eval_stencils: ranges must be ascending");
+    for (int s = 0; s < nS; ++s) {
+        const int nv = B->vert_ptr[s + 1] - B->vert_ptr[s];
+        for (int t = B->tri_ptr[s]; t < B->tri_ptr[s + 1]; ++t) for (int k = 0; k < 3; ++k)
+            if (B->F[3 * (size_t)t + k] < 0 || B->F[3 * (size_t)t + k] >= nv) return set_err(c, OCB_ERR_ARG, "ocb_eval_stencils: local vertex index out of range");
+    }
+    // one double arena + one int arena on the device
+    const size_t dIn = 3 * nV + 2 * nV + 2 * (size_t)nS, dOut = 2 * nV + 3 * (size_t)nS;
+    OCB_CUDA(c, c->stD.reserve(dIn + dOut + 8, c->stream));
+    const size_t iN = 2 * ((size_t)nS + 1) + 3 * nT + 2 * (size_t)nS + 2 + (nV + 3) / 4 + 4;
+    OCB_CUDA(c, c->stI.reserve(iN, c->stream));
+    double* dVr = c->stD.p; double* dUV = dVr + 3 * nV; double* dSc = dUV + 2 * nV; double* dOf = dSc + nS;
+    double* dUVo = dOf + nS; double* dE0 = dUVo + 2 * nV; double* dE1 = dE0 + nS; double* dScore = dE1 + nS;
+    int32_t* dVp = c->stI.p; int32_t* dTp = dVp + nS + 1; int32_t* dF = dTp + nS + 1; int32_t* dIt = dF + 3 * nT; int32_t* dSt = dIt + nS;
+    int32_t* dArg = dSt + nS; uint8_t* dFree = reinterpret_cast<uint8_t*>(dArg + 2);
+    OCB_TRY(upload_d(c, dVr, B->V_rest, 3 * nV)); OCB_TRY(upload_d(c, dUV, B->UV, 2 * nV));
+    if (B->score_scale) OCB_TRY(upload_d(c, dSc, B->score_scale, (size_t)nS));
+    if (B->score_offset) OCB_TRY(upload_d(c, dOf, B->score_offset, (size_t)nS));
+    OCB_TRY(upload_i(c, dVp, B->vert_ptr, (size_t)nS + 1)); OCB_TRY(upload_i(c, dTp, B->tri_ptr, (size_t)nS + 1));
+    OCB_TRY(upload_i(c, dF, B->F, 3 * nT));
+    OCB_CUDA(c, cudaMemcpyAsync(dFree, B->is_free, nV, cudaMemcpyHostToDevice, c->stream));
+    StencilHost h;
+    h.nStencil = nS; h.vertPtr = dVp; h.triPtr = dTp; h.Vrest = dVr; h.UV = dUV; h.F = dF; h.isFree = dFree;
+    h.scoreScale = B->score_scale ? dSc : nullptr; h.scoreOffset = B->score_offset ? dOf : nullptr;
+    h.maxIter = maxIter > 0 ? maxIter : 100; h.relGL2Tol = relGL2Tol > 0.0 ? relGL2Tol : 1.0e-6;
+    h.Einit = dE0; h.Efinal = dE1; h.UVout = dUVo; h.iters = dIt; h.score = dScore; h.status = dSt; h.argmax = dArg;
+    OCB_TRY(launch_stencils(c, h));
+    if (E_init) OCB_CUDA(c, cudaMemcpyAsync(E_init, dE0, sizeof(double) * nS, cudaMemcpyDeviceToHost, c->stream));
+    if (E_final) OCB_CUDA(c, cudaMemcpyAsync(E_final, dE1, sizeof(double) * nS, cudaMemcpyDeviceToHost, c->stream));
+    if (UV_out) OCB_CUDA(c, cudaMemcpyAsync(UV_out, dUVo, sizeof(double) * 2 * nV, cudaMemcpyDeviceToHost, c->stream));
+    if (iters) OCB_CUDA(c, cudaMemcpyAsync(iters, dIt, sizeof(int32_t) * nS, cudaMemcpyDeviceToHost, c->stream));
+    if (score) OCB_CUDA(c, cudaMemcpyAsync(score, dScore, sizeof(double) * nS, cudaMemcpyDeviceToHost, c->stream));
+    if (status) OCB_CUDA(c, cudaMemcpyAsync(status, dSt, sizeof(int32_t) * nS, cudaMemcpyDeviceToHost, c->stream));
+    int hArg = -1;
+    OCB_CUDA(c, cudaMemcpyAsync(&hArg, dArg, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (argmax) *argmax = hArg;
+    return OCB_OK;
 }
 
 }  // extern "C"

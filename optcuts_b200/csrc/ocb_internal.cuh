@@ -108,7 +108,8 @@ struct ocb_ctx {
     double* dScal = nullptr;                 // S_COUNT device scalars
     double* hScal = nullptr;                 // pinned mirror
     // scratch for uploads
-    ocb::DevBuf<double> scratchD, scratchV;
+    ocb::DevBuf<double> scratchD, scratchV, stD;
+    ocb::DevBuf<int32_t> stI;
     ocb::DevBuf<int32_t> scratchI;
     int pcgGrid = 0, pcgBlock = 0;
     size_t pcgSmemAttr = 0;
@@ -162,6 +163,12 @@ int launch_permute_scalar(ocb_ctx* c, int n, const double* in, double* out);
 int launch_rest_features(ocb_ctx* c, int nV, int nF, const double* dVrest, const int32_t* dF, double thres, double* dRest8);
 int launch_seam(ocb_ctx* c, int nCoh, const int32_t* dCoh, const double* dLen, const int32_t* dBnd, double thresLen, int triSoup);
 int launch_divgrad(ocb_ctx* c, double* d_out);
+struct StencilHost {     // device pointers of one uploaded stencil batch
+    int nStencil; const int32_t* vertPtr; const int32_t* triPtr; const double* Vrest; const double* UV; const int32_t* F;
+    const uint8_t* isFree; const double* scoreScale; const double* scoreOffset; int maxIter; double relGL2Tol;
+    double* Einit; double* Efinal; double* UVout; int32_t* iters; double* score; int32_t* status; int* argmax;
+};
+int launch_stencils(ocb_ctx* c, const StencilHost& h);
 int launch_spmv(ocb_ctx* c, const double* dx, double* dy);
 int launch_jacobi_setup(ocb_ctx* c);
 int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it);

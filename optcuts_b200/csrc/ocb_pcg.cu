@@ -107,6 +107,17 @@ __device__ __forceinline__ void grid_allreduce(SyncSlot* slots, int nB, unsigned
         if (lane == 0) sm[k][warp] = t;
     }
     __syncthreads();                       // orders every thread's vector stores before the fence below
+    if (nB == 1) {                         // the whole system lives in this CTA: no global traffic at all
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kPcgBlock / 32; ++w) t += sm[k][w];
+            out[k] = t;
+        }
+        __syncthreads();
+        return;
+    }
     SyncSlot* base = slots + (size_t)(epoch & 1ull) * nB;
     if (nB > kPacketMaxCtas) {
         // many CTAs: all-to-all packet polling costs O(nB^2) L2 requests (measured 3-6 us at 148 CTAs); instead
@@ -195,6 +206,8 @@ __device__ __forceinline__ void cluster_allreduce(double (*part)[kSyncVals][kClu
         if (lane == 0) sm[k][warp] = t;
     }
     __syncthreads();
+    // every CTA drops its partial into every peer's buffer (remote stores), then the cluster barrier; reading the
+    // partials remotely AFTER the barrier instead was measured 2x slower (remote shared-memory loads ~2 us here)
     if (warp == 0) {
         const unsigned rank = cluster.block_rank();
 #pragma unroll
@@ -263,7 +276,8 @@ __device__ __forceinline__ Slice carve(unsigned char* base, int nLoc, int W)
 // SMEM-mode SpMV with the fused direction update: one thread per SCALAR row (thread pair = block row), the row's
 // blocks walked serially out of the ELL slice.  ~14 instructions per block and no shuffles: the 16-lanes-per-row
 // mapping of the streaming path below costs ~10x more issue slots, which is what bounds a solve that runs on few SMs.
-__device__ __forceinline__ double spmv_fused_ell(const PcgParams& P, const Slice& S, int rowBeg, int rowEnd, const double* z,
+template <bool DSMEM>
+__device__ __forceinline__ double spmv_fused_ell(const PcgParams& P, const Slice& S, int rowBeg, int rowEnd, int rowsPer, const double* z,
                                                  const double* dOld, double* dNew, double beta,
                                                  const double2* __restrict__ sdOld, double2* __restrict__ sdNew)
 {
@@ -281,6 +295,12 @@ __device__ __forceinline__ double spmv_fused_ell(const PcgParams& P, const Slice
             const double2 a = S.val2[2 * (k * S.nLoc + lr) + half];
             double2 zz, dd;
             if (c >= rowBeg && c < rowEnd) { zz = S.z[c - rowBeg]; dd = sdOld[c - rowBeg]; }     // own range: no global traffic
+            else if (DSMEM) {                      // halo straight out of the owner CTA's shared memory (same cluster)
+                const int owner = c / rowsPer, lc = c - owner * rowsPer;
+                cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+                zz = cluster.map_shared_rank(S.z, owner)[lc];
+                dd = cluster.map_shared_rank(const_cast<double2*>(sdOld), owner)[lc];
+            }
             else { zz = __ldcg(z2 + c); dd = __ldcg(d2 + c); }
             acc += a.x * (zz.x + beta * dd.x) + a.y * (zz.y + beta * dd.y);
         }
@@ -289,13 +309,19 @@ __device__ __forceinline__ double spmv_fused_ell(const PcgParams& P, const Slice
         for (int b = __ldg(P.rowPtr + row) + len; b < gEnd; ++b) {       // rows longer than the slice width (rare)
             const int c = __ldg(P.colIdx + b);
             const double2 a = __ldg(gval2 + 2 * (size_t)b + half);
-            const double2 zz = __ldcg(z2 + c), dd = __ldcg(d2 + c);
+            double2 zz, dd;
+            if (DSMEM) {
+                const int owner = c / rowsPer, lc = c - owner * rowsPer;
+                cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+                zz = cluster.map_shared_rank(S.z, owner)[lc];
+                dd = cluster.map_shared_rank(const_cast<double2*>(sdOld), owner)[lc];
+            } else { zz = __ldcg(z2 + c); dd = __ldcg(d2 + c); }
             acc += a.x * (zz.x + beta * dd.x) + a.y * (zz.y + beta * dd.y);
         }
         const double dn = reinterpret_cast<const double*>(S.z)[2 * lr + half] + beta * reinterpret_cast<const double*>(sdOld)[2 * lr + half];
         reinterpret_cast<double*>(sdNew)[2 * lr + half] = dn;
         reinterpret_cast<double*>(S.Ap)[2 * lr + half] = acc;
-        dNew[2 * (size_t)row + half] = dn;
+        if (!DSMEM) dNew[2 * (size_t)row + half] = dn;          // peers of a cluster read it from shared memory instead
         dotAcc += acc * dn;
     }
     return dotAcc;
@@ -435,7 +461,7 @@ pcg_kernel(PcgParams P)
             double2* sdOld = cur ? S.d[1] : S.d[0];
             double2* sdNew = cur ? S.d[0] : S.d[1];
             double* dOldG = cur ? P.d2 : P.d;
-            double la[1] = {SMEM ? spmv_fused_ell(P, S, rowBeg, rowEnd, P.z, dOldG, dNew, beta, sdOld, sdNew)
+            double la[1] = {SMEM ? spmv_fused_ell<MODE == 2>(P, S, rowBeg, rowEnd, rowsPer, P.z, dOldG, dNew, beta, sdOld, sdNew)
                                  : spmv_fused(P, rowBeg, rowEnd, P.z, dOldG, dNew, beta)}, ra[1];
             if (P.dbg) { __syncthreads(); t1 = clock64(); }
             ALLREDUCE(1, la, ra);
@@ -457,7 +483,7 @@ pcg_kernel(PcgParams P)
                 double2 zz; zz.x = m.x * r2.x + m.y * r2.y; zz.y = m.y * r2.x + m.w * r2.y;
                 if (SMEM) { S.x[lr] = xx; S.r[lr] = r2; S.z[lr] = zz; }
                 else { reinterpret_cast<double2*>(P.x)[row] = xx; reinterpret_cast<double2*>(P.r)[row] = r2; }
-                reinterpret_cast<double2*>(P.z)[row] = zz;
+                if (MODE != 2) reinterpret_cast<double2*>(P.z)[row] = zz;
                 loc[0] += r2.x * zz.x + r2.y * zz.y;
                 loc[1] += r2.x * r2.x + r2.y * r2.y;
             }
@@ -480,6 +506,7 @@ pcg_kernel(PcgParams P)
         __syncthreads();
         for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) reinterpret_cast<double2*>(P.x)[row] = S.x[row - rowBeg];
     }
+    if (MODE == 2) cooperative_groups::this_cluster().sync();      // no CTA may exit while a peer still reads its shared memory
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.scal[S_PCG_ITERS] = (double)it;
         P.scal[S_PCG_RELRES] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
@@ -554,6 +581,11 @@ static PcgPlan pcg_plan(ocb_ctx* c)
         W = ellW;
         return slice_bytes((n + g - 1) / g, ellW);
     };
+    if (allowSmem) {                                           // tiny system: ONE CTA, block-level reductions only
+        int W = 0;
+        const size_t bytes = slice_need(1, W);
+        if (bytes <= limit) { pl.smem = true; pl.maxBlk = W; pl.smemBytes = bytes; pl.grid = 1; return pl; }
+    }
     if (allowSmem && allowCluster && c->clusterOk != 0) {      // one 16-CTA cluster if every slice fits
         int maxBlk = 0;
         const size_t bytes = slice_need(kClusterSize, maxBlk);

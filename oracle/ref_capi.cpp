@@ -261,6 +261,29 @@ void ref_opt_recompute_gradient(void* h) { OptProbe* p = ((OptHandle*)h)->opt; p
 double ref_opt_recompute_energy(void* h) { OptProbe* p = ((OptHandle*)h)->opt; double e; p->computeEnergyVal(p->result, p->scaffold, e); return e; }
 
 
+// ---------------------------------------------------------------- local stencil solve (topology candidates)
+// What TriMesh::computeLocalEdDec_* do after building the local mesh (TriMesh.cpp:2376-2381, 2498-2504, 2771-2781):
+// nested Optimizer(dense = true, mute, no scaffold), setRelGL2Tol(tol), solve(maxIter), energy of the result.
+void ref_mesh_reset_fixed(void* h, int n, const int32_t* fixed) {
+    std::set<int> fx(fixed, fixed + n);
+    ((TriMesh*)h)->resetFixedVert(fx);
+}
+// out: E_init (after precompute), E_final, iterations ; UV_out: nV x 2 col-major
+void ref_local_solve(void* meshH, double relGL2Tol, int maxIter, double* out, double* UV_out) {
+    TriMesh* m = (TriMesh*)meshH;
+    SymDirichletEnergy SD;
+    std::vector<Energy*> terms(1, &SD);
+    std::vector<double> params(1, 1.0);
+    OptProbe opt(*m, terms, params, 0, true, false, Eigen::MatrixXd(), Eigen::MatrixXi(), Eigen::VectorXi(), true);
+    opt.precompute();
+    out[0] = opt.getLastEnergyVal();
+    opt.setRelGL2Tol(relGL2Tol);
+    opt.solve(maxIter);
+    double e; opt.computeEnergyVal(opt.result, opt.scaffold, e, true);
+    out[1] = e; out[2] = opt.getIterNum();
+    std::memcpy(UV_out, opt.getResult().V.data(), sizeof(double) * opt.getResult().V.size());
+}
+
 // ---------------------------------------------------------------- Scaffold (air mesh) from a mesh
 // OptCuts::Scaffold(mesh) — boundary loops + bbox ring + Triangle (Scaffold.cpp:27-208); host-side work
 // of the caller that the parity tests need in order to free-run with bijectivity on.

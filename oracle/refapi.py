@@ -81,6 +81,8 @@ def lib():
         L.ref_scaffold_destroy.restype = None
         L.ref_scaffold_sizes.argtypes = [C.c_void_p, _l]
         L.ref_scaffold_get.argtypes = [C.c_void_p, _d, _i, _i, _d, _d, _i, _d]
+        L.ref_mesh_reset_fixed.argtypes = [C.c_void_p, C.c_int, _i]
+        L.ref_local_solve.argtypes = [C.c_void_p, C.c_double, C.c_int, _d, _d]
         L.ref_timers_get.argtypes = [_d, _d]
         L.ref_set_output_folder.argtypes = [C.c_char_p]
         _lib = L
@@ -190,6 +192,18 @@ class RefMesh:
         out = np.zeros(self.nV)
         lib().ref_sd_divgrad(self.h, _pd(out))
         return out
+
+
+def local_solve(V_rest, F, UV, is_free, relGL2Tol=1e-6, maxIter=100):
+    """The nested dense Optimizer of TriMesh::computeLocalEdDec_* on one local stencil (no air mesh)."""
+    m = RefMesh(V_rest, F, UV)
+    fixed = _i32(np.nonzero(~np.asarray(is_free, bool))[0])
+    lib().ref_mesh_reset_fixed(m.h, len(fixed), _pi(fixed))
+    out = np.zeros(3)
+    UVo = np.zeros((m.nV, 2), order="F")
+    lib().ref_local_solve(m.h, float(relGL2Tol), int(maxIter), _pd(out), _pd(UVo))
+    m.close()
+    return dict(E_init=out[0], E_final=out[1], iters=int(out[2]), UV=UVo)
 
 
 def build_scaffold(mesh):
