@@ -215,6 +215,18 @@ int ocb_eval_stencils(ocb_ctx* ctx, const ocb_stencil_batch* batch, int maxIter,
                       double* E_init, double* E_final, double* UV_out, int32_t* iters, double* score,
                       int32_t* status, int* argmax);
 
+/* ---- a12 (solver set-up): the multilevel additive Schwarz preconditioner that replaces the numeric
+ * factorisation (EigenLibSolver.cpp:80-93) is rebuilt by ocb_factorize; its hierarchy (row order by recursive
+ * coordinate bisection of the UVs, leaves of <= 8 vertices, groups of 8, 6 affine DOFs per node) is built with
+ * the sparsity pattern.  info[0] = 1 if active (0: block-Jacobi only, no UV was known at pattern time),
+ * info[1] = levels L, info[2] = CTA-local levels, info[3] = persistent CTAs, info[4..4+L) = nodes per level. */
+int ocb_precond_info(const ocb_ctx* ctx, int32_t* info16);
+/* Host-only (no CUDA work; unit tests and tools/mas_proto.py): the hierarchy for n free points xy (2 per point)
+ * and `grid` CTAs.  vert_of[n] = point of every solver row; child_beg = the per-level child ranges, level after
+ * level (nodes_l + 1 entries each, `cap` entries available).  Returns the entries written or an error. */
+int ocb_precond_hierarchy(ocb_ctx* ctx, int n, const double* xy, int grid, int32_t* vert_of, int32_t* info16,
+                          int32_t* child_beg, int cap);
+
 #ifdef __cplusplus
 }
 #endif

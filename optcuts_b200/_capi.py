@@ -94,8 +94,36 @@ _SIGS = [
     ("ocb_seam_energy", C.c_int, [C.c_void_p, C.c_int, _i, _d, _i, C.c_double, C.c_double, C.c_double, C.c_int, _d]),
     ("ocb_divgrad_scores", C.c_int, [C.c_void_p, _d]),
     ("ocb_eval_stencils", C.c_int, [C.c_void_p, C.POINTER(StencilBatch), C.c_int, C.c_double, _d, _d, _d, _i, _d, _i, C.POINTER(C.c_int)]),
+    ("ocb_precond_info", C.c_int, [C.c_void_p, _i]),
+    ("ocb_precond_hierarchy", C.c_int, [C.c_void_p, C.c_int, _d, C.c_int, _i, _i, _i, C.c_int]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
+
+
+def precond_hierarchy(xy, grid):
+    """Host-only: row order and multilevel hierarchy the solver would build for points xy (n x 2) and `grid` CTAs.
+    Returns (vert_of, [child_beg per level], local_levels)."""
+    L = load_library()
+    xy = _f64(np.asarray(xy, dtype=np.float64), order="C")
+    n = xy.shape[0]
+    h = C.c_void_p()
+    if L.ocb_create(C.byref(h), 0) != 0:
+        raise OcbError(-1, "ocb_create failed")
+    try:
+        vert_of, info = np.zeros(n, np.int32), np.zeros(16, np.int32)
+        cap = 2 * n + 64 * 16
+        cb = np.zeros(cap, np.int32)
+        w = L.ocb_precond_hierarchy(h, n, _pd(xy), int(grid), _pi(vert_of), _pi(info), _pi(cb), cap)
+        if w < 0:
+            raise OcbError(w, L.ocb_last_error(h).decode())
+        levels, o = [], 0
+        for l in range(int(info[1])):
+            m = int(info[4 + l]) + 1
+            levels.append(cb[o:o + m].copy())
+            o += m
+        return vert_of, levels, int(info[2])
+    finally:
+        L.ocb_destroy(h)
 
 
 def load_library():
@@ -295,6 +323,13 @@ class Context:
     # -- solve
     def factorize(self):
         self._chk(self._L.ocb_factorize(self._h))
+
+    def precond_info(self):
+        """The solver's multilevel preconditioner hierarchy (built with the pattern)."""
+        info = np.zeros(16, np.int32)
+        self._chk(self._L.ocb_precond_info(self._h, _pi(info)))
+        L = int(info[1])
+        return dict(enabled=bool(info[0]), levels=L, local_levels=int(info[2]), grid=int(info[3]), nodes=[int(v) for v in info[4:4 + L]])
 
     def solve(self, rhs=None, rel_tol=1e-12, max_it=0, download=True, allow_not_converged=False):
         rhs = None if rhs is None else _f64(np.asarray(rhs).ravel())

@@ -21,6 +21,7 @@ UNITS = [
     ("ocb_api.cu", []),
     ("ocb_kernels.cu", ["-fmad=false"]),
     ("ocb_pcg.cu", []),
+    ("ocb_mas.cu", []),
     ("ocb_stencils.cu", ["-fmad=false"]),
 ]
 

@@ -215,7 +215,8 @@ void ocb_destroy(ocb_ctx* c)
         c->pr.release(); c->pz.release(); c->pd.release(); c->pd2.release(); c->pAp.release(); c->pb.release(); c->minv.release();
         c->rowPtr.release(); c->colIdx.release(); c->val.release();
         c->partials.release(); c->sync.release(); c->scratchD.release(); c->scratchI.release();
-        c->xSaved.release();
+        c->xSaved.release(); c->px.release(); c->rowOf.release(); c->vertOf.release(); c->userRow.release();
+        c->masD.ints.release(); c->masD.geom.release(); c->masD.val.release(); c->masD.rcCta.release(); c->masD.inv.release(); c->masD.vinfo.release();
         prof_collect(c);
         for (auto e : c->profPool) cudaEventDestroy(e);
         if (c->dScal) cudaFree(c->dScal);
@@ -270,7 +271,7 @@ int ocb_profile_get(ocb_ctx* c, double* ms, int64_t* counts)
 const char* ocb_profile_name(int k)
 {
     static const char* names[K_COUNT] = {"energy", "gradient", "hessian_psd_scatter", "pcg", "step_bound", "step_forward",
-                                         "jacobi_setup", "spmv", "rest_features", "pattern_slots", "misc", "stencil_newton"};
+                                         "jacobi_setup", "spmv", "rest_features", "pattern_slots", "misc", "stencil_newton", "mas_setup"};
     return (k >= 0 && k < K_COUNT) ? names[k] : "";
 }
 int ocb_profile_classes(void) { return K_COUNT; }
@@ -490,15 +491,55 @@ int ocb_gradient(ocb_ctx* c, double p0, double* g_out, double* sqnorm)
 }
 
 // ------------------------------------------------------------------------------------------ pattern
+// The caller-visible pattern (hRowPtr/hColIdx, INTERNAL vertex order) is complete: choose the solver's row order
+// (recursive coordinate bisection of the current UVs when they are known, see ocb_mas.cu), permute the pattern
+// into it and upload; build the preconditioner hierarchy on top.
 static int install_pattern(ocb_ctx* c)
 {
+    static const bool masOff = []() { const char* e = getenv("OCB_NO_MAS"); return e && atoi(e); }();
+    const int n = c->nVtot;
     c->nnzb = (int)c->hColIdx.size();
-    OCB_CUDA(c, c->rowPtr.reserve((size_t)c->nVtot + 1, c->stream));
+    c->planGrid = pcg_plan_grid(c, n);
+    c->masH = MasHost();
+    if (!masOff && c->haveUV && c->nV > 0 && c->x.p && n >= 2 * kMasLeaf) {
+        std::vector<double> xy(2 * (size_t)n);
+        OCB_CUDA(c, cudaMemcpyAsync(xy.data(), c->x.p, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+        OCB_TRY(mas_build_hierarchy(c, xy.data(), c->planGrid));
+    } else {
+        c->hRowOf.resize((size_t)n); c->hVertOf.resize((size_t)n);
+        for (int v = 0; v < n; ++v) c->hRowOf[v] = c->hVertOf[v] = v;
+    }
+    c->hSRowPtr.assign((size_t)n + 1, 0);
+    c->hSColIdx.resize((size_t)c->nnzb);
+    c->hBlkMap.resize((size_t)c->nnzb);
+    {
+        std::vector<std::pair<int32_t, int32_t>> row;
+        int w = 0;
+        for (int r = 0; r < n; ++r) {
+            const int v = c->hVertOf[r];
+            row.clear();
+            for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) row.push_back(std::make_pair(c->hRowOf[c->hColIdx[b]], (int32_t)b));
+            std::sort(row.begin(), row.end());
+            for (const auto& cb : row) { c->hSColIdx[w] = cb.first; c->hBlkMap[cb.second] = w; ++w; }
+            c->hSRowPtr[r + 1] = w;
+        }
+    }
+    OCB_CUDA(c, c->rowPtr.reserve((size_t)n + 1, c->stream));
     OCB_CUDA(c, c->colIdx.reserve((size_t)c->nnzb + 1, c->stream));
     OCB_CUDA(c, c->val.reserve(4 * (size_t)c->nnzb + 4, c->stream));
-    OCB_TRY(upload_i(c, c->rowPtr.p, c->hRowPtr.data(), (size_t)c->nVtot + 1));
-    OCB_TRY(upload_i(c, c->colIdx.p, c->hColIdx.data(), (size_t)c->nnzb));
-    OCB_TRY(upload_fixed_mask(c));
+    OCB_CUDA(c, c->rowOf.reserve((size_t)n + 1, c->stream));
+    OCB_CUDA(c, c->vertOf.reserve((size_t)n + 1, c->stream));
+    OCB_CUDA(c, c->userRow.reserve((size_t)n + 1, c->stream));
+    OCB_TRY(upload_i(c, c->rowPtr.p, c->hSRowPtr.data(), (size_t)n + 1));
+    OCB_TRY(upload_i(c, c->colIdx.p, c->hSColIdx.data(), (size_t)c->nnzb));
+    OCB_TRY(upload_i(c, c->rowOf.p, c->hRowOf.data(), (size_t)n));
+    OCB_TRY(upload_i(c, c->vertOf.p, c->hVertOf.data(), (size_t)n));
+    std::vector<int32_t> userRow((size_t)n);
+    for (int u = 0; u < n; ++u) userRow[u] = c->hRowOf[c->hPerm[u]];
+    OCB_TRY(upload_i(c, c->userRow.p, userRow.data(), (size_t)n));
+    OCB_TRY(upload_fixed_mask(c));                    // synchronises the stream: the staging vectors may go
+    OCB_TRY(mas_install(c));
     c->patternValid = true; c->matrixValid = c->precondValid = false;
     return launch_build_slots(c);
 }
@@ -699,14 +740,14 @@ int ocb_download_csr(ocb_ctx* c, int32_t* ia, int32_t* ja, double* a)
         if (c->hFixed[vi]) {
             int bdiag = -1;
             for (int b = c->hRowPtr[vi]; b < c->hRowPtr[vi + 1]; ++b) if (c->hColIdx[b] == vi) bdiag = b;
-            ja[w] = 2 * v + 1; a[w] = val[4 * (size_t)bdiag]; ++w; ia[2 * v + 1] = (int32_t)(w + 1);
-            ja[w] = 2 * v + 2; a[w] = val[4 * (size_t)bdiag + 3]; ++w; ia[2 * v + 2] = (int32_t)(w + 1);
+            ja[w] = 2 * v + 1; a[w] = val[4 * (size_t)c->hBlkMap[bdiag]]; ++w; ia[2 * v + 1] = (int32_t)(w + 1);
+            ja[w] = 2 * v + 2; a[w] = val[4 * (size_t)c->hBlkMap[bdiag] + 3]; ++w; ia[2 * v + 2] = (int32_t)(w + 1);
             continue;
         }
         row.clear();
         for (int b = c->hRowPtr[vi]; b < c->hRowPtr[vi + 1]; ++b) {
             const int col = c->hInv[c->hColIdx[b]];
-            if (col >= v) row.push_back(std::make_pair((int32_t)col, (int32_t)b));
+            if (col >= v) row.push_back(std::make_pair((int32_t)col, c->hBlkMap[b]));
         }
         std::sort(row.begin(), row.end());
         for (int r = 0; r < 2; ++r) {
@@ -727,10 +768,12 @@ int ocb_multiply(ocb_ctx* c, const double* x, double* y)
     if (!c || !x || !y) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_multiply: no matrix"));
     const size_t n = c->nSys();
-    OCB_CUDA(c, c->scratchD.reserve(2 * n, c->stream));
+    OCB_CUDA(c, c->scratchD.reserve(3 * n, c->stream));
     OCB_TRY(vec_to_device(c, c->scratchD.p, x));
-    OCB_TRY(launch_spmv(c, c->scratchD.p, c->scratchD.p + n));
-    OCB_TRY(vec_to_host(c, y, c->scratchD.p + n));
+    OCB_TRY(launch_gather_rows(c, c->scratchD.p, c->scratchD.p + n, true));
+    OCB_TRY(launch_spmv(c, c->scratchD.p + n, c->scratchD.p + 2 * n));
+    OCB_TRY(launch_gather_rows(c, c->scratchD.p + 2 * n, c->scratchD.p, false));
+    OCB_TRY(vec_to_host(c, y, c->scratchD.p));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     return OCB_OK;
 }
@@ -741,6 +784,7 @@ int ocb_factorize(ocb_ctx* c)
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_factorize: no matrix"));
     OCB_TRY(launch_jacobi_setup(c));
+    OCB_TRY(launch_mas_setup(c));
     c->precondValid = true;
     return OCB_OK;
 }
@@ -785,6 +829,38 @@ int ocb_set_search_dir(ocb_ctx* c, const double* p)
     OCB_TRY(vec_to_device(c, c->p.p, p));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     return OCB_OK;
+}
+
+static void fill_precond_info(const MasHost& H, int32_t* info)
+{
+    for (int i = 0; i < 16; ++i) info[i] = 0;
+    info[0] = H.enabled ? 1 : 0; info[1] = H.L; info[2] = H.Lloc; info[3] = H.grid;
+    for (int l = 1; l <= H.L && l <= 12; ++l) info[3 + l] = (int32_t)H.lv[l - 1].childBeg.size() - 1;
+}
+int ocb_precond_info(const ocb_ctx* c, int32_t* info)
+{
+    if (!c || !info) return OCB_ERR_ARG;
+    fill_precond_info(c->masH, info);
+    return OCB_OK;
+}
+int ocb_precond_hierarchy(ocb_ctx* c, int n, const double* xy, int grid, int32_t* vert_of, int32_t* info, int32_t* child_beg, int cap)
+{
+    if (!c || n <= 0 || !xy || !vert_of || !info || !child_beg) return set_err(c, OCB_ERR_ARG, "ocb_precond_hierarchy: bad argument");
+    if (c->inited) return set_err(c, OCB_ERR_STATE, "ocb_precond_hierarchy needs a fresh context (it overwrites the system size)");
+    c->nVtot = n;
+    c->hFixed.assign((size_t)n, 0);
+    OCB_TRY(mas_build_hierarchy(c, xy, grid));
+    fill_precond_info(c->masH, info);
+    std::memcpy(vert_of, c->hVertOf.data(), sizeof(int32_t) * (size_t)n);
+    int w = 0;
+    for (int l = 1; l <= c->masH.L; ++l) {
+        const std::vector<int32_t>& cb = c->masH.lv[l - 1].childBeg;
+        if (w + (int)cb.size() > cap) return set_err(c, OCB_ERR_ARG, "ocb_precond_hierarchy: child_beg too small");
+        std::memcpy(child_beg + w, cb.data(), sizeof(int32_t) * cb.size());
+        w += (int)cb.size();
+    }
+    c->nVtot = 0; c->masH = MasHost(); c->hFixed.clear();
+    return w;
 }
 
 // ------------------------------------------------------------------------------- step bound / search

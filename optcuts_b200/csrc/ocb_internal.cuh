@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include "../../include/optcuts_b200.h"
+#include "ocb_mas.cuh"
 
 namespace ocb {
 
@@ -58,12 +59,31 @@ struct ElemView {
 // kernel classes for the optional per-kernel CUDA-event profile (ocb_profile_*)
 enum KernelClass {
     K_ENERGY = 0, K_GRADIENT, K_HESSIAN, K_PCG, K_STEP_BOUND, K_STEP_FORWARD, K_JACOBI_SETUP, K_SPMV,
-    K_FEATURES, K_PATTERN, K_MISC, K_STENCILS, K_COUNT
+    K_FEATURES, K_PATTERN, K_MISC, K_STENCILS, K_MAS_SETUP, K_COUNT
 };
 
 enum ScalarSlot {            // layout of the device/pinned scalar block
     S_E_MESH = 0, S_E_AIR, S_N_INVERTED, S_SQN_G, S_STEP_BOUND, S_PCG_ITERS, S_PCG_RELRES,
     S_PCG_STATUS, S_PCG_BNORM, S_MISC0, S_MISC1, S_MISC2, S_COUNT = 16
+};
+
+// MAS preconditioner: host-side hierarchy (built at pattern time) and its device mirror (ocb_mas.cu)
+struct MasHost {
+    bool enabled = false;
+    int L = 0, Lloc = 0, grid = 0, topNodes = 0, maxLocalNodes = 0;
+    struct Level {
+        std::vector<int32_t> childBeg, parent, ctaBeg;   // see MasLevel
+        std::vector<double> geom;                        // 4 per node
+        std::vector<int32_t> rowPtr, colIdx;             // node adjacency (pattern of the Galerkin matrix A_l, 6x6 blocks)
+    };
+    std::vector<Level> lv;
+    std::vector<float> vinfo;                            // 4 per row
+};
+struct MasDev {
+    DevBuf<int32_t> ints; DevBuf<double> geom, val, rcCta; DevBuf<float> inv, vinfo;
+    std::vector<const int32_t*> lvRowPtr, lvColIdx; std::vector<double*> lvVal; std::vector<int> lvNnz;
+    size_t valTotal = 0; int groupTotal = 0;
+    MasView view = {};
 };
 
 }  // namespace ocb
@@ -96,10 +116,18 @@ struct ocb_ctx {
     // state vectors, all nSys doubles (interleaved u,v per global vertex)
     ocb::DevBuf<double> x, x0, g, p;
     // PCG work vectors
-    ocb::DevBuf<double> pr, pz, pd, pd2, pAp, pb, minv;   // minv: 4 per block row
+    ocb::DevBuf<double> pr, pz, pd, pd2, pAp, pb, px, minv;   // minv: 4 per block row; px: x in solver order
     // BSR(2x2), full symmetric storage
     int nnzb = 0;
-    std::vector<int32_t> hRowPtr, hColIdx;
+    std::vector<int32_t> hRowPtr, hColIdx;   // pattern in INTERNAL vertex order (host only: download_csr, nnz)
+    // the solver's own row order (recursive coordinate bisection, ocb_mas.cu): the device BSR, the PCG vectors and
+    // the preconditioner live in it; identity when no UV was known at pattern time
+    std::vector<int32_t> hRowOf, hVertOf;    // internal vertex -> solver row and back
+    std::vector<int32_t> hSRowPtr, hSColIdx; // the device pattern (solver order)
+    std::vector<int32_t> hBlkMap;            // internal-order block -> device block
+    ocb::DevBuf<int32_t> rowOf, vertOf, userRow;   // device: internal vertex -> row, row -> internal vertex, caller vertex -> row
+    ocb::MasHost masH; ocb::MasDev masD;
+    int planGrid = 0;                        // persistent-CTA count the hierarchy was built for
     ocb::DevBuf<int32_t> rowPtr, colIdx;
     ocb::DevBuf<double> val;                 // 4 per block, row-major
     // reductions
@@ -172,5 +200,10 @@ int launch_stencils(ocb_ctx* c, const StencilHost& h);
 int launch_spmv(ocb_ctx* c, const double* dx, double* dy);
 int launch_jacobi_setup(ocb_ctx* c);
 int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it);
+int pcg_plan_grid(ocb_ctx* c, int nRows);            // CTA count launch_pcg will use for this system size
+int mas_build_hierarchy(ocb_ctx* c, const double* xy, int grid);
+int mas_install(ocb_ctx* c);
+int launch_mas_setup(ocb_ctx* c);
+int launch_gather_rows(ocb_ctx* c, const double* in_internal, double* out_rows, bool toRows);
 
 }  // namespace ocb

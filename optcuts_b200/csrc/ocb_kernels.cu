@@ -173,18 +173,20 @@ sqnorm_kernel(const double* __restrict__ v, int n, double* __restrict__ partials
 __global__ void __launch_bounds__(kBlock)
 build_slots_kernel(int n, const int32_t* __restrict__ v0, const int32_t* __restrict__ v1, const int32_t* __restrict__ v2,
                    const uint8_t* __restrict__ fixedMask, const int32_t* __restrict__ rowPtr,
-                   const int32_t* __restrict__ colIdx, int32_t* __restrict__ slot, int* __restrict__ missing)
+                   const int32_t* __restrict__ colIdx, int32_t* __restrict__ slot, int* __restrict__ missing,
+                   const int32_t* __restrict__ rowOf)
 {
     for (int t = blockIdx.x * kBlock + threadIdx.x; t < n; t += gridDim.x * kBlock) {
         const int idx[3] = {v0[t], v1[t], v2[t]};
+        const int rw[3] = {rowOf[idx[0]], rowOf[idx[1]], rowOf[idx[2]]};     // the BSR lives in the solver's row order
 #pragma unroll
         for (int k = 0; k < 3; ++k)
 #pragma unroll
             for (int l = 0; l < 3; ++l) {
                 int s = -1;
                 if (!fixedMask[idx[k]] && !fixedMask[idx[l]]) {
-                    int lo = rowPtr[idx[k]], hi = rowPtr[idx[k] + 1] - 1;
-                    const int col = idx[l];
+                    int lo = rowPtr[rw[k]], hi = rowPtr[rw[k] + 1] - 1;
+                    const int col = rw[l];
                     while (lo <= hi) {
                         const int mid = (lo + hi) >> 1;
                         const int cm = colIdx[mid];
@@ -201,7 +203,8 @@ build_slots_kernel(int n, const int32_t* __restrict__ v0, const int32_t* __restr
 // identity blocks for fixed vertices (IglUtils::addDiagonalToMatrix path, SymDirichletEnergy.cpp:541-548)
 __global__ void __launch_bounds__(kBlock)
 fixed_identity_kernel(int nVtot, const uint8_t* __restrict__ fixedMask, const int32_t* __restrict__ rowPtr,
-                      const int32_t* __restrict__ colIdx, double* __restrict__ val, double scaleMesh, double scaleAir)
+                      const int32_t* __restrict__ colIdx, double* __restrict__ val, double scaleMesh, double scaleAir,
+                      const int32_t* __restrict__ rowOf)
 {
     // the identity triplets are scaled like every other triplet of their term: energyParams[e] for the mesh
     // term (Optimizer.cpp:821-832), w_scaf/|Fa| for the air mesh (Scaffold.cpp:231-248).  mask bit 0 = fixed
@@ -210,8 +213,9 @@ fixed_identity_kernel(int nVtot, const uint8_t* __restrict__ fixedMask, const in
         const unsigned m = fixedMask[v];
         if (!m) continue;
         const double dgn = ((m & 1u) ? scaleMesh : 0.0) + ((m & 2u) ? scaleAir : 0.0);
-        for (int b = rowPtr[v]; b < rowPtr[v + 1]; ++b)
-            if (colIdx[b] == v) { val[4 * (size_t)b] = dgn; val[4 * (size_t)b + 1] = 0.0; val[4 * (size_t)b + 2] = 0.0; val[4 * (size_t)b + 3] = dgn; }
+        const int r = rowOf[v];
+        for (int b = rowPtr[r]; b < rowPtr[r + 1]; ++b)
+            if (colIdx[b] == r) { val[4 * (size_t)b] = dgn; val[4 * (size_t)b + 1] = 0.0; val[4 * (size_t)b + 2] = 0.0; val[4 * (size_t)b + 3] = dgn; }
     }
 }
 
@@ -529,7 +533,7 @@ int launch_build_slots(ocb_ctx* c)
         if (S.n == 0) continue;
         OCB_CUDA(c, S.slot.reserve((size_t)9 * S.n, c->stream));
         build_slots_kernel<<<grid_for(c, S.n), kBlock, 0, c->stream>>>(S.n, S.v.p, S.v.p + S.n, S.v.p + 2 * (size_t)S.n,
-                                                                      c->fixedMask.p, c->rowPtr.p, c->colIdx.p, S.slot.p, missing);
+                                                                      c->fixedMask.p, c->rowPtr.p, c->colIdx.p, S.slot.p, missing, c->rowOf.p);
         KCHECK(c);
     }
     int hMissing = 0;
@@ -545,7 +549,7 @@ int launch_hessian(ocb_ctx* c, double p0)
     ProfScope prof(c, K_HESSIAN);
     const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
     OCB_CUDA(c, cudaMemsetAsync(c->val.p, 0, sizeof(double) * 4 * (size_t)c->nnzb, c->stream));
-    fixed_identity_kernel<<<grid_for(c, c->nVtot, 4), kBlock, 0, c->stream>>>(c->nVtot, c->fixedMask.p, c->rowPtr.p, c->colIdx.p, c->val.p, p0, c->wScafOverFa);
+    fixed_identity_kernel<<<grid_for(c, c->nVtot, 4), kBlock, 0, c->stream>>>(c->nVtot, c->fixedMask.p, c->rowPtr.p, c->colIdx.p, c->val.p, p0, c->wScafOverFa, c->rowOf.p);
     KCHECK(c);
     hessian_kernel<true><<<grid_for(c, (long)M.n + A.n), kBlock, 0, c->stream>>>(M, A, c->x.p, c->val.p, nullptr);
     KCHECK(c);
@@ -588,7 +592,7 @@ int launch_triplet_scatter(ocb_ctx* c, int64_t nT, const int32_t* dI, const int3
     OCB_CUDA(c, cudaMemsetAsync(missing, 0, sizeof(int), c->stream));
     OCB_CUDA(c, cudaMemsetAsync(c->val.p, 0, sizeof(double) * 4 * (size_t)c->nnzb, c->stream));
     if (nT > 0) {
-        triplet_scatter_kernel<<<grid_for(c, nT), kBlock, 0, c->stream>>>((long)nT, dI, dJ, dS, c->rowPtr.p, c->colIdx.p, c->val.p, missing, c->perm.p);
+        triplet_scatter_kernel<<<grid_for(c, nT), kBlock, 0, c->stream>>>((long)nT, dI, dJ, dS, c->rowPtr.p, c->colIdx.p, c->val.p, missing, c->userRow.p);
         KCHECK(c);
     }
     int hMissing = 0;

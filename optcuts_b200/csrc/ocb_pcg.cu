@@ -13,6 +13,7 @@
 // HBM bytes per CG iteration and block row (7 blocks on average): 7*(32+4) matrix + 4 rowPtr +
 // vectors (d, Ap, x, r, z, minv) 144+48 = ~480 B  -> ~228 B per mesh face.
 #include "ocb_internal.cuh"
+#include "ocb_mas.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cstdlib>
@@ -31,6 +32,10 @@ struct PcgParams {
     double relTol; int maxIt;
     int maxBlkPerCta;          // SMEM mode: capacity of the per-CTA block arrays
     long long* dbg;            // optional: per-phase clock64 totals of CTA 0 (OCB_PCG_DEBUG=1)
+    const int32_t* vertOf;     // solver row -> internal vertex (rhs gather / result scatter); nullptr = identity
+    double* xOut;              // result in INTERNAL vertex order (x is the working copy in solver order)
+    size_t masSmemOff;         // byte offset of the MAS scratch in dynamic shared memory
+    MasView mas;               // mas.L == 0: block-Jacobi only
 };
 
 // y[rows of this CTA] = A * v ; returns this thread's share of v . y.
@@ -424,11 +429,35 @@ pcg_kernel(PcgParams P)
         }
     }
 
+    const bool MAS = P.mas.L > 0;
+    MasSmem MS = {};
+    if (MAS) { MS = mas_carve(smemRaw + P.masSmemOff, P.mas); mas_init(P.mas, MS, blockIdx.x); }
+    auto getR = [&](int lr) -> double2 { return SMEM ? S.r[lr] : reinterpret_cast<const double2*>(P.r)[rowBeg + lr]; };
+    // z = z0 (block-Jacobi part, already stored) + coarse correction of the row's leaf; returns this thread's share of r.z
+    auto mas_finish = [&]() -> double {
+        double acc = 0.0;
+        const int leaf0 = P.mas.lv[0].ctaBeg[blockIdx.x];
+        for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
+            const int lr = row - rowBeg;
+            const float4 vi = __ldg(P.mas.vinfo + row);
+            const double* e = MS.e + (size_t)(MS.off[0] + (__float_as_int(vi.w) - leaf0)) * kMasDof;
+            double2 zz = SMEM ? S.z[lr] : reinterpret_cast<const double2*>(P.z)[row];
+            const double2 r2 = getR(lr);
+            zz.x += (double)vi.x * e[0] + (double)vi.y * e[1] + (double)vi.z * e[2];
+            zz.y += (double)vi.x * e[3] + (double)vi.y * e[4] + (double)vi.z * e[5];
+            if (SMEM) S.z[lr] = zz;
+            if (MODE != 2) reinterpret_cast<double2*>(P.z)[row] = zz;
+            acc += r2.x * zz.x + r2.y * zz.y;
+        }
+        return acc;
+    };
+
     // ---- init: x = 0, r = b, z = Minv r, d = 0 ; rz = r.z, bb = b.b
     double loc[2] = {0.0, 0.0}, red[2];
     for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
-        const double b0 = P.negate ? -P.rhs[2 * row] : P.rhs[2 * row];
-        const double b1 = P.negate ? -P.rhs[2 * row + 1] : P.rhs[2 * row + 1];
+        const size_t src = P.vertOf ? (size_t)P.vertOf[row] : (size_t)row;
+        const double b0 = P.negate ? -P.rhs[2 * src] : P.rhs[2 * src];
+        const double b1 = P.negate ? -P.rhs[2 * src + 1] : P.rhs[2 * src + 1];
         const double4 m = reinterpret_cast<const double4*>(P.minv)[row];
         double2 zz; zz.x = m.x * b0 + m.y * b1; zz.y = m.y * b0 + m.w * b1;
         if (SMEM) {
@@ -446,9 +475,16 @@ pcg_kernel(PcgParams P)
         loc[0] += b0 * zz.x + b1 * zz.y;
         loc[1] += b0 * b0 + b1 * b1;
     }
+    if (MAS) { __syncthreads(); mas_up(P.mas, MS, blockIdx.x, rowBeg, getR); }
     ALLREDUCE(2, loc, red);
     double rz = red[0];
     const double bb = red[1];
+    if (MAS && bb > 0.0) {
+        mas_down(P.mas, MS, blockIdx.x);
+        double lz[1] = {mas_finish()}, rzv[1];
+        ALLREDUCE(1, lz, rzv);
+        rz = rzv[0];
+    }
     const double tol2 = P.relTol * P.relTol * bb;
     double rr = bb, beta = 0.0;
     int it = 0, status = 0, cur = 0;
@@ -483,29 +519,38 @@ pcg_kernel(PcgParams P)
                 double2 zz; zz.x = m.x * r2.x + m.y * r2.y; zz.y = m.y * r2.x + m.w * r2.y;
                 if (SMEM) { S.x[lr] = xx; S.r[lr] = r2; S.z[lr] = zz; }
                 else { reinterpret_cast<double2*>(P.x)[row] = xx; reinterpret_cast<double2*>(P.r)[row] = r2; }
-                if (MODE != 2) reinterpret_cast<double2*>(P.z)[row] = zz;
+                if (MAS ? !SMEM : MODE != 2) reinterpret_cast<double2*>(P.z)[row] = zz;
                 loc[0] += r2.x * zz.x + r2.y * zz.y;
                 loc[1] += r2.x * r2.x + r2.y * r2.y;
             }
+            if (MAS) { __syncthreads(); mas_up(P.mas, MS, blockIdx.x, rowBeg, getR); }
             if (P.dbg) { __syncthreads(); t3 = clock64(); }
             ALLREDUCE(2, loc, red);
-            if (P.dbg && threadIdx.x == 0 && blockIdx.x == 0) {
-                P.dbg[0] += t1 - t0; P.dbg[1] += t2 - t1; P.dbg[2] += t3 - t2; P.dbg[3] += clock64() - t3; P.dbg[4] += 1;
-            }
-            const double rzNew = red[0];
+            double rzNew = red[0];
             rr = red[1];
             ++it;
             cur ^= 1;
             if (rr <= tol2) { status = 0; break; }
             if (it >= P.maxIt) { status = 1; break; }
+            if (MAS) {
+                mas_down(P.mas, MS, blockIdx.x);
+                double lz[1] = {mas_finish()}, rzv[1];
+                ALLREDUCE(1, lz, rzv);
+                rzNew = rzv[0];
+            }
+            if (P.dbg && threadIdx.x == 0 && blockIdx.x == 0) {
+                P.dbg[0] += t1 - t0; P.dbg[1] += t2 - t1; P.dbg[2] += t3 - t2; P.dbg[3] += clock64() - t3; P.dbg[4] += 1;
+            }
             beta = rzNew / rz;
             rz = rzNew;
         }
     }
-    if (SMEM) {
-        __syncthreads();
-        for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) reinterpret_cast<double2*>(P.x)[row] = S.x[row - rowBeg];
+    __syncthreads();
+    for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
+        const size_t dst = P.vertOf ? (size_t)P.vertOf[row] : (size_t)row;
+        reinterpret_cast<double2*>(P.xOut)[dst] = (bb > 0.0) ? (SMEM ? S.x[row - rowBeg] : reinterpret_cast<const double2*>(P.x)[row]) : make_double2(0.0, 0.0);
     }
+
     if (MODE == 2) cooperative_groups::this_cluster().sync();      // no CTA may exit while a peer still reads its shared memory
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.scal[S_PCG_ITERS] = (double)it;
@@ -548,7 +593,8 @@ static PcgParams make_params(ocb_ctx* c)
 {
     PcgParams P;
     P.nRows = c->nVtot; P.rowPtr = c->rowPtr.p; P.colIdx = c->colIdx.p; P.val = c->val.p; P.minv = c->minv.p;
-    P.rhs = nullptr; P.negate = 0; P.x = c->p.p; P.r = c->pr.p; P.z = c->pz.p; P.d = c->pd.p; P.d2 = c->pd2.p; P.Ap = c->pAp.p;
+    P.rhs = nullptr; P.negate = 0; P.x = c->px.p; P.xOut = c->p.p; P.vertOf = nullptr; P.masSmemOff = 0; P.mas = MasView(); P.mas.L = 0;
+    P.r = c->pr.p; P.z = c->pz.p; P.d = c->pd.p; P.d2 = c->pd2.p; P.Ap = c->pAp.p;
     P.partials = c->partials.p; P.scal = c->dScal; P.relTol = 1e-12; P.maxIt = 1; P.maxBlkPerCta = 0; P.dbg = nullptr;
     return P;
 }
@@ -566,11 +612,20 @@ static int spmv_grid(ocb_ctx* c)
 // all-reduce costs ~0.9 us at 16 CTAs and ~3 us at 148) with the slice resident in shared memory;
 // large systems: one CTA per SM, slice streamed from L2/HBM.
 struct PcgPlan { int grid; bool smem; bool cluster; int maxBlk; size_t smemBytes; };
+// upper bound of the MAS scratch of one CTA (the hierarchy is built after the plan)
+static size_t mas_smem_estimate(int rowsPer, int grid)
+{
+    int local = 0, k = (rowsPer + kMasLeaf - 1) / kMasLeaf;
+    for (;;) { local += k; if (k <= 1) break; k = (k + kMasGroup - 1) / kMasGroup; }
+    int top = 0; k = grid;
+    for (;;) { top += k; if (k <= kMasGroup) break; k = (k + kMasGroup - 1) / kMasGroup; }
+    return mas_smem_bytes(local + kMasMaxLevels, top) + 64;
+}
 static PcgPlan pcg_plan(ocb_ctx* c)
 {
     static const int targetRows = []() { const char* e = getenv("OCB_PCG_ROWS_PER_CTA"); int v = e ? atoi(e) : 256; return v < 32 ? 32 : v; }();
     static const bool allowSmem = []() { const char* e = getenv("OCB_PCG_NO_SMEM"); return !(e && atoi(e)); }();
-    const size_t limit = 200 * 1024;
+    const size_t limit = 216 * 1024;
     static const bool allowCluster = []() { const char* e = getenv("OCB_PCG_NO_CLUSTER"); return !(e && atoi(e)); }();
     PcgPlan pl; pl.smem = false; pl.cluster = false; pl.maxBlk = 0; pl.smemBytes = 0;
     const int n = c->nVtot;
@@ -579,7 +634,7 @@ static PcgPlan pcg_plan(ocb_ctx* c)
     const int ellW = std::min(maxLen, 12);                  // longer rows (valence > 11) continue in the global BSR
     auto slice_need = [&](int g, int& W) {
         W = ellW;
-        return slice_bytes((n + g - 1) / g, ellW);
+        return slice_bytes((n + g - 1) / g, ellW) + mas_smem_estimate((n + g - 1) / g, g);
     };
     if (allowSmem) {                                           // tiny system: ONE CTA, block-level reductions only
         int W = 0;
@@ -591,7 +646,7 @@ static PcgPlan pcg_plan(ocb_ctx* c)
         const size_t bytes = slice_need(kClusterSize, maxBlk);
         if (bytes <= limit) {
             if (c->clusterOk < 0) {                           // probe once: can such a cluster be scheduled?
-                cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+                cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
                 cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(kClusterSize); cfg.blockDim = dim3(kPcgBlock); cfg.dynamicSmemBytes = limit;
@@ -619,6 +674,29 @@ static PcgPlan pcg_plan(ocb_ctx* c)
     if (!pl.smem) g = c->numSMs;
     pl.grid = g;
     return pl;
+}
+
+int pcg_plan_grid(ocb_ctx* c, int nRows)
+{
+    (void)nRows;
+    return pcg_plan(c).grid;
+}
+
+// system vector between INTERNAL vertex order and solver row order
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(int nRows, const int32_t* __restrict__ vertOf, const double2* __restrict__ in, double2* __restrict__ out, int toRows)
+{
+    for (int r = blockIdx.x * 256 + threadIdx.x; r < nRows; r += gridDim.x * 256) {
+        const int v = vertOf ? vertOf[r] : r;
+        if (toRows) out[r] = in[v]; else out[v] = in[r];
+    }
+}
+int launch_gather_rows(ocb_ctx* c, const double* in, double* out, bool toRows)
+{
+    int grid = (c->nVtot + 255) / 256; if (grid > c->numSMs * 8) grid = c->numSMs * 8; if (grid < 1) grid = 1;
+    gather_rows_kernel<<<grid, 256, 0, c->stream>>>(c->nVtot, c->vertOf.p, reinterpret_cast<const double2*>(in), reinterpret_cast<double2*>(out), toRows ? 1 : 0);
+    KCHECK(c);
+    return 0;
 }
 
 int launch_spmv(ocb_ctx* c, const double* dx, double* dy)
@@ -656,32 +734,45 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     OCB_CUDA(c, c->pd.reserve(n, c->stream)); OCB_CUDA(c, c->pAp.reserve(n, c->stream));
     OCB_CUDA(c, c->pd2.reserve(n, c->stream));
     OCB_CUDA(c, c->p.reserve(n, c->stream));
+    OCB_CUDA(c, c->px.reserve(n, c->stream));
     const PcgPlan pl = pcg_plan(c);
     const int grid = pl.grid;
     const size_t slotDoubles = 2 * (size_t)grid * (sizeof(SyncSlot) / sizeof(double));
     OCB_CUDA(c, c->partials.reserve(slotDoubles + 64, c->stream));
     PcgParams P = make_params(c);
     P.rhs = d_rhs; P.negate = negate_rhs ? 1 : 0; P.relTol = rel_tol; P.maxIt = max_it; P.maxBlkPerCta = pl.maxBlk;
+    P.vertOf = c->vertOf.p;
+    size_t smemBytes = pl.smem ? pl.smemBytes - mas_smem_estimate((c->nVtot + grid - 1) / grid, grid) : 0;     // the slice alone
+    smemBytes = (smemBytes + 15) / 16 * 16;
+    if (c->masH.enabled && c->masH.grid == grid && c->masD.view.L > 0) {
+        P.mas = c->masD.view;
+        P.masSmemOff = smemBytes;
+        smemBytes += mas_smem_bytes(P.mas.maxLocalNodes, P.mas.topNodes);
+    }
+    const size_t smemCap = 224 * 1024;
+    if (smemBytes > smemCap) return set_err(c, OCB_ERR_STATE, "PCG: shared-memory plan exceeds the SM capacity");
     OCB_CUDA(c, cudaMemsetAsync(c->partials.p, 0, slotDoubles * sizeof(double), c->stream));
     static const bool dbgOn = []() { const char* e = getenv("OCB_PCG_DEBUG"); return e && atoi(e); }();
     long long* dDbg = nullptr;
     if (dbgOn) { cudaMalloc((void**)&dDbg, 8 * sizeof(long long)); cudaMemset(dDbg, 0, 8 * sizeof(long long)); P.dbg = dDbg; }
     void* args[] = {&P};
+    if (!c->pcgSmemAttr) {
+        OCB_CUDA(c, cudaFuncSetAttribute(pcg_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemCap));
+        OCB_CUDA(c, cudaFuncSetAttribute(pcg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemCap));
+        OCB_CUDA(c, cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemCap));
+        c->pcgSmemAttr = smemCap;
+    }
     if (pl.cluster) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPcgBlock); cfg.dynamicSmemBytes = pl.smemBytes; cfg.stream = c->stream;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPcgBlock); cfg.dynamicSmemBytes = smemBytes; cfg.stream = c->stream;
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         OCB_CUDA(c, cudaLaunchKernelEx(&cfg, pcg_kernel<2>, P));
     } else if (pl.smem) {
-        if (pl.smemBytes > c->pcgSmemAttr) {
-            OCB_CUDA(c, cudaFuncSetAttribute(pcg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-            c->pcgSmemAttr = 200 * 1024;
-        }
-        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel<1>, dim3(grid), dim3(kPcgBlock), args, pl.smemBytes, c->stream));
+        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel<1>, dim3(grid), dim3(kPcgBlock), args, smemBytes, c->stream));
     } else {
-        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel<0>, dim3(grid), dim3(kPcgBlock), args, 0, c->stream));
+        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)pcg_kernel<0>, dim3(grid), dim3(kPcgBlock), args, smemBytes, c->stream));
     }
     c->launches++;
     if (dbgOn) {
