@@ -3,6 +3,7 @@
 // plugins (Optimizer.cpp:154-201, 203-261, 505-704, 764-843); every entry point cites its
 // reference counterpart in the header.
 #include "ocb_internal.cuh"
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <new>
@@ -51,6 +52,25 @@ static void prof_collect(ocb_ctx* c)
         c->profPool.push_back(r.a); c->profPool.push_back(r.b);
     }
     c->profRecs.clear();
+}
+
+static bool host_timing_on() { static const bool on = []() { const char* e = getenv("OCB_HOST_TIMING"); return e && atoi(e); }(); return on; }
+struct HostTimingRec { const char* name; double total; long count; };
+static std::vector<HostTimingRec>& host_timing_table() { static std::vector<HostTimingRec> t; return t; }
+static double wall_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+HostTimer::HostTimer(const char* n) : name(n), t0(host_timing_on() ? wall_now() : 0.0) {}
+HostTimer::~HostTimer()
+{
+    if (!host_timing_on()) return;
+    const double dt = wall_now() - t0;
+    for (auto& r : host_timing_table()) if (r.name == name) { r.total += dt; r.count++; return; }
+    host_timing_table().push_back(HostTimingRec{name, dt, 1});
+}
+void host_timing_report()
+{
+    if (!host_timing_on()) return;
+    for (auto& r : host_timing_table()) fprintf(stderr, "[ocb host] %-28s %8ld calls  %10.3f ms total  %8.3f us/call\n", r.name, r.count, 1e3 * r.total, 1e6 * r.total / (r.count ? r.count : 1));
+    host_timing_table().clear();
 }
 
 int ensure_init(ocb_ctx* c)
@@ -204,6 +224,7 @@ int ocb_create(ocb_ctx** out, int device)
 
 void ocb_destroy(ocb_ctx* c)
 {
+    host_timing_report();
     if (!c) return;
     if (c->inited) {
         cudaSetDevice(c->device);
@@ -314,6 +335,7 @@ static int upload_elems(ocb_ctx* c, ElemSet& S, std::vector<int32_t>& hostCopy, 
 int ocb_set_mesh(ocb_ctx* c, int nV, int nF, const int32_t* F, const double* rest8, double surfaceArea,
                  const int32_t* fixed, int nFixed)
 {
+    HostTimer _ht("set_mesh");
     if (!c || nV <= 0 || nF <= 0 || !F || !rest8 || !(surfaceArea > 0.0)) return set_err(c, OCB_ERR_ARG, "ocb_set_mesh: bad argument");
     for (size_t i = 0; i < (size_t)3 * nF; ++i) if (F[i] < 0 || F[i] >= nV) return set_err(c, OCB_ERR_ARG, "ocb_set_mesh: vertex index out of range");
     OCB_TRY(ensure_init(c));
@@ -340,6 +362,7 @@ int ocb_set_mesh(ocb_ctx* c, int nV, int nF, const int32_t* F, const double* res
 int ocb_set_air(ocb_ctx* c, int nVa, int nFa, const int32_t* Fa, const double* rest8, const int32_t* l2g, int nBnd,
                 const int32_t* fixedAir, int nFixedAir, double wScafOverFa)
 {
+    HostTimer _ht("set_air");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->nV > 0, "ocb_set_air before ocb_set_mesh"));
     OCB_TRY(ensure_init(c));
@@ -383,6 +406,7 @@ int ocb_set_air(ocb_ctx* c, int nVa, int nFa, const int32_t* Fa, const double* r
 
 int ocb_set_uv(ocb_ctx* c, const double* V, const double* Va)
 {
+    HostTimer _ht("set_uv");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->nV > 0, "ocb_set_uv before ocb_set_mesh"));
     OCB_TRY(ensure_init(c));
@@ -401,6 +425,7 @@ int ocb_set_uv(ocb_ctx* c, const double* V, const double* Va)
 
 int ocb_get_uv(ocb_ctx* c, double* V, double* Va)
 {
+    HostTimer _ht("get_uv");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->haveUV, "no UV on the device"));
     const size_t nv = V ? 2 * (size_t)c->nV : 0, na = (Va && c->nVa > 0) ? 2 * (size_t)c->nVa : 0;
@@ -481,6 +506,7 @@ int ocb_energy_per_elem(ocb_ctx* c, int uniform, double* out)
 
 int ocb_gradient(ocb_ctx* c, double p0, double* g_out, double* sqnorm)
 {
+    HostTimer _ht("gradient");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->haveUV, "ocb_gradient: no UV"));
     OCB_TRY(launch_gradient(c, p0));
@@ -496,6 +522,7 @@ int ocb_gradient(ocb_ctx* c, double p0, double* g_out, double* sqnorm)
 // into it and upload; build the preconditioner hierarchy on top.
 static int install_pattern(ocb_ctx* c)
 {
+    HostTimer _ht("install_pattern");
     static const bool masOff = []() { const char* e = getenv("OCB_NO_MAS"); return e && atoi(e); }();
     const int n = c->nVtot;
     c->nnzb = (int)c->hColIdx.size();
@@ -505,7 +532,7 @@ static int install_pattern(ocb_ctx* c)
         std::vector<double> xy(2 * (size_t)n);
         OCB_CUDA(c, cudaMemcpyAsync(xy.data(), c->x.p, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
         OCB_CUDA(c, cudaStreamSynchronize(c->stream));
-        OCB_TRY(mas_build_hierarchy(c, xy.data(), c->planGrid));
+        { HostTimer _h2("  mas_build_hierarchy"); OCB_TRY(mas_build_hierarchy(c, xy.data(), c->planGrid)); }
     } else {
         c->hRowOf.resize((size_t)n); c->hVertOf.resize((size_t)n);
         for (int v = 0; v < n; ++v) c->hRowOf[v] = c->hVertOf[v] = v;
@@ -514,16 +541,24 @@ static int install_pattern(ocb_ctx* c)
     c->hSColIdx.resize((size_t)c->nnzb);
     c->hBlkMap.resize((size_t)c->nnzb);
     {
-        std::vector<std::pair<int32_t, int32_t>> row;
+        HostTimer _h5("  solver_order_pattern");
         int w = 0;
         for (int r = 0; r < n; ++r) {
             const int v = c->hVertOf[r];
-            row.clear();
-            for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) row.push_back(std::make_pair(c->hRowOf[c->hColIdx[b]], (int32_t)b));
-            std::sort(row.begin(), row.end());
-            for (const auto& cb : row) { c->hSColIdx[w] = cb.first; c->hBlkMap[cb.second] = w; ++w; }
+            const int w0 = w;
+            for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) {       // insertion sort by solver column, carrying the source block
+                const int32_t col = c->hRowOf[c->hColIdx[b]];
+                int j = w - 1;
+                while (j >= w0 && c->hSColIdx[j] > col) { c->hSColIdx[j + 1] = c->hSColIdx[j]; c->hBlkMap[j + 1] = c->hBlkMap[j]; --j; }
+                c->hSColIdx[j + 1] = col; c->hBlkMap[j + 1] = b;
+                ++w;
+            }
             c->hSRowPtr[r + 1] = w;
         }
+        // hBlkMap holds device block -> source block so far; invert it
+        std::vector<int32_t> inv((size_t)c->nnzb);
+        for (int d = 0; d < c->nnzb; ++d) inv[c->hBlkMap[d]] = d;
+        c->hBlkMap.swap(inv);
     }
     OCB_CUDA(c, c->rowPtr.reserve((size_t)n + 1, c->stream));
     OCB_CUDA(c, c->colIdx.reserve((size_t)c->nnzb + 1, c->stream));
@@ -538,9 +573,13 @@ static int install_pattern(ocb_ctx* c)
     std::vector<int32_t> userRow((size_t)n);
     for (int u = 0; u < n; ++u) userRow[u] = c->hRowOf[c->hPerm[u]];
     OCB_TRY(upload_i(c, c->userRow.p, userRow.data(), (size_t)n));
-    OCB_TRY(upload_fixed_mask(c));                    // synchronises the stream: the staging vectors may go
-    OCB_TRY(mas_install(c));
+    OCB_CUDA(c, c->fixedMask.reserve((size_t)c->nVtot, c->stream));
+    c->hFixed.resize((size_t)c->nVtot, 0);
+    OCB_CUDA(c, cudaMemcpyAsync(c->fixedMask.p, c->hFixed.data(), (size_t)c->nVtot, cudaMemcpyHostToDevice, c->stream));
+    // (pageable sources: cudaMemcpyAsync returns once the data is staged, so the local vectors may go out of scope)
+    { HostTimer _h3("  mas_install"); OCB_TRY(mas_install(c)); }
     c->patternValid = true; c->matrixValid = c->precondValid = false;
+    HostTimer _h4("  build_slots");
     return launch_build_slots(c);
 }
 
@@ -613,6 +652,7 @@ int ocb_set_pattern(ocb_ctx* c, int nVtot, const int32_t* adjPtr, const int32_t*
 
 int ocb_set_pattern_from_elements(ocb_ctx* c)
 {
+    HostTimer _ht("set_pattern_from_elements");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->nV > 0, "ocb_set_pattern_from_elements before ocb_set_mesh"));
     OCB_TRY(ensure_init(c));
@@ -636,13 +676,20 @@ int ocb_set_pattern_from_elements(ocb_ctx* c)
     scatter(c->hF, c->nF); scatter(c->hFa, c->nFa);
     c->hRowPtr.assign((size_t)nVtot + 1, 0);
     c->hColIdx.clear(); c->hColIdx.reserve(buf.size() / 2 + nVtot);
+    std::vector<int32_t> stamp((size_t)nVtot, -1);         // de-duplicate with a stamp, then insertion-sort the short row
     for (int v = 0; v < nVtot; ++v) {
         if (c->hFixed[v]) { c->hColIdx.push_back(v); }
         else {
-            int32_t* b = buf.data() + cnt[v]; int32_t* e = buf.data() + fill[v];
-            std::sort(b, e);
-            e = std::unique(b, e);
-            for (int32_t* q = b; q < e; ++q) if (*q == v || !c->hFixed[*q]) c->hColIdx.push_back(*q);
+            const size_t w0 = c->hColIdx.size();
+            for (int32_t* q = buf.data() + cnt[v]; q < buf.data() + fill[v]; ++q) {
+                const int u = *q;
+                if (stamp[u] == v) continue;
+                stamp[u] = v;
+                if (u == v || !c->hFixed[u]) c->hColIdx.push_back(u);
+            }
+            int32_t* a = c->hColIdx.data() + w0;
+            const int m = (int)(c->hColIdx.size() - w0);
+            for (int i = 1; i < m; ++i) { const int32_t x = a[i]; int j = i - 1; while (j >= 0 && a[j] > x) { a[j + 1] = a[j]; --j; } a[j + 1] = x; }
         }
         c->hRowPtr[v + 1] = (int32_t)c->hColIdx.size();
     }
@@ -652,6 +699,7 @@ int ocb_set_pattern_from_elements(ocb_ctx* c)
 // ------------------------------------------------------------------------------------------ Hessian
 int ocb_hessian_assemble(ocb_ctx* c, double p0)
 {
+    HostTimer _ht("hessian_assemble");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->haveUV, "ocb_hessian_assemble: no UV"));
     OCB_TRY(need(c, c->patternValid && c->slotsValid, "ocb_hessian_assemble: no sparsity pattern (ocb_set_pattern)"));
@@ -781,6 +829,7 @@ int ocb_multiply(ocb_ctx* c, const double* x, double* y)
 // -------------------------------------------------------------------------------------------- solve
 int ocb_factorize(ocb_ctx* c)
 {
+    HostTimer _ht("factorize");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_factorize: no matrix"));
     OCB_TRY(launch_jacobi_setup(c));
@@ -791,6 +840,7 @@ int ocb_factorize(ocb_ctx* c)
 
 int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int max_it, int* iters, double* rel_res)
 {
+    HostTimer _ht("solve");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_solve: no matrix"));
     if (!c->precondValid) OCB_TRY(ocb_factorize(c));
@@ -850,6 +900,7 @@ int ocb_precond_hierarchy(ocb_ctx* c, int n, const double* xy, int grid, int32_t
     c->nVtot = n;
     c->hFixed.assign((size_t)n, 0);
     OCB_TRY(mas_build_hierarchy(c, xy, grid));
+    if (getenv("OCB_HIERARCHY_TWICE")) OCB_TRY(mas_build_hierarchy(c, xy, grid));     // timing aid: warm start from the previous order
     fill_precond_info(c->masH, info);
     std::memcpy(vert_of, c->hVertOf.data(), sizeof(int32_t) * (size_t)n);
     int w = 0;
@@ -866,6 +917,7 @@ int ocb_precond_hierarchy(ocb_ctx* c, int n, const double* xy, int grid, int32_t
 // ------------------------------------------------------------------------------- step bound / search
 int ocb_step_bound(ocb_ctx* c, const double* dir, double* alpha)
 {
+    HostTimer _ht("step_bound");
     if (!c || !alpha) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->haveUV, "ocb_step_bound: no UV"));
     const double* dDir = c->p.p;
@@ -892,6 +944,7 @@ int ocb_step_forward(ocb_ctx* c, double alpha)
 
 int ocb_line_search(ocb_ctx* c, double p0, double E_last, double alpha0, int allowEDecRelTol, ocb_linesearch_result* out)
 {
+    HostTimer _ht("line_search");
     if (!c || !out) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->haveUV, "ocb_line_search: no UV"));
     const bool scaf = c->nFa > 0;
@@ -946,6 +999,7 @@ int ocb_line_search(ocb_ctx* c, double p0, double E_last, double alpha0, int all
 int ocb_newton_step(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_tol, int pcg_max_it,
                     int allowEDecRelTol, ocb_newton_result* out)
 {
+    HostTimer _ht("newton_step");
     if (!c || !out) return OCB_ERR_ARG;
     std::memset(out, 0, sizeof(*out));
     out->targetGRes = targetGRes;

@@ -80,7 +80,8 @@ struct MasHost {
     std::vector<float> vinfo;                            // 4 per row
 };
 struct MasDev {
-    DevBuf<int32_t> ints; DevBuf<double> geom, val, rcCta; DevBuf<float> inv, vinfo;
+    DevBuf<int32_t> ints, tabI; DevBuf<double> geom, val, rcCta, tabD; DevBuf<float> inv, vinfo;
+    std::vector<MasLevel> lv;
     std::vector<const int32_t*> lvRowPtr, lvColIdx; std::vector<double*> lvVal; std::vector<int> lvNnz;
     size_t valTotal = 0; int groupTotal = 0;
     MasView view = {};
@@ -164,6 +165,13 @@ int cuda_fail(ocb_ctx* c, cudaError_t e, const char* where);
 #define OCB_TRY(call) do { int _r = (call); if (_r < 0) return _r; } while (0)
 
 int ensure_init(ocb_ctx* c);
+// OCB_HOST_TIMING=1: wall-clock per host-side section, printed by ocb_destroy (e2e tuning aid)
+struct HostTimer {
+    const char* name; double t0;
+    explicit HostTimer(const char* n);
+    ~HostTimer();
+};
+void host_timing_report();
 // RAII: brackets the launches of one kernel class with CUDA events when profiling is enabled
 struct ProfScope {
     ocb_ctx* c; int cls; cudaEvent_t a = nullptr, b = nullptr;

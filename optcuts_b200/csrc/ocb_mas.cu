@@ -15,29 +15,26 @@ namespace ocb {
 // ------------------------------------------------------------------------------------------------
 // host: recursive coordinate bisection into consecutive parts of prescribed sizes
 namespace {
+struct RcbPt { double x, y; int32_t id; };
 struct Rcb {
-    const double* xy;
-    int32_t* idx;
-    void split(int beg, int end, const int* pre, int nParts) const      // pre: prefix sums of the part sizes (nParts + 1)
+    RcbPt* pt;
+    // bounding box handed down the recursion (the cut value closes the children's boxes): no extra pass per level
+    void split(int beg, int end, const int* pre, int nParts, double lox, double hix, double loy, double hiy) const      // pre: prefix sums of the part sizes (nParts + 1)
     {
         if (nParts <= 1 || end - beg <= 1) return;
         const int h = nParts / 2;
         const int nl = pre[h] - pre[0];
+        double cut = 0.0; bool alongY = false, didCut = false;
         if (nl > 0 && nl < end - beg) {
-            double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
-            for (int i = beg; i < end; ++i) {
-                const double* p = xy + 2 * (size_t)idx[i];
-                for (int a = 0; a < 2; ++a) { if (p[a] < lo[a]) lo[a] = p[a]; if (p[a] > hi[a]) hi[a] = p[a]; }
-            }
-            const int ax = (hi[1] - lo[1] > hi[0] - lo[0]) ? 1 : 0;
-            const double* q = xy;
-            std::nth_element(idx + beg, idx + beg + nl, idx + end, [q, ax](int32_t a, int32_t b) {
-                const double va = q[2 * (size_t)a + ax], vb = q[2 * (size_t)b + ax];
-                return va < vb || (va == vb && a < b);
-            });
+            alongY = (hiy - loy) > (hix - lox);
+            if (alongY) std::nth_element(pt + beg, pt + beg + nl, pt + end, [](const RcbPt& a, const RcbPt& b) { return a.y < b.y || (a.y == b.y && a.id < b.id); });
+            else        std::nth_element(pt + beg, pt + beg + nl, pt + end, [](const RcbPt& a, const RcbPt& b) { return a.x < b.x || (a.x == b.x && a.id < b.id); });
+            cut = alongY ? pt[beg + nl].y : pt[beg + nl].x;
+            didCut = true;
         }
-        split(beg, beg + nl, pre, h);
-        split(beg + nl, end, pre + h, nParts - h);
+        if (didCut && alongY) { split(beg, beg + nl, pre, h, lox, hix, loy, cut); split(beg + nl, end, pre + h, nParts - h, lox, hix, cut, hiy); }
+        else if (didCut)      { split(beg, beg + nl, pre, h, lox, cut, loy, hiy); split(beg + nl, end, pre + h, nParts - h, cut, hix, loy, hiy); }
+        else                  { split(beg, beg + nl, pre, h, lox, hix, loy, hiy); split(beg + nl, end, pre + h, nParts - h, lox, hix, loy, hiy); }
     }
 };
 
@@ -65,10 +62,25 @@ int mas_build_hierarchy(ocb_ctx* c, const double* xyIn, int grid)
     for (int b = 0; b < grid; ++b) ctaPre[b + 1] = std::min(n, (b + 1) * rowsPer);
     int nonEmpty = 0;
     for (int b = 0; b < grid; ++b) if (ctaPre[b + 1] > ctaPre[b]) nonEmpty = b + 1;
-    c->hVertOf.resize((size_t)n);
-    for (int i = 0; i < n; ++i) c->hVertOf[i] = i;
-    Rcb R{xy.data(), c->hVertOf.data()};
-    R.split(0, n, ctaPre.data(), nonEmpty);
+    HostTimer* _t1 = new HostTimer("    h:rcb");
+    std::vector<RcbPt> pts((size_t)n);
+    double blo[2] = {1e300, 1e300}, bhi[2] = {-1e300, -1e300};
+    // start from the previous solver order when there is one: between Newton iterations the vertices barely move, and
+    // selecting on nearly-partitioned data costs a fraction of the swaps
+    {
+        std::vector<uint8_t> seen((size_t)n, 0);
+        int w = 0;
+        for (size_t r = 0; r < c->hVertOf.size(); ++r) { const int v = c->hVertOf[r]; if (v >= 0 && v < n && !seen[v]) { seen[v] = 1; pts[w++].id = v; } }
+        for (int v = 0; v < n; ++v) if (!seen[v]) pts[w++].id = v;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int v = pts[i].id;
+        pts[i].x = xy[2 * (size_t)v]; pts[i].y = xy[2 * (size_t)v + 1];
+        blo[0] = std::min(blo[0], pts[i].x); bhi[0] = std::max(bhi[0], pts[i].x); blo[1] = std::min(blo[1], pts[i].y); bhi[1] = std::max(bhi[1], pts[i].y);
+    }
+    Rcb R{pts.data()};
+    // two-stage: CTA chunks first, then the leaves of every chunk; the chunk boxes are recomputed (cheap, once)
+    R.split(0, n, ctaPre.data(), nonEmpty, blo[0], bhi[0], blo[1], bhi[1]);
     // stage 2: leaves inside every chunk
     H.grid = grid;
     H.lv.clear();
@@ -83,14 +95,21 @@ int mas_build_hierarchy(ocb_ctx* c, const double* xyIn, int grid)
             if (m > 0) {
                 const int nl = (m + kMasLeaf - 1) / kMasLeaf;
                 even_prefix(m, nl, pre);
-                R.split(beg, beg + m, pre.data(), nl);
+                double lo2[2] = {1e300, 1e300}, hi2[2] = {-1e300, -1e300};
+                for (int i = beg; i < beg + m; ++i) {
+                    lo2[0] = std::min(lo2[0], pts[i].x); hi2[0] = std::max(hi2[0], pts[i].x); lo2[1] = std::min(lo2[1], pts[i].y); hi2[1] = std::max(hi2[1], pts[i].y);
+                }
+                R.split(beg, beg + m, pre.data(), nl, lo2[0], hi2[0], lo2[1], hi2[1]);
                 for (int k = 1; k <= nl; ++k) L1.childBeg.push_back(beg + pre[k]);
             }
             L1.ctaBeg[b + 1] = (int32_t)L1.childBeg.size() - 1;
         }
     }
+    delete _t1;
+    HostTimer _t2("    h:levels");
+    c->hVertOf.resize((size_t)n);
     c->hRowOf.assign((size_t)n, 0);
-    for (int r = 0; r < n; ++r) c->hRowOf[c->hVertOf[r]] = r;
+    for (int r = 0; r < n; ++r) { c->hVertOf[r] = pts[r].id; c->hRowOf[pts[r].id] = r; }
     // geometry of the leaves + per-row info
     auto bbox_to_geom = [](const double* lo, const double* hi, double* g) {
         g[0] = 0.5 * (lo[0] + hi[0]); g[1] = 0.5 * (lo[1] + hi[1]);
@@ -199,24 +218,29 @@ int mas_install(ocb_ctx* c)
 {
     MasHost& H = c->masH;
     MasDev& D = c->masD;
-    if (!H.enabled) { D.view.L = 0; return 0; }
+    if (!H.enabled) { D.view = MasView(); D.view.L = 0; return 0; }
     const int n = c->nVtot;
     std::vector<int32_t> nodeOf((size_t)n);       // row -> node of the current level
     for (int r = 0; r < n; ++r) { int32_t id; std::memcpy(&id, &H.vinfo[4 * (size_t)r + 3], 4); nodeOf[r] = id; }
     const std::vector<int32_t>* fineRowPtr = &c->hSRowPtr; const std::vector<int32_t>* fineColIdx = &c->hSColIdx;
-    std::vector<int32_t> buf;
+    std::vector<int32_t> stamp;
     for (int l = 1; l <= H.L; ++l) {
         MasHost::Level& V = H.lv[l - 1];
         const int nn = (int)V.childBeg.size() - 1;
         V.rowPtr.assign((size_t)nn + 1, 0); V.colIdx.clear();
+        V.colIdx.reserve((size_t)nn * 10);
+        stamp.assign((size_t)nn, -1);
         for (int k = 0; k < nn; ++k) {
-            buf.clear();
-            buf.push_back(k);
+            const size_t w0 = V.colIdx.size();
+            V.colIdx.push_back(k); stamp[k] = k;
             for (int ch = V.childBeg[k]; ch < V.childBeg[k + 1]; ++ch)
-                for (int b = (*fineRowPtr)[ch]; b < (*fineRowPtr)[ch + 1]; ++b) buf.push_back(nodeOf[(*fineColIdx)[b]]);
-            std::sort(buf.begin(), buf.end());
-            buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
-            V.colIdx.insert(V.colIdx.end(), buf.begin(), buf.end());
+                for (int b = (*fineRowPtr)[ch]; b < (*fineRowPtr)[ch + 1]; ++b) {
+                    const int q = nodeOf[(*fineColIdx)[b]];
+                    if (stamp[q] != k) { stamp[q] = k; V.colIdx.push_back(q); }
+                }
+            int32_t* a = V.colIdx.data() + w0;
+            const int m = (int)(V.colIdx.size() - w0);
+            for (int i = 1; i < m; ++i) { const int32_t v = a[i]; int j = i - 1; while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; } a[j + 1] = v; }
             V.rowPtr[k + 1] = (int32_t)V.colIdx.size();
         }
         // next level: "rows" are this level's nodes, nodeOf = their parent
@@ -254,23 +278,17 @@ int mas_install(ocb_ctx* c)
     OCB_CUDA(c, cudaMemcpyAsync(D.ints.p, ints.data(), ints.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     OCB_CUDA(c, cudaMemcpyAsync(D.geom.p, geom.data(), geom.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     OCB_CUDA(c, cudaMemcpyAsync(D.vinfo.p, H.vinfo.data(), H.vinfo.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    OCB_CUDA(c, cudaStreamSynchronize(c->stream));       // the staging vectors die with this scope
-    MasView& W = D.view;
-    W = MasView();
-    W.L = H.L; W.Lloc = H.Lloc; W.grid = H.grid; W.topNodes = H.topNodes; W.maxLocalNodes = H.maxLocalNodes;
-    W.vinfo = reinterpret_cast<const float4*>(D.vinfo.p);
-    W.rcCta = D.rcCta.p;
+    D.lv.assign((size_t)H.L, MasLevel());
     D.lvRowPtr.assign((size_t)H.L, nullptr); D.lvColIdx.assign((size_t)H.L, nullptr); D.lvVal.assign((size_t)H.L, nullptr);
     D.lvNnz.assign((size_t)H.L, 0);
     D.valTotal = valTot;
     D.groupTotal = 0;
     for (int l = 1; l <= H.L; ++l) {
         const Off& o = off[l - 1];
-        MasLevel& V = W.lv[l - 1];
+        MasLevel& V = D.lv[l - 1];
         V.nNodes = o.nNodes; V.nGroups = o.nGroups;
         V.childBeg = D.ints.p + o.childBeg;
         V.parent = D.ints.p + o.parent;
-        V.ctaBeg = l <= H.Lloc ? D.ints.p + o.ctaBeg : nullptr;
         V.groupBeg = l < H.L ? D.ints.p + off[l].childBeg : D.ints.p + topGroupOff;
         V.geom = reinterpret_cast<const double4*>(D.geom.p + o.geom);
         V.inv = D.inv.p + o.inv;
@@ -278,6 +296,96 @@ int mas_install(ocb_ctx* c)
         D.lvNnz[l - 1] = o.nnz;
         D.groupTotal += o.nGroups;
     }
+    // ---- the apply's tables (CTA-local indices, see MasView)
+    const int grid = H.grid, Lloc = H.Lloc, L = H.L, nCh = L - Lloc + 1;
+    const int rowsPer = (n + grid - 1) / grid;
+    auto nodesOf = [&](int l) { return (int)H.lv[l - 1].childBeg.size() - 1; };
+    auto groupBegOf = [&](int l, int g) { return l < L ? H.lv[l].childBeg[g] : (g == 0 ? 0 : nodesOf(L)); };
+    auto xfer = [&](int l, int k, double* X) {         // node k of level l -> its parent (level l + 1)
+        X[0] = X[1] = 0.0; X[2] = 1.0; X[3] = 0.0;
+        if (l >= L) return;
+        const double* gc = H.lv[l - 1].geom.data() + 4 * (size_t)k;
+        const double* gp = H.lv[l].geom.data() + 4 * (size_t)H.lv[l - 1].parent[k];
+        X[0] = (gc[0] - gp[0]) / gp[2]; X[1] = (gc[1] - gp[1]) / gp[2]; X[2] = gc[2] / gp[2];
+    };
+    const int nCtaNodes = nodesOf(Lloc);
+    std::vector<int32_t> tI; std::vector<double> tD;
+    std::vector<int32_t> ctaNodeOff((size_t)grid + 1, 0), ctaSolve((size_t)grid, 0), ctaLvOff((size_t)grid * (kMasMaxLevels + 1), 0), ctaLeafBeg(H.lv[0].ctaBeg);
+    std::vector<int32_t> nodeA, nodeB; std::vector<double> nodeX;
+    { size_t tot = 0; for (int l = 1; l <= Lloc; ++l) tot += (size_t)nodesOf(l); nodeA.reserve(4 * tot); nodeB.reserve(4 * tot); nodeX.reserve(4 * tot); }
+    for (int b = 0; b < grid; ++b) {
+        int32_t* lvOff = ctaLvOff.data() + (size_t)b * (kMasMaxLevels + 1);
+        int o = 0;
+        for (int l = 1; l <= Lloc; ++l) { lvOff[l - 1] = o; o += H.lv[l - 1].ctaBeg[b + 1] - H.lv[l - 1].ctaBeg[b]; }
+        for (int l = Lloc; l <= kMasMaxLevels; ++l) lvOff[l] = o;
+        ctaNodeOff[b + 1] = ctaNodeOff[b] + o;
+        ctaSolve[b] = lvOff[Lloc - 1];
+        const int rowBeg = std::min(n, b * rowsPer);
+        for (int l = 1; l <= Lloc; ++l) {
+            const MasHost::Level& V = H.lv[l - 1];
+            const int n0 = V.ctaBeg[b];
+            for (int k = n0; k < V.ctaBeg[b + 1]; ++k) {
+                int32_t A[4] = {0, 0, 0, 0}, B[4] = {0, 0, 0, l};
+                if (l < Lloc) {
+                    const int g = V.parent[k], gb = groupBegOf(l, g), ge = groupBegOf(l, g + 1);
+                    A[0] = lvOff[l - 1] + (gb - n0); A[1] = kMasDof * (ge - gb); A[2] = kMasDof * (k - gb);
+                    A[3] = lvOff[l] + (g - H.lv[l].ctaBeg[b]);
+                    B[0] = (int32_t)(off[l - 1].inv + (size_t)g * kMasBlk * kMasBlk);
+                }
+                B[1] = l == 1 ? V.childBeg[k] - rowBeg : lvOff[l - 2] + (V.childBeg[k] - H.lv[l - 2].ctaBeg[b]);
+                B[2] = V.childBeg[k + 1] - V.childBeg[k];
+                nodeA.insert(nodeA.end(), A, A + 4); nodeB.insert(nodeB.end(), B, B + 4);
+                double X[4]; xfer(l, k, X);
+                nodeX.insert(nodeX.end(), X, X + 4);
+            }
+        }
+    }
+    std::vector<int32_t> topLevelOff((size_t)nCh + 1, 0);
+    for (int j = 0; j < nCh; ++j) topLevelOff[j + 1] = topLevelOff[j] + nodesOf(Lloc + j);
+    const int topNodes = topLevelOff[nCh];
+    std::vector<int32_t> topUp(2 * (size_t)topNodes, 0); std::vector<double> topX(4 * (size_t)topNodes, 0.0);
+    for (int j = 0; j < nCh; ++j) {
+        const int l = Lloc + j;
+        for (int k = 0; k < nodesOf(l); ++k) {
+            const int ti = topLevelOff[j] + k;
+            if (j > 0) { topUp[2 * ti] = topLevelOff[j - 1] + H.lv[l - 1].childBeg[k]; topUp[2 * ti + 1] = H.lv[l - 1].childBeg[k + 1] - H.lv[l - 1].childBeg[k]; }
+            xfer(l, k, topX.data() + 4 * (size_t)ti);
+        }
+    }
+    std::vector<int32_t> chainM((size_t)grid * kMasMaxLevels * 4, 0);
+    for (int b = 0; b < nCtaNodes; ++b) {
+        int anc[kMasMaxLevels + 2];
+        anc[Lloc] = b;
+        for (int l = Lloc; l < L; ++l) anc[l + 1] = H.lv[l - 1].parent[anc[l]];
+        for (int j = 0; j < nCh; ++j) {
+            const int l = L - j, a = anc[l], g = H.lv[l - 1].parent[a], gb = groupBegOf(l, g), ge = groupBegOf(l, g + 1);
+            int32_t* C = chainM.data() + ((size_t)b * kMasMaxLevels + j) * 4;
+            C[0] = topLevelOff[l - Lloc] + gb; C[1] = kMasDof * (ge - gb);
+            C[2] = (int32_t)(off[l - 1].inv + (size_t)g * kMasBlk * kMasBlk + (size_t)(a - gb) * kMasDof * kMasBlk);
+            C[3] = topLevelOff[l - Lloc] + a;
+        }
+    }
+    auto putI = [&tI](const std::vector<int32_t>& v) { size_t o = tI.size(); tI.insert(tI.end(), v.begin(), v.end()); while (tI.size() & 3) tI.push_back(0); return o; };
+    auto putD = [&tD](const std::vector<double>& v) { size_t o = tD.size(); tD.insert(tD.end(), v.begin(), v.end()); while (tD.size() & 3) tD.push_back(0.0); return o; };
+    const size_t oNodeOff = putI(ctaNodeOff), oSolve = putI(ctaSolve), oLvOff = putI(ctaLvOff), oLeafBeg = putI(ctaLeafBeg), oNodeA = putI(nodeA),
+                 oNodeB = putI(nodeB), oTopUp = putI(topUp), oTopLevelOff = putI(topLevelOff), oChainM = putI(chainM);
+    const size_t oNodeX = putD(nodeX), oTopX = putD(topX);
+    OCB_CUDA(c, D.tabI.reserve(tI.size() + 4, c->stream));
+    OCB_CUDA(c, D.tabD.reserve(tD.size() + 4, c->stream));
+    OCB_CUDA(c, cudaMemcpyAsync(D.tabI.p, tI.data(), tI.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    OCB_CUDA(c, cudaMemcpyAsync(D.tabD.p, tD.data(), tD.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // (pageable sources: cudaMemcpyAsync returns once the data is staged, the vectors may go out of scope)
+    MasView& W = D.view;
+    W = MasView();
+    W.L = L; W.Lloc = Lloc; W.grid = grid; W.nCh = nCh; W.topNodes = topNodes; W.nCtaNodes = nCtaNodes;
+    W.maxLocalNodes = H.maxLocalNodes; W.rowsPer = rowsPer;
+    W.ctaNodeOff = D.tabI.p + oNodeOff; W.ctaSolve = D.tabI.p + oSolve; W.ctaLvOff = D.tabI.p + oLvOff; W.ctaLeafBeg = D.tabI.p + oLeafBeg;
+    W.nodeA = reinterpret_cast<const int4*>(D.tabI.p + oNodeA); W.nodeB = reinterpret_cast<const int4*>(D.tabI.p + oNodeB);
+    W.nodeX = reinterpret_cast<const double4*>(D.tabD.p + oNodeX);
+    W.topUp = reinterpret_cast<const int2*>(D.tabI.p + oTopUp); W.topX = reinterpret_cast<const double4*>(D.tabD.p + oTopX);
+    W.topLevelOff = D.tabI.p + oTopLevelOff; W.chainM = reinterpret_cast<const int4*>(D.tabI.p + oChainM);
+    W.inv = D.inv.p; W.vinfo = reinterpret_cast<const float4*>(D.vinfo.p); W.rcCta = D.rcCta.p;
+    H.topNodes = topNodes;
     return 0;
 }
 
@@ -458,23 +566,23 @@ int launch_mas_setup(ocb_ctx* c)
     OCB_CUDA(c, cudaMemsetAsync(D.val.p, 0, D.valTotal * sizeof(double), c->stream));
     const int n = c->nVtot;
     int grid = (n + 255) / 256; if (grid > c->numSMs * 8) grid = c->numSMs * 8; if (grid < 1) grid = 1;
-    mas_galerkin_fine_kernel<<<grid, 256, 0, c->stream>>>(n, c->rowPtr.p, c->colIdx.p, c->val.p, D.view.vinfo, D.lvRowPtr[0], D.lvColIdx[0], D.lvVal[0]);
+    mas_galerkin_fine_kernel<<<grid, 256, 0, c->stream>>>(n, c->rowPtr.p, c->colIdx.p, c->val.p, reinterpret_cast<const float4*>(D.vinfo.p), D.lvRowPtr[0], D.lvColIdx[0], D.lvVal[0]);
     KCHECK(c);
     for (int l = 1; l < H.L; ++l) {
-        const MasLevel& V = D.view.lv[l - 1];
+        const MasLevel& V = D.lv[l - 1];
         int g = (V.nNodes + 127) / 128; if (g > c->numSMs * 8) g = c->numSMs * 8; if (g < 1) g = 1;
         mas_coarsen_kernel<<<g, 128, 0, c->stream>>>(V.nNodes, D.lvRowPtr[l - 1], D.lvColIdx[l - 1], D.lvVal[l - 1], V.parent, V.geom,
-                                                    D.view.lv[l].geom, D.lvRowPtr[l], D.lvColIdx[l], D.lvVal[l]);
+                                                    D.lv[l].geom, D.lvRowPtr[l], D.lvColIdx[l], D.lvVal[l]);
         KCHECK(c);
     }
     MasInvertArgs A;
     A.L = H.L;
     A.groupPre[0] = 0;
     for (int l = 1; l <= H.L; ++l) {
-        const MasLevel& V = D.view.lv[l - 1];
+        const MasLevel& V = D.lv[l - 1];
         A.groupPre[l] = A.groupPre[l - 1] + V.nGroups;
         A.rowPtr[l - 1] = D.lvRowPtr[l - 1]; A.colIdx[l - 1] = D.lvColIdx[l - 1]; A.val[l - 1] = D.lvVal[l - 1];
-        A.parent[l - 1] = V.parent; A.groupBeg[l - 1] = V.groupBeg; A.inv[l - 1] = const_cast<float*>(V.inv);
+        A.parent[l - 1] = V.parent; A.groupBeg[l - 1] = V.groupBeg; A.inv[l - 1] = V.inv;
     }
     mas_invert_kernel<<<A.groupPre[H.L], 256, 0, c->stream>>>(A);
     KCHECK(c);

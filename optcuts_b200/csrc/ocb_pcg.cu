@@ -97,46 +97,58 @@ __device__ __forceinline__ void st_packet(SyncPacket* p, double v, unsigned long
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(__double_as_longlong(v)), "l"(epoch) : "memory");
 }
 
+// The all-reduce is split into ARRIVE (publish this CTA's partials) and WAIT (collect everybody's), so that
+// CTA-local work that does not depend on the result -- the preconditioner's local group solves -- runs while the
+// slower CTAs are still on their way to the barrier.
+static constexpr int kPollMax = 256;          // CTAs whose packets are polled by one thread each
+struct ReduceSmem { double sm[kSyncVals][kPcgBlock / 32]; double bc[kSyncVals]; double vals[kSyncVals][kPollMax]; };
+
 template <int NV>
-__device__ __forceinline__ void grid_allreduce(SyncSlot* slots, int nB, unsigned long long epoch, double (&loc)[NV], double (&out)[NV])
+__device__ __forceinline__ void grid_allreduce_arrive(ReduceSmem& R, SyncSlot* slots, int nB, unsigned long long epoch, double (&loc)[NV])
 {
     static_assert(NV <= kSyncVals, "slot too small");
-    __shared__ double sm[NV][kPcgBlock / 32];
-    __shared__ double bc[NV];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double t = loc[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) sm[k][warp] = t;
+        if (lane == 0) R.sm[k][warp] = t;
     }
     __syncthreads();                       // orders every thread's vector stores before the fence below
-    if (nB == 1) {                         // the whole system lives in this CTA: no global traffic at all
+    if (warp == 0) {
+        SyncSlot* base = slots + (size_t)(epoch & 1ull) * nB;
+        double t[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            double t = 0.0;
+            t[k] = lane < kPcgBlock / 32 ? R.sm[k][lane] : 0.0;
 #pragma unroll
-            for (int w = 0; w < kPcgBlock / 32; ++w) t += sm[k][w];
-            out[k] = t;
+            for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
         }
-        __syncthreads();
-        return;
-    }
-    SyncSlot* base = slots + (size_t)(epoch & 1ull) * nB;
-    if (nB > kPacketMaxCtas) {
-        // many CTAs: all-to-all packet polling costs O(nB^2) L2 requests (measured 3-6 us at 148 CTAs); instead
-        // store the partial, cross ONE counter barrier (1.2 us flat, tools/micro/sync_bench.cu) and read all
-        // partials once, in the same fixed order everywhere.
-        if (warp == 0) {
+        if (lane == 0) {
+            if (nB == 1) {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                double t = lane < kPcgBlock / 32 ? sm[k][lane] : 0.0;
+                for (int k = 0; k < NV; ++k) R.bc[k] = t[k];
+            } else if (nB > kPacketMaxCtas) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                if (lane == 0) base[blockIdx.x].p[k].v = t;
+                for (int k = 0; k < NV; ++k) base[blockIdx.x].p[k].v = t[k];
+            } else {
+                __threadfence();           // cumulative: the whole CTA's stores are visible before the packets
+#pragma unroll
+                for (int k = 0; k < NV; ++k) st_packet(&base[blockIdx.x].p[k], t[k], epoch);
             }
         }
+    }
+}
+
+template <int NV>
+__device__ __forceinline__ void grid_allreduce_wait(ReduceSmem& R, SyncSlot* slots, int nB, unsigned long long epoch, double (&out)[NV])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SyncSlot* base = slots + (size_t)(epoch & 1ull) * nB;
+    if (nB > kPacketMaxCtas) {
+        // many CTAs: all-to-all packet polling costs O(nB^2) L2 requests; cross ONE counter barrier instead and read
+        // all partials once, in the same fixed order everywhere.
         cooperative_groups::this_grid().sync();
         if (warp == 0) {
             double acc[NV];
@@ -149,22 +161,35 @@ __device__ __forceinline__ void grid_allreduce(SyncSlot* slots, int nB, unsigned
             for (int k = 0; k < NV; ++k) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-                if (lane == 0) bc[k] = acc[k];
+                if (lane == 0) R.bc[k] = acc[k];
             }
         }
-    } else if (warp == 0) {
-        double t[NV];
+    } else if (nB > 1 && nB <= kPollMax) {
+        // one thread per peer: all packets are in flight at once (ONE L2 round trip instead of nB/32 serial ones),
+        // then warp 0 adds them in a fixed order, identical in every CTA
+        if ((int)threadIdx.x < nB) {
+            const int b = threadIdx.x;
+            SyncPacket q[NV];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            t[k] = lane < kPcgBlock / 32 ? sm[k][lane] : 0.0;
+            for (int k = 0; k < NV; ++k) q[k] = ld_packet(&base[b].p[k]);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+            for (int k = 0; k < NV; ++k) {
+                while (q[k].epoch < epoch) q[k] = ld_packet(&base[b].p[k]);
+                R.vals[k][b] = q[k].v;
+            }
         }
-        if (lane == 0) {
-            __threadfence();               // cumulative: the whole CTA's stores are visible before the packets
+        __syncthreads();
+        if (warp == 0) {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) st_packet(&base[blockIdx.x].p[k], t[k], epoch);
+            for (int k = 0; k < NV; ++k) {
+                double acc = 0.0;
+                for (int b = lane; b < nB; b += 32) acc += R.vals[k][b];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) R.bc[k] = acc;
+            }
         }
+    } else if (nB > 1 && warp == 0) {
         double acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
@@ -180,12 +205,12 @@ __device__ __forceinline__ void grid_allreduce(SyncSlot* slots, int nB, unsigned
         for (int k = 0; k < NV; ++k) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-            if (lane == 0) bc[k] = acc[k];
+            if (lane == 0) R.bc[k] = acc[k];
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < NV; ++k) out[k] = bc[k];
+    for (int k = 0; k < NV; ++k) out[k] = R.bc[k];
     __syncthreads();                       // sm / bc may be rewritten by the next call
 }
 
@@ -197,18 +222,17 @@ __device__ __forceinline__ void grid_allreduce(SyncSlot* slots, int nB, unsigned
 // packets: ~0.3 us instead of ~1-3 us.
 static constexpr int kClusterSize = 16;
 template <int NV>
-__device__ __forceinline__ void cluster_allreduce(double (*part)[kSyncVals][kClusterSize], unsigned long long epoch, double (&loc)[NV], double (&out)[NV])
+__device__ __forceinline__ void cluster_allreduce_arrive(ReduceSmem& R, double (*part)[kSyncVals][kClusterSize], unsigned long long epoch, double (&loc)[NV])
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    __shared__ double sm[NV][kPcgBlock / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double t = loc[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) sm[k][warp] = t;
+        if (lane == 0) R.sm[k][warp] = t;
     }
     __syncthreads();
     // every CTA drops its partial into every peer's buffer (remote stores), then the cluster barrier; reading the
@@ -217,7 +241,7 @@ __device__ __forceinline__ void cluster_allreduce(double (*part)[kSyncVals][kClu
         const unsigned rank = cluster.block_rank();
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            double t = lane < kPcgBlock / 32 ? sm[k][lane] : 0.0;
+            double t = lane < kPcgBlock / 32 ? R.sm[k][lane] : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             if (lane < kClusterSize) {          // lane l writes this CTA's partial into peer l's buffer
@@ -226,14 +250,30 @@ __device__ __forceinline__ void cluster_allreduce(double (*part)[kSyncVals][kClu
             }
         }
     }
-    cluster.sync();                              // release/acquire at cluster scope
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double t = 0.0;
-#pragma unroll
-        for (int r = 0; r < kClusterSize; ++r) t += part[epoch & 1ull][k][r];
-        out[k] = t;
+    // release: ONE cluster-scope fence by thread 0 (cumulative over the CTA's stores, which it observed through the
+    // __syncthreads above and the __syncwarp here) followed by relaxed arrives -- 1024 releasing arrives spent ~10 % of
+    // the solve in membar stalls (profiles/r1b_ncu_pcg10k_lines.txt).  The barrier completes only after thread 0 arrived.
+    if (warp == 0) {
+        __syncwarp();
+        if (lane == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
     }
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+template <int NV>
+__device__ __forceinline__ void cluster_allreduce_wait(ReduceSmem& R, double (*part)[kSyncVals][kClusterSize], unsigned long long epoch, double (&out)[NV])
+{
+    static_assert(kClusterSize == 16 && NV <= 2, "one half-warp per value");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x < 32) {                 // lanes 0-15: value 0, lanes 16-31: value 1; same tree in every CTA
+        const int lane = threadIdx.x, k = lane >> 4;
+        double t = k < NV ? part[epoch & 1ull][k][lane & 15] : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((lane & 15) == 0 && k < NV) R.bc[k] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) out[k] = R.bc[k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -407,7 +447,10 @@ pcg_kernel(PcgParams P)
 {
     constexpr bool SMEM = MODE >= 1;
     __shared__ double clusterPart[2][kSyncVals][kClusterSize];
-#define ALLREDUCE(NV, loc, out) do { ++epoch; if (MODE == 2) cluster_allreduce<NV>(clusterPart, epoch, loc, out); else grid_allreduce<NV>(slots, nB, epoch, loc, out); } while (0)
+    __shared__ ReduceSmem redSm;
+#define ARRIVE(NV, loc) do { ++epoch; if (MODE == 2) cluster_allreduce_arrive<NV>(redSm, clusterPart, epoch, loc); else grid_allreduce_arrive<NV>(redSm, slots, nB, epoch, loc); } while (0)
+#define WAIT(NV, out) do { if (MODE == 2) cluster_allreduce_wait<NV>(redSm, clusterPart, epoch, out); else grid_allreduce_wait<NV>(redSm, slots, nB, epoch, out); } while (0)
+#define ALLREDUCE(NV, loc, out) do { ARRIVE(NV, loc); WAIT(NV, out); } while (0)
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int nB = gridDim.x;
     const int rowsPer = (P.nRows + nB - 1) / nB;
@@ -431,16 +474,15 @@ pcg_kernel(PcgParams P)
 
     const bool MAS = P.mas.L > 0;
     MasSmem MS = {};
-    if (MAS) { MS = mas_carve(smemRaw + P.masSmemOff, P.mas); mas_init(P.mas, MS, blockIdx.x); }
+    if (MAS) { MS = mas_carve(smemRaw + P.masSmemOff, P.mas); mas_init(P.mas, MS, blockIdx.x, rowBeg, rowEnd); }
     auto getR = [&](int lr) -> double2 { return SMEM ? S.r[lr] : reinterpret_cast<const double2*>(P.r)[rowBeg + lr]; };
     // z = z0 (block-Jacobi part, already stored) + coarse correction of the row's leaf; returns this thread's share of r.z
     auto mas_finish = [&]() -> double {
         double acc = 0.0;
-        const int leaf0 = P.mas.lv[0].ctaBeg[blockIdx.x];
         for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
             const int lr = row - rowBeg;
-            const float4 vi = __ldg(P.mas.vinfo + row);
-            const double* e = MS.e + (size_t)(MS.off[0] + (__float_as_int(vi.w) - leaf0)) * kMasDof;
+            const float4 vi = MS.vinfo[lr];
+            const double* e = MS.e + (size_t)(__float_as_int(vi.w) - MS.leaf0) * kMasDof;
             double2 zz = SMEM ? S.z[lr] : reinterpret_cast<const double2*>(P.z)[row];
             const double2 r2 = getR(lr);
             zz.x += (double)vi.x * e[0] + (double)vi.y * e[1] + (double)vi.z * e[2];
@@ -475,8 +517,10 @@ pcg_kernel(PcgParams P)
         loc[0] += b0 * zz.x + b1 * zz.y;
         loc[1] += b0 * b0 + b1 * b1;
     }
-    if (MAS) { __syncthreads(); mas_up(P.mas, MS, blockIdx.x, rowBeg, getR); }
-    ALLREDUCE(2, loc, red);
+    if (MAS) { __syncthreads(); mas_restrict(P.mas, MS, blockIdx.x, getR); }
+    ARRIVE(2, loc);
+    if (MAS) mas_local_solves(P.mas, MS);
+    WAIT(2, red);
     double rz = red[0];
     const double bb = red[1];
     if (MAS && bb > 0.0) {
@@ -523,9 +567,11 @@ pcg_kernel(PcgParams P)
                 loc[0] += r2.x * zz.x + r2.y * zz.y;
                 loc[1] += r2.x * r2.x + r2.y * r2.y;
             }
-            if (MAS) { __syncthreads(); mas_up(P.mas, MS, blockIdx.x, rowBeg, getR); }
+            if (MAS) { __syncthreads(); mas_restrict(P.mas, MS, blockIdx.x, getR); }
             if (P.dbg) { __syncthreads(); t3 = clock64(); }
-            ALLREDUCE(2, loc, red);
+            ARRIVE(2, loc);
+            if (MAS) mas_local_solves(P.mas, MS);
+            WAIT(2, red);
             double rzNew = red[0];
             rr = red[1];
             ++it;
@@ -559,6 +605,8 @@ pcg_kernel(PcgParams P)
         P.scal[S_PCG_BNORM] = sqrt(bb);
     }
 #undef ALLREDUCE
+#undef ARRIVE
+#undef WAIT
 }
 
 // stand-alone y = A x (ocb_multiply; also used by tests)
@@ -617,15 +665,15 @@ static size_t mas_smem_estimate(int rowsPer, int grid)
 {
     int local = 0, k = (rowsPer + kMasLeaf - 1) / kMasLeaf;
     for (;;) { local += k; if (k <= 1) break; k = (k + kMasGroup - 1) / kMasGroup; }
-    int top = 0; k = grid;
-    for (;;) { top += k; if (k <= kMasGroup) break; k = (k + kMasGroup - 1) / kMasGroup; }
-    return mas_smem_bytes(local + kMasMaxLevels, top) + 64;
+    int top = 0, nCh = 0; k = grid;
+    for (;;) { top += k; ++nCh; if (k <= kMasGroup) break; k = (k + kMasGroup - 1) / kMasGroup; }
+    return mas_smem_bytes(local + kMasMaxLevels, top, rowsPer, nCh) + 64;
 }
 static PcgPlan pcg_plan(ocb_ctx* c)
 {
     static const int targetRows = []() { const char* e = getenv("OCB_PCG_ROWS_PER_CTA"); int v = e ? atoi(e) : 256; return v < 32 ? 32 : v; }();
     static const bool allowSmem = []() { const char* e = getenv("OCB_PCG_NO_SMEM"); return !(e && atoi(e)); }();
-    const size_t limit = 216 * 1024;
+    const size_t limit = 214 * 1024;
     static const bool allowCluster = []() { const char* e = getenv("OCB_PCG_NO_CLUSTER"); return !(e && atoi(e)); }();
     PcgPlan pl; pl.smem = false; pl.cluster = false; pl.maxBlk = 0; pl.smemBytes = 0;
     const int n = c->nVtot;
@@ -646,7 +694,7 @@ static PcgPlan pcg_plan(ocb_ctx* c)
         const size_t bytes = slice_need(kClusterSize, maxBlk);
         if (bytes <= limit) {
             if (c->clusterOk < 0) {                           // probe once: can such a cluster be scheduled?
-                cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
+                cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
                 cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(kClusterSize); cfg.blockDim = dim3(kPcgBlock); cfg.dynamicSmemBytes = limit;
@@ -747,9 +795,9 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     if (c->masH.enabled && c->masH.grid == grid && c->masD.view.L > 0) {
         P.mas = c->masD.view;
         P.masSmemOff = smemBytes;
-        smemBytes += mas_smem_bytes(P.mas.maxLocalNodes, P.mas.topNodes);
+        smemBytes += mas_smem_bytes(P.mas.maxLocalNodes, P.mas.topNodes, P.mas.rowsPer, P.mas.nCh);
     }
-    const size_t smemCap = 224 * 1024;
+    const size_t smemCap = 220 * 1024;      // + ~5 KB static (reduction scratch) <= 227 KB per CTA
     if (smemBytes > smemCap) return set_err(c, OCB_ERR_STATE, "PCG: shared-memory plan exceeds the SM capacity");
     OCB_CUDA(c, cudaMemsetAsync(c->partials.p, 0, slotDoubles * sizeof(double), c->stream));
     static const bool dbgOn = []() { const char* e = getenv("OCB_PCG_DEBUG"); return e && atoi(e); }();

@@ -45,7 +45,7 @@ def test_newton_iterations_inside_reference_host(obj, tmp_path):
     for k in range(n):
         # free-running (not teacher-forced): the ~1e-11 PCG-vs-LDLT difference of every step is amplified ~6x per
         # iteration on the steep Tutte-start landscape (see test_optimizer_free_run_with_reference_scaffold)
-        tol = 1e-9 if k < 3 else (1e-6 if k < 5 else 1e-4)
+        tol = 1e-9 if k < 2 else (1e-8 if k < 3 else (1e-6 if k < 5 else 1e-4))
         for key in ("E", "Enoscaf"):
             assert abs(float(got[k][key]) - float(want[k][key])) <= tol * float(want[k][key]), (k, key, got[k], want[k])
         for key in ("F", "V", "amF", "amV", "bnd", "cohE"):

@@ -146,7 +146,7 @@ def lib_hierarchy(X, grid):
     return np.asarray(vert_of, np.int64), levels
 
 
-def mas_setup(A, X, fixed, order, levels, basis=3, prec="f64", leaf_dense=True):
+def mas_setup(A, X, fixed, order, levels, basis=3, prec="f64", leaf_dense=True, exact_from=99):
     """Returns a function r -> z.  A in the NEW order."""
     n2 = A.shape[0]
     ops = []
@@ -189,6 +189,11 @@ def mas_setup(A, X, fixed, order, levels, basis=3, prec="f64", leaf_dense=True):
                     vals.append(f * free[b:e])
         Pm = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n2, 2 * basis * len(rng))).tocsr()
         Al = (Pm.T @ A @ Pm).tocsr()
+        if l + 1 >= exact_from:             # exact coarse solve on this level's Galerkin matrix, no levels above
+            D = Al.toarray()
+            d = np.diag(D).copy(); bad = d <= 1e-300 * max(1.0, d.max()); D[bad, bad] = 1.0
+            ops.append((Pm, sp.csr_matrix(quant(np.linalg.pinv(D, hermitian=True)))))
+            break
         parent = np.asarray(levels[l]["parent"])
         blocks = []
         for gidx in range(parent.max() + 1):
@@ -241,6 +246,7 @@ def main():
     ap.add_argument("--prec", default="f64")
     ap.add_argument("--no-leaf-dense", action="store_true")
     ap.add_argument("--jacobi", action="store_true")
+    ap.add_argument("--exact-from", type=int, default=99, help="level (1-based) solved exactly on its Galerkin matrix")
     ap.add_argument("--lib", action="store_true", help="use the hierarchy built by liboptcuts_b200.so")
     a = ap.parse_args()
     t0 = time.time()
@@ -259,7 +265,7 @@ def main():
     perm2 = np.stack([2 * order, 2 * order + 1], 1).ravel()
     Ap = A[perm2][:, perm2].tocsr()
     t0 = time.time()
-    M = mas_setup(Ap, X[order], fixed[order], order, levels, a.basis, a.prec, not a.no_leaf_dense)
+    M = mas_setup(Ap, X[order], fixed[order], order, levels, a.basis, a.prec, not a.no_leaf_dense, a.exact_from)
     t1 = time.time()
     x, it = pcg(Ap, b[perm2], M)
     print("MAS leaf %d group %d grid %d basis %d prec %s: levels %s -> %d iterations (setup %.1fs, solve %.1fs) resid %.2e"
