@@ -80,10 +80,10 @@ struct MasHost {
     std::vector<float> vinfo;                            // 4 per row
 };
 struct MasDev {
-    DevBuf<int32_t> ints, tabI; DevBuf<double> geom, val, rcCta, tabD; DevBuf<float> inv, vinfo;
+    DevBuf<int32_t> ints, tabI; DevBuf<double> geom, val, rcCta, tabD, dense; DevBuf<float> inv, vinfo, cinv;
     std::vector<MasLevel> lv;
     std::vector<const int32_t*> lvRowPtr, lvColIdx; std::vector<double*> lvVal; std::vector<int> lvNnz;
-    size_t valTotal = 0; int groupTotal = 0;
+    size_t valTotal = 0; int groupTotal = 0; bool denseAttr = false;
     MasView view = {};
 };
 

@@ -4,6 +4,7 @@
 // (EigenLibSolver.cpp:80-93) as the per-Newton-iteration solver set-up.
 #include "ocb_internal.cuh"
 #include "ocb_mas.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -180,32 +181,19 @@ int mas_build_hierarchy(ocb_ctx* c, const double* xyIn, int grid)
         finish_level(c2, nxt, groupPre);
     }
     if (H.Lloc == 0) return set_err(c, OCB_ERR_STATE, "MAS hierarchy: too many local levels");
-    // a CTA without rows owns no node; the level above must still see `grid`-indexed CTA nodes: only non-empty CTAs carry one
-    int l = H.Lloc;
-    for (; l < kMasMaxLevels; ++l) {
-        const int nn = (int)H.lv[l - 1].childBeg.size() - 1;
-        if (nn <= kMasGroup) break;
-        H.lv.emplace_back();
-        MasHost::Level& cur = H.lv[l - 1];
-        MasHost::Level& nxt = H.lv[l];
-        const int ng = (nn + kMasGroup - 1) / kMasGroup;
-        std::vector<int> groupPre;
-        even_prefix(nn, ng, groupPre);
-        finish_level(cur, nxt, groupPre);
-    }
-    H.L = l;
-    {
-        MasHost::Level& top = H.lv[H.L - 1];
-        const int nn = (int)top.childBeg.size() - 1;
-        if (nn > kMasGroup) return set_err(c, OCB_ERR_STATE, "MAS hierarchy: too many levels");
-        top.parent.assign((size_t)nn, 0);
-    }
+    // coarse level: the first level small enough for the exact dense inverse; everything above it is dropped
+    static const int coarseMax = []() { const char* e = getenv("OCB_MAS_COARSE_MAX"); int v = e ? atoi(e) : kMasCoarseMax; return v < kMasDof ? kMasDof : (v > kMasCoarseMax ? kMasCoarseMax : v); }();
+    int Lc = H.Lloc;
+    for (int l = 1; l <= H.Lloc; ++l) if (((int)H.lv[l - 1].childBeg.size() - 1) * kMasDof <= coarseMax) { Lc = l; break; }
+    if (((int)H.lv[Lc - 1].childBeg.size() - 1) * kMasDof > kMasCoarseMax) return set_err(c, OCB_ERR_STATE, "MAS hierarchy: coarse level too large");
+    H.lv.resize((size_t)Lc);
+    H.L = H.Lloc = Lc;
+    H.lv[Lc - 1].parent.assign(H.lv[Lc - 1].childBeg.size() - 1, 0);
     H.topNodes = 0;
-    for (int k = H.Lloc; k <= H.L; ++k) H.topNodes += (int)H.lv[k - 1].childBeg.size() - 1;
     H.maxLocalNodes = 0;
     for (int b = 0; b < grid; ++b) {
         int s = 0;
-        for (int k = 1; k <= H.Lloc; ++k) s += H.lv[k - 1].ctaBeg[b + 1] - H.lv[k - 1].ctaBeg[b];
+        for (int k = 1; k <= H.L; ++k) s += H.lv[k - 1].ctaBeg[b + 1] - H.lv[k - 1].ctaBeg[b];
         H.maxLocalNodes = std::max(H.maxLocalNodes, s);
     }
     H.enabled = true;
@@ -257,7 +245,7 @@ int mas_install(ocb_ctx* c)
         MasHost::Level& V = H.lv[l - 1];
         Off& o = off[l - 1];
         o.nNodes = (int)V.childBeg.size() - 1;
-        o.nGroups = l < H.L ? (int)H.lv[l].childBeg.size() - 1 : 1;
+        o.nGroups = l < H.L ? (int)H.lv[l].childBeg.size() - 1 : 0;
         o.nnz = (int)V.colIdx.size();
         o.childBeg = put(V.childBeg); o.parent = put(V.parent);
         o.ctaBeg = l <= H.Lloc ? put(V.ctaBeg) : 0;
@@ -266,15 +254,11 @@ int mas_install(ocb_ctx* c)
         o.val = valTot; valTot += 36 * (size_t)o.nnz;
         o.inv = invTot; invTot += (size_t)kMasBlk * kMasBlk * o.nGroups;
     }
-    // the top level's group list: [0, nNodes]
-    std::vector<int32_t> topGroup(2, 0); topGroup[1] = off[H.L - 1].nNodes;
-    const size_t topGroupOff = put(topGroup);
     OCB_CUDA(c, D.ints.reserve(ints.size() + 4, c->stream));
     OCB_CUDA(c, D.geom.reserve(geom.size() + 4, c->stream));
     OCB_CUDA(c, D.val.reserve(valTot + 4, c->stream));
     OCB_CUDA(c, D.inv.reserve(invTot + 4, c->stream));
     OCB_CUDA(c, D.vinfo.reserve(4 * (size_t)n + 4, c->stream));
-    OCB_CUDA(c, D.rcCta.reserve((size_t)H.grid * kMasDof + 8, c->stream));
     OCB_CUDA(c, cudaMemcpyAsync(D.ints.p, ints.data(), ints.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     OCB_CUDA(c, cudaMemcpyAsync(D.geom.p, geom.data(), geom.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     OCB_CUDA(c, cudaMemcpyAsync(D.vinfo.p, H.vinfo.data(), H.vinfo.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -289,7 +273,7 @@ int mas_install(ocb_ctx* c)
         V.nNodes = o.nNodes; V.nGroups = o.nGroups;
         V.childBeg = D.ints.p + o.childBeg;
         V.parent = D.ints.p + o.parent;
-        V.groupBeg = l < H.L ? D.ints.p + off[l].childBeg : D.ints.p + topGroupOff;
+        V.groupBeg = l < H.L ? D.ints.p + off[l].childBeg : nullptr;
         V.geom = reinterpret_cast<const double4*>(D.geom.p + o.geom);
         V.inv = D.inv.p + o.inv;
         D.lvRowPtr[l - 1] = D.ints.p + o.rowPtr; D.lvColIdx[l - 1] = D.ints.p + o.colIdx; D.lvVal[l - 1] = D.val.p + o.val;
@@ -297,10 +281,9 @@ int mas_install(ocb_ctx* c)
         D.groupTotal += o.nGroups;
     }
     // ---- the apply's tables (CTA-local indices, see MasView)
-    const int grid = H.grid, Lloc = H.Lloc, L = H.L, nCh = L - Lloc + 1;
+    const int grid = H.grid, L = H.L;
     const int rowsPer = (n + grid - 1) / grid;
     auto nodesOf = [&](int l) { return (int)H.lv[l - 1].childBeg.size() - 1; };
-    auto groupBegOf = [&](int l, int g) { return l < L ? H.lv[l].childBeg[g] : (g == 0 ? 0 : nodesOf(L)); };
     auto xfer = [&](int l, int k, double* X) {         // node k of level l -> its parent (level l + 1)
         X[0] = X[1] = 0.0; X[2] = 1.0; X[3] = 0.0;
         if (l >= L) return;
@@ -308,26 +291,27 @@ int mas_install(ocb_ctx* c)
         const double* gp = H.lv[l].geom.data() + 4 * (size_t)H.lv[l - 1].parent[k];
         X[0] = (gc[0] - gp[0]) / gp[2]; X[1] = (gc[1] - gp[1]) / gp[2]; X[2] = gc[2] / gp[2];
     };
-    const int nCtaNodes = nodesOf(Lloc);
     std::vector<int32_t> tI; std::vector<double> tD;
-    std::vector<int32_t> ctaNodeOff((size_t)grid + 1, 0), ctaSolve((size_t)grid, 0), ctaLvOff((size_t)grid * (kMasMaxLevels + 1), 0), ctaLeafBeg(H.lv[0].ctaBeg);
+    std::vector<int32_t> ctaNodeOff((size_t)grid + 1, 0), ctaSolve((size_t)grid, 0), ctaLvOff((size_t)grid * (kMasMaxLevels + 1), 0);
+    const std::vector<int32_t>& ctaLeafBeg = H.lv[0].ctaBeg;
+    const std::vector<int32_t>& ctaCBeg = H.lv[L - 1].ctaBeg;
     std::vector<int32_t> nodeA, nodeB; std::vector<double> nodeX;
-    { size_t tot = 0; for (int l = 1; l <= Lloc; ++l) tot += (size_t)nodesOf(l); nodeA.reserve(4 * tot); nodeB.reserve(4 * tot); nodeX.reserve(4 * tot); }
+    { size_t tot = 0; for (int l = 1; l <= L; ++l) tot += (size_t)nodesOf(l); nodeA.reserve(4 * tot); nodeB.reserve(4 * tot); nodeX.reserve(4 * tot); }
     for (int b = 0; b < grid; ++b) {
         int32_t* lvOff = ctaLvOff.data() + (size_t)b * (kMasMaxLevels + 1);
         int o = 0;
-        for (int l = 1; l <= Lloc; ++l) { lvOff[l - 1] = o; o += H.lv[l - 1].ctaBeg[b + 1] - H.lv[l - 1].ctaBeg[b]; }
-        for (int l = Lloc; l <= kMasMaxLevels; ++l) lvOff[l] = o;
+        for (int l = 1; l <= L; ++l) { lvOff[l - 1] = o; o += H.lv[l - 1].ctaBeg[b + 1] - H.lv[l - 1].ctaBeg[b]; }
+        for (int l = L; l <= kMasMaxLevels; ++l) lvOff[l] = o;
         ctaNodeOff[b + 1] = ctaNodeOff[b] + o;
-        ctaSolve[b] = lvOff[Lloc - 1];
+        ctaSolve[b] = lvOff[L - 1];
         const int rowBeg = std::min(n, b * rowsPer);
-        for (int l = 1; l <= Lloc; ++l) {
+        for (int l = 1; l <= L; ++l) {
             const MasHost::Level& V = H.lv[l - 1];
             const int n0 = V.ctaBeg[b];
             for (int k = n0; k < V.ctaBeg[b + 1]; ++k) {
                 int32_t A[4] = {0, 0, 0, 0}, B[4] = {0, 0, 0, l};
-                if (l < Lloc) {
-                    const int g = V.parent[k], gb = groupBegOf(l, g), ge = groupBegOf(l, g + 1);
+                if (l < L) {
+                    const int g = V.parent[k], gb = H.lv[l].childBeg[g], ge = H.lv[l].childBeg[g + 1];
                     A[0] = lvOff[l - 1] + (gb - n0); A[1] = kMasDof * (ge - gb); A[2] = kMasDof * (k - gb);
                     A[3] = lvOff[l] + (g - H.lv[l].ctaBeg[b]);
                     B[0] = (int32_t)(off[l - 1].inv + (size_t)g * kMasBlk * kMasBlk);
@@ -340,52 +324,31 @@ int mas_install(ocb_ctx* c)
             }
         }
     }
-    std::vector<int32_t> topLevelOff((size_t)nCh + 1, 0);
-    for (int j = 0; j < nCh; ++j) topLevelOff[j + 1] = topLevelOff[j] + nodesOf(Lloc + j);
-    const int topNodes = topLevelOff[nCh];
-    std::vector<int32_t> topUp(2 * (size_t)topNodes, 0); std::vector<double> topX(4 * (size_t)topNodes, 0.0);
-    for (int j = 0; j < nCh; ++j) {
-        const int l = Lloc + j;
-        for (int k = 0; k < nodesOf(l); ++k) {
-            const int ti = topLevelOff[j] + k;
-            if (j > 0) { topUp[2 * ti] = topLevelOff[j - 1] + H.lv[l - 1].childBeg[k]; topUp[2 * ti + 1] = H.lv[l - 1].childBeg[k + 1] - H.lv[l - 1].childBeg[k]; }
-            xfer(l, k, topX.data() + 4 * (size_t)ti);
-        }
-    }
-    std::vector<int32_t> chainM((size_t)grid * kMasMaxLevels * 4, 0);
-    for (int b = 0; b < nCtaNodes; ++b) {
-        int anc[kMasMaxLevels + 2];
-        anc[Lloc] = b;
-        for (int l = Lloc; l < L; ++l) anc[l + 1] = H.lv[l - 1].parent[anc[l]];
-        for (int j = 0; j < nCh; ++j) {
-            const int l = L - j, a = anc[l], g = H.lv[l - 1].parent[a], gb = groupBegOf(l, g), ge = groupBegOf(l, g + 1);
-            int32_t* C = chainM.data() + ((size_t)b * kMasMaxLevels + j) * 4;
-            C[0] = topLevelOff[l - Lloc] + gb; C[1] = kMasDof * (ge - gb);
-            C[2] = (int32_t)(off[l - 1].inv + (size_t)g * kMasBlk * kMasBlk + (size_t)(a - gb) * kMasDof * kMasBlk);
-            C[3] = topLevelOff[l - Lloc] + a;
-        }
-    }
     auto putI = [&tI](const std::vector<int32_t>& v) { size_t o = tI.size(); tI.insert(tI.end(), v.begin(), v.end()); while (tI.size() & 3) tI.push_back(0); return o; };
     auto putD = [&tD](const std::vector<double>& v) { size_t o = tD.size(); tD.insert(tD.end(), v.begin(), v.end()); while (tD.size() & 3) tD.push_back(0.0); return o; };
-    const size_t oNodeOff = putI(ctaNodeOff), oSolve = putI(ctaSolve), oLvOff = putI(ctaLvOff), oLeafBeg = putI(ctaLeafBeg), oNodeA = putI(nodeA),
-                 oNodeB = putI(nodeB), oTopUp = putI(topUp), oTopLevelOff = putI(topLevelOff), oChainM = putI(chainM);
-    const size_t oNodeX = putD(nodeX), oTopX = putD(topX);
+    const size_t oNodeOff = putI(ctaNodeOff), oSolve = putI(ctaSolve), oLvOff = putI(ctaLvOff), oLeafBeg = putI(ctaLeafBeg), oCBeg = putI(ctaCBeg),
+                 oNodeA = putI(nodeA), oNodeB = putI(nodeB);
+    const size_t oNodeX = putD(nodeX);
+    // dense coarse system: X / Y ping-pong (fp64), the fp32 inverse, the original diagonal, two pivot-block buffers
+    const int nC = kMasDof * nodesOf(L);
+    const int ldC = (nC + kMasCoarseBlk - 1) / kMasCoarseBlk * kMasCoarseBlk;
     OCB_CUDA(c, D.tabI.reserve(tI.size() + 4, c->stream));
     OCB_CUDA(c, D.tabD.reserve(tD.size() + 4, c->stream));
+    OCB_CUDA(c, D.dense.reserve(2 * (size_t)ldC * ldC + (size_t)ldC + 2 * kMasCoarseBlk * kMasCoarseBlk + 8, c->stream));
+    OCB_CUDA(c, D.cinv.reserve((size_t)ldC * ldC + 8, c->stream));
+    OCB_CUDA(c, D.rcCta.reserve((size_t)ldC + 8, c->stream));
     OCB_CUDA(c, cudaMemcpyAsync(D.tabI.p, tI.data(), tI.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     OCB_CUDA(c, cudaMemcpyAsync(D.tabD.p, tD.data(), tD.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     // (pageable sources: cudaMemcpyAsync returns once the data is staged, the vectors may go out of scope)
     MasView& W = D.view;
     W = MasView();
-    W.L = L; W.Lloc = Lloc; W.grid = grid; W.nCh = nCh; W.topNodes = topNodes; W.nCtaNodes = nCtaNodes;
+    W.L = L; W.nC = nC; W.ldC = ldC;
     W.maxLocalNodes = H.maxLocalNodes; W.rowsPer = rowsPer;
     W.ctaNodeOff = D.tabI.p + oNodeOff; W.ctaSolve = D.tabI.p + oSolve; W.ctaLvOff = D.tabI.p + oLvOff; W.ctaLeafBeg = D.tabI.p + oLeafBeg;
+    W.ctaCBeg = D.tabI.p + oCBeg;
     W.nodeA = reinterpret_cast<const int4*>(D.tabI.p + oNodeA); W.nodeB = reinterpret_cast<const int4*>(D.tabI.p + oNodeB);
     W.nodeX = reinterpret_cast<const double4*>(D.tabD.p + oNodeX);
-    W.topUp = reinterpret_cast<const int2*>(D.tabI.p + oTopUp); W.topX = reinterpret_cast<const double4*>(D.tabD.p + oTopX);
-    W.topLevelOff = D.tabI.p + oTopLevelOff; W.chainM = reinterpret_cast<const int4*>(D.tabI.p + oChainM);
-    W.inv = D.inv.p; W.vinfo = reinterpret_cast<const float4*>(D.vinfo.p); W.rcCta = D.rcCta.p;
-    H.topNodes = topNodes;
+    W.inv = D.inv.p; W.cinv = D.cinv.p; W.vinfo = reinterpret_cast<const float4*>(D.vinfo.p); W.rcC = D.rcCta.p;
     return 0;
 }
 
@@ -557,6 +520,194 @@ mas_invert_kernel(MasInvertArgs P)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// coarse level: dense Galerkin matrix and its exact inverse
+__global__ void __launch_bounds__(256)
+mas_dense_fill_kernel(int nNodes, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, const double* __restrict__ val,
+                      int ld, int nC, double* __restrict__ X)
+{
+    const int total = nNodes * 36;
+    for (int w = blockIdx.x * 256 + threadIdx.x; w < total; w += gridDim.x * 256) {
+        const int a = w / 36, ij = w % 36, i = ij / 6, j = ij % 6;
+        for (int blk = rowPtr[a]; blk < rowPtr[a + 1]; ++blk)
+            X[(size_t)(kMasDof * a + i) * ld + kMasDof * colIdx[blk] + j] = val[36 * (size_t)blk + ij];
+    }
+    for (int k = nC + blockIdx.x * 256 + threadIdx.x; k < ld; k += gridDim.x * 256) X[(size_t)k * ld + k] = 1.0;     // padding
+}
+
+// In-place inverse of the SPD coarse matrix by blocked Gauss-Jordan (48x48 tiles, no pivoting), one cooperative
+// launch over the whole GPU: step k turns buffer X into buffer Y tile by tile,
+//     Y_kk = P,  Y_kj = P X_kj,  Y_ik = -X_ik P,  Y_ij = X_ij - X_ik P X_kj      (P = X_kk^-1)
+// and the CTA that produces Y_(k+1)(k+1) inverts it right away (look-ahead) so that one grid barrier per step is
+// all the synchronisation there is.  A DOF whose pivot collapses (a coarse node of fixed vertices only, collinear
+// leaf) is dropped: zero row and column in the inverse.  Finally the symmetrised result is stored in fp32.
+static constexpr int kCB = kMasCoarseBlk, kCBs = kMasCoarseBlk + 2;      // tile and its padded shared-memory stride
+static constexpr int kDenseThreads = 576;                                // 18 warps: warp w owns the 8x8 sub-tiles 2w and 2w+1 (6x6 grid)
+struct DenseInvArgs { int nb, ld, nC; double* X; double* Y; double* P; double* diag0; float* out; };
+
+// The tile products run on the FP64 tensor cores (mma.sync m8n8k4: the only tensor path for doubles; nothing else on
+// this path is a dense contraction).  A thread owns 4 elements of a 48x48 tile, in the accumulator-fragment layout:
+// row = 8 * (warp / 3) + lane / 4, columns c0 + {0, 1, 8, 9} with c0 = 8 * ((2 * warp) % 6) + 2 * (lane % 4).
+struct TileMap { int r, c0; };
+__device__ __forceinline__ TileMap tile_map()
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TileMap m; m.r = 8 * (warp / 3) + (lane >> 2); m.c0 = 8 * ((2 * warp) % 6) + 2 * (lane & 3);
+    return m;
+}
+__device__ __forceinline__ int tile_col(const TileMap& m, int e) { return m.c0 + (e & 1) + 8 * (e >> 1); }
+
+__device__ __forceinline__ void tile_load_regs(double (&c)[4], const double* __restrict__ G, int ld, const TileMap& m)
+{
+    // through L2: the tile was written by another CTA in the previous step
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(G + (size_t)m.r * ld + m.c0)), b = __ldcg(reinterpret_cast<const double2*>(G + (size_t)m.r * ld + m.c0 + 8));
+    c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
+}
+__device__ __forceinline__ void tile_store_smem(double (*S)[kCBs], const double (&c)[4], const TileMap& m)
+{
+    *reinterpret_cast<double2*>(&S[m.r][m.c0]) = make_double2(c[0], c[1]);
+    *reinterpret_cast<double2*>(&S[m.r][m.c0 + 8]) = make_double2(c[2], c[3]);
+}
+__device__ __forceinline__ void tile_load(double (*S)[kCBs], const double* __restrict__ G, int ld, const TileMap& m)
+{
+    double c[4];
+    tile_load_regs(c, G, ld, m);
+    tile_store_smem(S, c, m);
+}
+// c += sign * A * B  (48x48 tiles in shared memory)
+__device__ __forceinline__ void tile_gemm(const double (*A)[kCBs], const double (*B)[kCBs], double (&c)[4], double sign)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rowA = 8 * (warp / 3) + (lane >> 2), kq = lane & 3;
+    const int colB0 = 8 * ((2 * warp) % 6) + (lane >> 2);
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < kCB / 4; ++kk) {
+        const double a = A[rowA][4 * kk + kq];
+        const double b0 = B[4 * kk + kq][colB0], b1 = B[4 * kk + kq][colB0 + 8];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b0));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d2), "+d"(d3) : "d"(a), "d"(b1));
+    }
+    c[0] += sign * d0; c[1] += sign * d1; c[2] += sign * d2; c[3] += sign * d3;
+}
+// Gauss-Jordan inverse of one SPD tile held in REGISTERS (4 elements per thread); per pivot the pivot row and column
+// cross through a double-buffered shared-memory line, one barrier per pivot.  buf: 2 x (48 row + 48 column) doubles.
+__device__ __forceinline__ void tile_invert(double (&d)[4], double* buf, const double* d0s, const TileMap& m)
+{
+    for (int k = 0; k < kCB; ++k) {
+        double* rowb = buf + (k & 1) * 2 * kCB;
+        double* colb = rowb + kCB;
+        if (m.r == k) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) rowb[tile_col(m, e)] = d[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (tile_col(m, e) == k) colb[m.r] = d[e];
+        __syncthreads();
+        const double p = rowb[k], dk0 = d0s[k];
+        const bool bad = !(dk0 > 0.0) || !(p > 1e-10 * dk0);
+        if (bad) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (m.r == k || tile_col(m, e) == k) d[e] = 0.0;
+            continue;
+        }
+        const double ip = 1.0 / p;
+        const double f = colb[m.r];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = tile_col(m, e);
+            if (m.r != k) d[e] = (j != k) ? d[e] - f * (rowb[j] * ip) : -f * ip;
+            else d[e] = (j != k) ? d[e] * ip : ip;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kDenseThreads, 1)
+mas_dense_invert_kernel(DenseInvArgs A)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double (*sP)[kCBs] = reinterpret_cast<double (*)[kCBs]>(smraw);
+    double (*sA)[kCBs] = sP + kCB;
+    double (*sB)[kCBs] = sA + kCB;
+    double (*sR)[kCBs] = sB + kCB;
+    double* d0s = reinterpret_cast<double*>(sR + kCB);
+    double* ibuf = d0s + kCB;                       // 4 x 48
+    const int tid = threadIdx.x;
+    const TileMap m = tile_map();
+    const int nb = A.nb, ld = A.ld;
+    for (int k = blockIdx.x * kDenseThreads + tid; k < ld; k += gridDim.x * kDenseThreads) A.diag0[k] = A.X[(size_t)k * ld + k];
+    grid.sync();
+    if (blockIdx.x == 0) {
+        if (tid < kCB) d0s[tid] = A.diag0[tid];
+        double d[4];
+        tile_load_regs(d, A.X, ld, m);
+        tile_invert(d, ibuf, d0s, m);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) A.P[(size_t)m.r * kCB + tile_col(m, e)] = d[e];
+    }
+    double* X = A.X; double* Y = A.Y;
+    for (int k = 0; k < nb; ++k) {
+        grid.sync();
+        tile_load(sP, A.P + (size_t)(k & 1) * kCB * kCB, kCB, m);
+        __syncthreads();
+        const int special = k + 1 < nb ? (k + 1) * nb + (k + 1) : -1;
+        const bool owner = special >= 0 && (int)blockIdx.x == special % (int)gridDim.x;
+        // tiles of this CTA, the look-ahead tile first
+        for (int it = owner ? -1 : 0;; ++it) {
+            int t;
+            if (it < 0) t = special;
+            else { t = blockIdx.x + it * gridDim.x; if (t >= nb * nb) break; if (t == special) continue; }
+            const int i = t / nb, j = t % nb;
+            const double* Xkj = X + (size_t)k * kCB * ld + (size_t)j * kCB;
+            const double* Xik = X + (size_t)i * kCB * ld + (size_t)k * kCB;
+            double c[4] = {0.0, 0.0, 0.0, 0.0};
+            if (i == k && j == k) {
+                c[0] = sP[m.r][m.c0]; c[1] = sP[m.r][m.c0 + 1]; c[2] = sP[m.r][m.c0 + 8]; c[3] = sP[m.r][m.c0 + 9];
+            } else if (i == k) {
+                tile_load(sB, Xkj, ld, m);
+                __syncthreads();
+                tile_gemm(sP, sB, c, 1.0);
+            } else if (j == k) {
+                tile_load(sA, Xik, ld, m);
+                __syncthreads();
+                tile_gemm(sA, sP, c, -1.0);
+            } else {
+                tile_load(sB, Xkj, ld, m);
+                tile_load(sA, Xik, ld, m);
+                tile_load_regs(c, X + (size_t)i * kCB * ld + (size_t)j * kCB, ld, m);
+                __syncthreads();
+                double r[4] = {0.0, 0.0, 0.0, 0.0};
+                tile_gemm(sP, sB, r, 1.0);
+                tile_store_smem(sR, r, m);
+                __syncthreads();
+                tile_gemm(sA, sR, c, -1.0);
+            }
+            double* Yij = Y + (size_t)i * kCB * ld + (size_t)j * kCB + (size_t)m.r * ld + m.c0;
+            *reinterpret_cast<double2*>(Yij) = make_double2(c[0], c[1]);
+            *reinterpret_cast<double2*>(Yij + 8) = make_double2(c[2], c[3]);
+            __syncthreads();                   // the shared tiles are reused by the next tile
+            if (it < 0) {                      // look-ahead: invert the next pivot tile now
+                if (tid < kCB) d0s[tid] = A.diag0[(k + 1) * kCB + tid];
+                __syncthreads();
+                tile_invert(c, ibuf, d0s, m);
+                double* Pn = A.P + (size_t)((k + 1) & 1) * kCB * kCB;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) Pn[(size_t)m.r * kCB + tile_col(m, e)] = c[e];
+            }
+        }
+        double* T = X; X = Y; Y = T;
+    }
+    grid.sync();
+    const size_t total = (size_t)ld * ld;
+    for (size_t e = (size_t)blockIdx.x * kDenseThreads + tid; e < total; e += (size_t)gridDim.x * kDenseThreads) {
+        const int i = (int)(e / ld), j = (int)(e % ld);
+        A.out[e] = (i < A.nC && j < A.nC) ? (float)(0.5 * (__ldcg(X + e) + __ldcg(X + (size_t)j * ld + i))) : 0.0f;
+    }
+}
+
 int launch_mas_setup(ocb_ctx* c)
 {
     MasHost& H = c->masH;
@@ -575,17 +726,40 @@ int launch_mas_setup(ocb_ctx* c)
                                                     D.lv[l].geom, D.lvRowPtr[l], D.lvColIdx[l], D.lvVal[l]);
         KCHECK(c);
     }
-    MasInvertArgs A;
-    A.L = H.L;
-    A.groupPre[0] = 0;
-    for (int l = 1; l <= H.L; ++l) {
-        const MasLevel& V = D.lv[l - 1];
-        A.groupPre[l] = A.groupPre[l - 1] + V.nGroups;
-        A.rowPtr[l - 1] = D.lvRowPtr[l - 1]; A.colIdx[l - 1] = D.lvColIdx[l - 1]; A.val[l - 1] = D.lvVal[l - 1];
-        A.parent[l - 1] = V.parent; A.groupBeg[l - 1] = V.groupBeg; A.inv[l - 1] = V.inv;
+    if (H.L > 1) {                             // group inverses of the levels below the coarse one
+        MasInvertArgs A;
+        A.L = H.L - 1;
+        A.groupPre[0] = 0;
+        for (int l = 1; l < H.L; ++l) {
+            const MasLevel& V = D.lv[l - 1];
+            A.groupPre[l] = A.groupPre[l - 1] + V.nGroups;
+            A.rowPtr[l - 1] = D.lvRowPtr[l - 1]; A.colIdx[l - 1] = D.lvColIdx[l - 1]; A.val[l - 1] = D.lvVal[l - 1];
+            A.parent[l - 1] = V.parent; A.groupBeg[l - 1] = V.groupBeg; A.inv[l - 1] = V.inv;
+        }
+        mas_invert_kernel<<<A.groupPre[H.L - 1], 256, 0, c->stream>>>(A);
+        KCHECK(c);
     }
-    mas_invert_kernel<<<A.groupPre[H.L], 256, 0, c->stream>>>(A);
-    KCHECK(c);
+    {                                          // the coarse level: dense fill + exact inverse
+        const MasView& W = D.view;
+        const MasLevel& V = D.lv[H.L - 1];
+        const size_t ld = (size_t)W.ldC;
+        DenseInvArgs A;
+        A.nb = W.ldC / kCB; A.ld = W.ldC; A.nC = W.nC;
+        A.X = D.dense.p; A.Y = A.X + ld * ld; A.diag0 = A.Y + ld * ld; A.P = A.diag0 + ld; A.out = D.cinv.p;
+        OCB_CUDA(c, cudaMemsetAsync(A.X, 0, ld * ld * sizeof(double), c->stream));
+        int g = (V.nNodes * 36 + 255) / 256; if (g > c->numSMs * 8) g = c->numSMs * 8; if (g < 1) g = 1;
+        mas_dense_fill_kernel<<<g, 256, 0, c->stream>>>(V.nNodes, D.lvRowPtr[H.L - 1], D.lvColIdx[H.L - 1], D.lvVal[H.L - 1], W.ldC, W.nC, A.X);
+        KCHECK(c);
+        const size_t smem = 4 * (size_t)kCB * kCBs * sizeof(double) + 5 * kCB * sizeof(double);
+        if (!D.denseAttr) {
+            OCB_CUDA(c, cudaFuncSetAttribute(mas_dense_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            D.denseAttr = true;
+        }
+        int gi = A.nb * A.nb; if (gi > c->numSMs) gi = c->numSMs;
+        void* args[] = {&A};
+        OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)mas_dense_invert_kernel, dim3(gi), dim3(kDenseThreads), args, smem, c->stream));
+        c->launches++;
+    }
     return 0;
 }
 

@@ -1,19 +1,20 @@
-// optcuts_b200 — multilevel additive Schwarz (MAS) preconditioner of the PCG solve: device-side view and the
-// CTA-level apply (included by ocb_pcg.cu; set up by ocb_mas.cu).
+// optcuts_b200 — two-level additive Schwarz preconditioner (multilevel below the coarse level) of the PCG solve:
+// device-side view and the CTA-level apply (included by ocb_pcg.cu; set up by ocb_mas.cu).
 //
-//   M^-1 = blockdiag2x2(A)^-1 + sum_{l=1..L} P_l D_l^-1 P_l^T
+//   M^-1 = blockdiag2x2(A)^-1 + sum_{l=1..L-1} P_l D_l^-1 P_l^T + P_L (P_L^T A P_L)^-1 P_L^T
 //
 // The solver rows are ordered by recursive coordinate bisection of the UV positions so that a persistent CTA's
 // contiguous row range is a compact patch, split into leaves of <= 8 vertices.  Level-l nodes carry 6 DOFs: the
 // affine displacement fields (1, x, y) x (u, v) on the node, x/y in node-local coordinates.  8 consecutive nodes
-// form a group (= a node of level l+1); D_l is the block diagonal of the Galerkin matrix P_l^T A P_l over the
-// groups (48x48 blocks, inverted on the device, kept in fp32).  Levels 1..Lloc live entirely inside one CTA
-// (level Lloc has exactly one node per CTA); the levels above are evaluated redundantly by every CTA from the
-// `grid x 6` restricted residuals, which cross CTAs through global memory at the grid barrier that also carries
-// |r|^2 — no other communication.  Everything an iteration needs except the group inverses (node tables, per-row
-// basis values, the inverse rows of the CTA's ancestor chain) is staged in shared memory once per solve, and the
-// CTA-local group solves run between the arrive and the wait of that barrier.  Measured on the reference's
-// matrices (tools/mas_proto.py): 2466 -> 276 CG iterations at 10k faces (Tutte state), 11 500 -> 760 at 160k.
+// form a group (= a node of level l+1); below the coarse level L, D_l is the block diagonal of the Galerkin
+// matrix P_l^T A P_l over the groups (48x48 blocks, inverted on the device, kept in fp32).  The coarse level L is
+// the first level with at most kMasCoarseMax DOFs: its Galerkin matrix is inverted EXACTLY (dense blocked
+// Gauss-Jordan in fp64 across the whole GPU, stored in fp32).  All levels live inside one CTA (groups never
+// straddle a CTA); the only communication is the coarse residual (6 values per coarse node), which crosses CTAs
+// through global memory at the grid barrier that also carries |r|^2.  Node tables and per-row basis values are
+// staged in shared memory once per solve, and the CTA-local group solves run between the arrive and the wait
+// of that barrier.  Measured on the reference's matrices (tools/mas_proto.py --exact-from): 2466 -> 174 CG
+// iterations at 10k faces (Tutte state; 276 with block-diagonal coarse levels), 11 500 -> 286 at 160k (757).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -25,7 +26,6 @@ static constexpr int kMasGroup = 8;         // nodes per group
 static constexpr int kMasDof = 6;           // DOFs per node
 static constexpr int kMasBlk = kMasGroup * kMasDof;   // 48
 static constexpr int kMasMaxLevels = 12;
-static constexpr int kMasChainRow = kMasDof * kMasBlk;   // 288 floats: the 6 inverse rows of one chain level
 
 // one level of the hierarchy as the set-up kernels see it (global node indices)
 struct MasLevel {
@@ -37,72 +37,64 @@ struct MasLevel {
     float* inv;                // nGroups x 48 x 48
 };
 
+static constexpr int kMasCoarseBlk = 48;    // tile of the dense coarse inversion
+static constexpr int kMasCoarseMax = 3072;  // largest coarse system (DOFs)
+
 // Host-precomputed tables, CTA-local indices.  A CTA's local nodes are numbered level 1 first, then level 2, ...
-// up to its single level-Lloc node; "top" nodes are the nodes of levels Lloc..L of the whole hierarchy.
+// up to its coarse-level nodes.
 struct MasView {
-    int L, Lloc, grid, nCh;    // L == 0: preconditioner disabled (block-Jacobi only); nCh = L - Lloc + 1
-    int topNodes;              // nodes of levels Lloc..L
-    int nCtaNodes;             // nodes of level Lloc (= CTAs that own rows)
-    int maxLocalNodes;         // max over CTAs of the nodes of levels 1..Lloc
+    int L;                     // coarse level; 0: preconditioner disabled (block-Jacobi only)
+    int nC, ldC;               // coarse DOFs and the row stride of cinv (multiple of 48)
+    int maxLocalNodes;         // max over CTAs of the nodes of levels 1..L
     int rowsPer;               // rows per CTA (vinfo staging)
     const int32_t* ctaNodeOff; // grid + 1: first entry of every CTA in nodeA/nodeB/nodeX
-    const int32_t* ctaSolve;   // grid: local nodes below level Lloc (they take part in a CTA-local group solve)
-    const int32_t* ctaLvOff;   // grid x (kMasMaxLevels + 1): first local node of level l at [l - 1]; [Lloc] = all local nodes
+    const int32_t* ctaSolve;   // grid: local nodes below level L (they take part in a CTA-local group solve)
+    const int32_t* ctaLvOff;   // grid x (kMasMaxLevels + 1): first local node of level l at [l - 1]; [L] = all local nodes
     const int32_t* ctaLeafBeg; // grid + 1: first (global) leaf of every CTA
+    const int32_t* ctaCBeg;    // grid + 1: first coarse node of every CTA
     const int4* nodeA;         // {local index of the group's first child, nk = 6 * children of the group, 6 * slot in the group, local index of the parent}
     const int4* nodeB;         // {float offset of the group's inverse, first child (local node; local row for leaves), children, level}
     const double4* nodeX;      // {tx, ty, rho, -}: transfer of the node's coefficients to its parent's basis
-    const int2* topUp;         // per top node: {first child (top index), children}; level Lloc: unused
-    const double4* topX;       // per top node: transfer to its parent (levels < L)
-    const int32_t* topLevelOff;// nCh + 1: first top index of levels Lloc, Lloc+1, ..., L
-    const int4* chainM;        // grid x kMasMaxLevels, entry j = level L - j: {top index of the group's first child, nk, float offset of the 6 inverse rows, top index of the CTA's ancestor}
-    const float* inv;          // all group inverses (48 x 48 each, symmetric)
+    const float* inv;          // group inverses of the levels below L (48 x 48 each, symmetric)
+    const float* cinv;         // inverse of the coarse Galerkin matrix, nC rows of ldC floats
     const float4* vinfo;       // per row: {m, m*lx, m*ly, leaf id (int bits)}, m = 0 for fixed vertices
-    double* rcCta;             // grid x 6: restricted residual of every CTA node (exchange buffer)
+    double* rcC;               // nC: restricted residual on the coarse level (exchange buffer)
 };
 
-__host__ __device__ inline size_t mas_smem_bytes(int maxLocalNodes, int topNodes, int rowsPer, int nCh)
+__host__ __device__ inline size_t mas_smem_bytes(int maxLocalNodes, int rowsPer, int ldC)
 {
     size_t b = 0;
     b += ((size_t)maxLocalNodes * kMasDof + kMasBlk) * 8 * 2;      // rc (+ zero pad), e
     b += (size_t)maxLocalNodes * (16 + 16 + 32);                   // nodeA, nodeB, nodeX
     b += (size_t)rowsPer * 16;                                     // vinfo
-    b += ((size_t)topNodes * kMasDof + kMasBlk) * 8;               // rcTop (+ zero pad)
-    b += (size_t)topNodes * (8 + 32);                              // topUp, topX
-    b += (size_t)nCh * (kMasChainRow * 4 + 16);                    // chain inverse rows + chainM
-    b += 32 * 8 + 2 * (kMasMaxLevels + 2) * 4 + 64;                // chain scratch, topLevelOff, lvOff, slack
+    b += (size_t)ldC * 8;                                          // coarse residual, all nodes
+    b += (kMasMaxLevels + 2) * 4 + 64;                             // lvOff, slack
     return (b + 15) / 16 * 16;
 }
 
 #ifdef __CUDACC__
 struct MasSmem {
-    double* rc; double* e; double* rcTop; double* chain;
-    int4* nodeA; int4* nodeB; double4* nodeX; float4* vinfo; int2* topUp; double4* topX; float* chainInv; int4* chainM; int* topLevelOff;
+    double* rc; double* e; double* rcAll;
+    int4* nodeA; int4* nodeB; double4* nodeX; float4* vinfo;
     int* lvOff;
-    int nLoc, nSolve, leaf0;
+    int nLoc, nSolve, leaf0, cBeg, nOwnC;
 };
 __device__ __forceinline__ MasSmem mas_carve(unsigned char* base, const MasView& M)
 {
     MasSmem S; size_t o = 0;
     S.nodeX = reinterpret_cast<double4*>(base + o);  o += (size_t)M.maxLocalNodes * 32;
-    S.topX = reinterpret_cast<double4*>(base + o);   o += (size_t)M.topNodes * 32;
     S.nodeA = reinterpret_cast<int4*>(base + o);     o += (size_t)M.maxLocalNodes * 16;
     S.nodeB = reinterpret_cast<int4*>(base + o);     o += (size_t)M.maxLocalNodes * 16;
     S.vinfo = reinterpret_cast<float4*>(base + o);   o += (size_t)M.rowsPer * 16;
-    S.chainM = reinterpret_cast<int4*>(base + o);    o += (size_t)M.nCh * 16;
-    S.chainInv = reinterpret_cast<float*>(base + o); o += (size_t)M.nCh * kMasChainRow * 4;
     S.rc = reinterpret_cast<double*>(base + o);      o += ((size_t)M.maxLocalNodes * kMasDof + kMasBlk) * 8;
     S.e = reinterpret_cast<double*>(base + o);       o += ((size_t)M.maxLocalNodes * kMasDof + kMasBlk) * 8;
-    S.rcTop = reinterpret_cast<double*>(base + o);   o += ((size_t)M.topNodes * kMasDof + kMasBlk) * 8;
-    S.chain = reinterpret_cast<double*>(base + o);   o += 32 * 8;
-    S.topUp = reinterpret_cast<int2*>(base + o);     o += (size_t)M.topNodes * 8;
-    S.topLevelOff = reinterpret_cast<int*>(base + o); o += (kMasMaxLevels + 2) * 4;
+    S.rcAll = reinterpret_cast<double*>(base + o);   o += (size_t)M.ldC * 8;
     S.lvOff = reinterpret_cast<int*>(base + o);
-    S.nLoc = 0; S.nSolve = 0; S.leaf0 = 0;
+    S.nLoc = 0; S.nSolve = 0; S.leaf0 = 0; S.cBeg = 0; S.nOwnC = 0;
     return S;
 }
 
-// stage the CTA's tables in shared memory; call once per solve (after ocb_factorize: the chain rows are VALUES)
+// stage the CTA's tables in shared memory; call once per solve
 __device__ __forceinline__ void mas_init(const MasView& M, MasSmem& S, int cta, int rowBeg, int rowEnd)
 {
     const int nT = blockDim.x, t = threadIdx.x;
@@ -110,18 +102,13 @@ __device__ __forceinline__ void mas_init(const MasView& M, MasSmem& S, int cta, 
     S.nLoc = M.ctaNodeOff[cta + 1] - n0;
     S.nSolve = M.ctaSolve[cta];
     S.leaf0 = M.ctaLeafBeg[cta];
+    S.cBeg = M.ctaCBeg[cta];
+    S.nOwnC = M.ctaCBeg[cta + 1] - S.cBeg;
     for (int i = t; i <= kMasMaxLevels; i += nT) S.lvOff[i] = M.ctaLvOff[(size_t)cta * (kMasMaxLevels + 1) + i];
     for (int i = t; i < S.nLoc; i += nT) { S.nodeA[i] = M.nodeA[n0 + i]; S.nodeB[i] = M.nodeB[n0 + i]; S.nodeX[i] = M.nodeX[n0 + i]; }
     for (int i = t; i < rowEnd - rowBeg; i += nT) S.vinfo[i] = M.vinfo[rowBeg + i];
-    for (int i = t; i < M.topNodes; i += nT) { S.topUp[i] = M.topUp[i]; S.topX[i] = M.topX[i]; }
-    for (int i = t; i <= M.nCh; i += nT) S.topLevelOff[i] = M.topLevelOff[i];
-    for (int i = t; i < M.nCh; i += nT) S.chainM[i] = M.chainM[(size_t)cta * kMasMaxLevels + i];
-    for (int i = t; i < M.nCh * kMasChainRow; i += nT) {
-        const int j = i / kMasChainRow;
-        S.chainInv[i] = M.inv[(size_t)M.chainM[(size_t)cta * kMasMaxLevels + j].z + (i - j * kMasChainRow)];
-    }
     for (int i = t; i < M.maxLocalNodes * kMasDof + kMasBlk; i += nT) { S.rc[i] = 0.0; S.e[i] = 0.0; }
-    for (int i = t; i < M.topNodes * kMasDof + kMasBlk; i += nT) S.rcTop[i] = 0.0;
+    for (int i = t; i < M.ldC; i += nT) S.rcAll[i] = 0.0;
     __syncthreads();
 }
 
@@ -132,11 +119,10 @@ __device__ __forceinline__ void mas_restrict(const MasView& M, const MasSmem& S,
 {
     const int nT = blockDim.x;
     // 8 lanes per (node, component): one child (a row for the leaves) per lane, then a 3-step shuffle reduction
-    for (int l = 1; l <= M.Lloc; ++l) {
+    for (int l = 1; l <= M.L; ++l) {
         const int done = S.lvOff[l - 1], end = S.lvOff[l];
         const int items = 16 * (end - done);
-        for (int w0 = 0; w0 < items; w0 += nT) {
-            const int w = w0 + threadIdx.x;
+        for (int w = threadIdx.x; w < ((items + 31) & ~31); w += nT) {       // whole warps beyond the range skip
             const bool valid = w < items;
             const int k = w & 7, pair = w >> 3, node = done + (valid ? pair >> 1 : 0), comp = pair & 1;
             const int4 B = S.nodeB[node];
@@ -164,17 +150,17 @@ __device__ __forceinline__ void mas_restrict(const MasView& M, const MasSmem& S,
         }
         __syncthreads();
     }
-    if (threadIdx.x < kMasDof && cta < M.nCtaNodes) M.rcCta[(size_t)cta * kMasDof + threadIdx.x] = S.rc[(size_t)(S.nLoc - 1) * kMasDof + threadIdx.x];
+    // publish the coarse residual of the own coarse nodes (the last local level)
+    for (int i = threadIdx.x; i < S.nOwnC * kMasDof; i += nT) M.rcC[(size_t)S.cBeg * kMasDof + i] = S.rc[(size_t)S.lvOff[M.L - 1] * kMasDof + i];
 }
 
-// ---- CTA-local group solves y = D_l^-1 rc_l for every local level below Lloc (4 threads per output, the inverse
+// ---- CTA-local group solves y = D_l^-1 rc_l for every local level below L (4 threads per output, the inverse
 // rows streamed from L2/HBM with three independent 16-byte loads per thread); y lands in S.e.  No barrier inside.
 __device__ __forceinline__ void mas_local_solves(const MasView& M, const MasSmem& S)
 {
     const int nT = blockDim.x;
     const int items = S.nSolve * kMasDof * 4;
-    for (int w0 = 0; w0 < items; w0 += nT) {
-        const int w = w0 + threadIdx.x;
+    for (int w = threadIdx.x; w < ((items + 31) & ~31); w += nT) {           // whole warps beyond the range skip
         const bool valid = w < items;
         const int node = valid ? w / (kMasDof * 4) : 0, rem = w % (kMasDof * 4), q = rem >> 2, part = rem & 3;
         const int4 A = S.nodeA[node];
@@ -198,74 +184,42 @@ __device__ __forceinline__ void mas_local_solves(const MasView& M, const MasSmem
     }
 }
 
-// ---- after the barrier: top levels (redundantly in every CTA, shared memory only), then the local down sweep
-// (prolongation adds).  Leaves the coarse correction coefficients of every local node in S.e; the caller adds
-// m * (e0 + lx e1 + ly e2, e3 + lx e4 + ly e5) of the row's leaf to the block-Jacobi part of z.
+// ---- after the barrier: the exact coarse solve for the own coarse nodes (one warp per output row, the inverse
+// rows streamed from L2 with 16-byte loads), then the local down sweep (prolongation adds).  Leaves the coarse
+// correction coefficients of every local node in S.e; the caller adds m * (e0 + lx e1 + ly e2, e3 + lx e4 + ly e5)
+// of the row's leaf to the block-Jacobi part of z.
 __device__ __forceinline__ void mas_down(const MasView& M, const MasSmem& S, int cta)
 {
-    const int nT = blockDim.x;
-    for (int i = threadIdx.x; i < M.nCtaNodes * kMasDof; i += nT) S.rcTop[i] = __ldcg(M.rcCta + i);
+    const int nT = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < M.nC; i += nT) S.rcAll[i] = __ldcg(M.rcC + i);
     __syncthreads();
-    for (int j = 1; j < M.nCh; ++j) {                 // top up-sweep: levels Lloc+1 .. L
-        const int n0 = S.topLevelOff[j], n1 = S.topLevelOff[j + 1];
-        const int items = 16 * (n1 - n0);
-        for (int w0 = 0; w0 < items; w0 += nT) {
-            const int w = w0 + threadIdx.x;
-            const bool valid = w < items;
-            const int k = w & 7, pair = w >> 3, node = n0 + (valid ? pair >> 1 : 0), comp = pair & 1;
-            const int2 U = S.topUp[node];
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            if (valid && k < U.y) {
-                const double4 X = S.topX[U.x + k];
-                const double* rc = S.rcTop + (size_t)(U.x + k) * kMasDof + 3 * comp;
-                a0 = rc[0]; a1 = X.x * rc[0] + X.z * rc[1]; a2 = X.y * rc[0] + X.z * rc[2];
+    {
+        const int rows = S.nOwnC * kMasDof, ld4 = M.ldC >> 2;
+        double* eC = S.e + (size_t)S.lvOff[M.L - 1] * kMasDof;
+        for (int row = warp; row < rows; row += nT >> 5) {
+            const float4* a = reinterpret_cast<const float4*>(M.cinv + (size_t)(S.cBeg * kMasDof + row) * M.ldC);
+            double y0 = 0.0, y1 = 0.0;
+            int c4 = lane;
+            for (; c4 + 32 < ld4; c4 += 64) {
+                const float4 u = __ldg(a + c4), v = __ldg(a + c4 + 32);
+                const double* r0 = S.rcAll + 4 * c4; const double* r1 = r0 + 128;
+                y0 += (double)u.x * r0[0] + (double)u.y * r0[1] + (double)u.z * r0[2] + (double)u.w * r0[3];
+                y1 += (double)v.x * r1[0] + (double)v.y * r1[1] + (double)v.z * r1[2] + (double)v.w * r1[3];
             }
+            if (c4 < ld4) {
+                const float4 u = __ldg(a + c4);
+                const double* r0 = S.rcAll + 4 * c4;
+                y0 += (double)u.x * r0[0] + (double)u.y * r0[1] + (double)u.z * r0[2] + (double)u.w * r0[3];
+            }
+            double y = y0 + y1;
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-            }
-            if (valid && k == 0) {
-                double* o = S.rcTop + (size_t)node * kMasDof + 3 * comp;
-                o[0] = a0; o[1] = a1; o[2] = a2;
-            }
+            for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+            if (lane == 0) eC[row] = y;
         }
-        __syncthreads();
-    }
-    // ancestor chain of this CTA, top down: warp 0, 4 lanes per DOF, shared memory only
-    if (threadIdx.x < 32 && cta < M.nCtaNodes) {
-        const int lane = threadIdx.x, q = lane >> 2, part = lane & 3;
-        double* ch = S.chain;                          // e of the level above at ch[0..5], new at ch[8..13]
-        if (lane < kMasDof) ch[lane] = 0.0;
-        __syncwarp();
-        for (int j = 0; j < M.nCh; ++j) {              // level L - j
-            const int4 C = S.chainM[j];
-            double y = 0.0;
-            if (q < kMasDof) {
-                const float* row = S.chainInv + j * kMasChainRow + q * kMasBlk;
-                const double* rc = S.rcTop + (size_t)C.x * kMasDof;
-                for (int k = part; k < C.y; k += 4) y += (double)row[k] * rc[k];
-            }
-            y += __shfl_xor_sync(0xffffffffu, y, 1);
-            y += __shfl_xor_sync(0xffffffffu, y, 2);
-            if (q < kMasDof && part == 0) {
-                double e = y;
-                if (j > 0) {
-                    const double4 X = S.topX[C.w];
-                    const double* ep = ch + 3 * (q / 3);
-                    const int qq = q % 3;
-                    e += qq == 0 ? ep[0] + X.x * ep[1] + X.y * ep[2] : X.z * ep[qq];
-                }
-                ch[8 + q] = e;
-            }
-            __syncwarp();
-            if (lane < kMasDof) ch[lane] = ch[8 + lane];
-            __syncwarp();
-        }
-        if (lane < kMasDof) S.e[(size_t)(S.nLoc - 1) * kMasDof + lane] = ch[lane];
     }
     __syncthreads();
     // local down sweep: e = y + prolongation of the parent's e; levels are contiguous and ascending in the node list
-    for (int l = M.Lloc - 1; l >= 1; --l) {
+    for (int l = M.L - 1; l >= 1; --l) {
         const int beg = S.lvOff[l - 1], end = S.lvOff[l];
         for (int w = threadIdx.x; w < kMasDof * (end - beg); w += nT) {
             const int node = beg + w / kMasDof, q = w % kMasDof, qq = q % 3;

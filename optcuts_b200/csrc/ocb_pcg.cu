@@ -663,11 +663,10 @@ struct PcgPlan { int grid; bool smem; bool cluster; int maxBlk; size_t smemBytes
 // upper bound of the MAS scratch of one CTA (the hierarchy is built after the plan)
 static size_t mas_smem_estimate(int rowsPer, int grid)
 {
+    (void)grid;
     int local = 0, k = (rowsPer + kMasLeaf - 1) / kMasLeaf;
     for (;;) { local += k; if (k <= 1) break; k = (k + kMasGroup - 1) / kMasGroup; }
-    int top = 0, nCh = 0; k = grid;
-    for (;;) { top += k; ++nCh; if (k <= kMasGroup) break; k = (k + kMasGroup - 1) / kMasGroup; }
-    return mas_smem_bytes(local + kMasMaxLevels, top, rowsPer, nCh) + 64;
+    return mas_smem_bytes(local + kMasMaxLevels, rowsPer, kMasCoarseMax) + 64;
 }
 static PcgPlan pcg_plan(ocb_ctx* c)
 {
@@ -795,7 +794,7 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     if (c->masH.enabled && c->masH.grid == grid && c->masD.view.L > 0) {
         P.mas = c->masD.view;
         P.masSmemOff = smemBytes;
-        smemBytes += mas_smem_bytes(P.mas.maxLocalNodes, P.mas.topNodes, P.mas.rowsPer, P.mas.nCh);
+        smemBytes += mas_smem_bytes(P.mas.maxLocalNodes, P.mas.rowsPer, P.mas.ldC);
     }
     const size_t smemCap = 220 * 1024;      // + ~5 KB static (reduction scratch) <= 227 KB per CTA
     if (smemBytes > smemCap) return set_err(c, OCB_ERR_STATE, "PCG: shared-memory plan exceeds the SM capacity");

@@ -1,5 +1,5 @@
 """GPU: the multilevel additive Schwarz preconditioned CG against the reference's search direction, and the
-iteration counts the CPU prototype (tools/mas_proto.py, same hierarchy) predicts: 276 (state 1) / 156 (state 100)."""
+iteration counts the CPU prototype (tools/mas_proto.py --lib, same hierarchy) predicts: 174 (state 1) / 107 (state 100)."""
 import numpy as np
 import pytest
 
@@ -18,10 +18,10 @@ def test_hierarchy_is_active(ctx, state1):
     _newton_system(ctx, state1)
     info = ctx.precond_info()
     assert info["enabled"] and info["levels"] >= 2 and info["nodes"][0] >= state1.nV // 8
-    assert info["nodes"][-1] <= 8
+    assert 6 * info["nodes"][-1] <= 3072                 # the coarse level, inverted exactly
 
 
-@pytest.mark.parametrize("which,bound", [("state1", 400), ("state100", 240)])
+@pytest.mark.parametrize("which,bound", [("state1", 260), ("state100", 170)])
 def test_mas_pcg_matches_reference_direction(ctx, request, which, bound):
     state = request.getfixturevalue(which)
     _newton_system(ctx, state)

@@ -20,13 +20,19 @@ def _check(xy, grid):
     for l in range(1, len(levels)):
         cb = levels[l]
         assert cb[0] == 0 and cb[-1] == sizes[l - 1] and np.all(np.diff(cb) >= 1) and np.all(np.diff(cb) <= 8)
-    assert sizes[-1] <= 8
-    # the last CTA-local level has one node per CTA that owns rows
-    assert sizes[lloc - 1] == -(-n // rows_per)
+    # the last level is the coarse one: small enough for the exact dense inverse, and the first such level
+    assert 6 * sizes[-1] <= 3072 and lloc == len(levels)
+    assert all(6 * s > 3072 for s in sizes[:-1])
+    # no node of any level straddles a CTA boundary: map every node to its row range
+    lo, hi = levels[0][:-1].copy(), levels[0][1:].copy()
+    for l in range(1, len(levels)):
+        cb = levels[l]
+        lo, hi = lo[cb[:-1]], hi[cb[1:] - 1]
+        assert np.all(lo // rows_per == (hi - 1) // rows_per)
     return vert_of, levels, lloc
 
 
-@pytest.mark.parametrize("n,grid", [(16, 1), (100, 1), (5358, 16), (5358, 1), (20000, 148), (1000, 148), (131, 16)])
+@pytest.mark.parametrize("n,grid", [(16, 1), (100, 1), (5358, 16), (5358, 1), (20000, 148), (1000, 148), (131, 16), (80000, 148), (300000, 148)])
 def test_hierarchy_invariants(n, grid):
     rng = np.random.default_rng(n)
     _check(rng.uniform(-1, 1, (n, 2)), grid)

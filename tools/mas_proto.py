@@ -262,6 +262,8 @@ def main():
         _, it = pcg(A, b, lambda r: Minv @ r)
         print("block-Jacobi: %d iterations" % it)
     order, levels = lib_hierarchy(X, a.grid) if a.lib else build_hierarchy(X, a.grid, a.leaf, a.group)
+    if a.lib:
+        a.exact_from = len(levels)          # the library's last level is the exactly solved coarse level
     perm2 = np.stack([2 * order, 2 * order + 1], 1).ravel()
     Ap = A[perm2][:, perm2].tocsr()
     t0 = time.time()
