@@ -38,7 +38,15 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "bimba_cfg2_states.npz")
 
 # algorithmic HBM bytes per unit of work (restated in DESIGN.md §4)
 BYTES_PER_FACE = {"energy": 60.0, "gradient": 68.0, "step_bound": 28.0, "hessian_psd_scatter": 172.0}
-PCG_BYTES_PER_FACE_PER_ITER = 228.0
+PCG_BYTES_PER_FACE_PER_ITER = 228.0          # BSR(2x2) SpMV 144 + block-Jacobi + dots + axpys
+# the two-level preconditioner's own compulsory traffic per CG iteration: fp32 group inverses of the
+# levels below the coarse one, 48x48 per 8 nodes = 2304*4 B per 64 vertices per level (x 8/7 for the geometric series
+# of levels) = 82 B/face, one extra pass over z (write + read, 16 B/face), and the fp32 coarse inverse, 4 * nC^2 bytes
+MAS_BYTES_PER_FACE_PER_ITER = 82.0 + 16.0
+
+
+def pcg_bytes_per_iter(faces, n_coarse):
+    return (PCG_BYTES_PER_FACE_PER_ITER + (MAS_BYTES_PER_FACE_PER_ITER if n_coarse else 0.0)) * faces + 4.0 * n_coarse * n_coarse
 
 
 def load_states(workload):
@@ -235,6 +243,8 @@ def run_ours(args):
     total_prof = sum(v[0] for v in prof.values()) or 1.0
     dom = max(prof, key=lambda k: prof[k][0])
     pcg_iters = float(np.mean([r["pcg_iters"] for r in res]))
+    pinfo = [c.precond_info() for c in ctxs]
+    n_coarse = float(np.mean([6 * p["nodes"][-1] if p["enabled"] else 0 for p in pinfo]))
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
 
@@ -244,7 +254,7 @@ def run_ours(args):
             return None
         per_launch_ms = pms / cnt
         if name == "pcg":
-            bytes_per_launch = PCG_BYTES_PER_FACE_PER_ITER * faces * pcg_iters
+            bytes_per_launch = pcg_bytes_per_iter(faces, n_coarse) * pcg_iters
         elif name in BYTES_PER_FACE:
             bytes_per_launch = BYTES_PER_FACE[name] * faces
         else:
@@ -260,7 +270,8 @@ def run_ours(args):
         traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": d.get("achieved_gbs"), "peak": peak, "peak_source": peak_src,
                 "unit": "GB/s", "frac": d.get("frac"), "traffic": traffic,
-                "note": "algorithmic bytes = %.0f B/face/CG-iteration x faces x CG iterations per launch" % PCG_BYTES_PER_FACE_PER_ITER
+                "note": ("algorithmic bytes = (%.0f B/face [SpMV + vectors] + %.0f B/face [preconditioner levels] ) x faces + 4 x %d^2 [coarse inverse] "
+                         "per CG iteration, x CG iterations per launch" % (PCG_BYTES_PER_FACE_PER_ITER, MAS_BYTES_PER_FACE_PER_ITER if n_coarse else 0.0, int(n_coarse)))
                 if dom == "pcg" else "algorithmic bytes per face x faces"}
 
     def air_bytes(s):
@@ -275,7 +286,9 @@ def run_ours(args):
                 else "synthetic: bimba Tutte state subdivided",
         "config": {"workload": args.workload, "faces": int(states[0]["F"].shape[0]), "states": len(states),
                    "air_faces": [int(s["air"]["F"].shape[0]) if s["air"] is not None else 0 for s in states],
-                   "pcg_rel_tol": pcg_tol, "pcg_iters_mean": pcg_iters, "l2": "flushed between timed iterations (256 MB memset)",
+                   "pcg_rel_tol": pcg_tol, "pcg_iters_mean": pcg_iters,
+                   "preconditioner": ("two-level additive Schwarz: levels %s, exact coarse inverse of %d DOFs" % (pinfo[0]["nodes"], 6 * pinfo[0]["nodes"][-1]))
+                                     if pinfo[0]["enabled"] else "block-Jacobi", "l2": "flushed between timed iterations (256 MB memset)",
                    "parallelism": "independent meshes per GPU, no collective"},
         "e2e": {"value": e2e_value, "unit": "it/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,

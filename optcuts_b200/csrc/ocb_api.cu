@@ -459,12 +459,13 @@ int ocb_restore_uv(ocb_ctx* c)
 
 static int64_t nnz_upper(const ocb_ctx* c)
 {
-    // LinSysSolver::set_pattern: free vertex rows: 2*k and 2*k-1 entries with k = #block cols >= row
+    // LinSysSolver::set_pattern: free vertex rows: 2*k and 2*k-1 entries with k = #block cols >= row; the total does
+    // not depend on the (symmetric) ordering, so it is counted on the solver-order pattern
     int64_t nnz = 0;
-    for (int v = 0; v < c->nVtot; ++v) {
-        if (c->hFixed[v]) { nnz += 2; continue; }
+    for (int r = 0; r < c->nVtot; ++r) {
+        if (c->hFixed[c->hVertOf[r]]) { nnz += 2; continue; }
         int k = 0;
-        for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) if (c->hColIdx[b] >= v) ++k;
+        for (int b = c->hSRowPtr[r]; b < c->hSRowPtr[r + 1]; ++b) if (c->hSColIdx[b] >= r) ++k;
         nnz += 4 * (int64_t)k - 1;
     }
     return nnz;
@@ -517,15 +518,12 @@ int ocb_gradient(ocb_ctx* c, double p0, double* g_out, double* sqnorm)
 }
 
 // ------------------------------------------------------------------------------------------ pattern
-// The caller-visible pattern (hRowPtr/hColIdx, INTERNAL vertex order) is complete: choose the solver's row order
-// (recursive coordinate bisection of the current UVs when they are known, see ocb_mas.cu), permute the pattern
-// into it and upload; build the preconditioner hierarchy on top.
-static int install_pattern(ocb_ctx* c)
+// The solver's own row order: recursive coordinate bisection of the current UVs when they are known (plus the
+// preconditioner hierarchy on top of it, see ocb_mas.cu), identity otherwise.
+static int choose_order(ocb_ctx* c)
 {
-    HostTimer _ht("install_pattern");
     static const bool masOff = []() { const char* e = getenv("OCB_NO_MAS"); return e && atoi(e); }();
     const int n = c->nVtot;
-    c->nnzb = (int)c->hColIdx.size();
     c->planGrid = pcg_plan_grid(c, n);
     c->masH = MasHost();
     if (!masOff && c->haveUV && c->nV > 0 && c->x.p && n >= 2 * kMasLeaf) {
@@ -537,29 +535,14 @@ static int install_pattern(ocb_ctx* c)
         c->hRowOf.resize((size_t)n); c->hVertOf.resize((size_t)n);
         for (int v = 0; v < n; ++v) c->hRowOf[v] = c->hVertOf[v] = v;
     }
-    c->hSRowPtr.assign((size_t)n + 1, 0);
-    c->hSColIdx.resize((size_t)c->nnzb);
-    c->hBlkMap.resize((size_t)c->nnzb);
-    {
-        HostTimer _h5("  solver_order_pattern");
-        int w = 0;
-        for (int r = 0; r < n; ++r) {
-            const int v = c->hVertOf[r];
-            const int w0 = w;
-            for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) {       // insertion sort by solver column, carrying the source block
-                const int32_t col = c->hRowOf[c->hColIdx[b]];
-                int j = w - 1;
-                while (j >= w0 && c->hSColIdx[j] > col) { c->hSColIdx[j + 1] = c->hSColIdx[j]; c->hBlkMap[j + 1] = c->hBlkMap[j]; --j; }
-                c->hSColIdx[j + 1] = col; c->hBlkMap[j + 1] = b;
-                ++w;
-            }
-            c->hSRowPtr[r + 1] = w;
-        }
-        // hBlkMap holds device block -> source block so far; invert it
-        std::vector<int32_t> inv((size_t)c->nnzb);
-        for (int d = 0; d < c->nnzb; ++d) inv[c->hBlkMap[d]] = d;
-        c->hBlkMap.swap(inv);
-    }
+    return 0;
+}
+
+// hSRowPtr/hSColIdx (the pattern in solver order) are complete: upload, preconditioner tables, element slots
+static int finish_install(ocb_ctx* c)
+{
+    const int n = c->nVtot;
+    c->nnzb = (int)c->hSColIdx.size();
     OCB_CUDA(c, c->rowPtr.reserve((size_t)n + 1, c->stream));
     OCB_CUDA(c, c->colIdx.reserve((size_t)c->nnzb + 1, c->stream));
     OCB_CUDA(c, c->val.reserve(4 * (size_t)c->nnzb + 4, c->stream));
@@ -581,6 +564,32 @@ static int install_pattern(ocb_ctx* c)
     c->patternValid = true; c->matrixValid = c->precondValid = false;
     HostTimer _h4("  build_slots");
     return launch_build_slots(c);
+}
+
+// hRowPtr/hColIdx hold the pattern in INTERNAL vertex order (the adjacency route): permute it into the solver order
+static int install_pattern(ocb_ctx* c)
+{
+    HostTimer _ht("install_pattern");
+    const int n = c->nVtot;
+    OCB_TRY(choose_order(c));
+    const int nnzb = (int)c->hColIdx.size();
+    c->hSRowPtr.assign((size_t)n + 1, 0);
+    c->hSColIdx.resize((size_t)nnzb);
+    int w = 0;
+    for (int r = 0; r < n; ++r) {
+        const int v = c->hVertOf[r];
+        const int w0 = w;
+        for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) {       // insertion sort by solver column
+            const int32_t col = c->hRowOf[c->hColIdx[b]];
+            int j = w - 1;
+            while (j >= w0 && c->hSColIdx[j] > col) { c->hSColIdx[j + 1] = c->hSColIdx[j]; --j; }
+            c->hSColIdx[j + 1] = col;
+            ++w;
+        }
+        c->hSRowPtr[r + 1] = w;
+    }
+    c->hRowPtr.clear(); c->hColIdx.clear();
+    return finish_install(c);
 }
 
 int ocb_set_pattern(ocb_ctx* c, int nVtot, const int32_t* adjPtr, const int32_t* adjIdx, const int32_t* fixed, int nFixed)
@@ -674,26 +683,31 @@ int ocb_set_pattern_from_elements(ocb_ctx* c)
         }
     };
     scatter(c->hF, c->nF); scatter(c->hFa, c->nFa);
-    c->hRowPtr.assign((size_t)nVtot + 1, 0);
-    c->hColIdx.clear(); c->hColIdx.reserve(buf.size() / 2 + nVtot);
-    std::vector<int32_t> stamp((size_t)nVtot, -1);         // de-duplicate with a stamp, then insertion-sort the short row
-    for (int v = 0; v < nVtot; ++v) {
-        if (c->hFixed[v]) { c->hColIdx.push_back(v); }
+    // the solver's row order first (it needs only the UVs), then the pattern directly in that order: rows de-duplicated
+    // with a stamp and insertion-sorted (they are ~7 entries long)
+    OCB_TRY(choose_order(c));
+    c->hRowPtr.clear(); c->hColIdx.clear();
+    c->hSRowPtr.assign((size_t)nVtot + 1, 0);
+    c->hSColIdx.clear(); c->hSColIdx.reserve(buf.size() / 2 + nVtot);
+    std::vector<int32_t> stamp((size_t)nVtot, -1);
+    for (int r = 0; r < nVtot; ++r) {
+        const int v = c->hVertOf[r];
+        if (c->hFixed[v]) { c->hSColIdx.push_back(r); }
         else {
-            const size_t w0 = c->hColIdx.size();
+            const size_t w0 = c->hSColIdx.size();
             for (int32_t* q = buf.data() + cnt[v]; q < buf.data() + fill[v]; ++q) {
                 const int u = *q;
                 if (stamp[u] == v) continue;
                 stamp[u] = v;
-                if (u == v || !c->hFixed[u]) c->hColIdx.push_back(u);
+                if (u == v || !c->hFixed[u]) c->hSColIdx.push_back(c->hRowOf[u]);
             }
-            int32_t* a = c->hColIdx.data() + w0;
-            const int m = (int)(c->hColIdx.size() - w0);
+            int32_t* a = c->hSColIdx.data() + w0;
+            const int m = (int)(c->hSColIdx.size() - w0);
             for (int i = 1; i < m; ++i) { const int32_t x = a[i]; int j = i - 1; while (j >= 0 && a[j] > x) { a[j + 1] = a[j]; --j; } a[j + 1] = x; }
         }
-        c->hRowPtr[v + 1] = (int32_t)c->hColIdx.size();
+        c->hSRowPtr[r + 1] = (int32_t)c->hSColIdx.size();
     }
-    return install_pattern(c);
+    return finish_install(c);
 }
 
 // ------------------------------------------------------------------------------------------ Hessian
@@ -784,18 +798,18 @@ int ocb_download_csr(ocb_ctx* c, int32_t* ia, int32_t* ja, double* a)
     ia[0] = 1;
     std::vector<std::pair<int32_t, int32_t>> row;         // (caller column id, block slot)
     for (int v = 0; v < c->nVtot; ++v) {                  // v: the caller's vertex, vi its internal row
-        const int vi = c->hPerm[v];
+        const int vi = c->hPerm[v], r = c->hRowOf[vi];                      // r: the solver row of the device BSR
         if (c->hFixed[vi]) {
             int bdiag = -1;
-            for (int b = c->hRowPtr[vi]; b < c->hRowPtr[vi + 1]; ++b) if (c->hColIdx[b] == vi) bdiag = b;
-            ja[w] = 2 * v + 1; a[w] = val[4 * (size_t)c->hBlkMap[bdiag]]; ++w; ia[2 * v + 1] = (int32_t)(w + 1);
-            ja[w] = 2 * v + 2; a[w] = val[4 * (size_t)c->hBlkMap[bdiag] + 3]; ++w; ia[2 * v + 2] = (int32_t)(w + 1);
+            for (int b = c->hSRowPtr[r]; b < c->hSRowPtr[r + 1]; ++b) if (c->hSColIdx[b] == r) bdiag = b;
+            ja[w] = 2 * v + 1; a[w] = val[4 * (size_t)bdiag]; ++w; ia[2 * v + 1] = (int32_t)(w + 1);
+            ja[w] = 2 * v + 2; a[w] = val[4 * (size_t)bdiag + 3]; ++w; ia[2 * v + 2] = (int32_t)(w + 1);
             continue;
         }
         row.clear();
-        for (int b = c->hRowPtr[vi]; b < c->hRowPtr[vi + 1]; ++b) {
-            const int col = c->hInv[c->hColIdx[b]];
-            if (col >= v) row.push_back(std::make_pair((int32_t)col, c->hBlkMap[b]));
+        for (int b = c->hSRowPtr[r]; b < c->hSRowPtr[r + 1]; ++b) {
+            const int col = c->hInv[c->hVertOf[c->hSColIdx[b]]];
+            if (col >= v) row.push_back(std::make_pair((int32_t)col, (int32_t)b));
         }
         std::sort(row.begin(), row.end());
         for (int r = 0; r < 2; ++r) {

@@ -365,19 +365,20 @@ __device__ __forceinline__ int find_col(const int32_t* __restrict__ colIdx, int 
     return -1;
 }
 
-// A_1 = P_1^T A P_1 on the leaf adjacency: one thread per fine block row
+// A_1 = P_1^T A P_1 on the leaf adjacency: 8 threads per fine block row (one block each, rows are ~7 blocks long)
 __global__ void __launch_bounds__(256)
 mas_galerkin_fine_kernel(int nRows, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, const double* __restrict__ val,
                          const float4* __restrict__ vinfo, const int32_t* __restrict__ rowPtr1, const int32_t* __restrict__ colIdx1,
                          double* __restrict__ val1)
 {
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < nRows; i += gridDim.x * 256) {
+    for (long w = blockIdx.x * 256L + threadIdx.x; w < 8L * nRows; w += gridDim.x * 256L) {
+        const int i = (int)(w >> 3), k8 = (int)(w & 7);
         const float4 vi = vinfo[i];
         if (vi.x == 0.0f) continue;
         const int a = __float_as_int(vi.w);
         const double fi[3] = {(double)vi.x, (double)vi.y, (double)vi.z};
         const int lo1 = rowPtr1[a], hi1 = rowPtr1[a + 1];
-        for (int b = rowPtr[i]; b < rowPtr[i + 1]; ++b) {
+        for (int b = rowPtr[i] + k8; b < rowPtr[i + 1]; b += 8) {
             const int j = colIdx[b];
             const float4 vj = vinfo[j];
             if (vj.x == 0.0f) continue;
@@ -399,19 +400,20 @@ mas_galerkin_fine_kernel(int nRows, const int32_t* __restrict__ rowPtr, const in
     }
 }
 
-// A_{l+1} = R A_l R^T: one thread per node row of level l
+// A_{l+1} = R A_l R^T: 16 threads per node row of level l (one 6x6 block each)
 __global__ void __launch_bounds__(128)
 mas_coarsen_kernel(int nNodes, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, const double* __restrict__ val,
                    const int32_t* __restrict__ parent, const double4* __restrict__ geom, const double4* __restrict__ geomUp,
                    const int32_t* __restrict__ rowPtrUp, const int32_t* __restrict__ colIdxUp, double* __restrict__ valUp)
 {
-    for (int a = blockIdx.x * 128 + threadIdx.x; a < nNodes; a += gridDim.x * 128) {
+    for (long w = blockIdx.x * 128L + threadIdx.x; w < 16L * nNodes; w += gridDim.x * 128L) {
+        const int a = (int)(w >> 4), k16 = (int)(w & 15);
         const int pa = parent[a];
         const double4 ga = geom[a], gpa = geomUp[pa];
         const double isa = 1.0 / gpa.z;
         const double Ra[3][3] = {{1.0, 0.0, 0.0}, {(ga.x - gpa.x) * isa, ga.z * isa, 0.0}, {(ga.y - gpa.y) * isa, 0.0, ga.z * isa}};
         const int lo = rowPtrUp[pa], hi = rowPtrUp[pa + 1];
-        for (int blk = rowPtr[a]; blk < rowPtr[a + 1]; ++blk) {
+        for (int blk = rowPtr[a] + k16; blk < rowPtr[a + 1]; blk += 16) {
             const int b = colIdx[blk];
             const int pb = parent[b];
             const int s = find_col(colIdxUp, lo, hi, pb);
@@ -445,78 +447,6 @@ mas_coarsen_kernel(int nNodes, const int32_t* __restrict__ rowPtr, const int32_t
                     }
                 }
         }
-    }
-}
-
-// group blocks D_l[g] (<= 48x48) gathered from A_l and inverted in shared memory (Gauss-Jordan, SPD, no pivoting;
-// a DOF whose pivot collapses -- a node of fixed vertices only, collinear vertices -- is dropped); all levels in
-// one launch: CTA -> (level, group) through the prefix table.
-struct MasInvertArgs {
-    int L;
-    int groupPre[kMasMaxLevels + 1];
-    const int32_t* rowPtr[kMasMaxLevels]; const int32_t* colIdx[kMasMaxLevels]; const double* val[kMasMaxLevels];
-    const int32_t* parent[kMasMaxLevels]; const int32_t* groupBeg[kMasMaxLevels]; float* inv[kMasMaxLevels];
-};
-__global__ void __launch_bounds__(256)
-mas_invert_kernel(MasInvertArgs P)
-{
-    __shared__ double D[kMasBlk][kMasBlk + 1];
-    __shared__ double d0[kMasBlk];
-    __shared__ int dead[kMasBlk];
-    int l = 0;
-    while (l + 1 < P.L && (int)blockIdx.x >= P.groupPre[l + 1]) ++l;
-    const int g = blockIdx.x - P.groupPre[l];
-    const int gb = P.groupBeg[l][g], nch = P.groupBeg[l][g + 1] - gb;
-    const int nd = nch * kMasDof;
-    for (int e = threadIdx.x; e < kMasBlk * kMasBlk; e += 256) D[e / kMasBlk][e % kMasBlk] = 0.0;
-    __syncthreads();
-    for (int sa = 0; sa < nch; ++sa) {
-        const int a = gb + sa;
-        const int b0 = P.rowPtr[l][a], nb = P.rowPtr[l][a + 1] - b0;
-        for (int e = threadIdx.x; e < nb * 36; e += 256) {
-            const int blk = b0 + e / 36, ij = e % 36;
-            const int b = P.colIdx[l][blk];
-            if (P.parent[l][b] != g) continue;
-            D[sa * kMasDof + ij / 6][(b - gb) * kMasDof + ij % 6] = P.val[l][36 * (size_t)blk + ij];
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < kMasBlk) {
-        const int k = threadIdx.x;
-        if (k >= nd) D[k][k] = 1.0;
-        d0[k] = D[k][k];
-        dead[k] = 0;
-    }
-    __syncthreads();
-    for (int k = 0; k < nd; ++k) {
-        const double p = D[k][k];
-        const bool bad = !(d0[k] > 0.0) || !(p > 1e-10 * d0[k]);
-        __syncthreads();
-        if (bad) {
-            if (threadIdx.x < kMasBlk) { D[k][threadIdx.x] = 0.0; D[threadIdx.x][k] = 0.0; }
-            if (threadIdx.x == 0) dead[k] = 1;
-            __syncthreads();
-            continue;
-        }
-        const double ip = 1.0 / p;
-        if (threadIdx.x < kMasBlk && threadIdx.x != k) D[k][threadIdx.x] *= ip;
-        __syncthreads();
-        for (int e = threadIdx.x; e < nd * nd; e += 256) {
-            const int i = e / nd, j = e % nd;
-            if (i != k && j != k) D[i][j] -= D[i][k] * D[k][j];
-        }
-        __syncthreads();
-        if (threadIdx.x < kMasBlk) {
-            if (threadIdx.x != k) D[threadIdx.x][k] *= -ip;
-            else D[k][k] = ip;
-        }
-        __syncthreads();
-    }
-    float* out = P.inv[l] + (size_t)g * kMasBlk * kMasBlk;
-    for (int e = threadIdx.x; e < kMasBlk * kMasBlk; e += 256) {
-        const int i = e / kMasBlk, j = e % kMasBlk;
-        const bool ok = i < nd && j < nd && !dead[i] && !dead[j];
-        out[e] = ok ? (float)(0.5 * (D[i][j] + D[j][i])) : 0.0f;
     }
 }
 
@@ -611,13 +541,13 @@ __device__ __forceinline__ void tile_invert(double (&d)[4], double* buf, const d
             for (int e = 0; e < 4; ++e) if (m.r == k || tile_col(m, e) == k) d[e] = 0.0;
             continue;
         }
-        const double ip = 1.0 / p;
-        const double f = colb[m.r];
+        const double ip = __drcp_rn(p);
+        const double g = m.r != k ? -colb[m.r] * ip : ip;     // -f/p for the other rows, 1/p for the pivot row
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int j = tile_col(m, e);
-            if (m.r != k) d[e] = (j != k) ? d[e] - f * (rowb[j] * ip) : -f * ip;
-            else d[e] = (j != k) ? d[e] * ip : ip;
+            if (m.r != k) d[e] = (j != k) ? d[e] + g * rowb[j] : g;
+            else d[e] = (j != k) ? d[e] * g : g;
         }
     }
     __syncthreads();
@@ -708,6 +638,58 @@ mas_dense_invert_kernel(DenseInvArgs A)
     }
 }
 
+// group blocks D_l[g] (<= 48x48) gathered from A_l straight into registers and inverted with the register-resident
+// Gauss-Jordan above (a DOF whose pivot collapses -- a node of fixed vertices only, collinear vertices -- is
+// dropped); all levels below the coarse one in one launch: CTA -> (level, group) through the prefix table.
+struct MasInvertArgs {
+    int L;
+    int groupPre[kMasMaxLevels + 1];
+    const int32_t* rowPtr[kMasMaxLevels]; const int32_t* colIdx[kMasMaxLevels]; const double* val[kMasMaxLevels];
+    const int32_t* parent[kMasMaxLevels]; const int32_t* groupBeg[kMasMaxLevels]; float* inv[kMasMaxLevels];
+};
+__global__ void __launch_bounds__(kDenseThreads)
+mas_invert_kernel(MasInvertArgs P)
+{
+    __shared__ double T[kCB][kCBs];
+    __shared__ double d0s[kCB];
+    __shared__ double ibuf[4 * kCB];
+    int l = 0;
+    while (l + 1 < P.L && (int)blockIdx.x >= P.groupPre[l + 1]) ++l;
+    const int g = blockIdx.x - P.groupPre[l];
+    const int gb = P.groupBeg[l][g], nch = P.groupBeg[l][g + 1] - gb;
+    const int nd = nch * kMasDof;
+    const TileMap m = tile_map();
+    double d[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                  // the thread's two column pairs lie in one 6x6 block each
+        const int c = m.c0 + 8 * h;
+        double v0 = 0.0, v1 = 0.0;
+        if (m.r < nd && c < nd) {
+            const int a = gb + m.r / kMasDof, b = gb + c / kMasDof;
+            for (int blk = P.rowPtr[l][a]; blk < P.rowPtr[l][a + 1]; ++blk)
+                if (P.colIdx[l][blk] == b) {
+                    const double* src = P.val[l] + 36 * (size_t)blk + (m.r % kMasDof) * 6 + c % kMasDof;
+                    v0 = src[0]; v1 = src[1];
+                }
+        } else {
+            v0 = m.r == c ? 1.0 : 0.0; v1 = m.r == c + 1 ? 1.0 : 0.0;      // identity padding
+        }
+        d[2 * h] = v0; d[2 * h + 1] = v1;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) if (tile_col(m, e) == m.r) d0s[m.r] = d[e];
+    __syncthreads();
+    tile_invert(d, ibuf, d0s, m);
+    tile_store_smem(T, d, m);
+    __syncthreads();
+    float* out = P.inv[l] + (size_t)g * kMasBlk * kMasBlk;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int j = tile_col(m, e);
+        out[m.r * kMasBlk + j] = (m.r < nd && j < nd) ? (float)(0.5 * (T[m.r][j] + T[j][m.r])) : 0.0f;
+    }
+}
+
 int launch_mas_setup(ocb_ctx* c)
 {
     MasHost& H = c->masH;
@@ -716,12 +698,12 @@ int launch_mas_setup(ocb_ctx* c)
     ProfScope prof(c, K_MAS_SETUP);
     OCB_CUDA(c, cudaMemsetAsync(D.val.p, 0, D.valTotal * sizeof(double), c->stream));
     const int n = c->nVtot;
-    int grid = (n + 255) / 256; if (grid > c->numSMs * 8) grid = c->numSMs * 8; if (grid < 1) grid = 1;
+    int grid = (int)((8L * n + 255) / 256); if (grid > c->numSMs * 16) grid = c->numSMs * 16; if (grid < 1) grid = 1;
     mas_galerkin_fine_kernel<<<grid, 256, 0, c->stream>>>(n, c->rowPtr.p, c->colIdx.p, c->val.p, reinterpret_cast<const float4*>(D.vinfo.p), D.lvRowPtr[0], D.lvColIdx[0], D.lvVal[0]);
     KCHECK(c);
     for (int l = 1; l < H.L; ++l) {
         const MasLevel& V = D.lv[l - 1];
-        int g = (V.nNodes + 127) / 128; if (g > c->numSMs * 8) g = c->numSMs * 8; if (g < 1) g = 1;
+        int g = (int)((16L * V.nNodes + 127) / 128); if (g > c->numSMs * 16) g = c->numSMs * 16; if (g < 1) g = 1;
         mas_coarsen_kernel<<<g, 128, 0, c->stream>>>(V.nNodes, D.lvRowPtr[l - 1], D.lvColIdx[l - 1], D.lvVal[l - 1], V.parent, V.geom,
                                                     D.lv[l].geom, D.lvRowPtr[l], D.lvColIdx[l], D.lvVal[l]);
         KCHECK(c);
@@ -736,7 +718,7 @@ int launch_mas_setup(ocb_ctx* c)
             A.rowPtr[l - 1] = D.lvRowPtr[l - 1]; A.colIdx[l - 1] = D.lvColIdx[l - 1]; A.val[l - 1] = D.lvVal[l - 1];
             A.parent[l - 1] = V.parent; A.groupBeg[l - 1] = V.groupBeg; A.inv[l - 1] = V.inv;
         }
-        mas_invert_kernel<<<A.groupPre[H.L - 1], 256, 0, c->stream>>>(A);
+        mas_invert_kernel<<<A.groupPre[H.L - 1], kDenseThreads, 0, c->stream>>>(A);
         KCHECK(c);
     }
     {                                          // the coarse level: dense fill + exact inverse

@@ -193,28 +193,34 @@ __device__ __forceinline__ void mas_down(const MasView& M, const MasSmem& S, int
     const int nT = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < M.nC; i += nT) S.rcAll[i] = __ldcg(M.rcC + i);
     __syncthreads();
-    {
+    {   // 16 lanes per output row: all rows of the CTA in one pass when there are <= 64, every lane keeps
+        // several independent 16-byte loads of the inverse row in flight
         const int rows = S.nOwnC * kMasDof, ld4 = M.ldC >> 2;
         double* eC = S.e + (size_t)S.lvOff[M.L - 1] * kMasDof;
-        for (int row = warp; row < rows; row += nT >> 5) {
-            const float4* a = reinterpret_cast<const float4*>(M.cinv + (size_t)(S.cBeg * kMasDof + row) * M.ldC);
+        const int sub = lane & 15;
+        for (int row0 = 0; row0 < rows; row0 += nT >> 4) {
+            const int row = row0 + (threadIdx.x >> 4);
+            const bool valid = row < rows;
+            const float4* a = reinterpret_cast<const float4*>(M.cinv + (size_t)(S.cBeg * kMasDof + (valid ? row : 0)) * M.ldC);
             double y0 = 0.0, y1 = 0.0;
-            int c4 = lane;
-            for (; c4 + 32 < ld4; c4 += 64) {
-                const float4 u = __ldg(a + c4), v = __ldg(a + c4 + 32);
-                const double* r0 = S.rcAll + 4 * c4; const double* r1 = r0 + 128;
-                y0 += (double)u.x * r0[0] + (double)u.y * r0[1] + (double)u.z * r0[2] + (double)u.w * r0[3];
-                y1 += (double)v.x * r1[0] + (double)v.y * r1[1] + (double)v.z * r1[2] + (double)v.w * r1[3];
-            }
-            if (c4 < ld4) {
-                const float4 u = __ldg(a + c4);
-                const double* r0 = S.rcAll + 4 * c4;
-                y0 += (double)u.x * r0[0] + (double)u.y * r0[1] + (double)u.z * r0[2] + (double)u.w * r0[3];
+            if (valid) {
+                int c4 = sub;
+                for (; c4 + 16 < ld4; c4 += 32) {
+                    const float4 u = __ldg(a + c4), v = __ldg(a + c4 + 16);
+                    const double* r0 = S.rcAll + 4 * c4; const double* r1 = r0 + 64;
+                    y0 += (double)u.x * r0[0] + (double)u.y * r0[1] + (double)u.z * r0[2] + (double)u.w * r0[3];
+                    y1 += (double)v.x * r1[0] + (double)v.y * r1[1] + (double)v.z * r1[2] + (double)v.w * r1[3];
+                }
+                if (c4 < ld4) {
+                    const float4 u = __ldg(a + c4);
+                    const double* r0 = S.rcAll + 4 * c4;
+                    y0 += (double)u.x * r0[0] + (double)u.y * r0[1] + (double)u.z * r0[2] + (double)u.w * r0[3];
+                }
             }
             double y = y0 + y1;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
-            if (lane == 0) eC[row] = y;
+            for (int o = 8; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+            if (valid && sub == 0) eC[row] = y;
         }
     }
     __syncthreads();

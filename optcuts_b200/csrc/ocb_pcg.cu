@@ -663,10 +663,17 @@ struct PcgPlan { int grid; bool smem; bool cluster; int maxBlk; size_t smemBytes
 // upper bound of the MAS scratch of one CTA (the hierarchy is built after the plan)
 static size_t mas_smem_estimate(int rowsPer, int grid)
 {
-    (void)grid;
-    int local = 0, k = (rowsPer + kMasLeaf - 1) / kMasLeaf;
-    for (;;) { local += k; if (k <= 1) break; k = (k + kMasGroup - 1) / kMasGroup; }
-    return mas_smem_bytes(local + kMasMaxLevels, rowsPer, kMasCoarseMax) + 64;
+    // mirrors mas_build_hierarchy: leaves of <= 8 rows, groups of <= 8 nodes inside a CTA, coarse level = the first
+    // level with <= kMasCoarseMax DOFs over the whole grid (upper bounds: every CTA as full as the fullest)
+    int local = 0, k = (rowsPer + kMasLeaf - 1) / kMasLeaf, nC = 0;
+    for (;;) {
+        local += k;
+        if ((long)k * grid * kMasDof <= kMasCoarseMax) { nC = k * grid * kMasDof; break; }
+        if (k <= 1) { nC = grid * kMasDof; break; }
+        k = (k + kMasGroup - 1) / kMasGroup;
+    }
+    const int ldC = (nC + kMasCoarseBlk - 1) / kMasCoarseBlk * kMasCoarseBlk;
+    return mas_smem_bytes(local + kMasMaxLevels, rowsPer, ldC) + 64;
 }
 static PcgPlan pcg_plan(ocb_ctx* c)
 {
@@ -676,9 +683,9 @@ static PcgPlan pcg_plan(ocb_ctx* c)
     static const bool allowCluster = []() { const char* e = getenv("OCB_PCG_NO_CLUSTER"); return !(e && atoi(e)); }();
     PcgPlan pl; pl.smem = false; pl.cluster = false; pl.maxBlk = 0; pl.smemBytes = 0;
     const int n = c->nVtot;
-    int maxLen = 1;
-    for (int v = 0; v < n; ++v) maxLen = std::max(maxLen, c->hRowPtr[v + 1] - c->hRowPtr[v]);
-    const int ellW = std::min(maxLen, 12);                  // longer rows (valence > 11) continue in the global BSR
+    const int ellW = 12;                                    // constant: the plan must not depend on the pattern (the row order and the
+                                                            // preconditioner hierarchy are built for this grid BEFORE the pattern
+                                                            // exists); longer rows (valence > 11) continue in the global BSR
     auto slice_need = [&](int g, int& W) {
         W = ellW;
         return slice_bytes((n + g - 1) / g, ellW) + mas_smem_estimate((n + g - 1) / g, g);
