@@ -334,7 +334,7 @@ int mas_install(ocb_ctx* c)
     const int ldC = (nC + kMasCoarseBlk - 1) / kMasCoarseBlk * kMasCoarseBlk;
     OCB_CUDA(c, D.tabI.reserve(tI.size() + 4, c->stream));
     OCB_CUDA(c, D.tabD.reserve(tD.size() + 4, c->stream));
-    OCB_CUDA(c, D.dense.reserve(2 * (size_t)ldC * ldC + (size_t)ldC + 2 * kMasCoarseBlk * kMasCoarseBlk + 8, c->stream));
+    OCB_CUDA(c, D.dense.reserve(2 * (size_t)ldC * ldC + (size_t)ldC + 2 * kMasCoarseBlk * kMasCoarseBlk + 8 + kMasCoarseMax / kMasCoarseBlk, c->stream));
     OCB_CUDA(c, D.cinv.reserve((size_t)ldC * ldC + 8, c->stream));
     OCB_CUDA(c, D.rcCta.reserve((size_t)ldC + 8, c->stream));
     OCB_CUDA(c, cudaMemcpyAsync(D.tabI.p, tI.data(), tI.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -473,7 +473,7 @@ mas_dense_fill_kernel(int nNodes, const int32_t* __restrict__ rowPtr, const int3
 // leaf) is dropped: zero row and column in the inverse.  Finally the symmetrised result is stored in fp32.
 static constexpr int kCB = kMasCoarseBlk, kCBs = kMasCoarseBlk + 2;      // tile and its padded shared-memory stride
 static constexpr int kDenseThreads = 576;                                // 18 warps: warp w owns the 8x8 sub-tiles 2w and 2w+1 (6x6 grid)
-struct DenseInvArgs { int nb, ld, nC; double* X; double* Y; double* P; double* diag0; float* out; };
+struct DenseInvArgs { int nb, ld, nC; double* X; double* Y; double* P; double* diag0; float* out; long long* dbg; int* ticket; };
 
 // The tile products run on the FP64 tensor cores (mma.sync m8n8k4: the only tensor path for doubles; nothing else on
 // this path is a dense contraction).  A thread owns 4 elements of a 48x48 tile, in the accumulator-fragment layout:
@@ -520,37 +520,72 @@ __device__ __forceinline__ void tile_gemm(const double (*A)[kCBs], const double 
     }
     c[0] += sign * d0; c[1] += sign * d1; c[2] += sign * d2; c[3] += sign * d3;
 }
-// Gauss-Jordan inverse of one SPD tile held in REGISTERS (4 elements per thread); per pivot the pivot row and column
-// cross through a double-buffered shared-memory line, one barrier per pivot.  buf: 2 x (48 row + 48 column) doubles.
-__device__ __forceinline__ void tile_invert(double (&d)[4], double* buf, const double* d0s, const TileMap& m)
+// Gauss-Jordan inverse of one SPD tile (in shared memory T on entry and exit).  The sequential chain of 48 pivots is
+// what bounds the whole blocked inversion, so it runs on 5 warps only (a named barrier over 160 threads is cheaper than
+// one over 18 warps, and no warp waits for an issue slot): thread t < 144 keeps row t / 3, columns 16 (t % 3) .. + 15 in
+// REGISTERS; per pivot the pivot row and column cross through a double-buffered shared-memory line, one barrier per
+// pivot.  buf: 2 x (48 row + 48 column) doubles.  A DOF whose pivot collapses is dropped (zero row and column).
+__device__ __forceinline__ void tile_invert_smem(double (*T)[kCBs], double* buf, const double* d0s)
 {
-    for (int k = 0; k < kCB; ++k) {
-        double* rowb = buf + (k & 1) * 2 * kCB;
-        double* colb = rowb + kCB;
-        if (m.r == k) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < 160) {
+        const bool act = t < 144;
+        const int r = act ? t / 3 : 0, c0 = act ? 16 * (t % 3) : 0;
+        double d[16];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) rowb[tile_col(m, e)] = d[e];
+        for (int e = 0; e < 16; e += 2) { const double2 v = *reinterpret_cast<const double2*>(&T[r][c0 + e]); d[e] = v.x; d[e + 1] = v.y; }
+        // The pivot loop is unrolled over the 16 columns of a segment so that every register index is a compile-time
+        // constant (a run-time index would push d[] into local memory; rotating the registers instead was measured 2x
+        // slower).  What bounds a pivot is the chain of DEPENDENT fp64 operations between two barriers (~700 cycles with
+        // the IEEE reciprocal), so the reciprocal is the hardware approximation plus ONE Newton step (relative error
+        // ~1e-12: this is a preconditioner, stored in fp32 anyway).
+        for (int kq = 0; kq < kCB / 16; ++kq) {
+            const bool mine = act && c0 == 16 * kq;           // this thread's segment holds the pivot columns of this round
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                const int k = 16 * kq + kk;
+                double* rowb = buf + (k & 1) * 2 * kCB;
+                double* colb = rowb + kCB;
+                if (act && r == k) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) *reinterpret_cast<double2*>(rowb + c0 + e) = make_double2(d[e], d[e + 1]);
+                }
+                if (mine) colb[r] = d[kk];
+                asm volatile("bar.sync 1, 160;" ::: "memory");
+                const double p = rowb[k], dk0 = d0s[k], f = colb[r];
+                const bool bad = !(dk0 > 0.0) || !(p > 1e-10 * dk0);
+                if (bad) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) if (r == k || (mine && e == kk)) d[e] = 0.0;
+                } else {
+                    double ip;
+                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ip) : "d"(p));
+                    ip = fma(ip, fma(-p, ip, 1.0), ip);
+                    // one FMA per element for every row: the pivot row's own values ARE the row buffer, so its scaling
+                    // d * g is d + (g - 1) * rowb; the pivot-column element is overwritten afterwards
+                    const double g = r != k ? -f * ip : ip;           // -f/p for the other rows, 1/p for the pivot row
+                    const double coef = r != k ? g : g - 1.0;
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        const double2 rj = *reinterpret_cast<const double2*>(rowb + c0 + e);
+                        d[e] += coef * rj.x; d[e + 1] += coef * rj.y;
+                    }
+                    if (mine) d[kk] = g;
+                }
+            }
         }
+        if (act) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (tile_col(m, e) == k) colb[m.r] = d[e];
-        __syncthreads();
-        const double p = rowb[k], dk0 = d0s[k];
-        const bool bad = !(dk0 > 0.0) || !(p > 1e-10 * dk0);
-        if (bad) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (m.r == k || tile_col(m, e) == k) d[e] = 0.0;
-            continue;
-        }
-        const double ip = __drcp_rn(p);
-        const double g = m.r != k ? -colb[m.r] * ip : ip;     // -f/p for the other rows, 1/p for the pivot row
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int j = tile_col(m, e);
-            if (m.r != k) d[e] = (j != k) ? d[e] + g * rowb[j] : g;
-            else d[e] = (j != k) ? d[e] * g : g;
+            for (int e = 0; e < 16; e += 2) *reinterpret_cast<double2*>(&T[r][c0 + e]) = make_double2(d[e], d[e + 1]);
         }
     }
     __syncthreads();
+}
+__device__ __forceinline__ void tile_load_from_smem(double (&c)[4], const double (*S)[kCBs], const TileMap& m)
+{
+    const double2 a = *reinterpret_cast<const double2*>(&S[m.r][m.c0]), b = *reinterpret_cast<const double2*>(&S[m.r][m.c0 + 8]);
+    c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
 }
 
 __global__ void __launch_bounds__(kDenseThreads, 1)
@@ -573,42 +608,66 @@ mas_dense_invert_kernel(DenseInvArgs A)
     if (blockIdx.x == 0) {
         if (tid < kCB) d0s[tid] = A.diag0[tid];
         double d[4];
-        tile_load_regs(d, A.X, ld, m);
-        tile_invert(d, ibuf, d0s, m);
+        tile_load(sA, A.X, ld, m);
+        tile_invert_smem(sA, ibuf, d0s);
+        tile_load_from_smem(d, sA, m);
 #pragma unroll
         for (int e = 0; e < 4; ++e) A.P[(size_t)m.r * kCB + tile_col(m, e)] = d[e];
     }
     double* X = A.X; double* Y = A.Y;
+    long long tSync = 0, tTile = 0, tInv = 0;
     for (int k = 0; k < nb; ++k) {
+        long long t0 = A.dbg ? clock64() : 0;
         grid.sync();
+        if (A.dbg) { const long long t1 = clock64(); tSync += t1 - t0; t0 = t1; }
         tile_load(sP, A.P + (size_t)(k & 1) * kCB * kCB, kCB, m);
         __syncthreads();
         const int special = k + 1 < nb ? (k + 1) * nb + (k + 1) : -1;
         const bool owner = special >= 0 && (int)blockIdx.x == special % (int)gridDim.x;
-        // tiles of this CTA, the look-ahead tile first
-        for (int it = owner ? -1 : 0;; ++it) {
-            int t;
-            if (it < 0) t = special;
-            else { t = blockIdx.x + it * gridDim.x; if (t >= nb * nb) break; if (t == special) continue; }
+        // tiles of this CTA, the look-ahead tile first; software-pipelined: the operands of the NEXT tile are already
+        // on their way from L2 into registers while the two tensor-core products of the current one run
+        // tiles are handed out by a ticket counter per step (the owner of the look-ahead tile spends a long time on
+        // its inversion and must not sit on a fixed share of the trailing tiles)
+        int q = owner ? -1 : 0;
+        __shared__ int sTicket;
+        auto advance = [&](int& qq) -> int {
+            if (qq < 0) { qq = 0; return special; }
+            for (;;) {
+                __syncthreads();
+                if (tid == 0) sTicket = atomicAdd(A.ticket + k, 1);
+                __syncthreads();
+                const int t = sTicket;
+                if (t >= nb * nb) return -1;
+                if (t != special) return t;
+            }
+        };
+        auto issue = [&](int t, double (&pb)[4], double (&pa)[4], double (&pc)[4]) {
             const int i = t / nb, j = t % nb;
-            const double* Xkj = X + (size_t)k * kCB * ld + (size_t)j * kCB;
-            const double* Xik = X + (size_t)i * kCB * ld + (size_t)k * kCB;
-            double c[4] = {0.0, 0.0, 0.0, 0.0};
+            if (j != k) tile_load_regs(pb, X + (size_t)k * kCB * ld + (size_t)j * kCB, ld, m);
+            if (i != k) tile_load_regs(pa, X + (size_t)i * kCB * ld + (size_t)k * kCB, ld, m);
+            if (i != k && j != k) tile_load_regs(pc, X + (size_t)i * kCB * ld + (size_t)j * kCB, ld, m);
+        };
+        int tcur = advance(q);
+        double cb[4] = {0.0, 0.0, 0.0, 0.0}, ca[4] = {0.0, 0.0, 0.0, 0.0}, cc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (tcur >= 0) issue(tcur, cb, ca, cc);
+        bool first = owner;
+        while (tcur >= 0) {
+            const int i = tcur / nb, j = tcur % nb;
+            if (j != k) tile_store_smem(sB, cb, m);
+            if (i != k) tile_store_smem(sA, ca, m);
+            double c[4] = {cc[0], cc[1], cc[2], cc[3]};
+            const int tnext = advance(q);
+            if (tnext >= 0) issue(tnext, cb, ca, cc);
+            __syncthreads();
             if (i == k && j == k) {
                 c[0] = sP[m.r][m.c0]; c[1] = sP[m.r][m.c0 + 1]; c[2] = sP[m.r][m.c0 + 8]; c[3] = sP[m.r][m.c0 + 9];
             } else if (i == k) {
-                tile_load(sB, Xkj, ld, m);
-                __syncthreads();
+                c[0] = c[1] = c[2] = c[3] = 0.0;
                 tile_gemm(sP, sB, c, 1.0);
             } else if (j == k) {
-                tile_load(sA, Xik, ld, m);
-                __syncthreads();
+                c[0] = c[1] = c[2] = c[3] = 0.0;
                 tile_gemm(sA, sP, c, -1.0);
             } else {
-                tile_load(sB, Xkj, ld, m);
-                tile_load(sA, Xik, ld, m);
-                tile_load_regs(c, X + (size_t)i * kCB * ld + (size_t)j * kCB, ld, m);
-                __syncthreads();
                 double r[4] = {0.0, 0.0, 0.0, 0.0};
                 tile_gemm(sP, sB, r, 1.0);
                 tile_store_smem(sR, r, m);
@@ -619,17 +678,24 @@ mas_dense_invert_kernel(DenseInvArgs A)
             *reinterpret_cast<double2*>(Yij) = make_double2(c[0], c[1]);
             *reinterpret_cast<double2*>(Yij + 8) = make_double2(c[2], c[3]);
             __syncthreads();                   // the shared tiles are reused by the next tile
-            if (it < 0) {                      // look-ahead: invert the next pivot tile now
+            if (first) {                       // look-ahead: invert the next pivot tile now
+                first = false;
+                const long long ti0 = A.dbg ? clock64() : 0;
                 if (tid < kCB) d0s[tid] = A.diag0[(k + 1) * kCB + tid];
-                __syncthreads();
-                tile_invert(c, ibuf, d0s, m);
+                tile_store_smem(sR, c, m);
+                tile_invert_smem(sR, ibuf, d0s);
+                tile_load_from_smem(c, sR, m);
                 double* Pn = A.P + (size_t)((k + 1) & 1) * kCB * kCB;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) Pn[(size_t)m.r * kCB + tile_col(m, e)] = c[e];
+                if (A.dbg) tInv += clock64() - ti0;
             }
+            tcur = tnext;
         }
+        if (A.dbg) tTile += clock64() - t0;
         double* T = X; X = Y; Y = T;
     }
+    if (A.dbg && tid == 0) { A.dbg[3 * blockIdx.x] = tSync; A.dbg[3 * blockIdx.x + 1] = tTile; A.dbg[3 * blockIdx.x + 2] = tInv; }
     grid.sync();
     const size_t total = (size_t)ld * ld;
     for (size_t e = (size_t)blockIdx.x * kDenseThreads + tid; e < total; e += (size_t)gridDim.x * kDenseThreads) {
@@ -678,10 +744,8 @@ mas_invert_kernel(MasInvertArgs P)
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) if (tile_col(m, e) == m.r) d0s[m.r] = d[e];
-    __syncthreads();
-    tile_invert(d, ibuf, d0s, m);
     tile_store_smem(T, d, m);
-    __syncthreads();
+    tile_invert_smem(T, ibuf, d0s);
     float* out = P.inv[l] + (size_t)g * kMasBlk * kMasBlk;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -728,6 +792,8 @@ int launch_mas_setup(ocb_ctx* c)
         DenseInvArgs A;
         A.nb = W.ldC / kCB; A.ld = W.ldC; A.nC = W.nC;
         A.X = D.dense.p; A.Y = A.X + ld * ld; A.diag0 = A.Y + ld * ld; A.P = A.diag0 + ld; A.out = D.cinv.p;
+        A.ticket = reinterpret_cast<int*>(A.P + 2 * kCB * kCB);
+        OCB_CUDA(c, cudaMemsetAsync(A.ticket, 0, sizeof(int) * (size_t)(A.nb + 1), c->stream));
         OCB_CUDA(c, cudaMemsetAsync(A.X, 0, ld * ld * sizeof(double), c->stream));
         int g = (V.nNodes * 36 + 255) / 256; if (g > c->numSMs * 8) g = c->numSMs * 8; if (g < 1) g = 1;
         mas_dense_fill_kernel<<<g, 256, 0, c->stream>>>(V.nNodes, D.lvRowPtr[H.L - 1], D.lvColIdx[H.L - 1], D.lvVal[H.L - 1], W.ldC, W.nC, A.X);
@@ -738,9 +804,22 @@ int launch_mas_setup(ocb_ctx* c)
             D.denseAttr = true;
         }
         int gi = A.nb * A.nb; if (gi > c->numSMs) gi = c->numSMs;
+        static const bool dbgOn = []() { const char* e = getenv("OCB_MAS_DEBUG"); return e && atoi(e); }();
+        A.dbg = nullptr;
+        if (dbgOn) { cudaMalloc((void**)&A.dbg, 3 * sizeof(long long) * gi); cudaMemset(A.dbg, 0, 3 * sizeof(long long) * gi); }
         void* args[] = {&A};
         OCB_CUDA(c, cudaLaunchCooperativeKernel((void*)mas_dense_invert_kernel, dim3(gi), dim3(kDenseThreads), args, smem, c->stream));
         c->launches++;
+        if (dbgOn) {
+            std::vector<long long> h(3 * (size_t)gi);
+            cudaStreamSynchronize(c->stream);
+            cudaMemcpy(h.data(), A.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            cudaFree(A.dbg);
+            long long mx[3] = {0, 0, 0}; double av[3] = {0, 0, 0};
+            for (int b = 0; b < gi; ++b) for (int q = 0; q < 3; ++q) { mx[q] = std::max(mx[q], h[3 * b + q]); av[q] += (double)h[3 * b + q] / gi; }
+            fprintf(stderr, "[ocb mas] dense inverse n %d (%d tiles^2) grid %d: cycles/step  grid.sync avg %.0f max %.0f | tiles avg %.0f max %.0f | invert (sum over CTAs) %.0f\n",
+                    A.nC, A.nb, gi, av[0] / A.nb, (double)mx[0] / A.nb, av[1] / A.nb, (double)mx[1] / A.nb, av[2] * gi / A.nb);
+        }
     }
     return 0;
 }
