@@ -668,6 +668,7 @@ int ocb_set_pattern_from_elements(ocb_ctx* c)
     const int nVtot = c->nVtot;
     c->hFixed.resize((size_t)nVtot, 0);
     // degree upper bound (with duplicates), fill, then sort + unique every short row
+    HostTimer* _ta = new HostTimer("  adjacency");
     std::vector<int32_t> cnt((size_t)nVtot + 1, 0);
     auto count = [&](const std::vector<int32_t>& F, int n) {
         for (int t = 0; t < n; ++t) for (int k = 0; k < 3; ++k) cnt[(size_t)F[(size_t)k * n + t] + 1] += 2;
@@ -683,9 +684,11 @@ int ocb_set_pattern_from_elements(ocb_ctx* c)
         }
     };
     scatter(c->hF, c->nF); scatter(c->hFa, c->nFa);
+    delete _ta;
     // the solver's row order first (it needs only the UVs), then the pattern directly in that order: rows de-duplicated
     // with a stamp and insertion-sorted (they are ~7 entries long)
-    OCB_TRY(choose_order(c));
+    { HostTimer _tb("  choose_order (incl. UV download)"); OCB_TRY(choose_order(c)); }
+    HostTimer* _tc = new HostTimer("  pattern rows");
     c->hRowPtr.clear(); c->hColIdx.clear();
     c->hSRowPtr.assign((size_t)nVtot + 1, 0);
     c->hSColIdx.clear(); c->hSColIdx.reserve(buf.size() / 2 + nVtot);
@@ -707,6 +710,8 @@ int ocb_set_pattern_from_elements(ocb_ctx* c)
         }
         c->hSRowPtr[r + 1] = (int32_t)c->hSColIdx.size();
     }
+    delete _tc;
+    HostTimer _td("  finish_install");
     return finish_install(c);
 }
 

@@ -190,7 +190,7 @@ __device__ __forceinline__ void mas_local_solves(const MasView& M, const MasSmem
 // of the row's leaf to the block-Jacobi part of z.
 __device__ __forceinline__ void mas_down(const MasView& M, const MasSmem& S, int cta)
 {
-    const int nT = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nT = blockDim.x, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < M.nC; i += nT) S.rcAll[i] = __ldcg(M.rcC + i);
     __syncthreads();
     {   // 16 lanes per output row: all rows of the CTA in one pass when there are <= 64, every lane keeps

@@ -86,6 +86,65 @@ def rcb(X, idx, nparts_sizes):
     return out
 
 
+def hilbert_order(X, bits=int(os.environ.get("HBITS", "10"))):
+    """Order points along a Hilbert curve of a 2^bits x 2^bits grid (alternative to recursive bisection)."""
+    lo, hi = X.min(0), X.max(0)
+    ext = max(float((hi - lo).max()), 1e-300)
+    q = np.minimum(((X - lo) / ext * (1 << bits)).astype(np.int64), (1 << bits) - 1)
+    x, y = q[:, 0].copy(), q[:, 1].copy()
+    d = np.zeros(len(X), np.int64)
+    s = 1 << (bits - 1)
+    while s > 0:
+        rx = ((x & s) > 0).astype(np.int64)
+        ry = ((y & s) > 0).astype(np.int64)
+        d += s * s * ((3 * rx) ^ ry)
+        # rotate
+        m = ry == 0
+        flip = m & (rx == 1)
+        x = np.where(flip, s - 1 - x, x)
+        y = np.where(flip, s - 1 - y, y)
+        x, y = np.where(m, y, x), np.where(m, x, y)
+        s >>= 1
+    return np.argsort(d, kind="stable")
+
+
+def build_hierarchy_curve(X, grid, leaf, group):
+    """Hierarchy from a space-filling-curve order: CTA chunks, leaves and groups are consecutive runs."""
+    n = X.shape[0]
+    order = hilbert_order(X)
+    rowsPer = -(-n // grid)
+    leaves, ctaOf = [], []
+    for c in range(grid):
+        b, e = c * rowsPer, min(n, (c + 1) * rowsPer)
+        if e <= b:
+            continue
+        nl = -(-(e - b) // leaf)
+        o = b
+        for sz in even_sizes(e - b, nl):
+            leaves.append((o, o + sz)); ctaOf.append(c); o += sz
+    levels = [dict(rng=leaves, cta=ctaOf)]
+    while len(levels[-1]["rng"]) > 1:
+        cur = levels[-1]
+        rng, cta, parent = [], [], []
+        nn = len(cur["rng"])
+        multi = len(set(cur["cta"])) < nn
+        i = 0
+        while i < nn:
+            # even group sizes inside a CTA
+            j = i
+            while j < nn and (not multi or cur["cta"][j] == cur["cta"][i]):
+                j += 1
+            k = j - i
+            for sz in even_sizes(k, -(-k // group)):
+                rng.append((cur["rng"][i][0], cur["rng"][i + sz - 1][1])); cta.append(cur["cta"][i]); parent.extend([len(rng) - 1] * sz); i += sz
+            if not multi:
+                break
+        cur["parent"] = parent
+        levels.append(dict(rng=rng, cta=cta))
+    levels[-1]["parent"] = [0]
+    return order, levels
+
+
 def even_sizes(n, k):
     return [n // k + (1 if i < n % k else 0) for i in range(k)]
 
@@ -247,6 +306,7 @@ def main():
     ap.add_argument("--no-leaf-dense", action="store_true")
     ap.add_argument("--jacobi", action="store_true")
     ap.add_argument("--exact-from", type=int, default=99, help="level (1-based) solved exactly on its Galerkin matrix")
+    ap.add_argument("--curve", action="store_true", help="Hilbert-curve order instead of recursive bisection")
     ap.add_argument("--lib", action="store_true", help="use the hierarchy built by liboptcuts_b200.so")
     a = ap.parse_args()
     t0 = time.time()
@@ -261,7 +321,7 @@ def main():
         Minv = sp.block_diag(blocks, format="csr")
         _, it = pcg(A, b, lambda r: Minv @ r)
         print("block-Jacobi: %d iterations" % it)
-    order, levels = lib_hierarchy(X, a.grid) if a.lib else build_hierarchy(X, a.grid, a.leaf, a.group)
+    order, levels = lib_hierarchy(X, a.grid) if a.lib else (build_hierarchy_curve if a.curve else build_hierarchy)(X, a.grid, a.leaf, a.group)
     if a.lib:
         a.exact_from = len(levels)          # the library's last level is the exactly solved coarse level
     perm2 = np.stack([2 * order, 2 * order + 1], 1).ravel()
