@@ -221,6 +221,12 @@ int ocb_eval_stencils(ocb_ctx* ctx, const ocb_stencil_batch* batch, int maxIter,
  * the sparsity pattern.  info[0] = 1 if active (0: block-Jacobi only, no UV was known at pattern time),
  * info[1] = levels L, info[2] = CTA-local levels, info[3] = persistent CTAs, info[4..4+L) = nodes per level. */
 int ocb_precond_info(const ocb_ctx* ctx, int32_t* info16);
+/* A bare LinSysSolver (ocb_set_pattern + ocb_update_values_triplets, no mesh on this context) has no geometry: the
+ * caller may hand over positions of the first n vertices of the NEXT ocb_set_pattern (Eigen column-major n x 2: all x,
+ * then all y — e.g. TriMesh::V of the mesh being optimised); vertices beyond n (interior air-mesh vertices) are placed
+ * at the mean of their neighbours.  Purely a hint for the preconditioner hierarchy: results do not depend on it,
+ * without it the solver falls back to block-Jacobi.  n = 0 clears the hint. */
+int ocb_set_coordinate_hint(ocb_ctx* ctx, int n, const double* xy_colmajor);
 /* Host-only (no CUDA work; unit tests and tools/mas_proto.py): the hierarchy for n free points xy (2 per point)
  * and `grid` CTAs.  vert_of[n] = point of every solver row; child_beg = the per-level child ranges, level after
  * level (nodes_l + 1 entries each, `cap` entries available).  Returns the entries written or an error. */

@@ -95,6 +95,7 @@ _SIGS = [
     ("ocb_divgrad_scores", C.c_int, [C.c_void_p, _d]),
     ("ocb_eval_stencils", C.c_int, [C.c_void_p, C.POINTER(StencilBatch), C.c_int, C.c_double, _d, _d, _d, _i, _d, _i, C.POINTER(C.c_int)]),
     ("ocb_precond_info", C.c_int, [C.c_void_p, _i]),
+    ("ocb_set_coordinate_hint", C.c_int, [C.c_void_p, C.c_int, _d]),
     ("ocb_precond_hierarchy", C.c_int, [C.c_void_p, C.c_int, _d, C.c_int, _i, _i, _i, C.c_int]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
@@ -323,6 +324,11 @@ class Context:
     # -- solve
     def factorize(self):
         self._chk(self._L.ocb_factorize(self._h))
+
+    def set_coordinate_hint(self, xy):
+        """Positions (n x 2) of the first n vertices of the next set_pattern of a solver-only context."""
+        xy = _f64(np.asarray(xy, dtype=np.float64).reshape(-1, 2))
+        self._chk(self._L.ocb_set_coordinate_hint(self._h, xy.shape[0], _pd(xy)))
 
     def precond_info(self):
         """The solver's multilevel preconditioner hierarchy (built with the pattern)."""

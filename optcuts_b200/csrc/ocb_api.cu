@@ -531,6 +531,9 @@ static int choose_order(ocb_ctx* c)
         OCB_CUDA(c, cudaMemcpyAsync(xy.data(), c->x.p, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
         OCB_CUDA(c, cudaStreamSynchronize(c->stream));
         { HostTimer _h2("  mas_build_hierarchy"); OCB_TRY(mas_build_hierarchy(c, xy.data(), c->planGrid)); }
+    } else if (!masOff && c->nV == 0 && (int)c->hCoords.size() == 2 * n && n >= 2 * kMasLeaf) {     // bare solver with a coordinate hint
+        HostTimer _h2("  mas_build_hierarchy");
+        OCB_TRY(mas_build_hierarchy(c, c->hCoords.data(), c->planGrid));
     } else {
         c->hRowOf.resize((size_t)n); c->hVertOf.resize((size_t)n);
         for (int v = 0; v < n; ++v) c->hRowOf[v] = c->hVertOf[v] = v;
@@ -632,6 +635,30 @@ int ocb_set_pattern(ocb_ctx* c, int nVtot, const int32_t* adjPtr, const int32_t*
     for (int i = 0; i < nFixed; ++i) {
         if (fixed[i] < 0 || fixed[i] >= nVtot) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range");
         c->hFixed[c->hPerm[fixed[i]]] = (c->nV > 0 && fixed[i] >= c->nV) ? 2 : 1;     // merged set (Scaffold::mergeFixedV): air-only ids follow the mesh's
+    }
+    c->hCoords.clear();
+    if (c->nV == 0 && !c->hHint.empty()) {                 // bare solver: positions from the hint, the rest by neighbour means
+        const int nKnown = std::min<int>((int)(c->hHint.size() / 2), nVtot);
+        std::vector<double> xy(2 * (size_t)nVtot, 0.0);
+        std::vector<uint8_t> known((size_t)nVtot, 0);
+        for (int v = 0; v < nKnown; ++v) { xy[2 * (size_t)v] = c->hHint[2 * (size_t)v]; xy[2 * (size_t)v + 1] = c->hHint[2 * (size_t)v + 1]; known[v] = 1; }
+        for (int sweep = 0, left = nVtot - nKnown; sweep < 32 && left > 0; ++sweep) {
+            std::vector<int> newly;
+            for (int v = nKnown; v < nVtot; ++v) {
+                if (known[v]) continue;
+                double sx = 0.0, sy = 0.0; int k = 0;
+                for (int q = adjPtr[v]; q < adjPtr[v + 1]; ++q) {
+                    const int u = adjIdx[q];
+                    if (u >= 0 && u < nVtot && known[u]) { sx += xy[2 * (size_t)u]; sy += xy[2 * (size_t)u + 1]; ++k; }
+                }
+                if (k > 0) { xy[2 * (size_t)v] = sx / k; xy[2 * (size_t)v + 1] = sy / k; newly.push_back(v); }
+            }
+            for (int v : newly) known[v] = 1;
+            left -= (int)newly.size();
+            if (newly.empty()) break;
+        }
+        c->hCoords.resize(2 * (size_t)nVtot);
+        for (int v = 0; v < nVtot; ++v) { c->hCoords[2 * (size_t)c->hPerm[v]] = xy[2 * (size_t)v]; c->hCoords[2 * (size_t)c->hPerm[v] + 1] = xy[2 * (size_t)v + 1]; }
     }
     c->hRowPtr.assign((size_t)nVtot + 1, 0);
     c->hColIdx.clear();
@@ -910,6 +937,13 @@ int ocb_precond_info(const ocb_ctx* c, int32_t* info)
 {
     if (!c || !info) return OCB_ERR_ARG;
     fill_precond_info(c->masH, info);
+    return OCB_OK;
+}
+int ocb_set_coordinate_hint(ocb_ctx* c, int n, const double* xy)
+{
+    if (!c || n < 0 || (n > 0 && !xy)) return set_err(c, OCB_ERR_ARG, "ocb_set_coordinate_hint: bad argument");
+    c->hHint.resize(2 * (size_t)n);
+    for (int v = 0; v < n; ++v) { c->hHint[2 * (size_t)v] = xy[v]; c->hHint[2 * (size_t)v + 1] = xy[(size_t)n + v]; }
     return OCB_OK;
 }
 int ocb_precond_hierarchy(ocb_ctx* c, int n, const double* xy, int grid, int32_t* vert_of, int32_t* info, int32_t* child_beg, int cap)

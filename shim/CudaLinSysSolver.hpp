@@ -20,7 +20,9 @@
 #include <string>
 #include <vector>
 
+#include "CudaCoordinateHint.hpp"
 namespace OptCuts {
+
 
 template <typename vectorTypeI, typename vectorTypeS>
 class CudaLinSysSolver : public LinSysSolver<vectorTypeI, vectorTypeS>
@@ -58,6 +60,13 @@ public:
         for (int v = 0; v < nV; ++v) {
             for (int nb : vNeighbor[v]) idx.push_back(nb);
             ptr[v + 1] = static_cast<int32_t>(idx.size());
+        }
+        // geometry hint for the preconditioner hierarchy: the UVs CudaSymDirichletEnergy saw last (the mesh being optimised;
+        // the air mesh's interior vertices follow it in the system and are placed by the library)
+        {
+            std::vector<double> xy; int n = 0;
+            cudaCoordinateHint(false, n, xy);
+            if (n > 0 && n <= nV) ocb_set_coordinate_hint(ctx, n, xy.data());
         }
         check(ocb_set_pattern(ctx, nV, ptr.data(), idx.data(), fixed.data(), static_cast<int>(fixed.size())), "ocb_set_pattern");
     }

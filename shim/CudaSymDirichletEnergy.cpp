@@ -1,4 +1,5 @@
 #include "CudaSymDirichletEnergy.hpp"
+#include "CudaCoordinateHint.hpp"
 
 #include <cstring>
 #include <stdexcept>
@@ -38,6 +39,11 @@ bool CudaSymDirichletEnergy::bind(const TriMesh& data, bool uniformWeight) const
         boundF = data.F; boundFixed = fixed; boundArea = data.triArea.data(); boundUniform = uniformWeight; boundNV = nV;
     }
     check(ocb_set_uv(ctx, data.V.data(), NULL), "ocb_set_uv");
+    if (!uniformWeight) {                             // the mesh (not the air mesh): publish its UVs for the solver's hierarchy
+        std::vector<double> xy(data.V.data(), data.V.data() + 2 * static_cast<size_t>(nV));
+        int n = nV;
+        cudaCoordinateHint(true, n, xy);
+    }
     return true;
 }
 

@@ -82,3 +82,35 @@ def test_pattern_without_uv_falls_back_to_block_jacobi(ctx, state1):
         assert np.linalg.norm(c2.multiply(x) - rhs) / np.linalg.norm(rhs) < 1e-10
     finally:
         c2.close()
+
+
+def test_bare_solver_with_coordinate_hint(ctx, state1):
+    """The drop-in route (shim/CudaLinSysSolver): a solver-only context fed with the reference's adjacency and triplets
+    gets its geometry through ocb_set_coordinate_hint (mesh UVs only; the air mesh's interior vertices are placed by
+    the library) and must build the two-level preconditioner, reproduce the reference direction and converge in the
+    prototype's iteration count."""
+    import optcuts_b200 as ob
+    from test_oracle_golden import _merged_adjacency
+    s = state1
+    (ptr, idx), nVtot = _merged_adjacency(s)
+    # the matrix: assembled by the full context, handed over as triplets of the reference CSR (upper triangle)
+    s.upload(ctx)
+    ctx.set_pattern(ptr, idx, s.fixed)
+    ctx.hessian_assemble(s.p0)
+    ia, ja, a = ctx.download_csr()
+    I = np.repeat(np.arange(len(ia) - 1, dtype=np.int32), np.diff(ia))
+    J = (ja - 1).astype(np.int32)
+    g, _ = ctx.gradient(s.p0)
+    c2 = ob.Context(0)
+    try:
+        c2.set_coordinate_hint(s.UV)
+        c2.set_pattern(ptr, idx, s.fixed)
+        info = c2.precond_info()
+        assert info["enabled"] and 6 * info["nodes"][-1] <= 3072
+        c2.update_values_triplets(I, J, a)
+        p, it = c2.solve(-g, 1e-12, 0)
+        ref = s.r("searchDir")
+        assert np.linalg.norm(p - ref) / np.linalg.norm(ref) < 1e-8
+        assert it["iters"] < 260, it
+    finally:
+        c2.close()
