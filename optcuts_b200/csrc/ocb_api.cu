@@ -581,14 +581,7 @@ static int install_pattern(ocb_ctx* c)
     int w = 0;
     for (int r = 0; r < n; ++r) {
         const int v = c->hVertOf[r];
-        const int w0 = w;
-        for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) {       // insertion sort by solver column
-            const int32_t col = c->hRowOf[c->hColIdx[b]];
-            int j = w - 1;
-            while (j >= w0 && c->hSColIdx[j] > col) { c->hSColIdx[j + 1] = c->hSColIdx[j]; --j; }
-            c->hSColIdx[j + 1] = col;
-            ++w;
-        }
+        for (int b = c->hRowPtr[v]; b < c->hRowPtr[v + 1]; ++b) c->hSColIdx[w++] = c->hRowOf[c->hColIdx[b]];     // unsorted rows
         c->hSRowPtr[r + 1] = w;
     }
     c->hRowPtr.clear(); c->hColIdx.clear();
@@ -717,25 +710,33 @@ int ocb_set_pattern_from_elements(ocb_ctx* c)
     { HostTimer _tb("  choose_order (incl. UV download)"); OCB_TRY(choose_order(c)); }
     HostTimer* _tc = new HostTimer("  pattern rows");
     c->hRowPtr.clear(); c->hColIdx.clear();
-    c->hSRowPtr.assign((size_t)nVtot + 1, 0);
-    c->hSColIdx.clear(); c->hSColIdx.reserve(buf.size() / 2 + nVtot);
-    std::vector<int32_t> stamp((size_t)nVtot, -1);
-    for (int r = 0; r < nVtot; ++r) {
-        const int v = c->hVertOf[r];
-        if (c->hFixed[v]) { c->hSColIdx.push_back(r); }
-        else {
-            const size_t w0 = c->hSColIdx.size();
-            for (int32_t* q = buf.data() + cnt[v]; q < buf.data() + fill[v]; ++q) {
-                const int u = *q;
-                if (stamp[u] == v) continue;
-                stamp[u] = v;
-                if (u == v || !c->hFixed[u]) c->hSColIdx.push_back(c->hRowOf[u]);
+    c->hSRowPtr.resize((size_t)nVtot + 1);
+    c->hSColIdx.resize(buf.size());                        // upper bound (duplicates included), trimmed below
+    c->hStamp.assign((size_t)nVtot, -1);
+    {
+        int32_t* out = c->hSColIdx.data();
+        int32_t* rowPtr = c->hSRowPtr.data();
+        int32_t* stamp = c->hStamp.data();
+        const int32_t* vertOf = c->hVertOf.data(); const int32_t* rowOf = c->hRowOf.data();
+        const uint8_t* fixed = c->hFixed.data();
+        const int32_t* bufp = buf.data();
+        int w = 0;
+        rowPtr[0] = 0;
+        for (int r = 0; r < nVtot; ++r) {
+            const int v = vertOf[r];
+            if (fixed[v]) out[w++] = r;
+            else {
+                for (const int32_t* q = bufp + cnt[v], *qe = bufp + fill[v]; q < qe; ++q) {
+                    const int u = *q;
+                    if (stamp[u] == v) continue;
+                    stamp[u] = v;
+                    if (u != v && fixed[u]) continue;
+                    out[w++] = rowOf[u];                   // rows stay unsorted: every look-up (host and device) is a linear scan
+                }
             }
-            int32_t* a = c->hSColIdx.data() + w0;
-            const int m = (int)(c->hSColIdx.size() - w0);
-            for (int i = 1; i < m; ++i) { const int32_t x = a[i]; int j = i - 1; while (j >= 0 && a[j] > x) { a[j + 1] = a[j]; --j; } a[j + 1] = x; }
+            rowPtr[r + 1] = w;
         }
-        c->hSRowPtr[r + 1] = (int32_t)c->hSColIdx.size();
+        c->hSColIdx.resize((size_t)w);
     }
     delete _tc;
     HostTimer _td("  finish_install");

@@ -129,6 +129,7 @@ struct ocb_ctx {
     ocb::DevBuf<int32_t> rowOf, vertOf, userRow;   // device: internal vertex -> row, row -> internal vertex, caller vertex -> row
     ocb::MasHost masH; ocb::MasDev masD;
     int planGrid = 0;                        // persistent-CTA count the hierarchy was built for
+    std::vector<int32_t> hStamp;             // scratch of the pattern builders
     std::vector<double> hHint;               // ocb_set_coordinate_hint: 2 per vertex (interleaved), caller numbering
     std::vector<double> hCoords;             // positions of all nVtot vertices for a solver-only context (INTERNAL numbering)
     ocb::DevBuf<int32_t> rowPtr, colIdx;

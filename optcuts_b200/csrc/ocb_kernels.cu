@@ -185,14 +185,10 @@ build_slots_kernel(int n, const int32_t* __restrict__ v0, const int32_t* __restr
             for (int l = 0; l < 3; ++l) {
                 int s = -1;
                 if (!fixedMask[idx[k]] && !fixedMask[idx[l]]) {
-                    int lo = rowPtr[rw[k]], hi = rowPtr[rw[k] + 1] - 1;
+                    // rows are ~7 blocks long and NOT sorted (the host skips the sort): linear scan
+                    const int lo = rowPtr[rw[k]], hi = rowPtr[rw[k] + 1];
                     const int col = rw[l];
-                    while (lo <= hi) {
-                        const int mid = (lo + hi) >> 1;
-                        const int cm = colIdx[mid];
-                        if (cm == col) { s = mid; break; }
-                        if (cm < col) lo = mid + 1; else hi = mid - 1;
-                    }
+                    for (int b = lo; b < hi; ++b) if (colIdx[b] == col) { s = b; break; }
                     if (s < 0) atomicAdd(missing, 1);
                 }
                 slot[(size_t)(3 * k + l) * n + t] = s;
@@ -317,12 +313,8 @@ triplet_scatter_kernel(long nT, const int32_t* __restrict__ I, const int32_t* __
         for (int pass = 0; pass < 2; ++pass) {
             const int row = pass ? bj : bi, col = pass ? bi : bj, rr = pass ? rj : ri, cc = pass ? ri : rj;
             if (pass && i == j) break;     // diagonal scalar entry: once
-            int lo = rowPtr[row], hi = rowPtr[row + 1] - 1, s = -1;
-            while (lo <= hi) {
-                const int mid = (lo + hi) >> 1, cm = colIdx[mid];
-                if (cm == col) { s = mid; break; }
-                if (cm < col) lo = mid + 1; else hi = mid - 1;
-            }
+            int s = -1;
+            for (int b = rowPtr[row], hi = rowPtr[row + 1]; b < hi; ++b) if (colIdx[b] == col) { s = b; break; }
             if (s < 0) { atomicAdd(missing, 1); continue; }
             atomicAdd(&val[4 * (size_t)s + 2 * rr + cc], S[k]);
         }

@@ -234,17 +234,13 @@ int mas_install(ocb_ctx* c)
         V.colIdx.reserve((size_t)nn * 10);
         stamp.assign((size_t)nn, -1);
         for (int k = 0; k < nn; ++k) {
-            const size_t w0 = V.colIdx.size();
             V.colIdx.push_back(k); stamp[k] = k;
             for (int ch = V.childBeg[k]; ch < V.childBeg[k + 1]; ++ch)
                 for (int b = (*fineRowPtr)[ch]; b < (*fineRowPtr)[ch + 1]; ++b) {
                     const int q = nodeOf[(*fineColIdx)[b]];
                     if (stamp[q] != k) { stamp[q] = k; V.colIdx.push_back(q); }
                 }
-            int32_t* a = V.colIdx.data() + w0;
-            const int m = (int)(V.colIdx.size() - w0);
-            for (int i = 1; i < m; ++i) { const int32_t v = a[i]; int j = i - 1; while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; } a[j + 1] = v; }
-            V.rowPtr[k + 1] = (int32_t)V.colIdx.size();
+            V.rowPtr[k + 1] = (int32_t)V.colIdx.size();      // rows stay unsorted: every device look-up is a linear scan
         }
         // next level: "rows" are this level's nodes, nodeOf = their parent
         nodeOf.assign(V.parent.begin(), V.parent.end());
@@ -371,12 +367,7 @@ int mas_install(ocb_ctx* c)
 // device set-up
 __device__ __forceinline__ int find_col(const int32_t* __restrict__ colIdx, int lo, int hi, int col)
 {
-    --hi;
-    while (lo <= hi) {
-        const int mid = (lo + hi) >> 1, cm = colIdx[mid];
-        if (cm == col) return mid;
-        if (cm < col) lo = mid + 1; else hi = mid - 1;
-    }
+    for (int b = lo; b < hi; ++b) if (colIdx[b] == col) return b;     // short, unsorted rows
     return -1;
 }
 
