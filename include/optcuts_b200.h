@@ -219,7 +219,8 @@ int ocb_eval_stencils(ocb_ctx* ctx, const ocb_stencil_batch* batch, int maxIter,
  * factorisation (EigenLibSolver.cpp:80-93) is rebuilt by ocb_factorize; its hierarchy (row order by recursive
  * coordinate bisection of the UVs, leaves of <= 8 vertices, groups of 8, 6 affine DOFs per node) is built with
  * the sparsity pattern.  info[0] = 1 if active (0: block-Jacobi only, no UV was known at pattern time),
- * info[1] = levels L, info[2] = CTA-local levels, info[3] = persistent CTAs, info[4..4+L) = nodes per level. */
+ * info[1] = levels L, info[2] = CTA-local levels, info[3] = persistent CTAs, info[4..4+L) = nodes per level,
+ * info[15] = solves that were repeated with block-Jacobi because the preconditioner came out indefinite. */
 int ocb_precond_info(const ocb_ctx* ctx, int32_t* info16);
 /* A bare LinSysSolver (ocb_set_pattern + ocb_update_values_triplets, no mesh on this context) has no geometry: the
  * caller may hand over positions of the first n vertices of the NEXT ocb_set_pattern (Eigen column-major n x 2: all x,

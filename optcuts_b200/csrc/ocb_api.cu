@@ -58,7 +58,11 @@ static bool host_timing_on() { static const bool on = []() { const char* e = get
 struct HostTimingRec { const char* name; double total; long count; };
 static std::vector<HostTimingRec>& host_timing_table() { static std::vector<HostTimingRec> t; return t; }
 static double wall_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-HostTimer::HostTimer(const char* n) : name(n), t0(host_timing_on() ? wall_now() : 0.0) {}
+HostTimer::HostTimer(const char* n) : name(n), t0(host_timing_on() ? wall_now() : 0.0)
+{
+    static const bool reg = []() { if (host_timing_on()) atexit(host_timing_report); return true; }();     // host programs that exit() without destroying their contexts
+    (void)reg;
+}
 HostTimer::~HostTimer()
 {
     if (!host_timing_on()) return;
@@ -482,6 +486,7 @@ int ocb_get_sizes(const ocb_ctx* c, int64_t* s)
 // ------------------------------------------------------------------------------------------- energy
 int ocb_energy(ocb_ctx* c, double p0, double* E_total, double* E_sd, double* E_scaf)
 {
+    HostTimer _ht("energy");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->haveUV, "ocb_energy: no UV"));
     OCB_TRY(launch_energy(c, p0, false, 0.0));
@@ -590,6 +595,7 @@ static int install_pattern(ocb_ctx* c)
 
 int ocb_set_pattern(ocb_ctx* c, int nVtot, const int32_t* adjPtr, const int32_t* adjIdx, const int32_t* fixed, int nFixed)
 {
+    HostTimer _ht("set_pattern(adjacency)");
     if (!c || !adjPtr || !adjIdx) return set_err(c, OCB_ERR_ARG, "ocb_set_pattern: bad argument");
     OCB_TRY(ensure_init(c));
     if (c->nV == 0) {     // solver-only use (a bare LinSysSolver): the system size comes from the adjacency
@@ -757,6 +763,7 @@ int ocb_hessian_assemble(ocb_ctx* c, double p0)
 
 int ocb_hessian_blocks(ocb_ctx* c, int uniform, double* out)
 {
+    HostTimer _ht("hessian_blocks");
     if (!c || !out) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->haveUV, "ocb_hessian_blocks: no UV"));
     OCB_CUDA(c, c->scratchD.reserve(36 * (size_t)c->nF, c->stream));
@@ -768,6 +775,7 @@ int ocb_hessian_blocks(ocb_ctx* c, int uniform, double* out)
 
 int ocb_hessian_triplets(ocb_ctx* c, int uniform, double* V, int32_t* I, int32_t* J, int64_t* n)
 {
+    HostTimer _ht("hessian_triplets");
     if (!c || !n) return OCB_ERR_ARG;
     // count first: dim^2 * free^2 per triangle with >=1 free vertex, + 2 per fixed vertex
     int64_t cntT = 0;
@@ -806,6 +814,7 @@ int ocb_hessian_triplets(ocb_ctx* c, int uniform, double* V, int32_t* I, int32_t
 
 int ocb_update_values_triplets(ocb_ctx* c, int64_t nT, const int32_t* I, const int32_t* J, const double* S)
 {
+    HostTimer _ht("update_values_triplets");
     if (!c || nT < 0 || (nT > 0 && (!I || !J || !S))) return set_err(c, OCB_ERR_ARG, "ocb_update_values_triplets: bad argument");
     OCB_TRY(need(c, c->patternValid, "ocb_update_values_triplets: no sparsity pattern"));
     OCB_CUDA(c, c->scratchI.reserve(2 * (size_t)nT + 2, c->stream));
@@ -902,13 +911,24 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
         dRhs = c->pb.p; negate = false;
     }
     OCB_TRY(launch_pcg(c, dRhs, negate, rel_tol, max_it));
-    if (x_out) OCB_TRY(vec_to_host(c, x_out, c->p.p));
     OCB_TRY(fetch_scalars(c));
-    if (iters) *iters = (int)c->hScal[S_PCG_ITERS];
+    int itersTotal = (int)c->hScal[S_PCG_ITERS];
+    if ((int)c->hScal[S_PCG_STATUS] == 3) {
+        // safety net: the two-level preconditioner came out indefinite (r.M^-1 r <= 0, detected on the device): repeat the
+        // solve with block-Jacobi only, which cannot fail on an SPD matrix
+        c->precondFallbacks++;
+        OCB_TRY(launch_pcg(c, dRhs, negate, rel_tol, max_it, false));
+        OCB_TRY(fetch_scalars(c));
+        itersTotal += (int)c->hScal[S_PCG_ITERS];
+    }
+    if (x_out) OCB_TRY(vec_to_host(c, x_out, c->p.p));
+    if (x_out) OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (iters) *iters = itersTotal;
     if (rel_res) *rel_res = c->hScal[S_PCG_RELRES];
     const int st = (int)c->hScal[S_PCG_STATUS];
     if (st == 2) return set_err(c, OCB_ERR_BREAKDOWN, "PCG breakdown: d^T A d <= 0 (matrix not SPD)");
     if (st == 1) return set_err(c, OCB_ERR_NOT_CONVERGED, "PCG reached max_it");
+    if (st == 3) return set_err(c, OCB_ERR_BREAKDOWN, "PCG breakdown: preconditioner not positive definite");
     return OCB_OK;
 }
 
@@ -938,6 +958,7 @@ int ocb_precond_info(const ocb_ctx* c, int32_t* info)
 {
     if (!c || !info) return OCB_ERR_ARG;
     fill_precond_info(c->masH, info);
+    info[15] = (int32_t)c->precondFallbacks;
     return OCB_OK;
 }
 int ocb_set_coordinate_hint(ocb_ctx* c, int n, const double* xy)

@@ -129,6 +129,7 @@ struct ocb_ctx {
     ocb::DevBuf<int32_t> rowOf, vertOf, userRow;   // device: internal vertex -> row, row -> internal vertex, caller vertex -> row
     ocb::MasHost masH; ocb::MasDev masD;
     int planGrid = 0;                        // persistent-CTA count the hierarchy was built for
+    int64_t precondFallbacks = 0;            // solves repeated with block-Jacobi after the two-level preconditioner failed
     std::vector<int32_t> hStamp;             // scratch of the pattern builders
     std::vector<double> hHint;               // ocb_set_coordinate_hint: 2 per vertex (interleaved), caller numbering
     std::vector<double> hCoords;             // positions of all nVtot vertices for a solver-only context (INTERNAL numbering)
@@ -210,7 +211,7 @@ struct StencilHost {     // device pointers of one uploaded stencil batch
 int launch_stencils(ocb_ctx* c, const StencilHost& h);
 int launch_spmv(ocb_ctx* c, const double* dx, double* dy);
 int launch_jacobi_setup(ocb_ctx* c);
-int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it);
+int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it, bool allowMas = true);
 int pcg_plan_grid(ocb_ctx* c, int nRows);            // CTA count launch_pcg will use for this system size
 int mas_build_hierarchy(ocb_ctx* c, const double* xy, int grid);
 int mas_install(ocb_ctx* c);

@@ -477,6 +477,11 @@ mas_dense_fill_kernel(int nNodes, const int32_t* __restrict__ rowPtr, const int3
 // and the CTA that produces Y_(k+1)(k+1) inverts it right away (look-ahead) so that one grid barrier per step is
 // all the synchronisation there is.  A DOF whose pivot collapses (a coarse node of fixed vertices only, collinear
 // leaf) is dropped: zero row and column in the inverse.  Finally the symmetrised result is stored in fp32.
+// A DOF is dropped (zero row and column of the inverse) when its pivot fell below this fraction of its original diagonal:
+// it is (nearly) in the span of the DOFs eliminated before it -- collinear vertices make a leaf's affine functions
+// dependent -- and its inverse entries would exceed what the fp32 storage resolves.  With 1e-10 such pivots were rounding
+// noise on a knife edge: ~1 solve in 20 got an indefinite preconditioner (tools/gpu_freerun_check.py).
+static constexpr double kMasPivotTol = 1e-6;
 static constexpr int kCB = kMasCoarseBlk, kCBs = kMasCoarseBlk + 2;      // tile and its padded shared-memory stride
 static constexpr int kDenseThreads = 576;                                // 18 warps: warp w owns the 8x8 sub-tiles 2w and 2w+1 (6x6 grid)
 struct DenseInvArgs { int nb, ld, nC; double* X; double* Y; double* P; double* diag0; float* out; long long* dbg; int* ticket; };
@@ -559,26 +564,28 @@ __device__ __forceinline__ void tile_invert_smem(double (*T)[kCBs], double* buf,
                 }
                 if (mine) colb[r] = d[kk];
                 asm volatile("bar.sync 1, 160;" ::: "memory");
+                // Everything below is straight-line code ordered for the in-order issue: the reciprocal goes first, the
+                // collapsed-pivot test runs in its shadow and is applied with selects, and the two candidates for the row
+                // coefficient are formed in parallel.  The reciprocal is the hardware approximation plus ONE Newton step
+                // (relative error ~1e-12).  The bare approximation (1e-6) is NOT enough: the coarse Galerkin matrices are
+                // ill-conditioned, the inverse came out indefinite on the third bimba iteration and CG stalled
+                // (tools/gpu_freerun_check.py).
                 const double p = rowb[k], dk0 = d0s[k], f = colb[r];
-                const bool bad = !(dk0 > 0.0) || !(p > 1e-10 * dk0);
-                if (bad) {
+                double ip;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ip) : "d"(p));
+                ip = fma(ip, fma(-p, ip, 1.0), ip);
+                const bool bad = !(dk0 > 0.0) || !(p > kMasPivotTol * dk0);
+                // one FMA per element for every row: the pivot row's own values ARE the row buffer, so its scaling d * g is
+                // d + (g - 1) * rowb; a collapsed pivot zeroes its row (coefficient -1) and leaves the other rows alone
+                const double gOther = -f * ip, gPivot = ip - 1.0;
+                const double coef = r != k ? (bad ? 0.0 : gOther) : (bad ? -1.0 : gPivot);
+                const double g = bad ? 0.0 : (r != k ? gOther : ip);       // new value of the pivot-column element
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) if (r == k || (mine && e == kk)) d[e] = 0.0;
-                } else {
-                    double ip;
-                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ip) : "d"(p));
-                    ip = fma(ip, fma(-p, ip, 1.0), ip);
-                    // one FMA per element for every row: the pivot row's own values ARE the row buffer, so its scaling
-                    // d * g is d + (g - 1) * rowb; the pivot-column element is overwritten afterwards
-                    const double g = r != k ? -f * ip : ip;           // -f/p for the other rows, 1/p for the pivot row
-                    const double coef = r != k ? g : g - 1.0;
-#pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        const double2 rj = *reinterpret_cast<const double2*>(rowb + c0 + e);
-                        d[e] += coef * rj.x; d[e + 1] += coef * rj.y;
-                    }
-                    if (mine) d[kk] = g;
+                for (int e = 0; e < 16; e += 2) {
+                    const double2 rj = *reinterpret_cast<const double2*>(rowb + c0 + e);
+                    d[e] += coef * rj.x; d[e + 1] += coef * rj.y;
                 }
+                if (mine) d[kk] = g;
             }
         }
         if (act) {

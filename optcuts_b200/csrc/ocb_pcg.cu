@@ -250,14 +250,11 @@ __device__ __forceinline__ void cluster_allreduce_arrive(ReduceSmem& R, double (
             }
         }
     }
-    // release: ONE cluster-scope fence by thread 0 (cumulative over the CTA's stores, which it observed through the
-    // __syncthreads above and the __syncwarp here) followed by relaxed arrives -- 1024 releasing arrives spent ~10 % of
-    // the solve in membar stalls (profiles/r1b_ncu_pcg10k_lines.txt).  The barrier completes only after thread 0 arrived.
-    if (warp == 0) {
-        __syncwarp();
-        if (lane == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
-    }
-    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    // barrier.cluster.arrive.release by EVERY thread: each thread's own shared-memory stores (z, d slices that the peers
+    // read through DSMEM) and global stores must be released by that thread.  A single cluster-scope fence by thread 0
+    // followed by relaxed arrives saved the ~10 % membar stalls this costs but produced wrong search directions in ~1 of
+    // 3 runs (tools/gpu_freerun_check.py): cumulativity does not cover the other threads' st.shared here.
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 }
 template <int NV>
 __device__ __forceinline__ void cluster_allreduce_wait(ReduceSmem& R, double (*part)[kSyncVals][kClusterSize], unsigned long long epoch, double (&out)[NV])
@@ -532,7 +529,8 @@ pcg_kernel(PcgParams P)
     const double tol2 = P.relTol * P.relTol * bb;
     double rr = bb, beta = 0.0;
     int it = 0, status = 0, cur = 0;
-    if (bb > 0.0) {
+    if (bb > 0.0 && !(rz > 0.0)) status = 3;
+    if (bb > 0.0 && status == 0) {
         for (;;) {
             // ---- phase A: d_new = z + beta d_old (fused) ; Ap = A d_new ; pAp
             double* dNew = cur ? P.d : P.d2;
@@ -587,6 +585,7 @@ pcg_kernel(PcgParams P)
             if (P.dbg && threadIdx.x == 0 && blockIdx.x == 0) {
                 P.dbg[0] += t1 - t0; P.dbg[1] += t2 - t1; P.dbg[2] += t3 - t2; P.dbg[3] += clock64() - t3; P.dbg[4] += 1;
             }
+            if (!(rzNew > 0.0)) { status = 3; break; }        // r.M^-1 r <= 0 (or NaN): the preconditioner is not SPD; the host retries with block-Jacobi
             beta = rzNew / rz;
             rz = rzNew;
         }
@@ -780,7 +779,7 @@ int launch_jacobi_setup(ocb_ctx* c)
     return 0;
 }
 
-int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it)
+int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it, bool allowMas)
 {
     ProfScope prof(c, K_PCG);
     const size_t n = c->nSys();
@@ -798,7 +797,7 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     P.vertOf = c->vertOf.p;
     size_t smemBytes = pl.smem ? pl.smemBytes - mas_smem_estimate((c->nVtot + grid - 1) / grid, grid) : 0;     // the slice alone
     smemBytes = (smemBytes + 15) / 16 * 16;
-    if (c->masH.enabled && c->masH.grid == grid && c->masD.view.L > 0) {
+    if (allowMas && c->masH.enabled && c->masH.grid == grid && c->masD.view.L > 0) {
         P.mas = c->masD.view;
         P.masSmemOff = smemBytes;
         smemBytes += mas_smem_bytes(P.mas.maxLocalNodes, P.mas.rowsPer, P.mas.ldC);

@@ -273,6 +273,8 @@ def test_optimizer_free_run_with_reference_scaffold(ctx, ref, state1):
         assert abs(opt.getLastEnergyVal() - float(want["E"])) <= tol * float(want["E"]), it
         assert abs(opt.getLastEnergyVal(True) - float(want["Enoscaf"])) <= tol * float(want["Enoscaf"]), it
         assert opt.getScaffold().F.shape[0] == int(want["amF"])
+        assert opt.last_step["pcg_iters"] < 400, opt.last_step              # a stalled / repeated solve must not pass silently
+    assert c2.precond_info()["fallbacks"] == 0
     c2.close()
 
 
