@@ -114,9 +114,10 @@ int mas_build_hierarchy(ocb_ctx* c, const double* xyIn, int grid)
         for (int b = 0; b < grid; ++b) {
             const int beg = ctaPre[b], m = ctaPre[b + 1] - beg;
             if (m > 0) {
+                // leaves of EXACTLY 8 rows (the last one of a CTA shorter): local row lr belongs to local leaf lr / 8, so the
+                // PCG kernel restricts the residual with an 8-lane shuffle reduction right where it updates it
                 const int nl = (m + kMasLeaf - 1) / kMasLeaf;
-                even_prefix(m, nl, pre);
-                for (int k = 1; k <= nl; ++k) L1.childBeg.push_back(beg + pre[k]);
+                for (int k = 1; k <= nl; ++k) L1.childBeg.push_back(beg + std::min(m, k * kMasLeaf));
             }
             L1.ctaBeg[b + 1] = (int32_t)L1.childBeg.size() - 1;
         }
@@ -355,6 +356,9 @@ int mas_install(ocb_ctx* c)
     W = MasView();
     W.L = L; W.nC = nC; W.ldC = ldC;
     W.maxLocalNodes = H.maxLocalNodes; W.rowsPer = rowsPer;
+    W.maxOwnC = 0;
+    for (int b = 0; b < grid; ++b) W.maxOwnC = std::max(W.maxOwnC, (int)(ctaCBeg[b + 1] - ctaCBeg[b]));
+    W.cinvInSmem = 0;                                  // decided per launch (it depends on the kernel's shared-memory mode)
     W.ctaNodeOff = D.tabI.p + oNodeOff; W.ctaSolve = D.tabI.p + oSolve; W.ctaLvOff = D.tabI.p + oLvOff; W.ctaLeafBeg = D.tabI.p + oLeafBeg;
     W.ctaCBeg = D.tabI.p + oCBeg;
     W.nodeA = reinterpret_cast<const int4*>(D.tabI.p + oNodeA); W.nodeB = reinterpret_cast<const int4*>(D.tabI.p + oNodeB);

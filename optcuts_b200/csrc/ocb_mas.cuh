@@ -47,6 +47,8 @@ struct MasView {
     int nC, ldC;               // coarse DOFs and the row stride of cinv (multiple of 48)
     int maxLocalNodes;         // max over CTAs of the nodes of levels 1..L
     int rowsPer;               // rows per CTA (vinfo staging)
+    int maxOwnC;               // max over CTAs of the coarse nodes a CTA owns
+    int cinvInSmem;            // 1: the CTA's rows of the coarse inverse are staged in shared memory for the whole solve
     const int32_t* ctaNodeOff; // grid + 1: first entry of every CTA in nodeA/nodeB/nodeX
     const int32_t* ctaSolve;   // grid: local nodes below level L (they take part in a CTA-local group solve)
     const int32_t* ctaLvOff;   // grid x (kMasMaxLevels + 1): first local node of level l at [l - 1]; [L] = all local nodes
@@ -61,9 +63,9 @@ struct MasView {
     double* rcC;               // nC: restricted residual on the coarse level (exchange buffer)
 };
 
-__host__ __device__ inline size_t mas_smem_bytes(int maxLocalNodes, int rowsPer, int ldC)
+__host__ __device__ inline size_t mas_smem_bytes(int maxLocalNodes, int rowsPer, int ldC, int cinvRows = 0)
 {
-    size_t b = 0;
+    size_t b = (size_t)cinvRows * ldC * 4;                         // the CTA's rows of the coarse inverse (optional)
     b += ((size_t)maxLocalNodes * kMasDof + kMasBlk) * 8 * 2;      // rc (+ zero pad), e
     b += (size_t)maxLocalNodes * (16 + 16 + 32);                   // nodeA, nodeB, nodeX
     b += (size_t)rowsPer * 16;                                     // vinfo
@@ -74,7 +76,7 @@ __host__ __device__ inline size_t mas_smem_bytes(int maxLocalNodes, int rowsPer,
 
 #ifdef __CUDACC__
 struct MasSmem {
-    double* rc; double* e; double* rcAll;
+    double* rc; double* e; double* rcAll; float* cinv;
     int4* nodeA; int4* nodeB; double4* nodeX; float4* vinfo;
     int* lvOff;
     int nLoc, nSolve, leaf0, cBeg, nOwnC;
@@ -89,7 +91,9 @@ __device__ __forceinline__ MasSmem mas_carve(unsigned char* base, const MasView&
     S.rc = reinterpret_cast<double*>(base + o);      o += ((size_t)M.maxLocalNodes * kMasDof + kMasBlk) * 8;
     S.e = reinterpret_cast<double*>(base + o);       o += ((size_t)M.maxLocalNodes * kMasDof + kMasBlk) * 8;
     S.rcAll = reinterpret_cast<double*>(base + o);   o += (size_t)M.ldC * 8;
-    S.lvOff = reinterpret_cast<int*>(base + o);
+    S.lvOff = reinterpret_cast<int*>(base + o);      o += (kMasMaxLevels + 2) * 4;
+    o = (o + 15) / 16 * 16;
+    S.cinv = reinterpret_cast<float*>(base + o);
     S.nLoc = 0; S.nSolve = 0; S.leaf0 = 0; S.cBeg = 0; S.nOwnC = 0;
     return S;
 }
@@ -109,17 +113,24 @@ __device__ __forceinline__ void mas_init(const MasView& M, MasSmem& S, int cta, 
     for (int i = t; i < rowEnd - rowBeg; i += nT) S.vinfo[i] = M.vinfo[rowBeg + i];
     for (int i = t; i < M.maxLocalNodes * kMasDof + kMasBlk; i += nT) { S.rc[i] = 0.0; S.e[i] = 0.0; }
     for (int i = t; i < M.ldC; i += nT) S.rcAll[i] = 0.0;
+    if (M.cinvInSmem) {                                // the CTA's rows of the coarse inverse: read from L2 once per solve instead of once per iteration
+        const float4* src = reinterpret_cast<const float4*>(M.cinv + (size_t)S.cBeg * kMasDof * M.ldC);
+        float4* dst = reinterpret_cast<float4*>(S.cinv);
+        const int n4 = S.nOwnC * kMasDof * (M.ldC >> 2);
+        for (int i = t; i < n4; i += nT) dst[i] = __ldg(src + i);
+    }
     __syncthreads();
 }
 
 // ---- restriction: r (own rows, via getR(localRow) -> double2) -> rc of every local level; publishes the CTA
 // node's 6 values.  The caller then ARRIVES at the grid barrier, runs mas_local_solves, and waits.
 template <class GetR>
-__device__ __forceinline__ void mas_restrict(const MasView& M, const MasSmem& S, int cta, GetR getR)
+__device__ __forceinline__ void mas_restrict(const MasView& M, const MasSmem& S, int cta, GetR getR, int firstLevel = 1)
 {
     const int nT = blockDim.x;
     // 8 lanes per (node, component): one child (a row for the leaves) per lane, then a 3-step shuffle reduction
-    for (int l = 1; l <= M.L; ++l) {
+    // (firstLevel = 2: the caller has already restricted the leaves, see mas_restrict_leaf)
+    for (int l = firstLevel; l <= M.L; ++l) {
         const int done = S.lvOff[l - 1], end = S.lvOff[l];
         const int items = 16 * (end - done);
         for (int w = threadIdx.x; w < ((items + 31) & ~31); w += nT) {       // whole warps beyond the range skip
@@ -152,6 +163,27 @@ __device__ __forceinline__ void mas_restrict(const MasView& M, const MasSmem& S,
     }
     // publish the coarse residual of the own coarse nodes (the last local level)
     for (int i = threadIdx.x; i < S.nOwnC * kMasDof; i += nT) M.rcC[(size_t)S.cBeg * kMasDof + i] = S.rc[(size_t)S.lvOff[M.L - 1] * kMasDof + i];
+}
+
+// ---- level 1 fused into the caller's row loop: leaves are exactly 8 consecutive rows, so the 8 lanes that hold a leaf's
+// residuals reduce them with three shuffle steps.  Must be called by ALL lanes of the warp (valid = the lane has a row).
+__device__ __forceinline__ void mas_restrict_leaf(const MasSmem& S, int lr, bool valid, double2 r)
+{
+    double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (valid) {
+        const float4 vi = S.vinfo[lr];
+        a[0] = (double)vi.x * r.x; a[1] = (double)vi.y * r.x; a[2] = (double)vi.z * r.x;
+        a[3] = (double)vi.x * r.y; a[4] = (double)vi.y * r.y; a[5] = (double)vi.z * r.y;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+    if (valid && (lr & 7) == 0) {
+        double* o = S.rc + (size_t)(lr >> 3) * kMasDof;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) o[q] = a[q];
+    }
 }
 
 // ---- CTA-local group solves y = D_l^-1 rc_l for every local level below L (4 threads per output, the inverse
@@ -201,18 +233,19 @@ __device__ __forceinline__ void mas_down(const MasView& M, const MasSmem& S, int
         for (int row0 = 0; row0 < rows; row0 += nT >> 4) {
             const int row = row0 + (threadIdx.x >> 4);
             const bool valid = row < rows;
-            const float4* a = reinterpret_cast<const float4*>(M.cinv + (size_t)(S.cBeg * kMasDof + (valid ? row : 0)) * M.ldC);
+            const float4* a = M.cinvInSmem ? reinterpret_cast<const float4*>(S.cinv + (size_t)(valid ? row : 0) * M.ldC)
+                                           : reinterpret_cast<const float4*>(M.cinv + (size_t)(S.cBeg * kMasDof + (valid ? row : 0)) * M.ldC);
             double y0 = 0.0, y1 = 0.0;
             if (valid) {
                 int c4 = sub;
                 for (; c4 + 16 < ld4; c4 += 32) {
-                    const float4 u = __ldg(a + c4), v = __ldg(a + c4 + 16);
+                    const float4 u = a[c4], v = a[c4 + 16];
                     const double* r0 = S.rcAll + 4 * c4; const double* r1 = r0 + 64;
                     y0 += (double)u.x * r0[0] + (double)u.y * r0[1] + (double)u.z * r0[2] + (double)u.w * r0[3];
                     y1 += (double)v.x * r1[0] + (double)v.y * r1[1] + (double)v.z * r1[2] + (double)v.w * r1[3];
                 }
                 if (c4 < ld4) {
-                    const float4 u = __ldg(a + c4);
+                    const float4 u = a[c4];
                     const double* r0 = S.rcAll + 4 * c4;
                     y0 += (double)u.x * r0[0] + (double)u.y * r0[1] + (double)u.z * r0[2] + (double)u.w * r0[3];
                 }

@@ -549,27 +549,37 @@ pcg_kernel(PcgParams P)
             const double alpha = rz / dAd;
             // ---- phase B (own rows only): x += alpha d ; r -= alpha Ap ; z = Minv r ; rz', rr
             loc[0] = 0.0; loc[1] = 0.0;
-            for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
-                const int lr = row - rowBeg;
-                const double2 dd = SMEM ? sdNew[lr] : reinterpret_cast<const double2*>(dNew)[row];
-                const double2 ap = SMEM ? S.Ap[lr] : reinterpret_cast<const double2*>(P.Ap)[row];
-                double2 xx = SMEM ? S.x[lr] : reinterpret_cast<double2*>(P.x)[row];
-                double2 r2 = SMEM ? S.r[lr] : reinterpret_cast<double2*>(P.r)[row];
-                xx.x += alpha * dd.x; xx.y += alpha * dd.y;
-                r2.x -= alpha * ap.x; r2.y -= alpha * ap.y;
-                const double4 m = SMEM ? S.minv[lr] : reinterpret_cast<const double4*>(P.minv)[row];
-                double2 zz; zz.x = m.x * r2.x + m.y * r2.y; zz.y = m.y * r2.x + m.w * r2.y;
-                if (SMEM) { S.x[lr] = xx; S.r[lr] = r2; S.z[lr] = zz; }
-                else { reinterpret_cast<double2*>(P.x)[row] = xx; reinterpret_cast<double2*>(P.r)[row] = r2; }
-                if (MAS ? !SMEM : MODE != 2) reinterpret_cast<double2*>(P.z)[row] = zz;
-                loc[0] += r2.x * zz.x + r2.y * zz.y;
-                loc[1] += r2.x * r2.x + r2.y * r2.y;
+            for (int lr = threadIdx.x; lr < ((nLoc + 31) & ~31); lr += kPcgBlock) {        // whole warps: the leaf restriction shuffles
+                const bool valid = lr < nLoc;
+                const int row = rowBeg + lr;
+                double2 r2 = make_double2(0.0, 0.0);
+                if (valid) {
+                    const double2 dd = SMEM ? sdNew[lr] : reinterpret_cast<const double2*>(dNew)[row];
+                    const double2 ap = SMEM ? S.Ap[lr] : reinterpret_cast<const double2*>(P.Ap)[row];
+                    double2 xx = SMEM ? S.x[lr] : reinterpret_cast<double2*>(P.x)[row];
+                    r2 = SMEM ? S.r[lr] : reinterpret_cast<double2*>(P.r)[row];
+                    xx.x += alpha * dd.x; xx.y += alpha * dd.y;
+                    r2.x -= alpha * ap.x; r2.y -= alpha * ap.y;
+                    const double4 m = SMEM ? S.minv[lr] : reinterpret_cast<const double4*>(P.minv)[row];
+                    double2 zz; zz.x = m.x * r2.x + m.y * r2.y; zz.y = m.y * r2.x + m.w * r2.y;
+                    if (SMEM) { S.x[lr] = xx; S.r[lr] = r2; S.z[lr] = zz; }
+                    else { reinterpret_cast<double2*>(P.x)[row] = xx; reinterpret_cast<double2*>(P.r)[row] = r2; }
+                    if (MAS ? !SMEM : MODE != 2) reinterpret_cast<double2*>(P.z)[row] = zz;
+                    loc[0] += r2.x * zz.x + r2.y * zz.y;
+                    loc[1] += r2.x * r2.x + r2.y * r2.y;
+                }
+                if (MAS) mas_restrict_leaf(MS, lr, valid, r2);          // one call site for all 32 lanes
             }
-            if (MAS) { __syncthreads(); mas_restrict(P.mas, MS, blockIdx.x, getR); }
+            long long u0 = 0, u1 = 0, u2 = 0, u3 = 0, u4 = 0, u5 = 0;
+            if (P.dbg) { __syncthreads(); u0 = clock64(); }
+            if (MAS) { __syncthreads(); mas_restrict(P.mas, MS, blockIdx.x, getR, 2); }
             if (P.dbg) { __syncthreads(); t3 = clock64(); }
             ARRIVE(2, loc);
+            if (P.dbg) { __syncthreads(); u1 = clock64(); }
             if (MAS) mas_local_solves(P.mas, MS);
+            if (P.dbg) { __syncthreads(); u2 = clock64(); }
             WAIT(2, red);
+            if (P.dbg) u3 = clock64();
             double rzNew = red[0];
             rr = red[1];
             ++it;
@@ -578,12 +588,17 @@ pcg_kernel(PcgParams P)
             if (it >= P.maxIt) { status = 1; break; }
             if (MAS) {
                 mas_down(P.mas, MS, blockIdx.x);
+                if (P.dbg) { __syncthreads(); u4 = clock64(); }
                 double lz[1] = {mas_finish()}, rzv[1];
+                if (P.dbg) { __syncthreads(); u5 = clock64(); }
                 ALLREDUCE(1, lz, rzv);
                 rzNew = rzv[0];
             }
             if (P.dbg && threadIdx.x == 0 && blockIdx.x == 0) {
                 P.dbg[0] += t1 - t0; P.dbg[1] += t2 - t1; P.dbg[2] += t3 - t2; P.dbg[3] += clock64() - t3; P.dbg[4] += 1;
+                // finer split: [5] phase B, [6] restriction, [7] arrive, [8] group solves, [9] wait, [10] coarse + down, [11] finish, [12] last all-reduce
+                P.dbg[5] += u0 - t2; P.dbg[6] += t3 - u0; P.dbg[7] += u1 - t3; P.dbg[8] += u2 - u1; P.dbg[9] += u3 - u2;
+                P.dbg[10] += u4 - u3; P.dbg[11] += u5 - u4; P.dbg[12] += clock64() - u5;
             }
             if (!(rzNew > 0.0)) { status = 3; break; }        // r.M^-1 r <= 0 (or NaN): the preconditioner is not SPD; the host retries with block-Jacobi
             beta = rzNew / rz;
@@ -800,14 +815,17 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     if (allowMas && c->masH.enabled && c->masH.grid == grid && c->masD.view.L > 0) {
         P.mas = c->masD.view;
         P.masSmemOff = smemBytes;
-        smemBytes += mas_smem_bytes(P.mas.maxLocalNodes, P.mas.rowsPer, P.mas.ldC);
+        // streaming mode has the shared memory to spare: keep the CTA's rows of the coarse inverse resident
+        const size_t cinvBytes = (size_t)P.mas.maxOwnC * kMasDof * P.mas.ldC * 4;
+        P.mas.cinvInSmem = (!pl.smem && cinvBytes <= 120 * 1024) ? 1 : 0;
+        smemBytes += mas_smem_bytes(P.mas.maxLocalNodes, P.mas.rowsPer, P.mas.ldC, P.mas.cinvInSmem ? P.mas.maxOwnC * kMasDof : 0);
     }
     const size_t smemCap = 220 * 1024;      // + ~5 KB static (reduction scratch) <= 227 KB per CTA
     if (smemBytes > smemCap) return set_err(c, OCB_ERR_STATE, "PCG: shared-memory plan exceeds the SM capacity");
     OCB_CUDA(c, cudaMemsetAsync(c->partials.p, 0, slotDoubles * sizeof(double), c->stream));
     static const bool dbgOn = []() { const char* e = getenv("OCB_PCG_DEBUG"); return e && atoi(e); }();
     long long* dDbg = nullptr;
-    if (dbgOn) { cudaMalloc((void**)&dDbg, 8 * sizeof(long long)); cudaMemset(dDbg, 0, 8 * sizeof(long long)); P.dbg = dDbg; }
+    if (dbgOn) { cudaMalloc((void**)&dDbg, 16 * sizeof(long long)); cudaMemset(dDbg, 0, 16 * sizeof(long long)); P.dbg = dDbg; }
     void* args[] = {&P};
     if (!c->pcgSmemAttr) {
         OCB_CUDA(c, cudaFuncSetAttribute(pcg_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemCap));
@@ -829,13 +847,15 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     }
     c->launches++;
     if (dbgOn) {
-        long long h[8];
+        long long h[16];
         cudaStreamSynchronize(c->stream);
         cudaMemcpy(h, dDbg, sizeof(h), cudaMemcpyDeviceToHost);
         cudaFree(dDbg);
         const double n = h[4] > 0 ? (double)h[4] : 1.0;
         fprintf(stderr, "[ocb pcg] mode %s grid %d iters %lld  cycles/iter: spmv %.0f  sync1 %.0f  update %.0f  sync2 %.0f\n",
                 pl.cluster ? "cluster" : (pl.smem ? "smem" : "global"), grid, h[4], h[0] / n, h[1] / n, h[2] / n, h[3] / n);
+        fprintf(stderr, "[ocb pcg]   update = phaseB %.0f + restrict %.0f ; sync2 = arrive %.0f + group solves %.0f + wait %.0f + coarse/down %.0f + finish %.0f + allreduce %.0f\n",
+                h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n, h[12] / n);
     }
     return 0;
 }
