@@ -150,9 +150,11 @@ int mas_build_hierarchy(ocb_ctx* c, const double* xyIn, int grid)
             for (int r = L1.childBeg[k]; r < L1.childBeg[k + 1]; ++r) {
                 const int v = c->hVertOf[r];
                 const double* p = xy.data() + 2 * (size_t)v;
-                const float m = c->hFixed[v] ? 0.0f : 1.0f;
+                const double m = c->hFixed[v] ? 0.0 : 1.0;
                 float* o = H.vinfo.data() + 4 * (size_t)r;
-                o[0] = m; o[1] = m * (float)((p[0] - g[0]) / g[2]); o[2] = m * (float)((p[1] - g[1]) / g[2]);
+                // packed like the inverses (high word of the fp64 value, see mas_pack): no conversion instruction per use
+                auto pack = [](double v) { uint64_t b; std::memcpy(&b, &v, 8); b += 0x80000000ull; const uint32_t h = (uint32_t)(b >> 32); float f; std::memcpy(&f, &h, 4); return f; };
+                o[0] = pack(m); o[1] = pack(m * (p[0] - g[0]) / g[2]); o[2] = pack(m * (p[1] - g[1]) / g[2]);
                 int32_t id = k; std::memcpy(o + 3, &id, 4);
             }
         }
@@ -386,7 +388,7 @@ mas_galerkin_fine_kernel(int nRows, const int32_t* __restrict__ rowPtr, const in
         const float4 vi = vinfo[i];
         if (vi.x == 0.0f) continue;
         const int a = __float_as_int(vi.w);
-        const double fi[3] = {(double)vi.x, (double)vi.y, (double)vi.z};
+        const double fi[3] = {mas_unpack(vi.x), mas_unpack(vi.y), mas_unpack(vi.z)};
         const int lo1 = rowPtr1[a], hi1 = rowPtr1[a + 1];
         for (int b = rowPtr[i] + k8; b < rowPtr[i + 1]; b += 8) {
             const int j = colIdx[b];
@@ -394,7 +396,7 @@ mas_galerkin_fine_kernel(int nRows, const int32_t* __restrict__ rowPtr, const in
             if (vj.x == 0.0f) continue;
             const int s = find_col(colIdx1, lo1, hi1, __float_as_int(vj.w));
             if (s < 0) continue;
-            const double fj[3] = {(double)vj.x, (double)vj.y, (double)vj.z};
+            const double fj[3] = {mas_unpack(vj.x), mas_unpack(vj.y), mas_unpack(vj.z)};
             const double A[2][2] = {{val[4 * (size_t)b], val[4 * (size_t)b + 1]}, {val[4 * (size_t)b + 2], val[4 * (size_t)b + 3]}};
             double* o = val1 + 36 * (size_t)s;
 #pragma unroll
@@ -717,7 +719,7 @@ mas_dense_invert_kernel(DenseInvArgs A)
     const size_t total = (size_t)ld * ld;
     for (size_t e = (size_t)blockIdx.x * kDenseThreads + tid; e < total; e += (size_t)gridDim.x * kDenseThreads) {
         const int i = (int)(e / ld), j = (int)(e % ld);
-        A.out[e] = (i < A.nC && j < A.nC) ? (float)(0.5 * (__ldcg(X + e) + __ldcg(X + (size_t)j * ld + i))) : 0.0f;
+        A.out[e] = (i < A.nC && j < A.nC) ? mas_pack(0.5 * (__ldcg(X + e) + __ldcg(X + (size_t)j * ld + i))) : 0.0f;
     }
 }
 
@@ -767,7 +769,7 @@ mas_invert_kernel(MasInvertArgs P)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int j = tile_col(m, e);
-        out[m.r * kMasBlk + j] = (m.r < nd && j < nd) ? (float)(0.5 * (T[m.r][j] + T[j][m.r])) : 0.0f;
+        out[m.r * kMasBlk + j] = (m.r < nd && j < nd) ? mas_pack(0.5 * (T[m.r][j] + T[j][m.r])) : 0.0f;
     }
 }
 

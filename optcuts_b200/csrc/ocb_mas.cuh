@@ -27,6 +27,21 @@ static constexpr int kMasDof = 6;           // DOFs per node
 static constexpr int kMasBlk = kMasGroup * kMasDof;   // 48
 static constexpr int kMasMaxLevels = 12;
 
+// Storage format of every inverse (group blocks and the coarse matrix): the HIGH 32 bits of the fp64 value, rounded to
+// nearest -- 4 bytes per entry like fp32, a 20-bit mantissa (the CG iteration counts are those of fp32 storage:
+// 158 / 93 / 286, tools/mas_proto.py --prec hi32) and NO conversion instruction on the way back: F2F.F64.F32 issues at
+// ~4 per clock per SM and was the whole cost of the group and coarse solves (5.2k of 8.0k cycles at 10k faces, 29k
+// cycles per CG iteration at 1M faces, profiles/r1e_pcg_phase_cycles.txt).  The buffers are typed float for the 16-byte
+// vector loads; the bits are never interpreted as fp32.
+#ifdef __CUDACC__
+__device__ __forceinline__ float mas_pack(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v) + 0x80000000ull;
+    return __uint_as_float((unsigned)(b >> 32));
+}
+__device__ __forceinline__ double mas_unpack(float w) { return __hiloint2double((int)__float_as_uint(w), 0); }
+#endif
+
 // one level of the hierarchy as the set-up kernels see it (global node indices)
 struct MasLevel {
     int nNodes, nGroups;
@@ -143,7 +158,7 @@ __device__ __forceinline__ void mas_restrict(const MasView& M, const MasSmem& S,
                     const float4 vi = S.vinfo[B.y + k];
                     const double2 rr = getR(B.y + k);
                     const double rv = comp ? rr.y : rr.x;
-                    a0 = (double)vi.x * rv; a1 = (double)vi.y * rv; a2 = (double)vi.z * rv;
+                    a0 = mas_unpack(vi.x) * rv; a1 = mas_unpack(vi.y) * rv; a2 = mas_unpack(vi.z) * rv;
                 } else {
                     const double4 X = S.nodeX[B.y + k];
                     const double* rc = S.rc + (size_t)(B.y + k) * kMasDof + 3 * comp;
@@ -172,8 +187,8 @@ __device__ __forceinline__ void mas_restrict_leaf(const MasSmem& S, int lr, bool
     double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (valid) {
         const float4 vi = S.vinfo[lr];
-        a[0] = (double)vi.x * r.x; a[1] = (double)vi.y * r.x; a[2] = (double)vi.z * r.x;
-        a[3] = (double)vi.x * r.y; a[4] = (double)vi.y * r.y; a[5] = (double)vi.z * r.y;
+        a[0] = mas_unpack(vi.x) * r.x; a[1] = mas_unpack(vi.y) * r.x; a[2] = mas_unpack(vi.z) * r.x;
+        a[3] = mas_unpack(vi.x) * r.y; a[4] = mas_unpack(vi.y) * r.y; a[5] = mas_unpack(vi.z) * r.y;
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1)
@@ -207,7 +222,7 @@ __device__ __forceinline__ void mas_local_solves(const MasView& M, const MasSmem
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const double* r4 = rc + 4 * (part + 4 * j);
-                y += (double)a[j].x * r4[0] + (double)a[j].y * r4[1] + (double)a[j].z * r4[2] + (double)a[j].w * r4[3];
+                y += mas_unpack(a[j].x) * r4[0] + mas_unpack(a[j].y) * r4[1] + mas_unpack(a[j].z) * r4[2] + mas_unpack(a[j].w) * r4[3];
             }
         }
         y += __shfl_xor_sync(0xffffffffu, y, 1);
@@ -220,11 +235,12 @@ __device__ __forceinline__ void mas_local_solves(const MasView& M, const MasSmem
 // rows streamed from L2 with 16-byte loads), then the local down sweep (prolongation adds).  Leaves the coarse
 // correction coefficients of every local node in S.e; the caller adds m * (e0 + lx e1 + ly e2, e3 + lx e4 + ly e5)
 // of the row's leaf to the block-Jacobi part of z.
-__device__ __forceinline__ void mas_down(const MasView& M, const MasSmem& S, int cta)
+__device__ __forceinline__ void mas_down(const MasView& M, const MasSmem& S, int cta, long long* stamp = nullptr)
 {
     const int nT = blockDim.x, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < M.nC; i += nT) S.rcAll[i] = __ldcg(M.rcC + i);
     __syncthreads();
+    if (stamp) stamp[0] = clock64();
     {   // 16 lanes per output row: all rows of the CTA in one pass when there are <= 64, every lane keeps
         // several independent 16-byte loads of the inverse row in flight
         const int rows = S.nOwnC * kMasDof, ld4 = M.ldC >> 2;
@@ -241,13 +257,13 @@ __device__ __forceinline__ void mas_down(const MasView& M, const MasSmem& S, int
                 for (; c4 + 16 < ld4; c4 += 32) {
                     const float4 u = a[c4], v = a[c4 + 16];
                     const double* r0 = S.rcAll + 4 * c4; const double* r1 = r0 + 64;
-                    y0 += (double)u.x * r0[0] + (double)u.y * r0[1] + (double)u.z * r0[2] + (double)u.w * r0[3];
-                    y1 += (double)v.x * r1[0] + (double)v.y * r1[1] + (double)v.z * r1[2] + (double)v.w * r1[3];
+                    y0 += mas_unpack(u.x) * r0[0] + mas_unpack(u.y) * r0[1] + mas_unpack(u.z) * r0[2] + mas_unpack(u.w) * r0[3];
+                    y1 += mas_unpack(v.x) * r1[0] + mas_unpack(v.y) * r1[1] + mas_unpack(v.z) * r1[2] + mas_unpack(v.w) * r1[3];
                 }
                 if (c4 < ld4) {
                     const float4 u = a[c4];
                     const double* r0 = S.rcAll + 4 * c4;
-                    y0 += (double)u.x * r0[0] + (double)u.y * r0[1] + (double)u.z * r0[2] + (double)u.w * r0[3];
+                    y0 += mas_unpack(u.x) * r0[0] + mas_unpack(u.y) * r0[1] + mas_unpack(u.z) * r0[2] + mas_unpack(u.w) * r0[3];
                 }
             }
             double y = y0 + y1;
@@ -257,6 +273,7 @@ __device__ __forceinline__ void mas_down(const MasView& M, const MasSmem& S, int
         }
     }
     __syncthreads();
+    if (stamp) stamp[1] = clock64();
     // local down sweep: e = y + prolongation of the parent's e; levels are contiguous and ascending in the node list
     for (int l = M.L - 1; l >= 1; --l) {
         const int beg = S.lvOff[l - 1], end = S.lvOff[l];

@@ -482,8 +482,8 @@ pcg_kernel(PcgParams P)
             const double* e = MS.e + (size_t)(__float_as_int(vi.w) - MS.leaf0) * kMasDof;
             double2 zz = SMEM ? S.z[lr] : reinterpret_cast<const double2*>(P.z)[row];
             const double2 r2 = getR(lr);
-            zz.x += (double)vi.x * e[0] + (double)vi.y * e[1] + (double)vi.z * e[2];
-            zz.y += (double)vi.x * e[3] + (double)vi.y * e[4] + (double)vi.z * e[5];
+            zz.x += mas_unpack(vi.x) * e[0] + mas_unpack(vi.y) * e[1] + mas_unpack(vi.z) * e[2];
+            zz.y += mas_unpack(vi.x) * e[3] + mas_unpack(vi.y) * e[4] + mas_unpack(vi.z) * e[5];
             if (SMEM) S.z[lr] = zz;
             if (MODE != 2) reinterpret_cast<double2*>(P.z)[row] = zz;
             acc += r2.x * zz.x + r2.y * zz.y;
@@ -587,8 +587,9 @@ pcg_kernel(PcgParams P)
             if (rr <= tol2) { status = 0; break; }
             if (it >= P.maxIt) { status = 1; break; }
             if (MAS) {
-                mas_down(P.mas, MS, blockIdx.x);
-                if (P.dbg) { __syncthreads(); u4 = clock64(); }
+                long long st[2] = {0, 0};
+                mas_down(P.mas, MS, blockIdx.x, P.dbg ? st : nullptr);
+                if (P.dbg) { __syncthreads(); u4 = clock64(); if (threadIdx.x == 0 && blockIdx.x == 0) { P.dbg[13] += st[0] - u3; P.dbg[14] += st[1] - st[0]; P.dbg[15] += u4 - st[1]; } }
                 double lz[1] = {mas_finish()}, rzv[1];
                 if (P.dbg) { __syncthreads(); u5 = clock64(); }
                 ALLREDUCE(1, lz, rzv);
@@ -854,6 +855,7 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
         const double n = h[4] > 0 ? (double)h[4] : 1.0;
         fprintf(stderr, "[ocb pcg] mode %s grid %d iters %lld  cycles/iter: spmv %.0f  sync1 %.0f  update %.0f  sync2 %.0f\n",
                 pl.cluster ? "cluster" : (pl.smem ? "smem" : "global"), grid, h[4], h[0] / n, h[1] / n, h[2] / n, h[3] / n);
+        fprintf(stderr, "[ocb pcg]   coarse/down = coarse residual load %.0f + coarse rows %.0f + down sweep %.0f\n", h[13] / n, h[14] / n, h[15] / n);
         fprintf(stderr, "[ocb pcg]   update = phaseB %.0f + restrict %.0f ; sync2 = arrive %.0f + group solves %.0f + wait %.0f + coarse/down %.0f + finish %.0f + allreduce %.0f\n",
                 h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n, h[12] / n);
     }

@@ -217,6 +217,10 @@ def mas_setup(A, X, fixed, order, levels, basis=3, prec="f64", leaf_dense=True, 
         if prec == "f16":
             s = np.abs(M).max()
             return (M / s).astype(np.float16).astype(np.float64) * s
+        if prec == "hi32":                  # the high 32 bits of the fp64 value (20-bit mantissa), rounded to nearest
+            v = np.ascontiguousarray(M, dtype=np.float64).view(np.uint64)
+            v = (v + np.uint64(0x80000000)) & np.uint64(0xFFFFFFFF00000000)
+            return v.view(np.float64)
         if prec == "bf16":
             v = M.astype(np.float32).view(np.uint32)
             v = ((v + 0x8000) & 0xFFFF0000).astype(np.uint32)
