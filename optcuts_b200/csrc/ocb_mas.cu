@@ -200,7 +200,8 @@ int mas_build_hierarchy(ocb_ctx* c, const double* xyIn, int grid)
     }
     if (H.Lloc == 0) return set_err(c, OCB_ERR_STATE, "MAS hierarchy: too many local levels");
     // coarse level: the first level small enough for the exact dense inverse; everything above it is dropped
-    static const int coarseMax = []() { const char* e = getenv("OCB_MAS_COARSE_MAX"); int v = e ? atoi(e) : kMasCoarseMax; return v < kMasDof ? kMasDof : (v > kMasCoarseMax ? kMasCoarseMax : v); }();
+    static const int coarseEnv = []() { const char* e = getenv("OCB_MAS_COARSE_MAX"); return e ? atoi(e) : 0; }();
+    const int coarseMax = coarseEnv >= kMasDof ? std::min(coarseEnv, kMasCoarseMax) : mas_coarse_cap(n);
     int Lc = H.Lloc;
     for (int l = 1; l <= H.Lloc; ++l) if (((int)H.lv[l - 1].childBeg.size() - 1) * kMasDof <= coarseMax) { Lc = l; break; }
     if (((int)H.lv[Lc - 1].childBeg.size() - 1) * kMasDof > kMasCoarseMax) return set_err(c, OCB_ERR_STATE, "MAS hierarchy: coarse level too large");

@@ -54,6 +54,14 @@ struct MasLevel {
 
 static constexpr int kMasCoarseBlk = 48;    // tile of the dense coarse inversion
 static constexpr int kMasCoarseMax = 3072;  // largest coarse system (DOFs)
+// Largest coarse system for a solve with n block rows: the dense inverse costs ~0.37 us per DOF (sequential pivots) plus a
+// cubic term (12 ms at 3072 DOFs), so small systems must not get a coarse level of thousands of DOFs (a 4096-vertex disk
+// of the batch workload did: 15 ms per Newton step instead of 1.5).  n/8 keeps the set-up at ~10-20 % of the solve.
+__host__ __device__ inline int mas_coarse_cap(int nRows)
+{
+    const int c = nRows / 8;
+    return c < 600 ? 600 : (c > kMasCoarseMax ? kMasCoarseMax : c);
+}
 
 // Host-precomputed tables, CTA-local indices.  A CTA's local nodes are numbered level 1 first, then level 2, ...
 // up to its coarse-level nodes.

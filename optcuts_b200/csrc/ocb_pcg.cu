@@ -683,7 +683,7 @@ static size_t mas_smem_estimate(int rowsPer, int grid)
     int local = 0, k = (rowsPer + kMasLeaf - 1) / kMasLeaf, nC = 0;
     for (;;) {
         local += k;
-        if ((long)k * grid * kMasDof <= kMasCoarseMax) { nC = k * grid * kMasDof; break; }
+        if ((long)k * grid * kMasDof <= mas_coarse_cap(rowsPer * grid)) { nC = k * grid * kMasDof; break; }
         if (k <= 1) { nC = grid * kMasDof; break; }
         k = (k + kMasGroup - 1) / kMasGroup;
     }

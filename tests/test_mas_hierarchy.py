@@ -20,9 +20,12 @@ def _check(xy, grid):
     for l in range(1, len(levels)):
         cb = levels[l]
         assert cb[0] == 0 and cb[-1] == sizes[l - 1] and np.all(np.diff(cb) >= 1) and np.all(np.diff(cb) <= 8)
-    # the last level is the coarse one: small enough for the exact dense inverse, and the first such level
+    # the last level is the coarse one: the first level small enough for the exact dense inverse (the cap grows with the
+    # system: n/8 DOFs, between 600 and 3072), or the level with one node per CTA if none is
+    cap = min(3072, max(600, n // 8))
     assert 6 * sizes[-1] <= 3072 and lloc == len(levels)
-    assert all(6 * s > 3072 for s in sizes[:-1])
+    assert 6 * sizes[-1] <= cap or sizes[-1] == -(-n // rows_per)
+    assert all(6 * s > cap for s in sizes[:-1])
     # no node of any level straddles a CTA boundary: map every node to its row range
     lo, hi = levels[0][:-1].copy(), levels[0][1:].copy()
     for l in range(1, len(levels)):
