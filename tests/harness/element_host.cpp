@@ -10,12 +10,13 @@ struct double2 { double x, y; };
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
-using std::sqrt; using std::fabs; using std::copysign;
+using std::sqrt; using std::fabs; using std::copysign; using std::fma;
 #define OCB_ELEMENT_HOST 1
 #include "../../optcuts_b200/csrc/ocb_element.cuh"
 
 using namespace ocb;
 extern "C" {
+long host_general_path(int reset) { const long n = host_general_path_count; if (reset) host_general_path_count = 0; return n; }
 // F: nF x 3 col-major; UV: nV x 2 col-major; rest8: 8 x nF
 void host_energy(int nV, int nF, const int32_t* F, const double* UV, const double* rest8, double surf, int uniform, double* out)
 {

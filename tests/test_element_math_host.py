@@ -58,6 +58,19 @@ def test_hessian_projection_matches_makePD(host, port, state):
         assert (cl > 0).sum() > 100          # the Tutte start has many indefinite element Hessians
 
 
+def test_projection_fast_path_covers_the_indefinite_elements(host, state):
+    """the rank-1 (smallest eigenpair) projection must handle practically every indefinite element: a fallback to
+    the general eigen-solve stalls the 31 other lanes of its warp"""
+    F, UV, rest8, a = _args(state.F, state.UV, state.rest8)
+    H = np.zeros((state.nF, 36))
+    cl = np.zeros(state.nF, np.int32)
+    host.host_general_path.restype = C.c_long
+    host.host_general_path(1)
+    host.host_hessian_blocks(*a, C.c_double(state.surfaceArea), 0, 1, H.ctypes.data_as(_d), cl.ctypes.data_as(_i))
+    general = host.host_general_path(1)
+    assert general <= max(1, (cl > 0).sum() // 1000), (general, (cl > 0).sum())
+
+
 def test_isometric_known_answer(host):
     """SymDirichletEnergy::checkEnergyVal (SymDirichletEnergy.cpp:612-645): isometry => E_t = 4 w, zero gradient,
     PSD Hessian with a 3-dimensional null space (2 translations + rotation)."""
