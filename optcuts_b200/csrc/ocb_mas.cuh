@@ -239,46 +239,73 @@ __device__ __forceinline__ void mas_local_solves(const MasView& M, const MasSmem
     }
 }
 
+// ---- rows of the exact coarse solve: eC[row] = cinv[row, :] . rc for the CTA's rows, LPR lanes per row
+__device__ __forceinline__ void mas_lds4(double (&r)[4], unsigned addr)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r[0]), "=d"(r[1]) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(r[2]), "=d"(r[3]) : "r"(addr));
+}
+template <int LPR, int UNR>
+__device__ __forceinline__ void mas_coarse_rows(const float* __restrict__ cbase, int ldC, int ld4, int rows, const double* rcAll, double* eC, int nT)
+{
+    const int sub = threadIdx.x & (LPR - 1);
+    const unsigned rcS = (unsigned)__cvta_generic_to_shared(rcAll) + 32u * sub;
+    for (int row0 = 0; row0 < rows; row0 += nT / LPR) {
+        const int row = row0 + threadIdx.x / LPR;
+        const bool valid = row < rows;
+        const float4* a = reinterpret_cast<const float4*>(cbase + (size_t)(valid ? row : 0) * ldC) + sub;
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+        if (valid) {
+            int c4 = sub;
+            for (; c4 + (UNR - 1) * LPR < ld4; c4 += UNR * LPR) {
+                float4 u[UNR];
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) u[j] = a[(c4 - sub) + j * LPR];
+                const unsigned rs = rcS + 32u * (c4 - sub);
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    double r[4];
+                    mas_lds4(r, rs + 32u * LPR * j);
+                    y0 = fma(mas_unpack(u[j].x), r[0], y0); y1 = fma(mas_unpack(u[j].y), r[1], y1);
+                    y2 = fma(mas_unpack(u[j].z), r[2], y2); y3 = fma(mas_unpack(u[j].w), r[3], y3);
+                }
+            }
+            for (; c4 < ld4; c4 += LPR) {
+                const float4 u = a[c4 - sub];
+                double r[4];
+                mas_lds4(r, rcS + 32u * (c4 - sub));
+                y0 = fma(mas_unpack(u.x), r[0], y0); y1 = fma(mas_unpack(u.y), r[1], y1);
+                y2 = fma(mas_unpack(u.z), r[2], y2); y3 = fma(mas_unpack(u.w), r[3], y3);
+            }
+        }
+        double y = (y0 + y1) + (y2 + y3);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+        if (valid && sub == 0) eC[row] = y;
+    }
+}
+
 // ---- after the barrier: the exact coarse solve for the own coarse nodes (one warp per output row, the inverse
 // rows streamed from L2 with 16-byte loads), then the local down sweep (prolongation adds).  Leaves the coarse
 // correction coefficients of every local node in S.e; the caller adds m * (e0 + lx e1 + ly e2, e3 + lx e4 + ly e5)
 // of the row's leaf to the block-Jacobi part of z.
+template <int UNR>
 __device__ __forceinline__ void mas_down(const MasView& M, const MasSmem& S, int cta, long long* stamp = nullptr)
 {
     const int nT = blockDim.x, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < M.nC; i += nT) S.rcAll[i] = __ldcg(M.rcC + i);
     __syncthreads();
     if (stamp) stamp[0] = clock64();
-    {   // 16 lanes per output row: all rows of the CTA in one pass when there are <= 64, every lane keeps
-        // several independent 16-byte loads of the inverse row in flight
+    {   // LPR lanes per output row (32 when the CTA's rows then still fit one pass, else 16).  The pass is bound by
+        // INSTRUCTION ISSUE, not by memory (measured: 7k cycles for 83 KB at 10k faces, the same with the loads or
+        // the shared-memory reads removed), so the main loop is straight-line code: UNR 16-byte loads of the inverse
+        // row per lane issued together, the residual read with 16-byte shared loads at immediate offsets, four
+        // independent FMA chains, no predicates; a predicated tail takes the rest of the row.
         const int rows = S.nOwnC * kMasDof, ld4 = M.ldC >> 2;
         double* eC = S.e + (size_t)S.lvOff[M.L - 1] * kMasDof;
-        const int sub = lane & 15;
-        for (int row0 = 0; row0 < rows; row0 += nT >> 4) {
-            const int row = row0 + (threadIdx.x >> 4);
-            const bool valid = row < rows;
-            const float4* a = M.cinvInSmem ? reinterpret_cast<const float4*>(S.cinv + (size_t)(valid ? row : 0) * M.ldC)
-                                           : reinterpret_cast<const float4*>(M.cinv + (size_t)(S.cBeg * kMasDof + (valid ? row : 0)) * M.ldC);
-            double y0 = 0.0, y1 = 0.0;
-            if (valid) {
-                int c4 = sub;
-                for (; c4 + 16 < ld4; c4 += 32) {
-                    const float4 u = a[c4], v = a[c4 + 16];
-                    const double* r0 = S.rcAll + 4 * c4; const double* r1 = r0 + 64;
-                    y0 += mas_unpack(u.x) * r0[0] + mas_unpack(u.y) * r0[1] + mas_unpack(u.z) * r0[2] + mas_unpack(u.w) * r0[3];
-                    y1 += mas_unpack(v.x) * r1[0] + mas_unpack(v.y) * r1[1] + mas_unpack(v.z) * r1[2] + mas_unpack(v.w) * r1[3];
-                }
-                if (c4 < ld4) {
-                    const float4 u = a[c4];
-                    const double* r0 = S.rcAll + 4 * c4;
-                    y0 += mas_unpack(u.x) * r0[0] + mas_unpack(u.y) * r0[1] + mas_unpack(u.z) * r0[2] + mas_unpack(u.w) * r0[3];
-                }
-            }
-            double y = y0 + y1;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
-            if (valid && sub == 0) eC[row] = y;
-        }
+        const float* cbase = M.cinvInSmem ? S.cinv : M.cinv + (size_t)S.cBeg * kMasDof * M.ldC;
+        if (rows * 32 <= nT) mas_coarse_rows<32, UNR>(cbase, M.ldC, ld4, rows, S.rcAll, eC, nT);
+        else mas_coarse_rows<16, UNR>(cbase, M.ldC, ld4, rows, S.rcAll, eC, nT);
     }
     __syncthreads();
     if (stamp) stamp[1] = clock64();

@@ -521,7 +521,7 @@ pcg_kernel(PcgParams P)
     double rz = red[0];
     const double bb = red[1];
     if (MAS && bb > 0.0) {
-        mas_down(P.mas, MS, blockIdx.x);
+        mas_down<MODE == 2 ? 9 : 5>(P.mas, MS, blockIdx.x);
         double lz[1] = {mas_finish()}, rzv[1];
         ALLREDUCE(1, lz, rzv);
         rz = rzv[0];
@@ -588,7 +588,7 @@ pcg_kernel(PcgParams P)
             if (it >= P.maxIt) { status = 1; break; }
             if (MAS) {
                 long long st[2] = {0, 0};
-                mas_down(P.mas, MS, blockIdx.x, P.dbg ? st : nullptr);
+                mas_down<MODE == 2 ? 9 : 5>(P.mas, MS, blockIdx.x, P.dbg ? st : nullptr);
                 if (P.dbg) { __syncthreads(); u4 = clock64(); if (threadIdx.x == 0 && blockIdx.x == 0) { P.dbg[13] += st[0] - u3; P.dbg[14] += st[1] - st[0]; P.dbg[15] += u4 - st[1]; } }
                 double lz[1] = {mas_finish()}, rzv[1];
                 if (P.dbg) { __syncthreads(); u5 = clock64(); }
