@@ -21,6 +21,10 @@
 namespace ocb {
 
 static constexpr int kPcgBlock = 1024;
+// the one-cluster mode runs 768 threads per CTA: its phases keep at most ~650 threads busy (two per block row of a
+// <= 350-row slice), and every thread more lengthens the block barriers and the releasing cluster arrives
+// (measured at 10k faces: 512 threads 1.94 ms, 768 1.73 ms, 1024 1.84 ms per solve; the grid modes lose with fewer)
+static constexpr int kPcgBlockCluster = 768;
 
 struct PcgParams {
     int nRows;                 // block rows (= global vertices)
@@ -121,7 +125,7 @@ __device__ __forceinline__ void grid_allreduce_arrive(ReduceSmem& R, SyncSlot* s
         double t[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            t[k] = lane < kPcgBlock / 32 ? R.sm[k][lane] : 0.0;
+            t[k] = lane < (int)(blockDim.x >> 5) ? R.sm[k][lane] : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
         }
@@ -241,7 +245,7 @@ __device__ __forceinline__ void cluster_allreduce_arrive(ReduceSmem& R, double (
         const unsigned rank = cluster.block_rank();
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            double t = lane < kPcgBlock / 32 ? R.sm[k][lane] : 0.0;
+            double t = lane < (int)(blockDim.x >> 5) ? R.sm[k][lane] : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             if (lane < kClusterSize) {          // lane l writes this CTA's partial into peer l's buffer
@@ -328,7 +332,7 @@ __device__ __forceinline__ double spmv_fused_ell(const PcgParams& P, const Slice
     const double2* __restrict__ gval2 = reinterpret_cast<const double2*>(P.val);
     const int nLoc = rowEnd - rowBeg, half = threadIdx.x & 1;
     double dotAcc = 0.0;
-    for (int lr = threadIdx.x >> 1; lr < nLoc; lr += kPcgBlock / 2) {
+    for (int lr = threadIdx.x >> 1; lr < nLoc; lr += blockDim.x >> 1) {
         const int len = S.len[lr];
         double acc = 0.0;
 #pragma unroll 4
@@ -439,10 +443,11 @@ __device__ __forceinline__ double spmv_fused(const PcgParams& P, int rowBeg, int
 // MODE 0: slice streamed from global, grid-wide packet all-reduce; 1: slice in shared memory, packets;
 // 2: slice in shared memory, one 16-CTA cluster, DSMEM all-reduce
 template <int MODE>
-__global__ void __launch_bounds__(kPcgBlock, 1)
+__global__ void __launch_bounds__(MODE == 2 ? kPcgBlockCluster : kPcgBlock, 1)
 pcg_kernel(PcgParams P)
 {
     constexpr bool SMEM = MODE >= 1;
+    constexpr int kBlk = MODE == 2 ? kPcgBlockCluster : kPcgBlock;
     __shared__ double clusterPart[2][kSyncVals][kClusterSize];
     __shared__ ReduceSmem redSm;
 #define ARRIVE(NV, loc) do { ++epoch; if (MODE == 2) cluster_allreduce_arrive<NV>(redSm, clusterPart, epoch, loc); else grid_allreduce_arrive<NV>(redSm, slots, nB, epoch, loc); } while (0)
@@ -459,7 +464,7 @@ pcg_kernel(PcgParams P)
     if (SMEM) {
         S = carve(smemRaw, rowsPer, P.maxBlkPerCta);          // maxBlkPerCta carries the ELL width W here
         const double2* gv = reinterpret_cast<const double2*>(P.val);
-        for (int lr = threadIdx.x >> 1; lr < nLoc; lr += kPcgBlock / 2) {
+        for (int lr = threadIdx.x >> 1; lr < nLoc; lr += kBlk / 2) {
             const int b0 = P.rowPtr[rowBeg + lr], len = min(S.W, P.rowPtr[rowBeg + lr + 1] - b0), half = threadIdx.x & 1;
             if (half == 0) S.len[lr] = len;
             for (int k = 0; k < len; ++k) {
@@ -476,7 +481,7 @@ pcg_kernel(PcgParams P)
     // z = z0 (block-Jacobi part, already stored) + coarse correction of the row's leaf; returns this thread's share of r.z
     auto mas_finish = [&]() -> double {
         double acc = 0.0;
-        for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
+        for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kBlk) {
             const int lr = row - rowBeg;
             const float4 vi = MS.vinfo[lr];
             const double* e = MS.e + (size_t)(__float_as_int(vi.w) - MS.leaf0) * kMasDof;
@@ -493,7 +498,7 @@ pcg_kernel(PcgParams P)
 
     // ---- init: x = 0, r = b, z = Minv r, d = 0 ; rz = r.z, bb = b.b
     double loc[2] = {0.0, 0.0}, red[2];
-    for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
+    for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kBlk) {
         const size_t src = P.vertOf ? (size_t)P.vertOf[row] : (size_t)row;
         const double b0 = P.negate ? -P.rhs[2 * src] : P.rhs[2 * src];
         const double b1 = P.negate ? -P.rhs[2 * src + 1] : P.rhs[2 * src + 1];
@@ -549,7 +554,7 @@ pcg_kernel(PcgParams P)
             const double alpha = rz / dAd;
             // ---- phase B (own rows only): x += alpha d ; r -= alpha Ap ; z = Minv r ; rz', rr
             loc[0] = 0.0; loc[1] = 0.0;
-            for (int lr = threadIdx.x; lr < ((nLoc + 31) & ~31); lr += kPcgBlock) {        // whole warps: the leaf restriction shuffles
+            for (int lr = threadIdx.x; lr < ((nLoc + 31) & ~31); lr += kBlk) {        // whole warps: the leaf restriction shuffles
                 const bool valid = lr < nLoc;
                 const int row = rowBeg + lr;
                 double2 r2 = make_double2(0.0, 0.0);
@@ -607,7 +612,7 @@ pcg_kernel(PcgParams P)
         }
     }
     __syncthreads();
-    for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kPcgBlock) {
+    for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kBlk) {
         const size_t dst = P.vertOf ? (size_t)P.vertOf[row] : (size_t)row;
         reinterpret_cast<double2*>(P.xOut)[dst] = (bb > 0.0) ? (SMEM ? S.x[row - rowBeg] : reinterpret_cast<const double2*>(P.x)[row]) : make_double2(0.0, 0.0);
     }
@@ -718,7 +723,7 @@ static PcgPlan pcg_plan(ocb_ctx* c)
                 cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
                 cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(kClusterSize); cfg.blockDim = dim3(kPcgBlock); cfg.dynamicSmemBytes = limit;
+                cfg.gridDim = dim3(kClusterSize); cfg.blockDim = dim3(kPcgBlockCluster); cfg.dynamicSmemBytes = limit;
                 cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
@@ -836,7 +841,7 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     }
     if (pl.cluster) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPcgBlock); cfg.dynamicSmemBytes = smemBytes; cfg.stream = c->stream;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPcgBlockCluster); cfg.dynamicSmemBytes = smemBytes; cfg.stream = c->stream;
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
