@@ -271,7 +271,10 @@ def run_ours(args):
     roofline = {"kernel": dom, "bound": "hbm", "achieved": d.get("achieved_gbs"), "peak": peak, "peak_source": peak_src,
                 "unit": "GB/s", "frac": d.get("frac"), "traffic": traffic,
                 "note": ("algorithmic bytes = (%.0f B/face [SpMV + vectors] + %.0f B/face [preconditioner levels] ) x faces + 4 x %d^2 [coarse inverse] "
-                         "per CG iteration, x CG iterations per launch" % (PCG_BYTES_PER_FACE_PER_ITER, MAS_BYTES_PER_FACE_PER_ITER if n_coarse else 0.0, int(n_coarse)))
+                         "per CG iteration, x CG iterations per launch%s" % (PCG_BYTES_PER_FACE_PER_ITER, MAS_BYTES_PER_FACE_PER_ITER if n_coarse else 0.0, int(n_coarse),
+                                                                              "; the working set of this workload (< 4 MB) stays in shared memory / L2 for the whole solve, so the "
+                                                                              "kernel is bound by barrier and instruction latency on 16 SMs, not by HBM (SURVEY 8d: quote it/s here, "
+                                                                              "the HBM fraction on the >= 100k-face workloads bimba_x4 / bimba_x10)" if faces < 50000 else ""))
                 if dom == "pcg" else "algorithmic bytes per face x faces"}
 
     def air_bytes(s):

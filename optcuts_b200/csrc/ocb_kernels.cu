@@ -274,20 +274,50 @@ fixed_identity_kernel(int nVtot, const uint8_t* __restrict__ fixedMask, const in
 // a5/a9/a11/a18: per-element Hessian, PSD projection, scatter into the BSR values.
 // One thread per element; the 6 upper blocks live in registers; each of the 9 (k,l) blocks is
 // one 32-byte sector of the value array, updated with 4 fp64 reductions.
+// queue of the Hessian pass: {v0,v1,v2}, the 9 BSR slots of the element's blocks and {area, areaSq, k0, k1, kd}, two
+// stages: the next element's 88 bytes travel while the current one is computed (~2-5k cycles), and the slot reads no
+// longer sit, one dependent load per block, between the projection and the scatter (42 % of the kernel's stall samples)
 template <bool SCATTER>
-__global__ void __launch_bounds__(kBlock)
+struct HessQueue {
+    int32_t qi[2][SCATTER ? 12 : 3][kBlock];
+    double qd[2][5][kBlock];
+    __device__ __forceinline__ void issue(const ElemView& M, const ElemView& A, int e, int total, int st) {
+        if (e < total) {
+            const bool isAir = e >= M.n;
+            const ElemView& S = isAir ? A : M;
+            const int t = isAir ? e - M.n : e;
+            const int tid = threadIdx.x;
+            cp_async4(&qi[st][0][tid], S.v0 + t); cp_async4(&qi[st][1][tid], S.v1 + t); cp_async4(&qi[st][2][tid], S.v2 + t);
+            if (SCATTER) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) cp_async4(&qi[st][3 + q][tid], S.slot + (size_t)q * S.n + t);
+            }
+            cp_async8(&qd[st][0][tid], S.area + t); cp_async8(&qd[st][1][tid], S.areaSq + t);
+            cp_async8(&qd[st][2][tid], S.k0 + t); cp_async8(&qd[st][3][tid], S.k1 + t); cp_async8(&qd[st][4][tid], S.kd + t);
+        }
+        cp_commit();
+    }
+};
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(kBlock, 2)
 hessian_kernel(ElemView M, ElemView A, const double* __restrict__ x, double* __restrict__ val,
                double* __restrict__ out36)
 {
-    const int total = M.n + (SCATTER ? A.n : 0);
-    for (int e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock) {
+    __shared__ HessQueue<SCATTER> Q;
+    const int total = M.n + (SCATTER ? A.n : 0), stride = gridDim.x * kBlock, tid = threadIdx.x;
+    int e = blockIdx.x * kBlock + tid, st = 0;
+    Q.issue(M, A, e, total, 0);
+    for (; e < total; e += stride, st ^= 1) {
+        Q.issue(M, A, e + stride, total, st ^ 1);
+        cp_wait<1>();
         const bool isAir = e >= M.n;
         const ElemView& S = isAir ? A : M;
         const int t = isAir ? e - M.n : e;
-        const Vec2 U1 = ld2(x, S.v0[t]), U2 = ld2(x, S.v1[t]), U3 = ld2(x, S.v2[t]);
-        const double w = S.uniform ? 1.0 : S.area[t] / S.surfaceArea;
+        const Vec2 U1 = ld2(x, Q.qi[st][0][tid]), U2 = ld2(x, Q.qi[st][1][tid]), U3 = ld2(x, Q.qi[st][2][tid]);
+        const double w = S.uniform ? 1.0 : Q.qd[st][0][tid] / S.surfaceArea;
         double Hb[6][2][2];
-        sd_hessian(U1, U2, U3, S.areaSq[t], S.k0[t], S.k1[t], S.kd[t], w, Hb);
+        sd_hessian(U1, U2, U3, Q.qd[st][1][tid], Q.qd[st][2][tid], Q.qd[st][3][tid], Q.qd[st][4][tid], w, Hb);
         sd_project_psd(Hb);
         if (SCATTER) {
             const double sc = S.scale;
@@ -296,7 +326,7 @@ hessian_kernel(ElemView M, ElemView A, const double* __restrict__ x, double* __r
             for (int k = 0; k < 3; ++k)
 #pragma unroll
                 for (int l = 0; l < 3; ++l) {
-                    const int s = S.slot[(size_t)(3 * k + l) * S.n + t];
+                    const int s = Q.qi[st][SCATTER ? 3 + 3 * k + l : 0][tid];
                     if (s < 0) continue;
                     double* dst = val + 4 * (size_t)s;
                     const int b = bOf[k][l];
@@ -620,7 +650,7 @@ int launch_hessian(ocb_ctx* c, double p0)
     OCB_CUDA(c, cudaMemsetAsync(c->val.p, 0, sizeof(double) * 4 * (size_t)c->nnzb, c->stream));
     fixed_identity_kernel<<<grid_for(c, c->nVtot, 4), kBlock, 0, c->stream>>>(c->nVtot, c->fixedMask.p, c->rowPtr.p, c->colIdx.p, c->val.p, p0, c->wScafOverFa, c->rowOf.p);
     KCHECK(c);
-    hessian_kernel<true><<<grid_for(c, (long)M.n + A.n), kBlock, 0, c->stream>>>(M, A, c->x.p, c->val.p, nullptr);
+    hessian_kernel<true><<<resident_grid<hessian_kernel<true>>(c, (long)M.n + A.n), kBlock, 0, c->stream>>>(M, A, c->x.p, c->val.p, nullptr);
     KCHECK(c);
     return 0;
 }
@@ -630,7 +660,7 @@ int launch_hessian_blocks(ocb_ctx* c, int uniform, double* d_out36)
     ProfScope prof(c, K_HESSIAN);
     const ElemView M = view_of(c, c->mesh, false, 1.0, uniform);
     ElemView A = M; A.n = 0;
-    hessian_kernel<false><<<grid_for(c, M.n), kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, d_out36);
+    hessian_kernel<false><<<resident_grid<hessian_kernel<false>>(c, M.n), kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, d_out36);
     KCHECK(c);
     return 0;
 }

@@ -14,8 +14,10 @@ python bench.py --impl reference --workload bimba_x4 --steps 2 --warmup 1 > gpur
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bimba10k.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'pcg_kernel' -s 3 -c 1 -f -o gpurun_out/prof_pcg10k python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'pcg_kernel' -s 3 -c 1 -f -o gpurun_out/prof_pcg_x10 python bench.py --workload bimba_x10 --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:'hessian_kernel|energy_kernel|gradient_kernel|step_bound|mas_dense_invert' -s 0 -c 8 -f -o gpurun_out/prof_elem_x10 python bench.py --workload bimba_x10 --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'hessian_kernel|energy_kernel|gradient_kernel|step_bound|mas_dense_invert' -s 0 -c 8 -f -o gpurun_out/prof_elem_x10 python bench.py --workload bimba_x10 --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 python bench.py --workload batch71 --steps 1 > gpurun_out/bench_batch71.json 2>/dev/null
+(for ny in 500 1000 2000 4000; do timeout 120 tools/micro/elem_bench 1000 $ny; done) > gpurun_out/elem_bench.txt 2>&1
+python tools/gpu_host_timing.py > gpurun_out/host_timing.txt 2>&1
 ls -la gpurun_out | tail -20
 python - <<PY
 import json
