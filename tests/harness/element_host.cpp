@@ -55,6 +55,21 @@ void host_hessian_blocks(int nV, int nF, const int32_t* F, const double* UV, con
             out[36 * t + (2 * k + i) * 6 + 2 * l + j] = (k <= l) ? Hb[bOf[k][l]][i][j] : Hb[bOf[k][l]][j][i];
     }
 }
+// the projection alone on caller-supplied symmetric 6x6 matrices (row-major, n x 36, in place); returns the clamp counts
+void host_project_psd(int n, double* H36, int* clamped)
+{
+    const int bOf[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    for (int t = 0; t < n; ++t) {
+        double* H = H36 + 36 * (size_t)t;
+        double Hb[6][2][2];
+        for (int k = 0; k < 3; ++k) for (int l = k; l < 3; ++l) for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j)
+            Hb[bOf[k][l]][i][j] = H[(2 * k + i) * 6 + 2 * l + j];
+        const int c = sd_project_psd(Hb);
+        if (clamped) clamped[t] = c;
+        for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j)
+            H[(2 * k + i) * 6 + 2 * l + j] = (k <= l) ? Hb[bOf[k][l]][i][j] : Hb[bOf[k][l]][j][i];
+    }
+}
 double host_step_bound(int nV, int nF, const int32_t* F, const double* UV, const double* dir /*interleaved*/, double alpha0)
 {
     double cur = alpha0;

@@ -71,6 +71,56 @@ def test_projection_fast_path_covers_the_indefinite_elements(host, state):
     assert general <= max(1, (cl > 0).sum() // 1000), (general, (cl > 0).sum())
 
 
+def test_projection_on_synthetic_spectra(host):
+    """sd_project_psd against a numpy eigen-clamp on translation-free 6x6 matrices with 0..4 negative eigenvalues,
+    clustered / repeated / tiny eigenvalues and bad scaling: the rank-1 fast path (exactly one negative eigenvalue) and
+    the general fallback must both reproduce makePD (IglUtils.hpp:71-90)"""
+    rng = np.random.default_rng(7)
+    s2, s6 = np.sqrt(0.5), 1.0 / np.sqrt(6.0)
+    W = np.kron(np.array([[s2, s6], [-s2, s6], [0.0, -2.0 * s6]]), np.eye(2))      # 6x4 basis of the translation-free space
+    mats, nneg = [], []
+    spectra = [
+        lambda: rng.uniform(0.1, 10.0, 4) * np.array([-1, 1, 1, 1]),                # the common case
+        lambda: rng.uniform(0.1, 10.0, 4) * np.array([-1, -1, 1, 1]),
+        lambda: rng.uniform(0.1, 10.0, 4) * np.array([-1, -1, -1, 1]),
+        lambda: -rng.uniform(0.1, 10.0, 4),
+        lambda: rng.uniform(0.1, 10.0, 4),
+        lambda: np.array([-1e-9, 1.0, 1.0, 2.0]) * rng.uniform(0.5, 2.0),           # tiny negative, repeated positive
+        lambda: np.array([-3.0, 1e-12, 1.0, 1e4]) * rng.uniform(0.5, 2.0),          # second eigenvalue ~ 0: hard for a naive RQI
+        lambda: np.array([-1e6, 1e-3, 1.0, 1e6]) * rng.uniform(0.5, 2.0),           # 12 decades
+        lambda: np.array([-2.0, -2.0, 3.0, 3.0]),                                   # repeated negative
+        lambda: np.array([-1.0, 1.0, 1.0, 1.0]) * 10.0 ** rng.uniform(-8, 8),       # scaling
+    ]
+    for make in spectra:
+        for _ in range(200):
+            lam = make()
+            Q, _ = np.linalg.qr(rng.standard_normal((4, 4)))
+            M = (Q * lam) @ Q.T
+            mats.append(W @ (0.5 * (M + M.T)) @ W.T)
+            nneg.append(int((lam < 0).sum()))
+    H = np.ascontiguousarray(np.array(mats).reshape(-1, 36))
+    want = []
+    for A in mats:
+        w, V = np.linalg.eigh(A)
+        want.append((V * np.maximum(w, 0.0)) @ V.T if w[0] < 0 else A)          # null space of W W^T stays null either way
+    cl = np.zeros(len(mats), np.int32)
+    host.host_general_path.restype = C.c_long
+    host.host_general_path(1)
+    host.host_project_psd(len(mats), H.ctypes.data_as(_d), cl.ctypes.data_as(_i))
+    general = host.host_general_path(1)
+    got = H.reshape(-1, 6, 6)
+    scale = np.array([np.abs(A).max() for A in mats])
+    err = np.array([np.abs(g - w_).max() for g, w_ in zip(got, want)]) / scale
+    assert err.max() < 5e-12, (err.max(), int(err.argmax()), nneg[int(err.argmax())])
+    for g, sc in zip(got, scale):
+        assert np.linalg.eigvalsh(g)[0] > -1e-10 * sc
+    nneg = np.array(nneg)
+    assert np.array_equal(cl[nneg != 1] > 0, nneg[nneg != 1] > 0)
+    # every matrix with 2+ negative eigenvalues must have gone through the general path; single-negative ones mostly not
+    assert general >= int((nneg >= 2).sum())
+    assert general <= int((nneg >= 2).sum()) + int(0.35 * (nneg == 1).sum())
+
+
 def test_isometric_known_answer(host):
     """SymDirichletEnergy::checkEnergyVal (SymDirichletEnergy.cpp:612-645): isometry => E_t = 4 w, zero gradient,
     PSD Hessian with a 3-dimensional null space (2 translations + rotation)."""
