@@ -888,7 +888,7 @@ int ocb_factorize(ocb_ctx* c)
     HostTimer _ht("factorize");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_factorize: no matrix"));
-    OCB_TRY(launch_jacobi_setup(c));
+    OCB_TRY(launch_jacobi_setup(c, !c->deferFactorCheck));
     OCB_TRY(launch_mas_setup(c));
     c->precondValid = true;
     return OCB_OK;
@@ -912,6 +912,10 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
     }
     OCB_TRY(launch_pcg(c, dRhs, negate, rel_tol, max_it));
     OCB_TRY(fetch_scalars(c));
+    if (c->hScal[S_JACOBI_BAD] != 0.0) {       // verdict of a set-up whose host check was deferred (ocb_newton_step)
+        c->precondValid = false;
+        return set_err(c, OCB_ERR_BREAKDOWN, "a diagonal 2x2 block of the matrix is not positive definite");
+    }
     int itersTotal = (int)c->hScal[S_PCG_ITERS];
     if ((int)c->hScal[S_PCG_STATUS] == 3) {
         // safety net: the two-level preconditioner came out indefinite (r.M^-1 r <= 0, detected on the device): repeat the
@@ -1017,27 +1021,20 @@ int ocb_step_forward(ocb_ctx* c, double alpha)
     return OCB_OK;
 }
 
-int ocb_line_search(ocb_ctx* c, double p0, double E_last, double alpha0, int allowEDecRelTol, ocb_linesearch_result* out)
+// Line search proper (Optimizer.cpp:575-673).  x0 already holds the start point.  firstTrialFetched: the energy at
+// x0 + alpha p has been launched AND fetched by the caller (ocb_newton_step chains it behind the step bound on the device).
+static int line_search_core(ocb_ctx* c, double p0, double E_last, double lastScaf, double alpha, bool firstTrialFetched,
+                            int allowEDecRelTol, ocb_linesearch_result* out)
 {
-    HostTimer _ht("line_search");
-    if (!c || !out) return OCB_ERR_ARG;
-    OCB_TRY(need(c, c->haveUV, "ocb_line_search: no UV"));
     const bool scaf = c->nFa > 0;
-    double lastScaf = 0.0;
-    OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
-    // the scaffold changed since E_last was computed (Optimizer.cpp:588-592); E_last <= 0 asks for a fresh
-    // evaluation (the Symmetric Dirichlet energy is >= 4 * energyParam0 > 0)
-    if (scaf || !(E_last > 0.0)) {
-        OCB_TRY(launch_energy(c, p0, false, 0.0));
-        OCB_TRY(fetch_scalars(c));
-        lastScaf = scaf ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
-        E_last = p0 * c->hScal[S_E_MESH] + lastScaf;
-    }
-    double alpha = alpha0, E = 0.0, Escaf = 0.0, Esd = 0.0;
+    double E = 0.0, Escaf = 0.0, Esd = 0.0;
     int halvings = 0, stopped = 0;
     for (;;) {
-        OCB_TRY(launch_energy(c, p0, true, alpha));
-        OCB_TRY(fetch_scalars(c));
+        if (!firstTrialFetched) {
+            OCB_TRY(launch_energy(c, p0, true, alpha));
+            OCB_TRY(fetch_scalars(c));
+        }
+        firstTrialFetched = false;
         Esd = c->hScal[S_E_MESH];
         Escaf = scaf ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
         E = p0 * Esd + Escaf;
@@ -1071,6 +1068,29 @@ int ocb_line_search(ocb_ctx* c, double p0, double E_last, double alpha0, int all
     return OCB_OK;
 }
 
+int ocb_line_search(ocb_ctx* c, double p0, double E_last, double alpha0, int allowEDecRelTol, ocb_linesearch_result* out)
+{
+    HostTimer _ht("line_search");
+    if (!c || !out) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->haveUV, "ocb_line_search: no UV"));
+    const bool scaf = c->nFa > 0;
+    double lastScaf = 0.0;
+    OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
+    // the scaffold changed since E_last was computed (Optimizer.cpp:588-592); E_last <= 0 asks for a fresh
+    // evaluation (the Symmetric Dirichlet energy is >= 4 * energyParam0 > 0)
+    if (scaf || !(E_last > 0.0)) {
+        OCB_TRY(launch_energy(c, p0, false, 0.0));
+        OCB_TRY(fetch_scalars(c));
+        lastScaf = scaf ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
+        E_last = p0 * c->hScal[S_E_MESH] + lastScaf;
+    }
+    return line_search_core(c, p0, E_last, lastScaf, alpha0, false, allowEDecRelTol, out);
+}
+
+// One Newton iteration (Optimizer::solve(1), Optimizer.cpp:203-261, 505-673) with three host round trips instead of the
+// six of the call-by-call sequence: {gradient norm, energy at x} | {block-Jacobi verdict, PCG status} | {step bound,
+// first line-search trial}.  Same kernels, same arithmetic, same results as ocb_gradient + ocb_hessian_assemble +
+// ocb_factorize + ocb_solve + ocb_step_bound + ocb_line_search.
 int ocb_newton_step(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_tol, int pcg_max_it,
                     int allowEDecRelTol, ocb_newton_result* out)
 {
@@ -1078,22 +1098,35 @@ int ocb_newton_step(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_tol
     if (!c || !out) return OCB_ERR_ARG;
     std::memset(out, 0, sizeof(*out));
     out->targetGRes = targetGRes;
-    double sqn = 0.0;
-    OCB_TRY(ocb_gradient(c, p0, nullptr, &sqn));
+    OCB_TRY(need(c, c->haveUV, "ocb_newton_step: no UV"));
+    const bool scaf = c->nFa > 0;
+    OCB_TRY(launch_gradient(c, p0));
+    OCB_TRY(launch_energy(c, p0, false, 0.0));               // E_last with the current scaffold (Optimizer.cpp:588-592)
+    OCB_TRY(fetch_scalars(c));
+    const double sqn = c->hScal[S_SQN_G];
+    const double lastScaf = scaf ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
+    const double E_last = p0 * c->hScal[S_E_MESH] + lastScaf;
     out->sqn_g = sqn;
     if (sqn < targetGRes) { out->converged = 1; return OCB_OK; }
     if (!c->patternValid) OCB_TRY(ocb_set_pattern_from_elements(c));
     OCB_TRY(ocb_hessian_assemble(c, p0));
-    OCB_TRY(ocb_factorize(c));
+    c->deferFactorCheck = true;
+    const int rf = ocb_factorize(c);
+    c->deferFactorCheck = false;
+    if (rf < 0) return rf;
     int its = 0; double rr = 0.0;
     int rs = ocb_solve(c, nullptr, nullptr, pcg_rel_tol, pcg_max_it, &its, &rr);
     out->pcg_iters = its; out->pcg_rel_res = rr;
     if (rs < 0 && rs != OCB_ERR_NOT_CONVERGED) return rs;
-    double alpha = 1.0;
-    OCB_TRY(ocb_step_bound(c, nullptr, &alpha));
-    alpha *= 0.99;                                           // Optimizer.cpp:580
+    // step bound, then the first trial at 0.99 * bound (Optimizer.cpp:580) chained on the device
+    OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
+    OCB_TRY(launch_step_bound(c, c->p.p, 1.0));
+    OCB_TRY(launch_energy(c, p0, true, 0.99, true));
+    OCB_TRY(fetch_scalars(c));
+    double alpha = c->hScal[S_STEP_BOUND];
+    alpha *= 0.99;
     ocb_linesearch_result ls;
-    OCB_TRY(ocb_line_search(c, p0, 0.0, alpha, allowEDecRelTol, &ls));
+    OCB_TRY(line_search_core(c, p0, E_last, lastScaf, alpha, true, allowEDecRelTol, &ls));
     out->alpha = ls.alpha; out->E_new = ls.E_new; out->E_scaf_new = ls.E_scaf_new; out->E_sd_new = ls.E_sd_new;
     out->lastEDec = ls.lastEDec; out->n_halvings = ls.n_halvings; out->stopped = ls.stopped;
     return rs == OCB_ERR_NOT_CONVERGED ? rs : OCB_OK;

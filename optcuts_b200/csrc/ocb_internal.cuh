@@ -64,7 +64,7 @@ enum KernelClass {
 
 enum ScalarSlot {            // layout of the device/pinned scalar block
     S_E_MESH = 0, S_E_AIR, S_N_INVERTED, S_SQN_G, S_STEP_BOUND, S_PCG_ITERS, S_PCG_RELRES,
-    S_PCG_STATUS, S_PCG_BNORM, S_MISC0, S_MISC1, S_MISC2, S_COUNT = 16
+    S_PCG_STATUS, S_PCG_BNORM, S_MISC0, S_MISC1, S_MISC2, S_JACOBI_BAD, S_COUNT = 16
 };
 
 // MAS preconditioner: host-side hierarchy (built at pattern time) and its device mirror (ocb_mas.cu)
@@ -129,6 +129,7 @@ struct ocb_ctx {
     ocb::DevBuf<int32_t> rowOf, vertOf, userRow;   // device: internal vertex -> row, row -> internal vertex, caller vertex -> row
     ocb::MasHost masH; ocb::MasDev masD;
     int planGrid = 0;                        // persistent-CTA count the hierarchy was built for
+    bool deferFactorCheck = false;           // ocb_newton_step: the block-Jacobi verdict is read together with the PCG status
     int64_t precondFallbacks = 0;            // solves repeated with block-Jacobi after the two-level preconditioner failed
     std::vector<int32_t> hStamp;             // scratch of the pattern builders
     std::vector<double> hHint;               // ocb_set_coordinate_hint: 2 per vertex (interleaved), caller numbering
@@ -186,7 +187,7 @@ ElemView view_of(const ocb_ctx* c, const ElemSet& s, bool isAir, double scale, i
 int fetch_scalars(ocb_ctx* c);   // D2H of the scalar block + stream sync
 
 // launchers implemented in ocb_kernels.cu / ocb_pcg.cu
-int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha);
+int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha, bool alphaFromStepBound = false);   // alphaFromStepBound: alpha * scal[S_STEP_BOUND], read on the device
 int launch_energy_per_elem(ocb_ctx* c, int uniform, double* d_out);
 int launch_gradient(ocb_ctx* c, double p0);
 int launch_sqnorm(ocb_ctx* c, const double* v, int n, int slot);
@@ -210,7 +211,7 @@ struct StencilHost {     // device pointers of one uploaded stencil batch
 };
 int launch_stencils(ocb_ctx* c, const StencilHost& h);
 int launch_spmv(ocb_ctx* c, const double* dx, double* dy);
-int launch_jacobi_setup(ocb_ctx* c);
+int launch_jacobi_setup(ocb_ctx* c, bool check = true);   // check = false: no host round trip, the verdict stays in scal[S_JACOBI_BAD]
 int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it, bool allowMas = true);
 int pcg_plan_grid(ocb_ctx* c, int nRows);            // CTA count launch_pcg will use for this system size
 int mas_build_hierarchy(ocb_ctx* c, const double* xy, int grid);

@@ -138,8 +138,11 @@ template <bool STEPPED>
 __global__ void __launch_bounds__(kBlock)
 energy_kernel(ElemView M, ElemView A, const double* __restrict__ x, const double* __restrict__ p,
               double alpha, double* __restrict__ partials, unsigned* __restrict__ ticket,
-              double* __restrict__ scal, Slots3 slots)
+              double* __restrict__ scal, Slots3 slots, int alphaFromStepBound)
 {
+    // first line-search trial without a host round trip: alpha = 0.99 * (step bound left by the previous launch),
+    // the same product the host forms after its fetch (Optimizer.cpp:580)
+    if (STEPPED && alphaFromStepBound) alpha = __dmul_rn(alpha, scal[S_STEP_BOUND]);
     __shared__ ElemQueue<5> Q;
     double acc[3] = {0.0, 0.0, 0.0};   // mesh sum, air sum, #elements with signed area < 0
     const int total = M.n + A.n, stride = gridDim.x * kBlock, tid = threadIdx.x;
@@ -575,15 +578,15 @@ static int ensure_reduce_bufs(ocb_ctx* c, int grid, int nv) {
     return 0;
 }
 
-int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha)
+int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha, bool alphaFromStepBound)
 {
     ProfScope prof(c, K_ENERGY);
     const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
     const int grid = stepped ? resident_grid<energy_kernel<true>>(c, (long)M.n + A.n) : resident_grid<energy_kernel<false>>(c, (long)M.n + A.n);
     OCB_TRY(ensure_reduce_bufs(c, grid, 3));
     Slots3 sl; sl.s[0] = S_E_MESH; sl.s[1] = S_E_AIR; sl.s[2] = S_N_INVERTED;
-    if (stepped) energy_kernel<true><<<grid, kBlock, 0, c->stream>>>(M, A, c->x0.p, c->p.p, alpha, c->partials.p, c->sync.p, c->dScal, sl);
-    else energy_kernel<false><<<grid, kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, 0.0, c->partials.p, c->sync.p, c->dScal, sl);
+    if (stepped) energy_kernel<true><<<grid, kBlock, 0, c->stream>>>(M, A, c->x0.p, c->p.p, alpha, c->partials.p, c->sync.p, c->dScal, sl, alphaFromStepBound ? 1 : 0);
+    else energy_kernel<false><<<grid, kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, 0.0, c->partials.p, c->sync.p, c->dScal, sl, 0);
     KCHECK(c);
     return 0;
 }

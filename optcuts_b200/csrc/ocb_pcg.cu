@@ -642,14 +642,14 @@ spmv_kernel(PcgParams P, const double* __restrict__ v, double* __restrict__ y)
 // block-Jacobi preconditioner: inverse of every 2x2 diagonal block
 __global__ void __launch_bounds__(256)
 jacobi_setup_kernel(int nRows, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx,
-                    const double* __restrict__ val, double* __restrict__ minv, int* __restrict__ bad)
+                    const double* __restrict__ val, double* __restrict__ minv, int* __restrict__ bad, double* __restrict__ scal)
 {
     for (int row = blockIdx.x * 256 + threadIdx.x; row < nRows; row += gridDim.x * 256) {
         double a00 = 0.0, a01 = 0.0, a11 = 0.0;
         for (int b = rowPtr[row]; b < rowPtr[row + 1]; ++b)
             if (colIdx[b] == row) { a00 = val[4 * (size_t)b]; a01 = 0.5 * (val[4 * (size_t)b + 1] + val[4 * (size_t)b + 2]); a11 = val[4 * (size_t)b + 3]; }
         const double det = a00 * a11 - a01 * a01;
-        if (!(a00 > 0.0) || !(det > 0.0)) { atomicAdd(bad, 1); minv[4 * (size_t)row] = 1.0; minv[4 * (size_t)row + 1] = 0.0; minv[4 * (size_t)row + 2] = 0.0; minv[4 * (size_t)row + 3] = 1.0; continue; }
+        if (!(a00 > 0.0) || !(det > 0.0)) { atomicAdd(bad, 1); scal[S_JACOBI_BAD] = 1.0; minv[4 * (size_t)row] = 1.0; minv[4 * (size_t)row + 1] = 0.0; minv[4 * (size_t)row + 2] = 0.0; minv[4 * (size_t)row + 3] = 1.0; continue; }
         minv[4 * (size_t)row] = a11 / det; minv[4 * (size_t)row + 1] = -a01 / det;
         minv[4 * (size_t)row + 2] = -a01 / det; minv[4 * (size_t)row + 3] = a00 / det;
     }
@@ -782,17 +782,19 @@ int launch_spmv(ocb_ctx* c, const double* dx, double* dy)
     return 0;
 }
 
-int launch_jacobi_setup(ocb_ctx* c)
+int launch_jacobi_setup(ocb_ctx* c, bool check)
 {
     int* bad = reinterpret_cast<int*>(c->sync.p + 8);
     OCB_CUDA(c, cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
+    OCB_CUDA(c, cudaMemsetAsync(c->dScal + S_JACOBI_BAD, 0, sizeof(double), c->stream));
     OCB_CUDA(c, c->minv.reserve(4 * (size_t)c->nVtot, c->stream));
     int grid = (c->nVtot + 255) / 256; if (grid > c->numSMs * 8) grid = c->numSMs * 8; if (grid < 1) grid = 1;
     {
         ProfScope prof(c, K_JACOBI_SETUP);
-        jacobi_setup_kernel<<<grid, 256, 0, c->stream>>>(c->nVtot, c->rowPtr.p, c->colIdx.p, c->val.p, c->minv.p, bad);
+        jacobi_setup_kernel<<<grid, 256, 0, c->stream>>>(c->nVtot, c->rowPtr.p, c->colIdx.p, c->val.p, c->minv.p, bad, c->dScal);
         KCHECK(c);
     }
+    if (!check) return 0;
     int hBad = 0;
     OCB_CUDA(c, cudaMemcpyAsync(&hBad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
