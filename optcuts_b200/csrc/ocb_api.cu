@@ -360,6 +360,7 @@ int ocb_set_mesh(ocb_ctx* c, int nV, int nF, const int32_t* F, const double* res
     OCB_TRY(resize_system(c));
     OCB_TRY(upload_fixed_mask(c));
     c->haveUV = false; c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
+    c->hXY.clear(); c->hXYMesh = c->hXYAir = false;
     return OCB_OK;
 }
 
@@ -402,6 +403,7 @@ int ocb_set_air(ocb_ctx* c, int nVa, int nFa, const int32_t* Fa, const double* r
             c->hFixed[c->hL2G[fixedAir[i]]] |= 2;
         }
     }
+    c->hXYAir = false;                                   // the air vertices are new: their mirror entries are stale
     OCB_TRY(resize_system(c));
     OCB_TRY(upload_fixed_mask(c));
     c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
@@ -421,6 +423,20 @@ int ocb_set_uv(ocb_ctx* c, const double* V, const double* Va)
     if (V) OCB_TRY(upload_d(c, dV, V, nv));
     if (na) OCB_TRY(upload_d(c, dVa, Va, na));
     OCB_TRY(launch_set_uv(c, dV, dVa));
+    {   // host mirror in the device's internal numbering (set_uv_kernel's mapping)
+        const size_t nTot = (size_t)c->nVtot;
+        if (c->hXY.size() != 2 * nTot) { c->hXY.resize(2 * nTot, 0.0); c->hXYAir = false; }      // the mesh part (ids < nV) survives a new air mesh
+        if (V) {
+            const int nV = c->nV;
+            for (int k = 0; k < nV; ++k) { const size_t q = (size_t)c->hPerm[k]; c->hXY[2 * q] = V[k]; c->hXY[2 * q + 1] = V[(size_t)nV + k]; }
+            c->hXYMesh = true;
+        }
+        if (na) {
+            const int nVa = c->nVa, nB = c->nBnd, nV = c->nV;
+            for (int k = 0; k < nVa - nB; ++k) { c->hXY[2 * ((size_t)nV + k)] = Va[nB + k]; c->hXY[2 * ((size_t)nV + k) + 1] = Va[(size_t)nVa + nB + k]; }
+            c->hXYAir = true;
+        }
+    }
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (V) c->haveUV = true;
     c->matrixValid = c->precondValid = false;
@@ -457,6 +473,7 @@ int ocb_restore_uv(ocb_ctx* c)
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->xSavedN == c->nSys() && c->xSavedN > 0, "ocb_restore_uv: no snapshot of this system size"));
     OCB_CUDA(c, cudaMemcpyAsync(c->x.p, c->xSaved.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
+    c->hXYMesh = c->hXYAir = false;
     c->matrixValid = c->precondValid = false;
     return OCB_OK;
 }
@@ -532,10 +549,15 @@ static int choose_order(ocb_ctx* c)
     c->planGrid = pcg_plan_grid(c, n);
     c->masH = MasHost();
     if (!masOff && c->haveUV && c->nV > 0 && c->x.p && n >= 2 * kMasLeaf) {
-        std::vector<double> xy(2 * (size_t)n);
-        OCB_CUDA(c, cudaMemcpyAsync(xy.data(), c->x.p, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-        OCB_CUDA(c, cudaStreamSynchronize(c->stream));
-        { HostTimer _h2("  mas_build_hierarchy"); OCB_TRY(mas_build_hierarchy(c, xy.data(), c->planGrid)); }
+        const char* noMirror = getenv("OCB_NO_UV_MIRROR");      // test switch: always download
+        const bool mirrored = c->hXY.size() == 2 * (size_t)n && c->hXYMesh && (c->hXYAir || c->nVa - c->nBnd <= 0) && !(noMirror && atoi(noMirror));
+        std::vector<double> xy;
+        if (!mirrored) {                                   // x moved on the device since the last ocb_set_uv
+            xy.resize(2 * (size_t)n);
+            OCB_CUDA(c, cudaMemcpyAsync(xy.data(), c->x.p, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+            OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+        { HostTimer _h2("  mas_build_hierarchy"); OCB_TRY(mas_build_hierarchy(c, mirrored ? c->hXY.data() : xy.data(), c->planGrid)); }
     } else if (!masOff && c->nV == 0 && (int)c->hCoords.size() == 2 * n && n >= 2 * kMasLeaf) {     // bare solver with a coordinate hint
         HostTimer _h2("  mas_build_hierarchy");
         OCB_TRY(mas_build_hierarchy(c, c->hCoords.data(), c->planGrid));
@@ -1017,6 +1039,7 @@ int ocb_step_forward(ocb_ctx* c, double alpha)
     OCB_TRY(need(c, c->haveUV, "ocb_step_forward: no UV"));
     OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
     OCB_TRY(launch_step_forward(c, alpha));
+    c->hXYMesh = c->hXYAir = false;
     c->matrixValid = c->precondValid = false;
     return OCB_OK;
 }
@@ -1059,6 +1082,7 @@ static int line_search_core(ocb_ctx* c, double p0, double E_last, double lastSca
         E = p0 * Esd + Escaf;
     }
     OCB_TRY(launch_step_forward(c, alpha));
+    c->hXYMesh = c->hXYAir = false;
     double eDec = E_last - E;
     if (scaf) eDec += (-lastScaf + Escaf);
     if (allowEDecRelTol && (eDec / E_last < 1.0e-6 * alpha) && (alpha > 1.0e-3)) stopped = 1;

@@ -133,6 +133,8 @@ struct ocb_ctx {
     int64_t precondFallbacks = 0;            // solves repeated with block-Jacobi after the two-level preconditioner failed
     std::vector<int32_t> hStamp;             // scratch of the pattern builders
     std::vector<double> hHint;               // ocb_set_coordinate_hint: 2 per vertex (interleaved), caller numbering
+    std::vector<double> hXY;                 // host mirror of x (INTERNAL numbering) as last written by ocb_set_uv: spares the
+    bool hXYMesh = false, hXYAir = false;    // row-order code its download; a device-side update of x invalidates it
     std::vector<double> hCoords;             // positions of all nVtot vertices for a solver-only context (INTERNAL numbering)
     ocb::DevBuf<int32_t> rowPtr, colIdx;
     ocb::DevBuf<double> val;                 // 4 per block, row-major

@@ -35,6 +35,33 @@ def test_mas_pcg_matches_reference_direction(ctx, request, which, bound):
     assert np.linalg.norm(res) / np.linalg.norm(g) < 1e-10
 
 
+def test_row_order_from_the_host_uv_mirror_equals_the_downloaded_one(state1, monkeypatch):
+    """ocb_set_pattern_* orders the rows along a curve through the UVs; it takes them from the host mirror ocb_set_uv
+    keeps (no download + sync) when x has not moved on the device since: same order, hence the same iteration counts and
+    the same solution up to the summation order of the atomically assembled matrix."""
+    import optcuts_b200 as ob
+    got = []
+    for no_mirror in ("0", "1"):
+        monkeypatch.setenv("OCB_NO_UV_MIRROR", no_mirror)
+        c = ob.Context(0)
+        try:
+            _newton_system(c, state1)
+            p, info = c.solve(None, 1e-12, 0)
+            got.append((p.copy(), info["iters"]))
+            # after a device-side step the mirror is stale: the next pattern must come from a download again
+            r = c.newton_step(state1.p0, 0.0)
+            c.set_pattern_from_elements()
+            c.gradient(state1.p0, download=False)
+            c.hessian_assemble(state1.p0)
+            p2, info2 = c.solve(None, 1e-12, 0)
+            got[-1] += (p2.copy(), info2["iters"], r["E_new"])
+        finally:
+            c.close()
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert got[0][1] == got[1][1] and rel(got[0][0], got[1][0]) < 1e-9
+    assert got[0][3] == got[1][3] and rel(got[0][2], got[1][2]) < 1e-9 and abs(got[0][4] - got[1][4]) <= 1e-11 * got[1][4]
+
+
 def test_solve_with_explicit_rhs_and_fixed_rows(ctx, state1):
     """LinSysSolver::solve(rhs, result) with an arbitrary right-hand side, also on the fixed vertex's rows."""
     _newton_system(ctx, state1)
