@@ -540,16 +540,20 @@ __device__ __forceinline__ void tile_gemm(const double (*A)[kCBs], const double 
 }
 // Gauss-Jordan inverse of one SPD tile (in shared memory T on entry and exit).  The sequential chain of 48 pivots is
 // what bounds the whole blocked inversion, so it runs on 5 warps only (a named barrier over 160 threads is cheaper than
-// one over 18 warps, and no warp waits for an issue slot): thread t < 144 keeps row t / 3, columns 16 (t % 3) .. + 15 in
+// one over 18 warps, and no warp waits for an issue slot): thread t < 144 keeps row t % 48, columns 16 (t / 48) .. + 15 in
 // REGISTERS; per pivot the pivot row and column cross through a double-buffered shared-memory line, one barrier per
 // pivot.  buf: 2 x (48 row + 48 column) doubles.  A DOF whose pivot collapses is dropped (zero row and column).
+// The mapping is SEGMENT-major on purpose: the lanes of a warp then read the same 16 bytes of the pivot row (a pure
+// broadcast).  Row-major (row t / 3, segment t % 3) put the three segments of a warp 128 bytes apart, i.e. on the same
+// banks: 3-way conflicts on every one of the 8 loads per pivot, 602 cycles per pivot against 285 now
+// (tools/micro/tile_invert_bench.cu, which also shows that 2x2 block pivots and 9 / 18 warps are slower).
 __device__ __forceinline__ void tile_invert_smem(double (*T)[kCBs], double* buf, const double* d0s)
 {
     __syncthreads();
     const int t = threadIdx.x;
     if (t < 160) {
         const bool act = t < 144;
-        const int r = act ? t / 3 : 0, c0 = act ? 16 * (t % 3) : 0;
+        const int r = act ? t % kCB : 0, c0 = act ? 16 * (t / kCB) : 0;
         double d[16];
 #pragma unroll
         for (int e = 0; e < 16; e += 2) { const double2 v = *reinterpret_cast<const double2*>(&T[r][c0 + e]); d[e] = v.x; d[e + 1] = v.y; }
