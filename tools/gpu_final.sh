@@ -18,6 +18,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'hes
 python bench.py --workload batch71 --steps 1 > gpurun_out/bench_batch71.json 2>/dev/null
 (for ny in 500 1000 2000 4000; do timeout 120 tools/micro/elem_bench 1000 $ny; done) > gpurun_out/elem_bench.txt 2>&1
 python tools/gpu_host_timing.py > gpurun_out/host_timing.txt 2>&1
+(OCB_MAS_DEBUG=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep 'ocb mas' | tail -1; OCB_MAS_DEBUG=1 python bench.py --workload bimba_x4 --steps 1 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep 'ocb mas' | tail -1; timeout 60 tools/micro/tile_invert_bench) > gpurun_out/mas_dense_phases.txt 2>&1
 ls -la gpurun_out | tail -20
 python - <<PY
 import json
