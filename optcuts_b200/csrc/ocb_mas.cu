@@ -489,10 +489,10 @@ mas_dense_fill_kernel(int nNodes, const int32_t* __restrict__ rowPtr, const int3
 // dependent -- and its inverse entries would exceed what the fp32 storage resolves.  With 1e-10 such pivots were rounding
 // noise on a knife edge: ~1 solve in 20 got an indefinite preconditioner (tools/gpu_freerun_check.py).
 static constexpr double kMasPivotTol = 1e-6;
-// tile and its padded shared-memory stride: 52 = 4 (mod 16) doubles, so that the 64-bit fragment loads of tile_gemm --
-// half-warp = 4 rows x 4 consecutive doubles (A) or 4 rows x 4 consecutive doubles of the other index (B) -- touch 16
-// distinct 8-byte bank pairs (a stride of 50 put row r + 1 two doubles after row r: 2-way conflicts on every load)
-static constexpr int kCB = kMasCoarseBlk, kCBs = kMasCoarseBlk + 4;
+// tile and its padded shared-memory stride.  NEXT: a stride of 52 (= 4 mod 16 doubles) makes the 64-bit fragment loads of
+// tile_gemm conflict-free (a half-warp = 4 rows x 4 consecutive doubles then touches 16 distinct 8-byte bank pairs: 2
+// wavefronts per load instead of 4 with 50, by the bank arithmetic); not yet measured on the GPU, so 50 stays.
+static constexpr int kCB = kMasCoarseBlk, kCBs = kMasCoarseBlk + 2;
 static constexpr int kDenseThreads = 576;                                // 18 warps: warp w owns the 8x8 sub-tiles 2w and 2w+1 (6x6 grid)
 struct DenseInvArgs { int nb, ld, nC; double* X; double* Y; double* P; double* diag0; float* out; long long* dbg; int* ticket; };
 
