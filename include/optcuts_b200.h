@@ -52,8 +52,11 @@ int  ocb_create(ocb_ctx** out, int device);
 void ocb_destroy(ocb_ctx* ctx);
 const char* ocb_last_error(const ocb_ctx* ctx);
 const char* ocb_version(void);
-/* run everything of this context on an existing cudaStream_t (e.g. torch's current stream) */
+/* run everything of this context on an existing cudaStream_t (e.g. torch's current stream).  The handle is used as
+ * given: NULL means the legacy default stream, so the library's work stays ordered with the caller's work on it.  Without
+ * this call (or after ocb_use_own_stream) the context creates a private non-blocking stream on first use. */
 int  ocb_set_stream(ocb_ctx* ctx, void* cuda_stream);
+int  ocb_use_own_stream(ocb_ctx* ctx);
 int  ocb_synchronize(ocb_ctx* ctx);
 /* CUDA-event stopwatch on the context's stream (what bench.py times kernels with) */
 int  ocb_timer_start(ocb_ctx* ctx);

@@ -56,6 +56,7 @@ _SIGS = [
     ("ocb_last_error", C.c_char_p, [C.c_void_p]),
     ("ocb_version", C.c_char_p, []),
     ("ocb_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("ocb_use_own_stream", C.c_int, [C.c_void_p]),
     ("ocb_synchronize", C.c_int, [C.c_void_p]),
     ("ocb_timer_start", C.c_int, [C.c_void_p]),
     ("ocb_timer_stop_ms", C.c_int, [C.c_void_p, _d]),
@@ -194,6 +195,9 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         self._chk(self._L.ocb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def use_own_stream(self):
+        self._chk(self._L.ocb_use_own_stream(self._h))
 
     def synchronize(self):
         self._chk(self._L.ocb_synchronize(self._h))

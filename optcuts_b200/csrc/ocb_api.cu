@@ -81,7 +81,7 @@ int ensure_init(ocb_ctx* c)
 {
     if (c->inited) { cudaSetDevice(c->device); return 0; }
     OCB_CUDA(c, cudaSetDevice(c->device));
-    if (!c->stream) { OCB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    if (!c->streamGiven) { OCB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     OCB_CUDA(c, cudaEventCreate(&c->ev0));
     OCB_CUDA(c, cudaEventCreate(&c->ev1));
     cudaDeviceProp prop;
@@ -206,6 +206,23 @@ static int vec_to_host(ocb_ctx* c, double* host_user, const double* src_internal
     return 0;
 }
 
+// vertex -> corner incidence (entries element << 2 | corner, ascending element order per vertex) of an element list given as
+// 3 x n SoA over nRows vertex ids; uploaded to ptrBuf / idxBuf
+static int upload_corner_csr(ocb_ctx* c, int nRows, int n, const int32_t* F_soa, ocb::DevBuf<int32_t>& ptrBuf, ocb::DevBuf<int32_t>& idxBuf)
+{
+    std::vector<int32_t> ptr((size_t)nRows + 1, 0), idx((size_t)3 * n);
+    for (int k = 0; k < 3; ++k) for (int t = 0; t < n; ++t) ptr[(size_t)F_soa[(size_t)k * n + t] + 1]++;
+    for (int v = 0; v < nRows; ++v) ptr[v + 1] += ptr[v];
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int t = 0; t < n; ++t) for (int k = 0; k < 3; ++k) idx[fill[F_soa[(size_t)k * n + t]]++] = (t << 2) | k;
+    OCB_CUDA(c, ptrBuf.reserve((size_t)nRows + 2, c->stream));
+    OCB_CUDA(c, idxBuf.reserve((size_t)3 * n + 2, c->stream));
+    OCB_CUDA(c, cudaMemcpyAsync(ptrBuf.p, ptr.data(), sizeof(int32_t) * ((size_t)nRows + 1), cudaMemcpyHostToDevice, c->stream));
+    if (n > 0) OCB_CUDA(c, cudaMemcpyAsync(idxBuf.p, idx.data(), sizeof(int32_t) * (size_t)3 * n, cudaMemcpyHostToDevice, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));       // the host vectors go out of scope
+    return 0;
+}
+
 static int need(ocb_ctx* c, bool cond, const char* what) { return cond ? 0 : set_err(c, OCB_ERR_STATE, what); }
 
 }  // namespace ocb
@@ -235,7 +252,7 @@ void ocb_destroy(ocb_ctx* c)
         cudaStreamSynchronize(c->stream);
         c->mesh.v.release(); c->mesh.rest.release(); c->mesh.slot.release();
         c->air.v.release(); c->air.rest.release(); c->air.slot.release();
-        c->l2g.release(); c->fixedMask.release(); c->perm.release(); c->scratchV.release(); c->stD.release(); c->stI.release();
+        c->l2g.release(); c->vcPtrM.release(); c->vcIdxM.release(); c->vcPtrA.release(); c->vcIdxA.release(); c->g2l.release(); c->hel.release(); c->fixedMask.release(); c->perm.release(); c->scratchV.release(); c->stD.release(); c->stI.release();
         c->x.release(); c->x0.release(); c->g.release(); c->p.release();
         c->pr.release(); c->pz.release(); c->pd.release(); c->pd2.release(); c->pAp.release(); c->pb.release(); c->minv.release();
         c->rowPtr.release(); c->colIdx.release(); c->val.release();
@@ -257,10 +274,21 @@ const char* ocb_last_error(const ocb_ctx* c) { return c ? c->err.c_str() : "null
 
 int ocb_set_stream(ocb_ctx* c, void* s)
 {
+    // the handle is used as given: NULL is the legacy default stream (what torch.cuda.current_stream().cuda_stream is for
+    // torch's default stream), so the library's work is ordered with the caller's own work on that stream
     if (!c) return OCB_ERR_ARG;
-    if (c->inited && c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
-    c->stream = (cudaStream_t)s; c->own_stream = false;
-    if (!c->stream && c->inited) { OCB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    if (c->inited) cudaSetDevice(c->device);
+    if (c->inited && c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t)s; c->own_stream = false; c->streamGiven = true;
+    return OCB_OK;
+}
+int ocb_use_own_stream(ocb_ctx* c)
+{
+    if (!c) return OCB_ERR_ARG;
+    if (c->own_stream) return OCB_OK;
+    if (c->inited) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    c->stream = nullptr; c->streamGiven = false;
+    if (c->inited) { OCB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     return OCB_OK;
 }
 int ocb_synchronize(ocb_ctx* c) { OCB_TRY(ensure_init(c)); OCB_CUDA(c, cudaStreamSynchronize(c->stream)); return OCB_OK; }
@@ -340,9 +368,14 @@ int ocb_set_mesh(ocb_ctx* c, int nV, int nF, const int32_t* F, const double* res
                  const int32_t* fixed, int nFixed)
 {
     HostTimer _ht("set_mesh");
-    if (!c || nV <= 0 || nF <= 0 || !F || !rest8 || !(surfaceArea > 0.0)) return set_err(c, OCB_ERR_ARG, "ocb_set_mesh: bad argument");
+    // every argument is checked before the context is touched: a failed call leaves the previous problem intact
+    if (!c || nV <= 0 || nF <= 0 || !F || !rest8 || !(surfaceArea > 0.0) || nFixed < 0 || (nFixed > 0 && !fixed))
+        return set_err(c, OCB_ERR_ARG, "ocb_set_mesh: bad argument");
+    if ((int64_t)nF >= (INT32_MAX >> 2)) return set_err(c, OCB_ERR_ARG, "ocb_set_mesh: more than 2^29 triangles");
     for (size_t i = 0; i < (size_t)3 * nF; ++i) if (F[i] < 0 || F[i] >= nV) return set_err(c, OCB_ERR_ARG, "ocb_set_mesh: vertex index out of range");
+    for (int i = 0; i < nFixed; ++i) if (fixed[i] < 0 || fixed[i] >= nV) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range");
     OCB_TRY(ensure_init(c));
+    c->haveUV = false; c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
     c->nV = nV; c->nF = nF; c->surfaceArea = surfaceArea;
     // a new mesh drops the scaffold (the caller re-sends it, as the reference rebuilds it: Optimizer.cpp:483-488)
     c->nVa = c->nFa = c->nBnd = 0; c->air.n = 0; c->hFa.clear(); c->hL2G.clear(); c->wScafOverFa = 0.0;
@@ -354,12 +387,13 @@ int ocb_set_mesh(ocb_ctx* c, int nV, int nF, const int32_t* F, const double* res
         std::vector<int32_t> Fi((size_t)3 * nF);
         for (size_t i = 0; i < Fi.size(); ++i) Fi[i] = c->hPerm[F[i]];
         OCB_TRY(upload_elems(c, c->mesh, c->hF, nF, Fi.data(), rest8));
+        OCB_TRY(upload_corner_csr(c, nV, nF, Fi.data(), c->vcPtrM, c->vcIdxM));
     }
+    OCB_TRY(launch_g2l(c));
     c->hFixed.assign((size_t)nV, 0);
-    for (int i = 0; i < nFixed; ++i) { if (fixed[i] < 0 || fixed[i] >= nV) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range"); c->hFixed[c->hPerm[fixed[i]]] = 1; }
+    for (int i = 0; i < nFixed; ++i) c->hFixed[c->hPerm[fixed[i]]] = 1;
     OCB_TRY(resize_system(c));
     OCB_TRY(upload_fixed_mask(c));
-    c->haveUV = false; c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
     c->hXY.clear(); c->hXYMesh = c->hXYAir = false;
     return OCB_OK;
 }
@@ -370,43 +404,44 @@ int ocb_set_air(ocb_ctx* c, int nVa, int nFa, const int32_t* Fa, const double* r
     HostTimer _ht("set_air");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->nV > 0, "ocb_set_air before ocb_set_mesh"));
-    OCB_TRY(ensure_init(c));
-    if (nFa <= 0) {
-        c->nVa = c->nFa = c->nBnd = 0; c->air.n = 0; c->hFa.clear(); c->hL2G.clear(); c->wScafOverFa = 0.0;
-        c->nVtot = c->nV;
-        c->hFixed.resize((size_t)c->nV);
-        OCB_TRY(upload_perm(c));
-    } else {
-        if (!Fa || !rest8 || !l2g || nVa <= 0 || nBnd < 0 || nBnd > nVa) return set_err(c, OCB_ERR_ARG, "ocb_set_air: bad argument");
-        const int nVtot = c->nV + nVa - nBnd;
+    if (nFa > 0) {      // validate everything before the context is touched
+        if (!Fa || !rest8 || !l2g || nVa <= 0 || nBnd < 0 || nBnd > nVa || nFixedAir < 0 || (nFixedAir > 0 && !fixedAir))
+            return set_err(c, OCB_ERR_ARG, "ocb_set_air: bad argument");
         for (int i = 0; i < nVa; ++i) {
             const bool ok = (i < nBnd) ? (l2g[i] >= 0 && l2g[i] < c->nV) : (l2g[i] == c->nV + i - nBnd);
             if (!ok) return set_err(c, OCB_ERR_ARG, "ocb_set_air: localVI2Global does not follow Scaffold.cpp:179-184");
         }
+        for (size_t i = 0; i < (size_t)3 * nFa; ++i) if (Fa[i] < 0 || Fa[i] >= nVa) return set_err(c, OCB_ERR_ARG, "ocb_set_air: vertex index out of range");
+        for (int i = 0; i < nFixedAir; ++i) if (fixedAir[i] < 0 || fixedAir[i] >= nVa) return set_err(c, OCB_ERR_ARG, "fixed air vertex out of range");
+    }
+    OCB_TRY(ensure_init(c));
+    c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
+    // fixed flags: the mesh's own (bit 0) survive, what a previous air mesh set (bit 1) does not
+    c->hFixed.resize((size_t)c->nV);
+    for (auto& f : c->hFixed) f &= 1;
+    if (nFa <= 0) {
+        c->nVa = c->nFa = c->nBnd = 0; c->air.n = 0; c->hFa.clear(); c->hL2G.clear(); c->wScafOverFa = 0.0;
+        c->nVtot = c->nV;
+        OCB_TRY(upload_perm(c));
+    } else {
+        const int nVtot = c->nV + nVa - nBnd;
         c->hL2G.resize((size_t)nVa);                      // air-local id -> INTERNAL global id
         for (int i = 0; i < nVa; ++i) c->hL2G[i] = i < nBnd ? c->hPerm[l2g[i]] : l2g[i];
         std::vector<int32_t> Fg((size_t)3 * nFa);
-        for (size_t i = 0; i < (size_t)3 * nFa; ++i) {
-            if (Fa[i] < 0 || Fa[i] >= nVa) return set_err(c, OCB_ERR_ARG, "ocb_set_air: vertex index out of range");
-            Fg[i] = c->hL2G[Fa[i]];
-        }
+        for (size_t i = 0; i < (size_t)3 * nFa; ++i) Fg[i] = c->hL2G[Fa[i]];
         c->nVa = nVa; c->nFa = nFa; c->nBnd = nBnd; c->nVtot = nVtot; c->wScafOverFa = wScafOverFa;
         OCB_TRY(upload_perm(c));
         OCB_TRY(upload_elems(c, c->air, c->hFa, nFa, Fg.data(), rest8));
+        OCB_TRY(upload_corner_csr(c, nVa, nFa, Fa, c->vcPtrA, c->vcIdxA));
         OCB_CUDA(c, c->l2g.reserve((size_t)nVa, c->stream));
         OCB_TRY(upload_i(c, c->l2g.p, c->hL2G.data(), (size_t)nVa));
-        // fixed: keep the mesh part, reset the air part
-        c->hFixed.resize((size_t)c->nV);
         c->hFixed.resize((size_t)nVtot, 0);
-        for (int i = 0; i < nFixedAir; ++i) {
-            if (fixedAir[i] < 0 || fixedAir[i] >= nVa) return set_err(c, OCB_ERR_ARG, "fixed air vertex out of range");
-            c->hFixed[c->hL2G[fixedAir[i]]] |= 2;
-        }
+        for (int i = 0; i < nFixedAir; ++i) c->hFixed[c->hL2G[fixedAir[i]]] |= 2;
     }
+    OCB_TRY(launch_g2l(c));
     c->hXYAir = false;                                   // the air vertices are new: their mirror entries are stale
     OCB_TRY(resize_system(c));
     OCB_TRY(upload_fixed_mask(c));
-    c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
     return OCB_OK;
 }
 
@@ -447,6 +482,7 @@ int ocb_get_uv(ocb_ctx* c, double* V, double* Va)
 {
     HostTimer _ht("get_uv");
     if (!c) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "no UV on the device"));
     const size_t nv = V ? 2 * (size_t)c->nV : 0, na = (Va && c->nVa > 0) ? 2 * (size_t)c->nVa : 0;
     OCB_CUDA(c, c->scratchD.reserve(nv + na + 2, c->stream));
@@ -462,6 +498,7 @@ int ocb_get_uv(ocb_ctx* c, double* V, double* Va)
 int ocb_save_uv(ocb_ctx* c)
 {
     if (!c) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_save_uv: no UV on the device"));
     OCB_CUDA(c, c->xSaved.reserve((size_t)c->nSys(), c->stream));
     OCB_CUDA(c, cudaMemcpyAsync(c->xSaved.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
@@ -471,6 +508,7 @@ int ocb_save_uv(ocb_ctx* c)
 int ocb_restore_uv(ocb_ctx* c)
 {
     if (!c) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->xSavedN == c->nSys() && c->xSavedN > 0, "ocb_restore_uv: no snapshot of this system size"));
     OCB_CUDA(c, cudaMemcpyAsync(c->x.p, c->xSaved.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
     c->hXYMesh = c->hXYAir = false;
@@ -505,6 +543,7 @@ int ocb_energy(ocb_ctx* c, double p0, double* E_total, double* E_sd, double* E_s
 {
     HostTimer _ht("energy");
     if (!c) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_energy: no UV"));
     OCB_TRY(launch_energy(c, p0, false, 0.0));
     OCB_TRY(fetch_scalars(c));
@@ -519,6 +558,7 @@ int ocb_energy(ocb_ctx* c, double p0, double* E_total, double* E_sd, double* E_s
 int ocb_energy_per_elem(ocb_ctx* c, int uniform, double* out)
 {
     if (!c || !out) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_energy_per_elem: no UV"));
     OCB_CUDA(c, c->scratchD.reserve((size_t)c->nF, c->stream));
     OCB_TRY(launch_energy_per_elem(c, uniform, c->scratchD.p));
@@ -531,6 +571,7 @@ int ocb_gradient(ocb_ctx* c, double p0, double* g_out, double* sqnorm)
 {
     HostTimer _ht("gradient");
     if (!c) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_gradient: no UV"));
     OCB_TRY(launch_gradient(c, p0));
     if (g_out) OCB_TRY(vec_to_host(c, g_out, c->g.p));
@@ -776,6 +817,7 @@ int ocb_hessian_assemble(ocb_ctx* c, double p0)
 {
     HostTimer _ht("hessian_assemble");
     if (!c) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_hessian_assemble: no UV"));
     OCB_TRY(need(c, c->patternValid && c->slotsValid, "ocb_hessian_assemble: no sparsity pattern (ocb_set_pattern)"));
     OCB_TRY(launch_hessian(c, p0));
@@ -787,6 +829,7 @@ int ocb_hessian_blocks(ocb_ctx* c, int uniform, double* out)
 {
     HostTimer _ht("hessian_blocks");
     if (!c || !out) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_hessian_blocks: no UV"));
     OCB_CUDA(c, c->scratchD.reserve(36 * (size_t)c->nF, c->stream));
     OCB_TRY(launch_hessian_blocks(c, uniform, c->scratchD.p));
@@ -838,6 +881,7 @@ int ocb_update_values_triplets(ocb_ctx* c, int64_t nT, const int32_t* I, const i
 {
     HostTimer _ht("update_values_triplets");
     if (!c || nT < 0 || (nT > 0 && (!I || !J || !S))) return set_err(c, OCB_ERR_ARG, "ocb_update_values_triplets: bad argument");
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->patternValid, "ocb_update_values_triplets: no sparsity pattern"));
     OCB_CUDA(c, c->scratchI.reserve(2 * (size_t)nT + 2, c->stream));
     OCB_CUDA(c, c->scratchD.reserve((size_t)nT + 1, c->stream));
@@ -854,6 +898,7 @@ int ocb_update_values_triplets(ocb_ctx* c, int64_t nT, const int32_t* I, const i
 int ocb_download_csr(ocb_ctx* c, int32_t* ia, int32_t* ja, double* a)
 {
     if (!c || !ia || !ja || !a) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_download_csr: no matrix"));
     std::vector<double> val(4 * (size_t)c->nnzb);
     OCB_CUDA(c, cudaMemcpyAsync(val.data(), c->val.p, sizeof(double) * val.size(), cudaMemcpyDeviceToHost, c->stream));
@@ -892,6 +937,7 @@ int ocb_download_csr(ocb_ctx* c, int32_t* ia, int32_t* ja, double* a)
 int ocb_multiply(ocb_ctx* c, const double* x, double* y)
 {
     if (!c || !x || !y) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_multiply: no matrix"));
     const size_t n = c->nSys();
     OCB_CUDA(c, c->scratchD.reserve(3 * n, c->stream));
@@ -909,6 +955,7 @@ int ocb_factorize(ocb_ctx* c)
 {
     HostTimer _ht("factorize");
     if (!c) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_factorize: no matrix"));
     OCB_TRY(launch_jacobi_setup(c, !c->deferFactorCheck));
     OCB_TRY(launch_mas_setup(c));
@@ -920,6 +967,7 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
 {
     HostTimer _ht("solve");
     if (!c) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_solve: no matrix"));
     if (!c->precondValid) OCB_TRY(ocb_factorize(c));
     const size_t n = c->nSys();
@@ -961,6 +1009,7 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
 int ocb_get_search_dir(ocb_ctx* c, double* p)
 {
     if (!c || !p) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(vec_to_host(c, p, c->p.p));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     return OCB_OK;
@@ -968,6 +1017,7 @@ int ocb_get_search_dir(ocb_ctx* c, double* p)
 int ocb_set_search_dir(ocb_ctx* c, const double* p)
 {
     if (!c || !p) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->nVtot > 0, "ocb_set_search_dir before the system size is known"));
     OCB_TRY(vec_to_device(c, c->p.p, p));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1020,6 +1070,7 @@ int ocb_step_bound(ocb_ctx* c, const double* dir, double* alpha)
 {
     HostTimer _ht("step_bound");
     if (!c || !alpha) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_step_bound: no UV"));
     const double* dDir = c->p.p;
     if (dir) {
@@ -1036,6 +1087,7 @@ int ocb_step_bound(ocb_ctx* c, const double* dir, double* alpha)
 int ocb_step_forward(ocb_ctx* c, double alpha)
 {
     if (!c) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_step_forward: no UV"));
     OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
     OCB_TRY(launch_step_forward(c, alpha));
@@ -1096,6 +1148,7 @@ int ocb_line_search(ocb_ctx* c, double p0, double E_last, double alpha0, int all
 {
     HostTimer _ht("line_search");
     if (!c || !out) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_line_search: no UV"));
     const bool scaf = c->nFa > 0;
     double lastScaf = 0.0;
@@ -1120,12 +1173,12 @@ int ocb_newton_step(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_tol
 {
     HostTimer _ht("newton_step");
     if (!c || !out) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     std::memset(out, 0, sizeof(*out));
     out->targetGRes = targetGRes;
     OCB_TRY(need(c, c->haveUV, "ocb_newton_step: no UV"));
     const bool scaf = c->nFa > 0;
-    OCB_TRY(launch_gradient(c, p0));
-    OCB_TRY(launch_energy(c, p0, false, 0.0));               // E_last with the current scaffold (Optimizer.cpp:588-592)
+    OCB_TRY(launch_gradient(c, p0));                         // also E_last with the current scaffold (Optimizer.cpp:588-592): one fused pass
     OCB_TRY(fetch_scalars(c));
     const double sqn = c->hScal[S_SQN_G];
     const double lastScaf = scaf ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
@@ -1161,6 +1214,7 @@ int ocb_seam_energy(ocb_ctx* c, int nCoh, const int32_t* cohE, const double* edg
                     double initSeamLen, double virtualRadius, double avgEdgeLen, int triSoup, double* E_se)
 {
     if (!c || !E_se || nCoh < 0) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_seam_energy: no UV"));
     double sum = 0.0;
     if (nCoh > 0) {
@@ -1184,6 +1238,7 @@ int ocb_seam_energy(ocb_ctx* c, int nCoh, const int32_t* cohE, const double* edg
 int ocb_divgrad_scores(ocb_ctx* c, double* out)
 {
     if (!c || !out) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_divgrad_scores: no UV"));
     OCB_CUDA(c, c->pb.reserve(2 * (size_t)c->nV, c->stream));
     OCB_TRY(launch_divgrad(c, c->pb.p));

@@ -66,6 +66,29 @@ __device__ __forceinline__ void sd_gradient(Vec2 U1, Vec2 U2, Vec2 U3, double A2
     g[2] = mk(w * ((ar * n3.x) * R + r3.x * L), w * ((ar * n3.y) * R + r3.y * L));
 }
 
+// ---- gradient w.r.t. ONE corner k (the vertex-gather assembly visits a triangle once per incident vertex) plus the
+// element value.  Same operations in the same order as sd_gradient / sd_energy, so gk is bit-identical to g[k] and E to
+// sd_energy's result: the corner's opposite-edge normal and the two coefficients of r_k = (cA v + cB u) / 2 / A^2 are
+// selected without branches (k = 1, 2 use the commuted sums  -d v + e1 u  and  e0 v + (-d) u, which round like the
+// reference's  e1 u - d v  and  e0 v - d u).
+__device__ __forceinline__ void sd_corner(Vec2 U1, Vec2 U2, Vec2 U3, double A2, double e0, double e1, double d, double w,
+                                          int k, Vec2& gk, double& E, double& dbArea)
+{
+    const Vec2 u = U2 - U1, v = U3 - U1;
+    dbArea = cross(u, v);
+    const double a = 0.5 * dbArea;
+    const double L = 1.0 + A2 / a / a;
+    const double R = (dot(v, v) * e0 + dot(u, u) * e1) / 4 / A2 - dot(v, u) * d / 2 / A2;
+    const double ar = A2 / a / a / a;
+    const Vec2 opp = (k == 0) ? (U3 - U2) : ((k == 1) ? (U1 - U3) : (U2 - U1));
+    const Vec2 n = perp(opp);
+    const double cA = (k == 0) ? (d - e0) : ((k == 1) ? -d : e0);
+    const double cB = (k == 0) ? (d - e1) : ((k == 1) ? e1 : -d);
+    const Vec2 r = mk((cA * v.x + cB * u.x) / 2.0 / A2, (cA * v.y + cB * u.y) / 2.0 / A2);
+    gk = mk(w * ((ar * n.x) * R + r.x * L), w * ((ar * n.y) * R + r.y * L));
+    E = w * L * R;
+}
+
 // ---- exact 6x6 Hessian, upper block triangle: Hb[b][i][j], b = 0:(1,1) 1:(1,2) 2:(1,3) 3:(2,2)
 // 4:(2,3) 5:(3,3); uses the precomputed k0 = |e0|^2/(2A^2), k1 = |e1|^2/(2A^2), kd = e0.e1/(2A^2)
 __device__ __forceinline__ void sd_hessian(Vec2 U1, Vec2 U2, Vec2 U3, double A2, double k0, double k1,

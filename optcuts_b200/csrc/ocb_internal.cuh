@@ -64,7 +64,7 @@ enum KernelClass {
 
 enum ScalarSlot {            // layout of the device/pinned scalar block
     S_E_MESH = 0, S_E_AIR, S_N_INVERTED, S_SQN_G, S_STEP_BOUND, S_PCG_ITERS, S_PCG_RELRES,
-    S_PCG_STATUS, S_PCG_BNORM, S_MISC0, S_MISC1, S_MISC2, S_JACOBI_BAD, S_COUNT = 16
+    S_PCG_STATUS, S_PCG_BNORM, S_MISC0, S_MISC1, S_MISC2, S_JACOBI_BAD, S_SQN_G_MESH, S_COUNT = 16
 };
 
 // MAS preconditioner: host-side hierarchy (built at pattern time) and its device mirror (ocb_mas.cu)
@@ -93,6 +93,7 @@ struct ocb_ctx {
     int device = 0;
     bool inited = false;
     bool own_stream = false;
+    bool streamGiven = false;                // ocb_set_stream was called: use that handle, NULL included (legacy default stream)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
@@ -113,6 +114,12 @@ struct ocb_ctx {
     std::vector<uint8_t> hFixed;             // per global vertex
     ocb::DevBuf<int32_t> l2g;
     ocb::DevBuf<uint8_t> fixedMask;          // nVtot
+    // vertex -> corner incidence (deterministic gather assembly: every vertex sums its incident element contributions in
+    // ascending element order, which is the order the reference's serial loops add them in, SymDirichletEnergy.cpp:264-298,
+    // LinSysSolver.hpp:147-157).  Entries are (element << 2 | corner).  Mesh list by INTERNAL vertex id; air list by
+    // air-LOCAL vertex id; g2l: internal mesh vertex -> air-local id of the air vertex aliasing it (-1: none).
+    ocb::DevBuf<int32_t> vcPtrM, vcIdxM, vcPtrA, vcIdxA, g2l;
+    ocb::DevBuf<double> hel;                 // projected element Hessians, 6 upper 2x2 blocks x (nF + nFa), block-major
 
     // state vectors, all nSys doubles (interleaved u,v per global vertex)
     ocb::DevBuf<double> x, x0, g, p;
@@ -193,6 +200,7 @@ int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha, bool alphaF
 int launch_energy_per_elem(ocb_ctx* c, int uniform, double* d_out);
 int launch_gradient(ocb_ctx* c, double p0);
 int launch_sqnorm(ocb_ctx* c, const double* v, int n, int slot);
+int launch_g2l(ocb_ctx* c);                          // mesh-vertex -> air-local alias table after a new air mesh
 int launch_build_slots(ocb_ctx* c);
 int launch_hessian(ocb_ctx* c, double p0);
 int launch_hessian_blocks(ocb_ctx* c, int uniform, double* d_out36);

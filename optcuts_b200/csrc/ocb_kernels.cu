@@ -10,6 +10,7 @@
 // therefore deterministic.
 #include "ocb_internal.cuh"
 #include "ocb_element.cuh"
+#include <algorithm>
 
 namespace ocb {
 
@@ -180,50 +181,86 @@ energy_per_elem_kernel(ElemView M, const double* __restrict__ x, double* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// a4/a13: gradient, scattered with fp64 reductions in L2 (RED.ADD.F64); the entries of fixed vertices are
-// zeroed by the norm pass that always follows (sqnorm_kernel<true>), which saves 3 mask gathers per element here
-__global__ void __launch_bounds__(kBlock, 4)
-gradient_kernel(ElemView M, ElemView A, const double* __restrict__ x, double* __restrict__ g)
+// a2/a4/a13: gradient + energy + ||g||^2 in ONE pass, assembled by a vertex gather (no atomics, no memset): the thread
+// of vertex v walks its incident corners in ascending element order -- the order in which the reference's serial loop
+// adds them (SymDirichletEnergy.cpp:264-298) -- first the mesh's, then (through g2l / the air-local numbering) the air
+// mesh's, and forms  g_v = energyParam0 * g_mesh_v + (w_scaf/|Fa|) * g_air_v  exactly like Optimizer::computeGradient
+// + Scaffold::augmentGradient (Optimizer.cpp:783-797, Scaffold.cpp:210-229).  With the element unit compiled
+// -fmad=false the gradient is therefore bit-identical to the reference's, run after run.  A triangle's value is added
+// by the thread of its corner 0, so the energy and the inversion count come out of the same pass.
+struct GatherView {
+    const int32_t* vcPtrM; const int32_t* vcIdxM;     // mesh corners by internal vertex
+    const int32_t* vcPtrA; const int32_t* vcIdxA;     // air corners by air-local vertex
+    const int32_t* g2l;                               // mesh vertex -> air-local alias or -1
+    int nV, nVtot, nBnd;
+};
+struct Slots5 { int s[5]; };
+
+template <bool AIR_SET>
+__device__ __forceinline__ void gather_corners(const ElemView& S, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, int row,
+                                               const double* __restrict__ x, Vec2& gsum, double& Esum, double& nInv)
 {
-    __shared__ ElemQueue<5> Q;
-    const int total = M.n + A.n, stride = gridDim.x * kBlock, tid = threadIdx.x;
-    int e = blockIdx.x * kBlock + tid, st = 0;
-#pragma unroll
-    for (int k = 0; k < kDepth - 1; ++k) Q.issue(M, A, e + k * stride, total, k);
-    for (; e < total; e += stride, st = (st + 1 == kDepth) ? 0 : st + 1) {
-        Q.issue(M, A, e + (kDepth - 1) * stride, total, (st + kDepth - 1) % kDepth);
-        cp_wait<kDepth - 1>();
-        const bool isAir = e >= M.n;
-        const ElemView& S = isAir ? A : M;
-        const int idx[3] = {Q.qi[st][0][tid], Q.qi[st][1][tid], Q.qi[st][2][tid]};
-        const double area = Q.qd[st][0][tid], A2 = Q.qd[st][1][tid], e0 = Q.qd[st][2][tid], e1 = Q.qd[st][3][tid], d = Q.qd[st][4][tid];
-        const Vec2 U1 = ld2(x, idx[0]), U2 = ld2(x, idx[1]), U3 = ld2(x, idx[2]);
-        const double w = S.uniform ? 1.0 : area / S.surfaceArea;
-        Vec2 gr[3];
-        sd_gradient(U1, U2, U3, A2, e0, e1, d, w, gr);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            atomicAdd(&g[2 * idx[k]], S.scale * gr[k].x);
-            atomicAdd(&g[2 * idx[k] + 1], S.scale * gr[k].y);
-        }
+    for (int q = ptr[row], qe = ptr[row + 1]; q < qe; ++q) {
+        const int code = __ldg(idx + q), t = code >> 2, k = code & 3;
+        const int i0 = __ldg(S.v0 + t), i1 = __ldg(S.v1 + t), i2 = __ldg(S.v2 + t);
+        const double area = __ldg(S.area + t), A2 = __ldg(S.areaSq + t), e0 = __ldg(S.e0 + t), e1 = __ldg(S.e1 + t), d = __ldg(S.d + t);
+        const double w = AIR_SET ? 1.0 : area / S.surfaceArea;
+        Vec2 gk; double E, dbArea;
+        sd_corner(ld2(x, i0), ld2(x, i1), ld2(x, i2), A2, e0, e1, d, w, k, gk, E, dbArea);
+        gsum.x += gk.x; gsum.y += gk.y;
+        if (k == 0) { Esum += E; if (dbArea < 0.0) nInv += 1.0; }
     }
 }
 
-template <bool MASK>
 __global__ void __launch_bounds__(kBlock)
-sqnorm_kernel(double* __restrict__ v, int n, const uint8_t* __restrict__ fixedMask, double* __restrict__ partials,
+grad_gather_kernel(ElemView M, ElemView A, GatherView G, const double* __restrict__ x, const uint8_t* __restrict__ fixedMask,
+                   double* __restrict__ g, double* __restrict__ partials, unsigned* __restrict__ ticket,
+                   double* __restrict__ scal, Slots5 slots)
+{
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // E mesh, E air, #inverted, ||g||^2, ||g_mesh||^2 (unscaled mesh term)
+    double2* g2 = reinterpret_cast<double2*>(g);
+    for (int v = blockIdx.x * kBlock + threadIdx.x; v < G.nVtot; v += gridDim.x * kBlock) {
+        Vec2 gm = mk(0.0, 0.0), ga = mk(0.0, 0.0);
+        int la = -1;
+        if (v < G.nV) {
+            gather_corners<false>(M, G.vcPtrM, G.vcIdxM, v, x, gm, acc[0], acc[2]);
+            if (A.n > 0) la = __ldg(G.g2l + v);
+        } else la = G.nBnd + (v - G.nV);
+        if (la >= 0) gather_corners<true>(A, G.vcPtrA, G.vcIdxA, la, x, ga, acc[1], acc[2]);
+        const unsigned fx = fixedMask[v];
+        // per-term masking like the reference: the mesh term zeroes the mesh's fixed vertices, the air term the air mesh's
+        if (fx & 1u) gm = mk(0.0, 0.0);
+        if (fx & 2u) ga = mk(0.0, 0.0);
+        Vec2 gv = mk(M.scale * gm.x, M.scale * gm.y);
+        if (la >= 0) { gv.x += A.scale * ga.x; gv.y += A.scale * ga.y; }
+        if (fx) gv = mk(0.0, 0.0);                // the merged fixed set (Scaffold::mergeFixedV) has no free DOF here
+        g2[v] = make_double2(gv.x, gv.y);
+        acc[3] += gv.x * gv.x; acc[3] += gv.y * gv.y;
+        acc[4] += gm.x * gm.x; acc[4] += gm.y * gm.y;
+    }
+    reduce_finalize<5, false>(acc, partials, ticket, scal, slots.s);
+}
+
+// plain ||v||^2 of a system vector (solver-side helpers)
+__global__ void __launch_bounds__(kBlock)
+sqnorm_kernel(const double* __restrict__ v, int n, double* __restrict__ partials,
               unsigned* __restrict__ ticket, double* __restrict__ scal, Slots1 slots)
 {
-    // one vertex (u, v) per thread and round
     double acc[1] = {0.0};
-    double2* v2 = reinterpret_cast<double2*>(v);
+    const double2* v2 = reinterpret_cast<const double2*>(v);
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < n / 2; i += gridDim.x * kBlock) {
-        double2 t = v2[i];
-        if (MASK && fixedMask[i]) { t.x = 0.0; t.y = 0.0; v2[i] = t; }
+        const double2 t = v2[i];
         acc[0] += t.x * t.x;
         acc[0] += t.y * t.y;
     }
     reduce_finalize<1, false>(acc, partials, ticket, scal, slots.s);
+}
+
+// vertex -> corner incidence of the air mesh is rebuilt with every new air mesh: alias table of the mesh boundary
+__global__ void __launch_bounds__(kBlock)
+g2l_set_kernel(int nBnd, const int32_t* __restrict__ l2g, int32_t* __restrict__ g2l)
+{
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < nBnd; i += gridDim.x * kBlock) g2l[l2g[i]] = i;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,35 +291,20 @@ build_slots_kernel(int n, const int32_t* __restrict__ v0, const int32_t* __restr
     }
 }
 
-// identity blocks for fixed vertices (IglUtils::addDiagonalToMatrix path, SymDirichletEnergy.cpp:541-548)
-__global__ void __launch_bounds__(kBlock)
-fixed_identity_kernel(int nVtot, const uint8_t* __restrict__ fixedMask, const int32_t* __restrict__ rowPtr,
-                      const int32_t* __restrict__ colIdx, double* __restrict__ val, double scaleMesh, double scaleAir,
-                      const int32_t* __restrict__ rowOf)
-{
-    // the identity triplets are scaled like every other triplet of their term: energyParams[e] for the mesh
-    // term (Optimizer.cpp:821-832), w_scaf/|Fa| for the air mesh (Scaffold.cpp:231-248).  mask bit 0 = fixed
-    // by the mesh, bit 1 = fixed by the air mesh.
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < nVtot; v += gridDim.x * kBlock) {
-        const unsigned m = fixedMask[v];
-        if (!m) continue;
-        const double dgn = ((m & 1u) ? scaleMesh : 0.0) + ((m & 2u) ? scaleAir : 0.0);
-        const int r = rowOf[v];
-        for (int b = rowPtr[r]; b < rowPtr[r + 1]; ++b)
-            if (colIdx[b] == r) { val[4 * (size_t)b] = dgn; val[4 * (size_t)b + 1] = 0.0; val[4 * (size_t)b + 2] = 0.0; val[4 * (size_t)b + 3] = dgn; }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// a5/a9/a11/a18: per-element Hessian, PSD projection, scatter into the BSR values.
-// One thread per element; the 6 upper blocks live in registers; each of the 9 (k,l) blocks is
-// one 32-byte sector of the value array, updated with 4 fp64 reductions.
-// queue of the Hessian pass: {v0,v1,v2}, the 9 BSR slots of the element's blocks and {area, areaSq, k0, k1, kd}, two
-// stages: the next element's 88 bytes travel while the current one is computed (~2-5k cycles), and the slot reads no
-// longer sit, one dependent load per block, between the projection and the scatter (42 % of the kernel's stall samples)
-template <bool SCATTER>
+// a5/a9/a11/a18: per-element Hessian + PSD projection, then a deterministic row gather into the BSR values.
+//
+// Pass 1 (hessian_elem_kernel, one thread per element): the 6 upper 2x2 blocks live in registers; after the projection
+// they are scaled (energyParams[0] for the mesh, w_scaf/|Fa| for the air mesh: Optimizer.cpp:821-832, Scaffold.cpp:231-248)
+// and stored block-major, hel[b][e] = one 32-byte sector per block, so a warp writes 1 KB runs.
+// Pass 2 (hessian_rows_kernel, one thread per block row = vertex): walks the vertex's incident corners in ascending
+// element order (mesh, then air) and adds row k of each element block matrix into the row's BSR blocks, accumulating in
+// shared memory; every value of the matrix is therefore the sum, in the reference's triplet order
+// (LinSysSolver::update_a, LinSysSolver.hpp:147-157), of the same addends: no atomics, no memset, bit-reproducible.
+// Fixed vertices get their identity row here (addDiagonalToMatrix, SymDirichletEnergy.cpp:541-548).
+template <bool TO_HEL>
 struct HessQueue {
-    int32_t qi[2][SCATTER ? 12 : 3][kBlock];
+    int32_t qi[2][3][kBlock];
     double qd[2][5][kBlock];
     __device__ __forceinline__ void issue(const ElemView& M, const ElemView& A, int e, int total, int st) {
         if (e < total) {
@@ -291,10 +313,6 @@ struct HessQueue {
             const int t = isAir ? e - M.n : e;
             const int tid = threadIdx.x;
             cp_async4(&qi[st][0][tid], S.v0 + t); cp_async4(&qi[st][1][tid], S.v1 + t); cp_async4(&qi[st][2][tid], S.v2 + t);
-            if (SCATTER) {
-#pragma unroll
-                for (int q = 0; q < 9; ++q) cp_async4(&qi[st][3 + q][tid], S.slot + (size_t)q * S.n + t);
-            }
             cp_async8(&qd[st][0][tid], S.area + t); cp_async8(&qd[st][1][tid], S.areaSq + t);
             cp_async8(&qd[st][2][tid], S.k0 + t); cp_async8(&qd[st][3][tid], S.k1 + t); cp_async8(&qd[st][4][tid], S.kd + t);
         }
@@ -302,13 +320,13 @@ struct HessQueue {
     }
 };
 
-template <bool SCATTER>
+template <bool TO_HEL>
 __global__ void __launch_bounds__(kBlock, 2)
-hessian_kernel(ElemView M, ElemView A, const double* __restrict__ x, double* __restrict__ val,
-               double* __restrict__ out36)
+hessian_elem_kernel(ElemView M, ElemView A, const double* __restrict__ x, double* __restrict__ hel,
+                    double* __restrict__ out36)
 {
-    __shared__ HessQueue<SCATTER> Q;
-    const int total = M.n + (SCATTER ? A.n : 0), stride = gridDim.x * kBlock, tid = threadIdx.x;
+    __shared__ HessQueue<TO_HEL> Q;
+    const int total = M.n + (TO_HEL ? A.n : 0), stride = gridDim.x * kBlock, tid = threadIdx.x;
     int e = blockIdx.x * kBlock + tid, st = 0;
     Q.issue(M, A, e, total, 0);
     for (; e < total; e += stride, st ^= 1) {
@@ -322,25 +340,14 @@ hessian_kernel(ElemView M, ElemView A, const double* __restrict__ x, double* __r
         double Hb[6][2][2];
         sd_hessian(U1, U2, U3, Q.qd[st][1][tid], Q.qd[st][2][tid], Q.qd[st][3][tid], Q.qd[st][4][tid], w, Hb);
         sd_project_psd(Hb);
-        if (SCATTER) {
+        if (TO_HEL) {
             const double sc = S.scale;
-            const int bOf[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-                for (int l = 0; l < 3; ++l) {
-                    const int s = Q.qi[st][SCATTER ? 3 + 3 * k + l : 0][tid];
-                    if (s < 0) continue;
-                    double* dst = val + 4 * (size_t)s;
-                    const int b = bOf[k][l];
-                    if (k <= l) {
-                        atomicAdd(dst + 0, sc * Hb[b][0][0]); atomicAdd(dst + 1, sc * Hb[b][0][1]);
-                        atomicAdd(dst + 2, sc * Hb[b][1][0]); atomicAdd(dst + 3, sc * Hb[b][1][1]);
-                    } else {   // transpose of the stored upper block
-                        atomicAdd(dst + 0, sc * Hb[b][0][0]); atomicAdd(dst + 1, sc * Hb[b][1][0]);
-                        atomicAdd(dst + 2, sc * Hb[b][0][1]); atomicAdd(dst + 3, sc * Hb[b][1][1]);
-                    }
-                }
+            for (int b = 0; b < 6; ++b) {
+                double2* dst = reinterpret_cast<double2*>(hel + 4 * ((size_t)b * total + e));
+                dst[0] = make_double2(sc * Hb[b][0][0], sc * Hb[b][0][1]);
+                dst[1] = make_double2(sc * Hb[b][1][0], sc * Hb[b][1][1]);
+            }
         } else {
             // dense 6x6, row-major, for parity tests against makePD
             double* o = out36 + 36 * (size_t)t;
@@ -354,6 +361,85 @@ hessian_kernel(ElemView M, ElemView A, const double* __restrict__ x, double* __r
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
                             o[(2 * k + i) * 6 + (2 * l + j)] = (k <= l) ? Hb[bOf[k][l]][i][j] : Hb[bOf[k][l]][j][i];
+        }
+    }
+}
+
+static constexpr int kRowBlock = 64;       // threads (= block rows) per CTA of the row gather
+static constexpr int kRowMaxB = 16;        // BSR blocks of a row accumulated in shared memory; longer rows go through global memory
+
+// adds row k of element e's block matrix into the accumulators of the BSR row [lo, lo + nb)
+template <bool IN_SMEM>
+__device__ __forceinline__ void row_add_elem(const double* __restrict__ hel, size_t nE, size_t e, int k, const int32_t* __restrict__ slot,
+                                             int nS, int t, int lo, double (*acc)[4][kRowBlock], double* __restrict__ val)
+{
+    const int bOf[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const int s = __ldg(slot + (size_t)(3 * k + l) * nS + t);
+        if (s < 0) continue;
+        // block (k,l): stored as is for k <= l, as the transpose of (l,k) otherwise
+        const int b = (k == 0) ? bOf[0][l] : ((k == 1) ? bOf[1][l] : bOf[2][l]);
+        const double2* src = reinterpret_cast<const double2*>(hel + 4 * ((size_t)b * nE + e));
+        const double2 r0 = __ldcg(src), r1 = __ldcg(src + 1);
+        const bool tr = k > l;
+        const double h00 = r0.x, h01 = tr ? r1.x : r0.y, h10 = tr ? r0.y : r1.x, h11 = r1.y;
+        if (IN_SMEM) {
+            const int j = s - lo, tid = threadIdx.x;
+            acc[j][0][tid] += h00; acc[j][1][tid] += h01; acc[j][2][tid] += h10; acc[j][3][tid] += h11;
+        } else {
+            double* o = val + 4 * (size_t)s;
+            o[0] += h00; o[1] += h01; o[2] += h10; o[3] += h11;
+        }
+    }
+}
+
+template <bool IN_SMEM>
+__device__ __forceinline__ void row_gather(const ElemView& M, const ElemView& A, const GatherView& G, int v, int la, const double* __restrict__ hel,
+                                           int lo, double (*acc)[4][kRowBlock], double* __restrict__ val)
+{
+    const size_t nE = (size_t)M.n + A.n;
+    if (v < G.nV)
+        for (int q = G.vcPtrM[v], qe = G.vcPtrM[v + 1]; q < qe; ++q) {
+            const int code = __ldg(G.vcIdxM + q);
+            row_add_elem<IN_SMEM>(hel, nE, (size_t)(code >> 2), code & 3, M.slot, M.n, code >> 2, lo, acc, val);
+        }
+    if (la >= 0)
+        for (int q = G.vcPtrA[la], qe = G.vcPtrA[la + 1]; q < qe; ++q) {
+            const int code = __ldg(G.vcIdxA + q);
+            row_add_elem<IN_SMEM>(hel, nE, (size_t)M.n + (code >> 2), code & 3, A.slot, A.n, code >> 2, lo, acc, val);
+        }
+}
+
+__global__ void __launch_bounds__(kRowBlock)
+hessian_rows_kernel(ElemView M, ElemView A, GatherView G, const double* __restrict__ hel, const uint8_t* __restrict__ fixedMask,
+                    const int32_t* __restrict__ rowOf, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx,
+                    double* __restrict__ val)
+{
+    __shared__ double acc[kRowMaxB][4][kRowBlock];
+    const int tid = threadIdx.x;
+    for (int v = blockIdx.x * kRowBlock + tid; v < G.nVtot; v += gridDim.x * kRowBlock) {
+        const int r = rowOf[v], lo = rowPtr[r], nb = rowPtr[r + 1] - lo;
+        const unsigned fx = fixedMask[v];
+        if (fx) {
+            // identity scaled like every other triplet of its term (mask bit 0: fixed by the mesh, bit 1: by the air mesh)
+            const double dgn = ((fx & 1u) ? M.scale : 0.0) + ((fx & 2u) ? A.scale : 0.0);
+            for (int b = lo; b < lo + nb; ++b)
+                if (colIdx[b] == r) { double2* o = reinterpret_cast<double2*>(val + 4 * (size_t)b); o[0] = make_double2(dgn, 0.0); o[1] = make_double2(0.0, dgn); }
+            continue;
+        }
+        const int la = (v < G.nV) ? (A.n > 0 ? __ldg(G.g2l + v) : -1) : G.nBnd + (v - G.nV);
+        if (nb <= kRowMaxB) {
+            for (int j = 0; j < nb; ++j) { acc[j][0][tid] = 0.0; acc[j][1][tid] = 0.0; acc[j][2][tid] = 0.0; acc[j][3][tid] = 0.0; }
+            row_gather<true>(M, A, G, v, la, hel, lo, acc, val);
+            for (int j = 0; j < nb; ++j) {
+                double2* o = reinterpret_cast<double2*>(val + 4 * (size_t)(lo + j));
+                o[0] = make_double2(acc[j][0][tid], acc[j][1][tid]); o[1] = make_double2(acc[j][2][tid], acc[j][3][tid]);
+            }
+        } else {
+            // long row (high-valence vertex): the owning thread accumulates straight in global memory, same order
+            for (int j = 0; j < 4 * nb; ++j) val[4 * (size_t)lo + j] = 0.0;
+            row_gather<false>(M, A, G, v, la, hel, lo, acc, val);
         }
     }
 }
@@ -522,37 +608,28 @@ seam_kernel(int nCoh, const int32_t* __restrict__ coh, const double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// a8: per-vertex std-dev of incident corner gradients (mesh term, area weights)
-// pass 1: sum of corner gradients + incidence count; pass 2: squared deviations; pass 3: sqrt
+// a8: per-vertex sample standard deviation of the incident corner gradients (mesh term, area weights):
+// SymDirichletEnergy::computeLocalGradient (:215-256) + computeDivGradPerVert (:108-149).  One thread per vertex, two
+// walks over its corners in ascending triangle order (mean, then squared deviations): the reference's summation
+// order, no atomics, so the candidate ordering it feeds (TriMesh.cpp:562-596) is reproducible to the bit.
 __global__ void __launch_bounds__(kBlock)
-divgrad_pass_kernel(ElemView M, const double* __restrict__ x, int pass, double* __restrict__ sum /*2 per vertex*/,
-                    double* __restrict__ cnt, double* __restrict__ dev)
+divgrad_gather_kernel(ElemView M, GatherView G, const double* __restrict__ x, double* __restrict__ out)
 {
-    for (int t = blockIdx.x * kBlock + threadIdx.x; t < M.n; t += gridDim.x * kBlock) {
-        const int idx[3] = {M.v0[t], M.v1[t], M.v2[t]};
-        const Vec2 U1 = ld2(x, idx[0]), U2 = ld2(x, idx[1]), U3 = ld2(x, idx[2]);
-        const double w = M.area[t] / M.surfaceArea;
-        Vec2 gr[3];
-        sd_gradient(U1, U2, U3, M.areaSq[t], M.e0[t], M.e1[t], M.d[t], w, gr);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (pass == 0) {
-                atomicAdd(&sum[2 * idx[k]], gr[k].x); atomicAdd(&sum[2 * idx[k] + 1], gr[k].y);
-                atomicAdd(&cnt[idx[k]], 1.0);
-            } else {
-                const double n = cnt[idx[k]];
-                const double dx = gr[k].x - sum[2 * idx[k]] / n, dy = gr[k].y - sum[2 * idx[k] + 1] / n;
-                atomicAdd(&dev[idx[k]], dx * dx + dy * dy);
+    for (int v = blockIdx.x * kBlock + threadIdx.x; v < G.nV; v += gridDim.x * kBlock) {
+        const int q0 = G.vcPtrM[v], q1 = G.vcPtrM[v + 1], n = q1 - q0;
+        double mx = 0.0, my = 0.0, dev = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int q = q0; q < q1; ++q) {
+                const int code = __ldg(G.vcIdxM + q), t = code >> 2, k = code & 3;
+                const double w = M.area[t] / M.surfaceArea;
+                Vec2 gk; double E, dbArea;
+                sd_corner(ld2(x, M.v0[t]), ld2(x, M.v1[t]), ld2(x, M.v2[t]), M.areaSq[t], M.e0[t], M.e1[t], M.d[t], w, k, gk, E, dbArea);
+                if (pass == 0) { mx += gk.x; my += gk.y; }
+                else { const double dx = gk.x - mx, dy = gk.y - my; dev += dx * dx + dy * dy; }
             }
+            if (pass == 0) { mx /= n; my /= n; }
         }
-    }
-}
-__global__ void __launch_bounds__(kBlock)
-divgrad_final_kernel(int nV, const double* __restrict__ cnt, const double* __restrict__ dev, double* __restrict__ out)
-{
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < nV; v += gridDim.x * kBlock) {
-        const double n = cnt[v];
-        out[v] = (n == 1.0 || n == 0.0) ? 0.0 : sqrt(dev[v] / (n - 1.0));
+        out[v] = (n <= 1) ? 0.0 : sqrt(dev / (n - 1.0));
     }
 }
 
@@ -600,30 +677,47 @@ int launch_energy_per_elem(ocb_ctx* c, int uniform, double* d_out)
     return 0;
 }
 
-static int launch_sqnorm_impl(ocb_ctx* c, double* v, int n, int slot, bool maskFixed)
+int launch_sqnorm(ocb_ctx* c, const double* v, int n, int slot)
 {
     if (n & 1) return set_err(c, OCB_ERR_ARG, "sqnorm: system vectors hold two entries per vertex");
     const int grid = grid_for(c, n / 2, 4);
     OCB_TRY(ensure_reduce_bufs(c, grid, 1));
     Slots1 sl; sl.s[0] = slot;
-    if (maskFixed) sqnorm_kernel<true><<<grid, kBlock, 0, c->stream>>>(v, n, c->fixedMask.p, c->partials.p, c->sync.p, c->dScal, sl);
-    else sqnorm_kernel<false><<<grid, kBlock, 0, c->stream>>>(v, n, nullptr, c->partials.p, c->sync.p, c->dScal, sl);
+    sqnorm_kernel<<<grid, kBlock, 0, c->stream>>>(v, n, c->partials.p, c->sync.p, c->dScal, sl);
     KCHECK(c);
     return 0;
 }
-int launch_sqnorm(ocb_ctx* c, const double* v, int n, int slot)
+
+static GatherView gather_of(const ocb_ctx* c)
 {
-    return launch_sqnorm_impl(c, const_cast<double*>(v), n, slot, false);
+    GatherView G;
+    G.vcPtrM = c->vcPtrM.p; G.vcIdxM = c->vcIdxM.p; G.vcPtrA = c->vcPtrA.p; G.vcIdxA = c->vcIdxA.p; G.g2l = c->g2l.p;
+    G.nV = c->nV; G.nVtot = c->nVtot; G.nBnd = c->nBnd;
+    return G;
 }
 
+// gradient + energy at x + ||g||^2 in one launch (scalars: S_E_MESH, S_E_AIR, S_N_INVERTED, S_SQN_G, S_SQN_G_MESH)
 int launch_gradient(ocb_ctx* c, double p0)
 {
     ProfScope prof(c, K_GRADIENT);
     const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
-    OCB_CUDA(c, cudaMemsetAsync(c->g.p, 0, sizeof(double) * c->nSys(), c->stream));
-    gradient_kernel<<<resident_grid<gradient_kernel>(c, (long)M.n + A.n), kBlock, 0, c->stream>>>(M, A, c->x.p, c->g.p);
+    const int grid = grid_for(c, c->nVtot, 8);
+    OCB_TRY(ensure_reduce_bufs(c, grid, 5));
+    Slots5 sl; sl.s[0] = S_E_MESH; sl.s[1] = S_E_AIR; sl.s[2] = S_N_INVERTED; sl.s[3] = S_SQN_G; sl.s[4] = S_SQN_G_MESH;
+    grad_gather_kernel<<<grid, kBlock, 0, c->stream>>>(M, A, gather_of(c), c->x.p, c->fixedMask.p, c->g.p, c->partials.p, c->sync.p, c->dScal, sl);
     KCHECK(c);
-    return launch_sqnorm_impl(c, c->g.p, c->nSys(), S_SQN_G, true);
+    return 0;
+}
+
+int launch_g2l(ocb_ctx* c)
+{
+    OCB_CUDA(c, c->g2l.reserve((size_t)c->nV + 1, c->stream));
+    OCB_CUDA(c, cudaMemsetAsync(c->g2l.p, 0xFF, sizeof(int32_t) * (size_t)c->nV, c->stream));
+    if (c->nBnd > 0) {
+        g2l_set_kernel<<<grid_for(c, c->nBnd, 1), kBlock, 0, c->stream>>>(c->nBnd, c->l2g.p, c->g2l.p);
+        KCHECK(c);
+    }
+    return 0;
 }
 
 int launch_build_slots(ocb_ctx* c)
@@ -650,10 +744,12 @@ int launch_hessian(ocb_ctx* c, double p0)
 {
     ProfScope prof(c, K_HESSIAN);
     const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
-    OCB_CUDA(c, cudaMemsetAsync(c->val.p, 0, sizeof(double) * 4 * (size_t)c->nnzb, c->stream));
-    fixed_identity_kernel<<<grid_for(c, c->nVtot, 4), kBlock, 0, c->stream>>>(c->nVtot, c->fixedMask.p, c->rowPtr.p, c->colIdx.p, c->val.p, p0, c->wScafOverFa, c->rowOf.p);
+    const size_t nE = (size_t)M.n + A.n;
+    OCB_CUDA(c, c->hel.reserve(24 * nE + 4, c->stream));
+    hessian_elem_kernel<true><<<resident_grid<hessian_elem_kernel<true>>(c, (long)nE), kBlock, 0, c->stream>>>(M, A, c->x.p, c->hel.p, nullptr);
     KCHECK(c);
-    hessian_kernel<true><<<resident_grid<hessian_kernel<true>>(c, (long)M.n + A.n), kBlock, 0, c->stream>>>(M, A, c->x.p, c->val.p, nullptr);
+    const int grid = (int)std::min<long>(((long)c->nVtot + kRowBlock - 1) / kRowBlock, (long)c->numSMs * 16);
+    hessian_rows_kernel<<<grid < 1 ? 1 : grid, kRowBlock, 0, c->stream>>>(M, A, gather_of(c), c->hel.p, c->fixedMask.p, c->rowOf.p, c->rowPtr.p, c->colIdx.p, c->val.p);
     KCHECK(c);
     return 0;
 }
@@ -663,7 +759,7 @@ int launch_hessian_blocks(ocb_ctx* c, int uniform, double* d_out36)
     ProfScope prof(c, K_HESSIAN);
     const ElemView M = view_of(c, c->mesh, false, 1.0, uniform);
     ElemView A = M; A.n = 0;
-    hessian_kernel<false><<<resident_grid<hessian_kernel<false>>(c, M.n), kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, d_out36);
+    hessian_elem_kernel<false><<<resident_grid<hessian_elem_kernel<false>>(c, M.n), kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, d_out36);
     KCHECK(c);
     return 0;
 }
@@ -763,14 +859,8 @@ int launch_divgrad(ocb_ctx* c, double* d_out)
 {
     ProfScope prof(c, K_MISC);
     const ElemView M = view_of(c, c->mesh, false, 1.0, 0);
-    const size_t nV = c->nV;
-    OCB_CUDA(c, c->scratchD.reserve(4 * nV, c->stream));
-    double* sum = c->scratchD.p; double* cnt = sum + 2 * nV; double* dev = cnt + nV;
-    OCB_CUDA(c, cudaMemsetAsync(sum, 0, sizeof(double) * 4 * nV, c->stream));
-    const int grid = grid_for(c, M.n);
-    divgrad_pass_kernel<<<grid, kBlock, 0, c->stream>>>(M, c->x.p, 0, sum, cnt, dev); KCHECK(c);
-    divgrad_pass_kernel<<<grid, kBlock, 0, c->stream>>>(M, c->x.p, 1, sum, cnt, dev); KCHECK(c);
-    divgrad_final_kernel<<<grid_for(c, c->nV, 4), kBlock, 0, c->stream>>>(c->nV, cnt, dev, d_out); KCHECK(c);
+    divgrad_gather_kernel<<<grid_for(c, c->nV, 8), kBlock, 0, c->stream>>>(M, gather_of(c), c->x.p, d_out);
+    KCHECK(c);
     return 0;
 }
 

@@ -378,87 +378,108 @@ __device__ __forceinline__ int find_col(const int32_t* __restrict__ colIdx, int 
     return -1;
 }
 
-// A_1 = P_1^T A P_1 on the leaf adjacency: 8 threads per fine block row (one block each, rows are ~7 blocks long)
+// A_1 = P_1^T A P_1 on the leaf adjacency, as a GATHER: 8 lanes per leaf row, lane q owns the leaf blocks q, q + 8, ...
+// of that row and sums, over the leaf's fine rows in ascending order and their blocks in stored order, the contributions
+// that fall into its block.  36 register accumulators, one plain store: no atomics and no memset, so the preconditioner
+// (and with it the CG iteration count and the search direction) is reproducible to the bit.
 __global__ void __launch_bounds__(256)
-mas_galerkin_fine_kernel(int nRows, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, const double* __restrict__ val,
-                         const float4* __restrict__ vinfo, const int32_t* __restrict__ rowPtr1, const int32_t* __restrict__ colIdx1,
-                         double* __restrict__ val1)
+mas_galerkin_fine_kernel(int nLeaves, const int32_t* __restrict__ childBeg, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx,
+                         const double* __restrict__ val, const float4* __restrict__ vinfo, const int32_t* __restrict__ rowPtr1,
+                         const int32_t* __restrict__ colIdx1, double* __restrict__ val1)
 {
-    for (long w = blockIdx.x * 256L + threadIdx.x; w < 8L * nRows; w += gridDim.x * 256L) {
-        const int i = (int)(w >> 3), k8 = (int)(w & 7);
-        const float4 vi = vinfo[i];
-        if (vi.x == 0.0f) continue;
-        const int a = __float_as_int(vi.w);
-        const double fi[3] = {mas_unpack(vi.x), mas_unpack(vi.y), mas_unpack(vi.z)};
-        const int lo1 = rowPtr1[a], hi1 = rowPtr1[a + 1];
-        for (int b = rowPtr[i] + k8; b < rowPtr[i + 1]; b += 8) {
-            const int j = colIdx[b];
-            const float4 vj = vinfo[j];
-            if (vj.x == 0.0f) continue;
-            const int s = find_col(colIdx1, lo1, hi1, __float_as_int(vj.w));
-            if (s < 0) continue;
-            const double fj[3] = {mas_unpack(vj.x), mas_unpack(vj.y), mas_unpack(vj.z)};
-            const double A[2][2] = {{val[4 * (size_t)b], val[4 * (size_t)b + 1]}, {val[4 * (size_t)b + 2], val[4 * (size_t)b + 3]}};
-            double* o = val1 + 36 * (size_t)s;
+    const float* vleaf = reinterpret_cast<const float*>(vinfo);
+    for (long w = blockIdx.x * 256L + threadIdx.x; w < 8L * nLeaves; w += gridDim.x * 256L) {
+        const int a = (int)(w >> 3), k8 = (int)(w & 7);
+        const int r0 = childBeg[a], r1 = childBeg[a + 1];
+        for (int s = rowPtr1[a] + k8; s < rowPtr1[a + 1]; s += 8) {
+            const int a2 = colIdx1[s];
+            double acc[36];
 #pragma unroll
-            for (int ci = 0; ci < 2; ++ci)
+            for (int q = 0; q < 36; ++q) acc[q] = 0.0;
+            for (int i = r0; i < r1; ++i) {
+                const float4 vi = vinfo[i];
+                if (vi.x == 0.0f) continue;
+                const double fi[3] = {mas_unpack(vi.x), mas_unpack(vi.y), mas_unpack(vi.z)};
+                for (int b = rowPtr[i], be = rowPtr[i + 1]; b < be; ++b) {
+                    const int j = colIdx[b];
+                    if (__float_as_int(vleaf[4 * (size_t)j + 3]) != a2) continue;
+                    const float4 vj = vinfo[j];
+                    if (vj.x == 0.0f) continue;
+                    const double fj[3] = {mas_unpack(vj.x), mas_unpack(vj.y), mas_unpack(vj.z)};
+                    const double2 A0 = *reinterpret_cast<const double2*>(val + 4 * (size_t)b), A1 = *reinterpret_cast<const double2*>(val + 4 * (size_t)b + 2);
+                    const double A[2][2] = {{A0.x, A0.y}, {A1.x, A1.y}};
 #pragma unroll
-                for (int qi = 0; qi < 3; ++qi)
+                    for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
-                    for (int cj = 0; cj < 2; ++cj)
+                        for (int qi = 0; qi < 3; ++qi)
 #pragma unroll
-                        for (int qj = 0; qj < 3; ++qj)
-                            atomicAdd(o + (ci * 3 + qi) * 6 + cj * 3 + qj, fi[qi] * A[ci][cj] * fj[qj]);
+                            for (int cj = 0; cj < 2; ++cj)
+#pragma unroll
+                                for (int qj = 0; qj < 3; ++qj)
+                                    acc[(ci * 3 + qi) * 6 + cj * 3 + qj] += fi[qi] * A[ci][cj] * fj[qj];
+                }
+            }
+            double2* o = reinterpret_cast<double2*>(val1 + 36 * (size_t)s);
+#pragma unroll
+            for (int q = 0; q < 18; ++q) o[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
         }
     }
 }
 
-// A_{l+1} = R A_l R^T: 16 threads per node row of level l (one 6x6 block each)
+// A_{l+1} = R A_l R^T, gathered the same way: 8 lanes per node row of level l + 1, lane q owns the blocks q, q + 8, ... and
+// sums R_a S R_b^T over the children a of its row (ascending) and their blocks (stored order) whose column's parent is its column
 __global__ void __launch_bounds__(128)
-mas_coarsen_kernel(int nNodes, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, const double* __restrict__ val,
-                   const int32_t* __restrict__ parent, const double4* __restrict__ geom, const double4* __restrict__ geomUp,
-                   const int32_t* __restrict__ rowPtrUp, const int32_t* __restrict__ colIdxUp, double* __restrict__ valUp)
+mas_coarsen_kernel(int nUp, const int32_t* __restrict__ groupBeg, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx,
+                   const double* __restrict__ val, const int32_t* __restrict__ parent, const double4* __restrict__ geom,
+                   const double4* __restrict__ geomUp, const int32_t* __restrict__ rowPtrUp, const int32_t* __restrict__ colIdxUp,
+                   double* __restrict__ valUp)
 {
-    for (long w = blockIdx.x * 128L + threadIdx.x; w < 16L * nNodes; w += gridDim.x * 128L) {
-        const int a = (int)(w >> 4), k16 = (int)(w & 15);
-        const int pa = parent[a];
-        const double4 ga = geom[a], gpa = geomUp[pa];
+    for (long w = blockIdx.x * 128L + threadIdx.x; w < 8L * nUp; w += gridDim.x * 128L) {
+        const int pa = (int)(w >> 3), k8 = (int)(w & 7);
+        const int c0 = groupBeg[pa], c1 = groupBeg[pa + 1];
+        const double4 gpa = geomUp[pa];
         const double isa = 1.0 / gpa.z;
-        const double Ra[3][3] = {{1.0, 0.0, 0.0}, {(ga.x - gpa.x) * isa, ga.z * isa, 0.0}, {(ga.y - gpa.y) * isa, 0.0, ga.z * isa}};
-        const int lo = rowPtrUp[pa], hi = rowPtrUp[pa + 1];
-        for (int blk = rowPtr[a] + k16; blk < rowPtr[a + 1]; blk += 16) {
-            const int b = colIdx[blk];
-            const int pb = parent[b];
-            const int s = find_col(colIdxUp, lo, hi, pb);
-            if (s < 0) continue;
-            const double4 gb = geom[b], gpb = geomUp[pb];
+        for (int s = rowPtrUp[pa] + k8; s < rowPtrUp[pa + 1]; s += 8) {
+            const int pb = colIdxUp[s];
+            const double4 gpb = geomUp[pb];
             const double isb = 1.0 / gpb.z;
-            const double Rb[3][3] = {{1.0, 0.0, 0.0}, {(gb.x - gpb.x) * isb, gb.z * isb, 0.0}, {(gb.y - gpb.y) * isb, 0.0, gb.z * isb}};
-            const double* M = val + 36 * (size_t)blk;
-            double* o = valUp + 36 * (size_t)s;
+            double acc[36];
 #pragma unroll
-            for (int ci = 0; ci < 2; ++ci)
+            for (int q = 0; q < 36; ++q) acc[q] = 0.0;
+            for (int a = c0; a < c1; ++a) {
+                const double4 ga = geom[a];
+                const double Ra10 = (ga.x - gpa.x) * isa, Ra11 = ga.z * isa, Ra20 = (ga.y - gpa.y) * isa, Ra22 = ga.z * isa;
+                for (int blk = rowPtr[a], be = rowPtr[a + 1]; blk < be; ++blk) {
+                    const int b = colIdx[blk];
+                    if (parent[b] != pb) continue;
+                    const double4 gb = geom[b];
+                    const double Rb10 = (gb.x - gpb.x) * isb, Rb11 = gb.z * isb, Rb20 = (gb.y - gpb.y) * isb, Rb22 = gb.z * isb;
+                    const double* M = val + 36 * (size_t)blk;
 #pragma unroll
-                for (int cj = 0; cj < 2; ++cj) {
-                    double S[3][3], T[3][3];
+                    for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
-                    for (int i = 0; i < 3; ++i)
+                        for (int cj = 0; cj < 2; ++cj) {
+                            double T[3][3];
+                            // T = S Rb^T
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) S[i][j] = M[(ci * 3 + i) * 6 + cj * 3 + j];
-                    // T = S Rb^T
+                            for (int i = 0; i < 3; ++i) {
+                                const double S0 = M[(ci * 3 + i) * 6 + cj * 3], S1 = M[(ci * 3 + i) * 6 + cj * 3 + 1], S2 = M[(ci * 3 + i) * 6 + cj * 3 + 2];
+                                T[i][0] = S0;
+                                T[i][1] = S0 * Rb10 + S1 * Rb11;
+                                T[i][2] = S0 * Rb20 + S2 * Rb22;
+                            }
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        T[i][0] = S[i][0];
-                        T[i][1] = S[i][0] * Rb[1][0] + S[i][1] * Rb[1][1];
-                        T[i][2] = S[i][0] * Rb[2][0] + S[i][2] * Rb[2][2];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        atomicAdd(o + (ci * 3 + 0) * 6 + cj * 3 + j, T[0][j]);
-                        atomicAdd(o + (ci * 3 + 1) * 6 + cj * 3 + j, Ra[1][0] * T[0][j] + Ra[1][1] * T[1][j]);
-                        atomicAdd(o + (ci * 3 + 2) * 6 + cj * 3 + j, Ra[2][0] * T[0][j] + Ra[2][2] * T[2][j]);
-                    }
+                            for (int j = 0; j < 3; ++j) {
+                                acc[(ci * 3 + 0) * 6 + cj * 3 + j] += T[0][j];
+                                acc[(ci * 3 + 1) * 6 + cj * 3 + j] += Ra10 * T[0][j] + Ra11 * T[1][j];
+                                acc[(ci * 3 + 2) * 6 + cj * 3 + j] += Ra20 * T[0][j] + Ra22 * T[2][j];
+                            }
+                        }
                 }
+            }
+            double2* o = reinterpret_cast<double2*>(valUp + 36 * (size_t)s);
+#pragma unroll
+            for (int q = 0; q < 18; ++q) o[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
         }
     }
 }
@@ -787,15 +808,18 @@ int launch_mas_setup(ocb_ctx* c)
     MasDev& D = c->masD;
     if (!H.enabled) return 0;
     ProfScope prof(c, K_MAS_SETUP);
-    OCB_CUDA(c, cudaMemsetAsync(D.val.p, 0, D.valTotal * sizeof(double), c->stream));
-    const int n = c->nVtot;
-    int grid = (int)((8L * n + 255) / 256); if (grid > c->numSMs * 16) grid = c->numSMs * 16; if (grid < 1) grid = 1;
-    mas_galerkin_fine_kernel<<<grid, 256, 0, c->stream>>>(n, c->rowPtr.p, c->colIdx.p, c->val.p, reinterpret_cast<const float4*>(D.vinfo.p), D.lvRowPtr[0], D.lvColIdx[0], D.lvVal[0]);
-    KCHECK(c);
+    {   // every block of every level is written by exactly one thread (gather): no memset
+        const MasLevel& V1 = D.lv[0];
+        int grid = (int)((8L * V1.nNodes + 255) / 256); if (grid > c->numSMs * 16) grid = c->numSMs * 16; if (grid < 1) grid = 1;
+        mas_galerkin_fine_kernel<<<grid, 256, 0, c->stream>>>(V1.nNodes, V1.childBeg, c->rowPtr.p, c->colIdx.p, c->val.p, reinterpret_cast<const float4*>(D.vinfo.p),
+                                                             D.lvRowPtr[0], D.lvColIdx[0], D.lvVal[0]);
+        KCHECK(c);
+    }
     for (int l = 1; l < H.L; ++l) {
         const MasLevel& V = D.lv[l - 1];
-        int g = (int)((16L * V.nNodes + 127) / 128); if (g > c->numSMs * 16) g = c->numSMs * 16; if (g < 1) g = 1;
-        mas_coarsen_kernel<<<g, 128, 0, c->stream>>>(V.nNodes, D.lvRowPtr[l - 1], D.lvColIdx[l - 1], D.lvVal[l - 1], V.parent, V.geom,
+        const int nUp = D.lv[l].nNodes;
+        int g = (int)((8L * nUp + 127) / 128); if (g > c->numSMs * 16) g = c->numSMs * 16; if (g < 1) g = 1;
+        mas_coarsen_kernel<<<g, 128, 0, c->stream>>>(nUp, V.groupBeg, D.lvRowPtr[l - 1], D.lvColIdx[l - 1], D.lvVal[l - 1], V.parent, V.geom,
                                                     D.lv[l].geom, D.lvRowPtr[l], D.lvColIdx[l], D.lvVal[l]);
         KCHECK(c);
     }

@@ -3,6 +3,7 @@
 // tests/test_element_math_host.py into a scratch directory; never shipped, never imported by the package.
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #define __device__
 #define __forceinline__ inline
 #define __ldg(p) (*(p))
@@ -68,6 +69,66 @@ void host_project_psd(int n, double* H36, int* clamped)
         if (clamped) clamped[t] = c;
         for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j)
             H[(2 * k + i) * 6 + 2 * l + j] = (k <= l) ? Hb[bOf[k][l]][i][j] : Hb[bOf[k][l]][j][i];
+    }
+}
+// the vertex-gather gradient of grad_gather_kernel (ocb_kernels.cu), restated for the host with the SAME element function
+// (sd_corner) and the same order: per vertex, incident corners in ascending triangle order.  Per-corner values vs the
+// per-triangle function (sd_gradient): returns the number of corners whose bits differ.
+long host_corner_vs_triangle(int nV, int nF, const int32_t* F, const double* UV, const double* rest8, double surf, int uniform)
+{
+    long bad = 0;
+    for (int t = 0; t < nF; ++t) {
+        const int i0 = F[t], i1 = F[nF + t], i2 = F[2 * nF + t];
+        const Vec2 U1 = mk(UV[i0], UV[nV + i0]), U2 = mk(UV[i1], UV[nV + i1]), U3 = mk(UV[i2], UV[nV + i2]);
+        const double w = uniform ? 1.0 : rest8[t] / surf;
+        Vec2 g[3];
+        sd_gradient(U1, U2, U3, rest8[nF + t], rest8[2 * nF + t], rest8[3 * nF + t], rest8[4 * nF + t], w, g);
+        double db0;
+        const double E0 = sd_energy(U2 - U1, U3 - U1, rest8[nF + t], rest8[2 * nF + t], rest8[3 * nF + t], rest8[4 * nF + t], w, db0);
+        for (int k = 0; k < 3; ++k) {
+            Vec2 gk; double E, db;
+            sd_corner(U1, U2, U3, rest8[nF + t], rest8[2 * nF + t], rest8[3 * nF + t], rest8[4 * nF + t], w, k, gk, E, db);
+            if (std::memcmp(&gk.x, &g[k].x, 8) || std::memcmp(&gk.y, &g[k].y, 8) || std::memcmp(&E, &E0, 8) || std::memcmp(&db, &db0, 8)) ++bad;
+        }
+    }
+    return bad;
+}
+// out: 2 * nV (interleaved), sums in ascending triangle order per vertex, unscaled, fixed vertices NOT masked
+void host_gather_gradient(int nV, int nF, const int32_t* F, const double* UV, const double* rest8, double surf, int uniform, double* out)
+{
+    for (int v = 0; v < 2 * nV; ++v) out[v] = 0.0;
+    for (int t = 0; t < nF; ++t) {       // ascending t per vertex == the order a vertex's corner list is walked in
+        const int i0 = F[t], i1 = F[nF + t], i2 = F[2 * nF + t];
+        const int idx[3] = {i0, i1, i2};
+        const Vec2 U1 = mk(UV[i0], UV[nV + i0]), U2 = mk(UV[i1], UV[nV + i1]), U3 = mk(UV[i2], UV[nV + i2]);
+        const double w = uniform ? 1.0 : rest8[t] / surf;
+        for (int k = 0; k < 3; ++k) {
+            Vec2 gk; double E, db;
+            sd_corner(U1, U2, U3, rest8[nF + t], rest8[2 * nF + t], rest8[3 * nF + t], rest8[4 * nF + t], w, k, gk, E, db);
+            out[2 * idx[k]] += gk.x; out[2 * idx[k] + 1] += gk.y;
+        }
+    }
+}
+// divgrad_gather_kernel restated for the host (same element function, same two walks per vertex)
+void host_divgrad(int nV, int nF, const int32_t* F, const double* UV, const double* rest8, double surf, double* out)
+{
+    for (int v = 0; v < nV; ++v) {
+        double mx = 0.0, my = 0.0, dev = 0.0; int n = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            n = 0;
+            for (int t = 0; t < nF; ++t) for (int k = 0; k < 3; ++k) {
+                if (F[k * nF + t] != v) continue;
+                ++n;
+                const int i0 = F[t], i1 = F[nF + t], i2 = F[2 * nF + t];
+                Vec2 gk; double E, db;
+                sd_corner(mk(UV[i0], UV[nV + i0]), mk(UV[i1], UV[nV + i1]), mk(UV[i2], UV[nV + i2]), rest8[nF + t], rest8[2 * nF + t], rest8[3 * nF + t],
+                          rest8[4 * nF + t], rest8[t] / surf, k, gk, E, db);
+                if (pass == 0) { mx += gk.x; my += gk.y; }
+                else { const double dx = gk.x - mx, dy = gk.y - my; dev += dx * dx + dy * dy; }
+            }
+            if (pass == 0) { mx /= n; my /= n; }
+        }
+        out[v] = (n <= 1) ? 0.0 : sqrt(dev / (n - 1.0));
     }
 }
 double host_step_bound(int nV, int nF, const int32_t* F, const double* UV, const double* dir /*interleaved*/, double alpha0)

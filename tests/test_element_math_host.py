@@ -44,6 +44,47 @@ def test_energy_and_gradient_bit_exact(host, port, state):
     assert relerr(g, port.gradient(F, UV, rest8, state.surfaceArea, fixed=state.fixed)) < 1e-14
 
 
+def test_gather_gradient_is_bit_identical_to_the_reference(host, state):
+    """The vertex-gather assembly (grad_gather_kernel) sums, per vertex, the corner gradients in ascending triangle order
+    and combines  energyParam0 * g_mesh + w_scaf/|Fa| * g_air  like Optimizer::computeGradient + Scaffold::augmentGradient:
+    restated on the host with the product's own element function it reproduces the gradient recorded from the reference
+    BIT FOR BIT (mesh + air mesh, both golden states)."""
+    F, UV, rest8, a = _args(state.F, state.UV, state.rest8)
+    host.host_corner_vs_triangle.restype = C.c_long
+    assert host.host_corner_vs_triangle(*a, C.c_double(state.surfaceArea), 0) == 0
+    gm = np.zeros(2 * state.nV)
+    host.host_gather_gradient(*a, C.c_double(state.surfaceArea), 0, gm.ctypes.data_as(_d))
+    gm[2 * state.fixed] = 0
+    gm[2 * state.fixed + 1] = 0
+    air = state.air
+    Fa, Va, r8a, aa = _args(air["F"], air["V"], air["rest8"])
+    ga = np.zeros(2 * Va.shape[0])
+    host.host_gather_gradient(*aa, C.c_double(1.0), 1, ga.ctypes.data_as(_d))
+    w = state.w_scaf / Fa.shape[0]
+    nB, nVa = air["nBnd"], Va.shape[0]
+    g = np.zeros(2 * (state.nV + nVa - nB))
+    g[:2 * state.nV] = state.p0 * gm
+    l2g = air["localVI2Global"]
+    for i in range(nB):
+        g[2 * l2g[i]] += w * ga[2 * i]
+        g[2 * l2g[i] + 1] += w * ga[2 * i + 1]
+    g[2 * state.nV:] = w * ga[2 * nB:]
+    ref = state.r("gradient")
+    assert g.shape == ref.shape
+    assert np.array_equal(g, ref), "max abs diff %g" % np.max(np.abs(g - ref))
+
+
+def test_divgrad_gather_is_bit_identical_to_the_port(host, port):
+    """divgrad_gather_kernel's arithmetic (per vertex: mean of the incident corner gradients, then squared deviations, both in
+    ascending triangle order) against the oracle's restatement of computeLocalGradient + computeDivGradPerVert."""
+    V_rest, F, UV = random_mesh(5, n=12)
+    rest8, sc, _ = port.rest_features(V_rest, F)
+    F, UV, rest8, a = _args(F, UV, rest8)
+    out = np.zeros(UV.shape[0])
+    host.host_divgrad(*a, C.c_double(sc["surfaceArea"]), out.ctypes.data_as(_d))
+    assert np.array_equal(out, port.divgrad(F, UV, rest8, sc["surfaceArea"]))
+
+
 def test_hessian_projection_matches_makePD(host, port, state):
     """closed-form 4x4 projection in the translation-free basis == eigen-clamp of the 6x6"""
     F, UV, rest8, a = _args(state.F, state.UV, state.rest8)

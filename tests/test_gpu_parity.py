@@ -67,6 +67,9 @@ def test_gradient(ctx, state):
     state.upload(ctx)
     g, sq = ctx.gradient(state.p0)
     assert relerr(g, state.r("gradient")) < 1e-13
+    # the vertex gather adds the corner gradients in the reference's order (ascending triangle index, mesh term then
+    # the scaffold's) with the reference's operations: the result is the SAME doubles, not merely close ones
+    assert np.array_equal(g, state.r("gradient")), "max abs diff %g" % np.max(np.abs(g - state.r("gradient")))
     assert abs(sq - float(state.r("sqn_g"))) <= 1e-12 * sq
     assert np.all(g[2 * state.fixed] == 0) and np.all(g[2 * state.fixed + 1] == 0)
 
