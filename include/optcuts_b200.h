@@ -17,7 +17,9 @@
  *  - matrices are column-major exactly as Eigen hands them over (MatrixXd V: all u then all v;
  *    MatrixXi F: |F|x3 col-major); gradient / search direction / solver vectors are interleaved
  *    [u0 v0 u1 v1 ...] (Optimizer.cpp:666-668, SymDirichletEnergy.cpp:287).
- *  - indices are int32, scalars IEEE fp64.  Nothing here uses tensor cores.
+ *  - indices are int32, scalars IEEE fp64.  The one dense contraction on the path (the exact inverse of the coarse
+ *    Galerkin matrix of the preconditioner) runs on the FP64 tensor cores (mma.sync m8n8k4); everything else is CUDA-core
+ *    streaming work.
  *  - one CUDA stream per context; distinct contexts may be used from distinct threads.
  *  - ocb_create does no CUDA work beyond selecting the device lazily on first upload, so the C++
  *    shim objects are cheap to construct (nested optimizers create thousands: SURVEY H7).
@@ -144,10 +146,12 @@ int ocb_download_csr(ocb_ctx* ctx, int32_t* ia, int32_t* ja, double* a);
 int ocb_multiply(ocb_ctx* ctx, const double* x, double* y);
 
 /* ---- a12: solve — EigenLibSolver::analyze_pattern/factorize/solve (EigenLibSolver.cpp:71-107),
- * replaced by block-Jacobi PCG (persistent cooperative kernel).  rhs==NULL solves A x = -gradient
+ * replaced by a preconditioned CG in one persistent cooperative kernel (two-level additive Schwarz: 8-vertex leaves along
+ * a Hilbert curve through the UVs, affine coarse spaces, exact dense coarse inverse; 2x2 block-Jacobi when no geometry is
+ * known).  rhs==NULL solves A x = -gradient
  * (Optimizer.cpp:557-563) with the gradient left on the device by ocb_gradient; the solution stays
  * on the device as the search direction; x_out may be NULL.  rel_tol <= 0 -> 1e-12, max_it <= 0 -> 20*n */
-int ocb_factorize(ocb_ctx* ctx);   /* builds the block-Jacobi preconditioner; OCB_ERR_BREAKDOWN if a diagonal block is not SPD */
+int ocb_factorize(ocb_ctx* ctx);   /* builds the preconditioner (Galerkin products, group inverses, coarse inverse); OCB_ERR_BREAKDOWN if a diagonal 2x2 block is not SPD */
 int ocb_solve(ocb_ctx* ctx, const double* rhs, double* x_out, double rel_tol, int max_it,
               int* iters, double* rel_res);
 int ocb_get_search_dir(ocb_ctx* ctx, double* p_out);
@@ -174,13 +178,31 @@ int ocb_line_search(ocb_ctx* ctx, double energyParam0, double E_last, double alp
 int ocb_step_forward(ocb_ctx* ctx, double alpha);
 
 /* ---- one whole Newton iteration of Optimizer::solve(1) (Optimizer.cpp:203-261, 505-573):
- * gradient -> convergence test -> Hessian -> PCG -> step bound -> line search, device resident. */
+ * gradient (+ energy at x, same pass) -> convergence test -> Hessian -> preconditioner -> PCG -> step bound -> line
+ * search, device resident, three host round trips.  ocb_newton_step_ex lets the host program's own control flow keep
+ * the parts it already did:
+ *   OCB_STEP_REUSE_GRADIENT        ocb_gradient ran at this x with this energyParam0 (Optimizer::solve computes the
+ *                                  gradient and tests convergence itself, Optimizer.cpp:209-221)
+ *   OCB_STEP_REUSE_MATRIX          ocb_hessian_assemble ran at this x (fractureInitiated: the topology step assembled
+ *                                  the matrix for the Newton step that follows it, Optimizer.cpp:428, 512-514, 567)
+ *   OCB_STEP_SKIP_CONVERGENCE_TEST the caller has tested ||g||^2 < targetGRes already
+ * ms_solve / ms_line_search: host wall clock of {assembly, set-up, PCG} and {step bound, line search} (the reference's
+ * timer_step activities 0-4 and 5). */
+#define OCB_STEP_REUSE_GRADIENT 1
+#define OCB_STEP_REUSE_MATRIX 2
+#define OCB_STEP_SKIP_CONVERGENCE_TEST 4
 typedef struct {
     double sqn_g, targetGRes, alpha, E_new, E_scaf_new, E_sd_new, lastEDec, pcg_rel_res;
     int converged, stopped, n_halvings, pcg_iters;
+    double alpha_init, E_last, ms_solve, ms_line_search;
 } ocb_newton_result;
 int ocb_newton_step(ocb_ctx* ctx, double energyParam0, double targetGRes, double pcg_rel_tol,
                     int pcg_max_it, int allowEDecRelTol, ocb_newton_result* out);
+int ocb_newton_step_ex(ocb_ctx* ctx, double energyParam0, double targetGRes, double pcg_rel_tol,
+                       int pcg_max_it, int allowEDecRelTol, int flags, ocb_newton_result* out);
+/* what the last gradient pass left besides g: ||g||^2, ||g_mesh||^2 (the unscaled mesh term, gradient_ET[0] of
+ * Optimizer::writeGradL2NormToFile), E_sd and E_scaf at x.  OCB_ERR_STATE when x moved since. */
+int ocb_gradient_info(ocb_ctx* ctx, double* info4);
 
 /* ---- a15: seam energy — TriMesh::computeSeamSparsity (TriMesh.cpp:1542-1558); returns
  * (sum + initSeamLen) / virtualRadius in *E_se (Optimizer.cpp:709-710). */
@@ -219,8 +241,8 @@ int ocb_eval_stencils(ocb_ctx* ctx, const ocb_stencil_batch* batch, int maxIter,
                       int32_t* status, int* argmax);
 
 /* ---- a12 (solver set-up): the multilevel additive Schwarz preconditioner that replaces the numeric
- * factorisation (EigenLibSolver.cpp:80-93) is rebuilt by ocb_factorize; its hierarchy (row order by recursive
- * coordinate bisection of the UVs, leaves of <= 8 vertices, groups of 8, 6 affine DOFs per node) is built with
+ * factorisation (EigenLibSolver.cpp:80-93) is rebuilt by ocb_factorize; its hierarchy (row order along a Hilbert curve
+ * through the UVs, leaves of <= 8 vertices, groups of 8, 6 affine DOFs per node) is built with
  * the sparsity pattern.  info[0] = 1 if active (0: block-Jacobi only, no UV was known at pattern time),
  * info[1] = levels L, info[2] = CTA-local levels, info[3] = persistent CTAs, info[4..4+L) = nodes per level,
  * info[15] = solves that were repeated with block-Jacobi because the preconditioner came out indefinite. */

@@ -37,7 +37,8 @@ class NewtonResult(C.Structure):
     _fields_ = [("sqn_g", C.c_double), ("targetGRes", C.c_double), ("alpha", C.c_double), ("E_new", C.c_double),
                 ("E_scaf_new", C.c_double), ("E_sd_new", C.c_double), ("lastEDec", C.c_double),
                 ("pcg_rel_res", C.c_double), ("converged", C.c_int), ("stopped", C.c_int),
-                ("n_halvings", C.c_int), ("pcg_iters", C.c_int)]
+                ("n_halvings", C.c_int), ("pcg_iters", C.c_int),
+                ("alpha_init", C.c_double), ("E_last", C.c_double), ("ms_solve", C.c_double), ("ms_line_search", C.c_double)]
 
 
 class StencilBatch(C.Structure):
@@ -92,6 +93,8 @@ _SIGS = [
     ("ocb_line_search", C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(LineSearchResult)]),
     ("ocb_step_forward", C.c_int, [C.c_void_p, C.c_double]),
     ("ocb_newton_step", C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(NewtonResult)]),
+    ("ocb_newton_step_ex", C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(NewtonResult)]),
+    ("ocb_gradient_info", C.c_int, [C.c_void_p, _d]),
     ("ocb_seam_energy", C.c_int, [C.c_void_p, C.c_int, _i, _d, _i, C.c_double, C.c_double, C.c_double, C.c_int, _d]),
     ("ocb_divgrad_scores", C.c_int, [C.c_void_p, _d]),
     ("ocb_eval_stencils", C.c_int, [C.c_void_p, C.POINTER(StencilBatch), C.c_int, C.c_double, _d, _d, _d, _i, _d, _i, C.POINTER(C.c_int)]),
@@ -374,10 +377,10 @@ class Context:
     def step_forward(self, alpha):
         self._chk(self._L.ocb_step_forward(self._h, float(alpha)))
 
-    def newton_step(self, energyParam0, targetGRes, pcg_rel_tol=1e-12, pcg_max_it=0, allowEDecRelTol=True):
+    def newton_step(self, energyParam0, targetGRes, pcg_rel_tol=1e-12, pcg_max_it=0, allowEDecRelTol=True, flags=0):
         r = NewtonResult()
-        self._chk(self._L.ocb_newton_step(self._h, float(energyParam0), float(targetGRes), float(pcg_rel_tol),
-                                          int(pcg_max_it), int(allowEDecRelTol), C.byref(r)), allow=(OCB_ERR_NOT_CONVERGED,))
+        self._chk(self._L.ocb_newton_step_ex(self._h, float(energyParam0), float(targetGRes), float(pcg_rel_tol),
+                                             int(pcg_max_it), int(allowEDecRelTol), int(flags), C.byref(r)), allow=(OCB_ERR_NOT_CONVERGED,))
         return {k: getattr(r, k) for k, _ in NewtonResult._fields_}
 
     # -- seam / candidate filter

@@ -375,7 +375,7 @@ int ocb_set_mesh(ocb_ctx* c, int nV, int nF, const int32_t* F, const double* res
     for (size_t i = 0; i < (size_t)3 * nF; ++i) if (F[i] < 0 || F[i] >= nV) return set_err(c, OCB_ERR_ARG, "ocb_set_mesh: vertex index out of range");
     for (int i = 0; i < nFixed; ++i) if (fixed[i] < 0 || fixed[i] >= nV) return set_err(c, OCB_ERR_ARG, "fixed vertex out of range");
     OCB_TRY(ensure_init(c));
-    c->haveUV = false; c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
+    c->haveUV = false; c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false; c->gradValid = false;
     c->nV = nV; c->nF = nF; c->surfaceArea = surfaceArea;
     // a new mesh drops the scaffold (the caller re-sends it, as the reference rebuilds it: Optimizer.cpp:483-488)
     c->nVa = c->nFa = c->nBnd = 0; c->air.n = 0; c->hFa.clear(); c->hL2G.clear(); c->wScafOverFa = 0.0;
@@ -415,7 +415,7 @@ int ocb_set_air(ocb_ctx* c, int nVa, int nFa, const int32_t* Fa, const double* r
         for (int i = 0; i < nFixedAir; ++i) if (fixedAir[i] < 0 || fixedAir[i] >= nVa) return set_err(c, OCB_ERR_ARG, "fixed air vertex out of range");
     }
     OCB_TRY(ensure_init(c));
-    c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false;
+    c->patternValid = c->matrixValid = c->precondValid = c->slotsValid = false; c->gradValid = false;
     // fixed flags: the mesh's own (bit 0) survive, what a previous air mesh set (bit 1) does not
     c->hFixed.resize((size_t)c->nV);
     for (auto& f : c->hFixed) f &= 1;
@@ -474,7 +474,7 @@ int ocb_set_uv(ocb_ctx* c, const double* V, const double* Va)
     }
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (V) c->haveUV = true;
-    c->matrixValid = c->precondValid = false;
+    c->matrixValid = c->precondValid = false; c->gradValid = false;
     return OCB_OK;
 }
 
@@ -512,7 +512,7 @@ int ocb_restore_uv(ocb_ctx* c)
     OCB_TRY(need(c, c->xSavedN == c->nSys() && c->xSavedN > 0, "ocb_restore_uv: no snapshot of this system size"));
     OCB_CUDA(c, cudaMemcpyAsync(c->x.p, c->xSaved.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
     c->hXYMesh = c->hXYAir = false;
-    c->matrixValid = c->precondValid = false;
+    c->matrixValid = c->precondValid = false; c->gradValid = false;
     return OCB_OK;
 }
 
@@ -577,6 +577,9 @@ int ocb_gradient(ocb_ctx* c, double p0, double* g_out, double* sqnorm)
     if (g_out) OCB_TRY(vec_to_host(c, g_out, c->g.p));
     OCB_TRY(fetch_scalars(c));
     if (sqnorm) *sqnorm = c->hScal[S_SQN_G];
+    // the fused pass also left the energy at x: ocb_newton_step_ex(OCB_STEP_REUSE_GRADIENT) continues from here
+    c->gradValid = true; c->gradP0 = p0;
+    c->gradSqn = c->hScal[S_SQN_G]; c->gradEMesh = c->hScal[S_E_MESH]; c->gradEAir = c->hScal[S_E_AIR]; c->gradSqnMesh = c->hScal[S_SQN_G_MESH];
     return OCB_OK;
 }
 
@@ -819,6 +822,7 @@ int ocb_hessian_assemble(ocb_ctx* c, double p0)
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->haveUV, "ocb_hessian_assemble: no UV"));
+    if (!c->patternValid && c->nV > 0) OCB_TRY(ocb_set_pattern_from_elements(c));     // no pattern handed over: the element lists define it
     OCB_TRY(need(c, c->patternValid && c->slotsValid, "ocb_hessian_assemble: no sparsity pattern (ocb_set_pattern)"));
     OCB_TRY(launch_hessian(c, p0));
     c->matrixValid = true; c->precondValid = false;
@@ -1092,7 +1096,7 @@ int ocb_step_forward(ocb_ctx* c, double alpha)
     OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
     OCB_TRY(launch_step_forward(c, alpha));
     c->hXYMesh = c->hXYAir = false;
-    c->matrixValid = c->precondValid = false;
+    c->matrixValid = c->precondValid = false; c->gradValid = false;
     return OCB_OK;
 }
 
@@ -1140,7 +1144,7 @@ static int line_search_core(ocb_ctx* c, double p0, double E_last, double lastSca
     if (allowEDecRelTol && (eDec / E_last < 1.0e-6 * alpha) && (alpha > 1.0e-3)) stopped = 1;
     out->alpha = alpha; out->E_new = E; out->E_scaf_new = Escaf; out->E_sd_new = Esd; out->E_last = E_last;
     out->lastEDec = eDec; out->n_halvings = halvings; out->stopped = stopped;
-    c->matrixValid = c->precondValid = false;
+    c->matrixValid = c->precondValid = false; c->gradValid = false;
     return OCB_OK;
 }
 
@@ -1168,33 +1172,39 @@ int ocb_line_search(ocb_ctx* c, double p0, double E_last, double alpha0, int all
 // six of the call-by-call sequence: {gradient norm, energy at x} | {block-Jacobi verdict, PCG status} | {step bound,
 // first line-search trial}.  Same kernels, same arithmetic, same results as ocb_gradient + ocb_hessian_assemble +
 // ocb_factorize + ocb_solve + ocb_step_bound + ocb_line_search.
-int ocb_newton_step(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_tol, int pcg_max_it,
-                    int allowEDecRelTol, ocb_newton_result* out)
+int ocb_newton_step_ex(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_tol, int pcg_max_it,
+                       int allowEDecRelTol, int flags, ocb_newton_result* out)
 {
     HostTimer _ht("newton_step");
     if (!c || !out) return OCB_ERR_ARG;
-    OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
+    OCB_TRY(ensure_init(c));
     std::memset(out, 0, sizeof(*out));
     out->targetGRes = targetGRes;
     OCB_TRY(need(c, c->haveUV, "ocb_newton_step: no UV"));
     const bool scaf = c->nFa > 0;
-    OCB_TRY(launch_gradient(c, p0));                         // also E_last with the current scaffold (Optimizer.cpp:588-592): one fused pass
-    OCB_TRY(fetch_scalars(c));
-    const double sqn = c->hScal[S_SQN_G];
-    const double lastScaf = scaf ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
-    const double E_last = p0 * c->hScal[S_E_MESH] + lastScaf;
+    const double tA = wall_now();
+    if (!((flags & OCB_STEP_REUSE_GRADIENT) && c->gradValid && c->gradP0 == p0)) {
+        OCB_TRY(launch_gradient(c, p0));                     // also E_last with the current scaffold (Optimizer.cpp:588-592): one fused pass
+        OCB_TRY(fetch_scalars(c));
+        c->gradValid = true; c->gradP0 = p0;
+        c->gradSqn = c->hScal[S_SQN_G]; c->gradEMesh = c->hScal[S_E_MESH]; c->gradEAir = c->hScal[S_E_AIR];
+    }
+    const double sqn = c->gradSqn;
+    const double lastScaf = scaf ? c->wScafOverFa * c->gradEAir : 0.0;
+    const double E_last = p0 * c->gradEMesh + lastScaf;
     out->sqn_g = sqn;
-    if (sqn < targetGRes) { out->converged = 1; return OCB_OK; }
+    if (!(flags & OCB_STEP_SKIP_CONVERGENCE_TEST) && sqn < targetGRes) { out->converged = 1; return OCB_OK; }
     if (!c->patternValid) OCB_TRY(ocb_set_pattern_from_elements(c));
-    OCB_TRY(ocb_hessian_assemble(c, p0));
+    if (!((flags & OCB_STEP_REUSE_MATRIX) && c->matrixValid)) OCB_TRY(ocb_hessian_assemble(c, p0));
     c->deferFactorCheck = true;
-    const int rf = ocb_factorize(c);
+    const int rf = c->precondValid ? 0 : ocb_factorize(c);
     c->deferFactorCheck = false;
     if (rf < 0) return rf;
     int its = 0; double rr = 0.0;
     int rs = ocb_solve(c, nullptr, nullptr, pcg_rel_tol, pcg_max_it, &its, &rr);
     out->pcg_iters = its; out->pcg_rel_res = rr;
     if (rs < 0 && rs != OCB_ERR_NOT_CONVERGED) return rs;
+    const double tB = wall_now();
     // step bound, then the first trial at 0.99 * bound (Optimizer.cpp:580) chained on the device
     OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
     OCB_TRY(launch_step_bound(c, c->p.p, 1.0));
@@ -1202,11 +1212,28 @@ int ocb_newton_step(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_tol
     OCB_TRY(fetch_scalars(c));
     double alpha = c->hScal[S_STEP_BOUND];
     alpha *= 0.99;
+    out->alpha_init = alpha;
     ocb_linesearch_result ls;
     OCB_TRY(line_search_core(c, p0, E_last, lastScaf, alpha, true, allowEDecRelTol, &ls));
     out->alpha = ls.alpha; out->E_new = ls.E_new; out->E_scaf_new = ls.E_scaf_new; out->E_sd_new = ls.E_sd_new;
     out->lastEDec = ls.lastEDec; out->n_halvings = ls.n_halvings; out->stopped = ls.stopped;
+    out->E_last = E_last;
+    out->ms_solve = 1e3 * (tB - tA); out->ms_line_search = 1e3 * (wall_now() - tB);
     return rs == OCB_ERR_NOT_CONVERGED ? rs : OCB_OK;
+}
+
+int ocb_newton_step(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_tol, int pcg_max_it,
+                    int allowEDecRelTol, ocb_newton_result* out)
+{
+    return ocb_newton_step_ex(c, p0, targetGRes, pcg_rel_tol, pcg_max_it, allowEDecRelTol, 0, out);
+}
+
+int ocb_gradient_info(ocb_ctx* c, double* info4)
+{
+    if (!c || !info4) return OCB_ERR_ARG;
+    OCB_TRY(need(c, c->gradValid, "ocb_gradient_info: no gradient at the current x"));
+    info4[0] = c->gradSqn; info4[1] = c->gradSqnMesh; info4[2] = c->gradEMesh; info4[3] = c->nFa > 0 ? c->wScafOverFa * c->gradEAir : 0.0;
+    return OCB_OK;
 }
 
 // ------------------------------------------------------------------------------------------- seam

@@ -24,6 +24,8 @@ struct DevBuf {
         T* q = nullptr;
         cudaError_t e = cudaMalloc((void**)&q, ncap * sizeof(T));
         if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(q, 0, ncap * sizeof(T), s);      // growth slack is defined memory (compute-sanitizer initcheck)
+        if (e != cudaSuccess) { cudaFree(q); return e; }
         if (keep && p && cap) {
             e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
             if (e != cudaSuccess) { cudaFree(q); return e; }
@@ -136,6 +138,8 @@ struct ocb_ctx {
     ocb::DevBuf<int32_t> rowOf, vertOf, userRow;   // device: internal vertex -> row, row -> internal vertex, caller vertex -> row
     ocb::MasHost masH; ocb::MasDev masD;
     int planGrid = 0;                        // persistent-CTA count the hierarchy was built for
+    // what the last ocb_gradient / fused gradient pass left (ocb_newton_step_ex(OCB_STEP_REUSE_GRADIENT) continues from it)
+    bool gradValid = false; double gradP0 = 0.0, gradSqn = 0.0, gradEMesh = 0.0, gradEAir = 0.0, gradSqnMesh = 0.0;
     bool deferFactorCheck = false;           // ocb_newton_step: the block-Jacobi verdict is read together with the PCG status
     int64_t precondFallbacks = 0;            // solves repeated with block-Jacobi after the two-level preconditioner failed
     std::vector<int32_t> hStamp;             // scratch of the pattern builders

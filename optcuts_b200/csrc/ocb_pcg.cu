@@ -460,6 +460,10 @@ pcg_kernel(PcgParams P)
     const int nLoc = rowEnd - rowBeg;
     SyncSlot* slots = reinterpret_cast<SyncSlot*>(P.partials);
     unsigned long long epoch = 0;
+    // distributed shared memory may only be touched once every CTA of the cluster has started executing: without this
+    // barrier the first all-reduce's remote stores could land in a CTA that is not resident yet (compute-sanitizer
+    // racecheck: "block that might not have entered yet", profiles/r2_sanitizer_*.log)
+    if (MODE == 2) cooperative_groups::this_cluster().sync();
     Slice S = {};
     if (SMEM) {
         S = carve(smemRaw, rowsPer, P.maxBlkPerCta);          // maxBlkPerCta carries the ELL width W here

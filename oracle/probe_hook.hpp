@@ -57,6 +57,16 @@ static void oracle_dump_state(const std::string& path)
     std::fclose(f);
 }
 
+// FNV-1a over the raw bytes: identical mesh connectivity <=> identical hash, iteration by iteration, so two traces with
+// equal Fhash / cohEhash columns went through the SAME sequence of topology operations (type AND path of every split / merge)
+static unsigned long long oracle_fnv(const void* data, size_t bytes)
+{
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    unsigned long long h = 1469598103934665603ull;
+    for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
 static void oracle_probe_iteration(void)
 {
     static FILE* trace = NULL;
@@ -79,8 +89,9 @@ static void oracle_probe_iteration(void)
         const OptCuts::TriMesh& r = optimizer->getResult();
         double E_se; r.computeSeamSparsity(E_se, !fractureMode); E_se /= r.virtualRadius;
         const bool sc = optimizer->isScaffolding();
-        std::fprintf(trace, "it=%d conv=%d topo=%d F=%d V=%d cohE=%d amF=%d amV=%d bnd=%d E=%.17g Enoscaf=%.17g Ese=%.17g p0=%.17g\n",
-                     iterNum, converged, optimizer->getTopoIter(), (int)r.F.rows(), (int)r.V.rows(), (int)r.cohE.rows(),
+        std::fprintf(trace, "it=%d conv=%d topo=%d Fhash=%016llx cohEhash=%016llx F=%d V=%d cohE=%d amF=%d amV=%d bnd=%d E=%.17g Enoscaf=%.17g Ese=%.17g p0=%.17g\n",
+                     iterNum, converged, optimizer->getTopoIter(), oracle_fnv(r.F.data(), sizeof(int) * r.F.size()),
+                     oracle_fnv(r.cohE.data(), sizeof(int) * r.cohE.size()), (int)r.F.rows(), (int)r.V.rows(), (int)r.cohE.rows(),
                      sc ? (int)optimizer->getAirMesh().F.rows() : 0, sc ? (int)optimizer->getAirMesh().V.rows() : 0,
                      sc ? (int)optimizer->getScaffold().bnd.size() : 0,
                      optimizer->getLastEnergyVal(), optimizer->getLastEnergyVal(true), E_se, energyParams[0]);

@@ -23,6 +23,17 @@
 #include "CudaCoordinateHint.hpp"
 namespace OptCuts {
 
+// What the device holds for the Optimizer that owns this solver (written by shim/CudaOptimizer.cpp, the hooks of
+// shim/CudaOptimizerHooks.hpp): copies of the host data last uploaded, so only what changed travels again.
+struct CudaNewtonState {
+    bool deviceResident = false;             // the Optimizer hooks drive this context: set_pattern / update_a are no-ops
+    bool meshBound = false, uvBound = false, airBound = false, airUvBound = false;
+    Eigen::MatrixXi F, Fa; Eigen::MatrixXd V, Va; Eigen::VectorXd triArea, airArea; Eigen::VectorXi l2g;
+    std::vector<int> fixed, fixedAir;
+    double surfaceArea = 0.0, wScaf = 0.0; long nBnd = 0;
+    int lastIters = 0; long totalIters = 0, steps = 0;
+};
+
 
 template <typename vectorTypeI, typename vectorTypeS>
 class CudaLinSysSolver : public LinSysSolver<vectorTypeI, vectorTypeS>
@@ -41,6 +52,9 @@ protected:
     }
 
 public:
+    CudaNewtonState newton;
+    ocb_ctx* context(void) const { return ctx; }
+
     CudaLinSysSolver(void) : ctx(NULL), relTol(1.0e-12), maxIter(0), lastIters(0), lastRelRes(0.0) {
         if (ocb_create(&ctx, 0) != OCB_OK) throw std::runtime_error("ocb_create failed");
         Base::numRows = 0;
@@ -53,6 +67,7 @@ public:
     void set_pattern(const std::vector<std::set<int>>& vNeighbor, const std::set<int>& fixedVert) {
         const int nV = static_cast<int>(vNeighbor.size());
         Base::numRows = nV * DIM;
+        if (newton.deviceResident) return;        // the pattern is derived on the device from the uploaded element lists
         std::vector<int32_t> ptr(nV + 1, 0), idx, fixed(fixedVert.begin(), fixedVert.end());
         size_t tot = 0;
         for (const auto& s : vNeighbor) tot += s.size();
@@ -76,6 +91,7 @@ public:
 
     // LinSysSolver::update_a (LinSysSolver.hpp:138-159): zero, accumulate triplets with i <= j
     void update_a(const vectorTypeI& II, const vectorTypeI& JJ, const vectorTypeS& SS) {
+        if (newton.deviceResident) return;        // the element blocks were assembled on the device (ocb_hessian_assemble)
         check(ocb_update_values_triplets(ctx, static_cast<int64_t>(SS.size()), II.data(), JJ.data(), SS.data()), "ocb_update_values_triplets");
     }
 

@@ -8,7 +8,7 @@
 namespace OptCuts {
 
 CudaSymDirichletEnergy::CudaSymDirichletEnergy(int p_minFaces)
-    : minFaces(p_minFaces), ctx(NULL), boundArea(NULL), boundUniform(false), boundNV(-1)
+    : minFaces(p_minFaces), ctx(NULL), boundSurface(0.0), boundUniform(false), boundNV(-1)
 {
     if (ocb_create(&ctx, 0) != OCB_OK) throw std::runtime_error("ocb_create failed");
 }
@@ -26,9 +26,12 @@ bool CudaSymDirichletEnergy::bind(const TriMesh& data, bool uniformWeight) const
     const int nF = static_cast<int>(data.F.rows()), nV = static_cast<int>(data.V.rows());
     if (nF < minFaces) return false;
     std::vector<int> fixed(data.fixedVert.begin(), data.fixedVert.end());
-    const bool same = boundNV == nV && boundUniform == uniformWeight && boundArea == data.triArea.data() &&
-                      boundF.rows() == nF && fixed == boundFixed &&
-                      std::memcmp(boundF.data(), data.F.data(), sizeof(int) * 3 * nF) == 0;
+    // keyed on CONTENT (F, fixed vertices, triangle areas): Eigen keeps a buffer's address across reassignments of the same
+    // size, and a freed buffer can be handed to another TriMesh, so the address says nothing
+    const bool same = boundNV == nV && boundUniform == uniformWeight && boundF.rows() == nF && fixed == boundFixed &&
+                      boundTriArea.size() == data.triArea.size() && boundSurface == data.surfaceArea &&
+                      std::memcmp(boundF.data(), data.F.data(), sizeof(int) * 3 * nF) == 0 &&
+                      std::memcmp(boundTriArea.data(), data.triArea.data(), sizeof(double) * nF) == 0;
     if (!same) {
         Eigen::MatrixXd rest8(nF, 8);                 // column k = feature k  ==  8 x nF SoA in memory
         if (uniformWeight) rest8.col(0).setOnes(); else rest8.col(0) = data.triArea;   // w = 1 (Optimizer.cpp:775,794,838)
@@ -36,7 +39,7 @@ bool CudaSymDirichletEnergy::bind(const TriMesh& data, bool uniformWeight) const
         rest8.col(5) = data.e0SqLen_div_dbAreaSq; rest8.col(6) = data.e1SqLen_div_dbAreaSq; rest8.col(7) = data.e0dote1_div_dbAreaSq;
         check(ocb_set_mesh(ctx, nV, nF, data.F.data(), rest8.data(), uniformWeight ? 1.0 : data.surfaceArea,
                            fixed.data(), static_cast<int>(fixed.size())), "ocb_set_mesh");
-        boundF = data.F; boundFixed = fixed; boundArea = data.triArea.data(); boundUniform = uniformWeight; boundNV = nV;
+        boundF = data.F; boundFixed = fixed; boundTriArea = data.triArea; boundSurface = data.surfaceArea; boundUniform = uniformWeight; boundNV = nV;
     }
     check(ocb_set_uv(ctx, data.V.data(), NULL), "ocb_set_uv");
     if (!uniformWeight) {                             // the mesh (not the air mesh): publish its UVs for the solver's hierarchy

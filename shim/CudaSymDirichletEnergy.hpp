@@ -41,7 +41,8 @@ protected:
     mutable ocb_ctx* ctx;
     mutable Eigen::MatrixXi boundF;                  // what is on the device
     mutable std::vector<int> boundFixed;
-    mutable const double* boundArea;
+    mutable Eigen::VectorXd boundTriArea;
+    mutable double boundSurface;
     mutable bool boundUniform;
     mutable int boundNV;
 };

@@ -30,11 +30,14 @@ def obj(tmp_path_factory, golden):
     return p
 
 
-def test_newton_iterations_inside_reference_host(obj, tmp_path):
+@pytest.mark.parametrize("device_newton", ["1", "0"], ids=["optimizer-hooks", "plugins-call-by-call"])
+def test_newton_iterations_inside_reference_host(obj, tmp_path, device_newton):
+    """device_newton=1: the Optimizer hooks keep the whole Newton iteration on the device (shim/CudaOptimizer.cpp);
+    device_newton=0: only the Energy / LinSysSolver virtuals are served by the GPU, call by call through Eigen triplets."""
     if not os.path.exists(CUDA_PROBE):
         pytest.skip("shim/_build/OptCuts_cuda_probe not built (make -C shim needs the reference headers)")
     n = 10
-    env = dict(os.environ, ORACLE_TRACE=str(tmp_path / "trace.txt"), ORACLE_MAX_ITERS=str(n))
+    env = dict(os.environ, ORACLE_TRACE=str(tmp_path / "trace.txt"), ORACLE_MAX_ITERS=str(n), OCB_DEVICE_NEWTON=device_newton)
     r = subprocess.run([CUDA_PROBE, "100", obj] + ARGS, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     got = parse_trace(tmp_path / "trace.txt")

@@ -1,0 +1,55 @@
+"""GPU: teacher-forced sweep: for ~20 iterations spread over the reference run of BASELINE.json configs[1] and
+~12 of configs[0] (dual update on, energyParam0 changes along the run), upload the reference's state BEFORE the iteration
+(mesh, UVs, the air mesh it triangulated), run ONE Newton iteration on the GPU and compare with what the reference got:
+E_w and E_SD of the trace at north_star's 1e-9 relative, the new UVs at 1e-7 of the UV extent (a PCG at 1e-12 relative
+residual against a sparse LDL^T of a matrix with kappa ~ 1e6-1e8).  Fixtures: tests/golden/sweep_*.npz (make_sweep.py)."""
+import os
+
+import numpy as np
+import pytest
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(name):
+    p = os.path.join(GOLDEN, "sweep_%s.npz" % name)
+    if not os.path.exists(p):
+        pytest.skip(p + " missing")
+    g = np.load(p)
+    return {k: g[k] for k in g.files}
+
+
+@pytest.mark.parametrize("name", ["bimba_cfg2", "bimba_cfg1"])
+def test_teacher_forced_newton_iterations(ctx, name):
+    g = _load(name)
+    w_scaf = 0.01 * (1.0 - float(g["lambda_init"]))              # frozen at Optimizer construction (Optimizer.cpp:87)
+    feat = {}
+    worst = dict(E=0.0, Esd=0.0, uv=0.0)
+    assert len(g["iters"]) >= (20 if name == "bimba_cfg2" else 10)
+    for k in g["iters"]:
+        p = "k%d_" % k
+        m = "m%d_" % int(g[p + "mesh"])
+        V_rest, F = g[m + "V_rest"], g[m + "F"]
+        if m not in feat:
+            feat[m] = ctx.rest_features(V_rest, F)
+        rest8, sc = feat[m]
+        p0 = float(g[p + "p0"])
+        UV, aV, aF = g[p + "V"], g[p + "air_V"], g[p + "air_F"]
+        ctx.set_mesh(UV.shape[0], F, rest8, sc["surfaceArea"], g[m + "fixedVert"])
+        ctx.set_uv(UV)
+        r8a, _ = ctx.rest_features(np.hstack([aV, np.zeros((len(aV), 1))]), aF, float(g[p + "air_scalars"][2]))
+        ctx.set_air(aF, r8a, g[p + "air_localVI2Global"], len(g[p + "air_bnd"]), g[p + "air_fixedVert"], w_scaf / aF.shape[0])
+        ctx.set_uv(None, aV)
+        r = ctx.newton_step(p0, 0.0)
+        E, Enoscaf = g[p + "E_next"]
+        eE = abs(r["E_new"] - E) / E
+        eS = abs((r["E_new"] - r["E_scaf_new"]) - Enoscaf) / Enoscaf
+        V1 = ctx.get_uv()
+        eV = np.max(np.abs(V1 - g[p + "V_next"])) / np.max(np.abs(g[p + "V_next"]))
+        worst = dict(E=max(worst["E"], eE), Esd=max(worst["Esd"], eS), uv=max(worst["uv"], eV))
+        assert eE <= 1e-9 and eS <= 1e-9, (name, int(k), r, E, Enoscaf)
+        assert eV <= 1e-7, (name, int(k), eV)
+        # the state before the iteration: same energy as the reference had (its scalars record), to rounding
+        assert abs(r["E_last"] - float(g[p + "scalars"][4])) <= 1e-12 * r["E_last"], (name, int(k))
+    print(name, "worst relative differences over", len(g["iters"]), "iterations:", worst)
