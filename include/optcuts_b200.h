@@ -60,6 +60,10 @@ const char* ocb_version(void);
 int  ocb_set_stream(ocb_ctx* ctx, void* cuda_stream);
 int  ocb_use_own_stream(ocb_ctx* ctx);
 int  ocb_synchronize(ocb_ctx* ctx);
+/* tuning switches: "pcg_plain_norm" (0 / 1): 1 = ocb_solve stops on ||r||_2 <= rel_tol ||b||_2; default 0 = on the
+ * block-Jacobi-scaled norm sqrt(r^T D^-1 r) (D = the 2x2 diagonal blocks), in which the soft rows of the scaffold
+ * converge relative to their own stiffness (needed for the line search's step bound to match the reference's LDL^T) */
+int  ocb_set_option(ocb_ctx* ctx, const char* key, double value);
 /* CUDA-event stopwatch on the context's stream (what bench.py times kernels with) */
 int  ocb_timer_start(ocb_ctx* ctx);
 int  ocb_timer_stop_ms(ocb_ctx* ctx, double* ms);
@@ -150,7 +154,8 @@ int ocb_multiply(ocb_ctx* ctx, const double* x, double* y);
  * a Hilbert curve through the UVs, affine coarse spaces, exact dense coarse inverse; 2x2 block-Jacobi when no geometry is
  * known).  rhs==NULL solves A x = -gradient
  * (Optimizer.cpp:557-563) with the gradient left on the device by ocb_gradient; the solution stays
- * on the device as the search direction; x_out may be NULL.  rel_tol <= 0 -> 1e-12, max_it <= 0 -> 20*n */
+ * on the device as the search direction; x_out may be NULL.  rel_tol <= 0 -> 1e-12 (relative residual in the D-scaled
+ * norm, see ocb_set_option), max_it <= 0 -> 20*n; *rel_res returns the value reached in the same norm */
 int ocb_factorize(ocb_ctx* ctx);   /* builds the preconditioner (Galerkin products, group inverses, coarse inverse); OCB_ERR_BREAKDOWN if a diagonal 2x2 block is not SPD */
 int ocb_solve(ocb_ctx* ctx, const double* rhs, double* x_out, double rel_tol, int max_it,
               int* iters, double* rel_res);

@@ -59,6 +59,7 @@ _SIGS = [
     ("ocb_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
     ("ocb_use_own_stream", C.c_int, [C.c_void_p]),
     ("ocb_synchronize", C.c_int, [C.c_void_p]),
+    ("ocb_set_option", C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     ("ocb_timer_start", C.c_int, [C.c_void_p]),
     ("ocb_timer_stop_ms", C.c_int, [C.c_void_p, _d]),
     ("ocb_launch_count", C.c_int64, [C.c_void_p]),
@@ -201,6 +202,9 @@ class Context:
 
     def use_own_stream(self):
         self._chk(self._L.ocb_use_own_stream(self._h))
+
+    def set_option(self, key, value):
+        self._chk(self._L.ocb_set_option(self._h, key.encode(), float(value)))
 
     def synchronize(self):
         self._chk(self._L.ocb_synchronize(self._h))

@@ -239,6 +239,7 @@ int ocb_create(ocb_ctx** out, int device)
     ocb_ctx* c = new (std::nothrow) ocb_ctx();
     if (!c) return OCB_ERR_ARG;
     c->device = device;
+    { const char* e = getenv("OCB_PCG_PLAIN_NORM"); c->pcgPlainNorm = e && atoi(e); }
     *out = c;
     return OCB_OK;
 }
@@ -291,6 +292,12 @@ int ocb_use_own_stream(ocb_ctx* c)
     if (c->inited) { OCB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     return OCB_OK;
 }
+int ocb_set_option(ocb_ctx* c, const char* key, double value)
+{
+    if (!c || !key) return OCB_ERR_ARG;
+    if (!std::strcmp(key, "pcg_plain_norm")) { c->pcgPlainNorm = value != 0.0; return OCB_OK; }
+    return set_err(c, OCB_ERR_ARG, "ocb_set_option: unknown key");
+}
 int ocb_synchronize(ocb_ctx* c) { OCB_TRY(ensure_init(c)); OCB_CUDA(c, cudaStreamSynchronize(c->stream)); return OCB_OK; }
 int ocb_timer_start(ocb_ctx* c) { OCB_TRY(ensure_init(c)); OCB_CUDA(c, cudaEventRecord(c->ev0, c->stream)); return OCB_OK; }
 int ocb_timer_stop_ms(ocb_ctx* c, double* ms)
@@ -324,7 +331,7 @@ int ocb_profile_get(ocb_ctx* c, double* ms, int64_t* counts)
 const char* ocb_profile_name(int k)
 {
     static const char* names[K_COUNT] = {"energy", "gradient", "hessian_psd_scatter", "pcg", "step_bound", "step_forward",
-                                         "jacobi_setup", "spmv", "rest_features", "pattern_slots", "misc", "stencil_newton", "mas_setup"};
+                                         "jacobi_setup", "spmv", "rest_features", "pattern_slots", "misc", "stencil_newton", "mas_setup", "hessian_rows"};
     return (k >= 0 && k < K_COUNT) ? names[k] : "";
 }
 int ocb_profile_classes(void) { return K_COUNT; }

@@ -61,7 +61,7 @@ struct ElemView {
 // kernel classes for the optional per-kernel CUDA-event profile (ocb_profile_*)
 enum KernelClass {
     K_ENERGY = 0, K_GRADIENT, K_HESSIAN, K_PCG, K_STEP_BOUND, K_STEP_FORWARD, K_JACOBI_SETUP, K_SPMV,
-    K_FEATURES, K_PATTERN, K_MISC, K_STENCILS, K_MAS_SETUP, K_COUNT
+    K_FEATURES, K_PATTERN, K_MISC, K_STENCILS, K_MAS_SETUP, K_HESSIAN_ROWS, K_COUNT
 };
 
 enum ScalarSlot {            // layout of the device/pinned scalar block
@@ -140,6 +140,7 @@ struct ocb_ctx {
     int planGrid = 0;                        // persistent-CTA count the hierarchy was built for
     // what the last ocb_gradient / fused gradient pass left (ocb_newton_step_ex(OCB_STEP_REUSE_GRADIENT) continues from it)
     bool gradValid = false; double gradP0 = 0.0, gradSqn = 0.0, gradEMesh = 0.0, gradEAir = 0.0, gradSqnMesh = 0.0;
+    bool pcgPlainNorm = false;               // ocb_set_option("pcg_plain_norm"): stop on ||r|| / ||b|| instead of the D-scaled norm
     bool deferFactorCheck = false;           // ocb_newton_step: the block-Jacobi verdict is read together with the PCG status
     int64_t precondFallbacks = 0;            // solves repeated with block-Jacobi after the two-level preconditioner failed
     std::vector<int32_t> hStamp;             // scratch of the pattern builders

@@ -196,37 +196,59 @@ struct GatherView {
 };
 struct Slots5 { int s[5]; };
 
+static constexpr int kGradLanes = 4;        // lanes per vertex: the corner evaluations (7 fp64 divisions each) of a vertex run side by side
+
+// The kGradLanes lanes of a vertex evaluate its corners round-robin (corner j on lane j % kGradLanes); the sum is then
+// formed in corner order from shuffled values -- every lane ends up with the same, order-exact sum -- so the gradient
+// is bit-identical to a serial walk.  Element values / inversion counts are accumulated by the lane that evaluated
+// corner 0 of the triangle.
 template <bool AIR_SET>
 __device__ __forceinline__ void gather_corners(const ElemView& S, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, int row,
-                                               const double* __restrict__ x, Vec2& gsum, double& Esum, double& nInv)
+                                               const double* __restrict__ x, int lane, unsigned groupMask, int groupBase,
+                                               Vec2& gsum, double& Esum, double& nInv)
 {
-    for (int q = ptr[row], qe = ptr[row + 1]; q < qe; ++q) {
-        const int code = __ldg(idx + q), t = code >> 2, k = code & 3;
-        const int i0 = __ldg(S.v0 + t), i1 = __ldg(S.v1 + t), i2 = __ldg(S.v2 + t);
-        const double area = __ldg(S.area + t), A2 = __ldg(S.areaSq + t), e0 = __ldg(S.e0 + t), e1 = __ldg(S.e1 + t), d = __ldg(S.d + t);
-        const double w = AIR_SET ? 1.0 : area / S.surfaceArea;
-        Vec2 gk; double E, dbArea;
-        sd_corner(ld2(x, i0), ld2(x, i1), ld2(x, i2), A2, e0, e1, d, w, k, gk, E, dbArea);
-        gsum.x += gk.x; gsum.y += gk.y;
-        if (k == 0) { Esum += E; if (dbArea < 0.0) nInv += 1.0; }
+    const int q0 = row >= 0 ? ptr[row] : 0, q1 = row >= 0 ? ptr[row + 1] : 0;
+    // the trip count is uniform over the group (same row) but not over the warp: shuffles are masked per group
+    for (int base = q0; base < q1; base += kGradLanes) {
+        const int q = base + lane;
+        Vec2 gk = mk(0.0, 0.0);
+        if (q < q1) {
+            const int code = __ldg(idx + q), t = code >> 2, k = code & 3;
+            const int i0 = __ldg(S.v0 + t), i1 = __ldg(S.v1 + t), i2 = __ldg(S.v2 + t);
+            const double area = __ldg(S.area + t), A2 = __ldg(S.areaSq + t), e0 = __ldg(S.e0 + t), e1 = __ldg(S.e1 + t), d = __ldg(S.d + t);
+            const double w = AIR_SET ? 1.0 : area / S.surfaceArea;
+            double E, dbArea;
+            sd_corner(ld2(x, i0), ld2(x, i1), ld2(x, i2), A2, e0, e1, d, w, k, gk, E, dbArea);
+            if (k == 0) { Esum += E; if (dbArea < 0.0) nInv += 1.0; }
+        }
+#pragma unroll
+        for (int l = 0; l < kGradLanes; ++l) {
+            const double gx = __shfl_sync(groupMask, gk.x, groupBase + l), gy = __shfl_sync(groupMask, gk.y, groupBase + l);
+            if (base + l < q1) { gsum.x += gx; gsum.y += gy; }
+        }
     }
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 3)
 grad_gather_kernel(ElemView M, ElemView A, GatherView G, const double* __restrict__ x, const uint8_t* __restrict__ fixedMask,
                    double* __restrict__ g, double* __restrict__ partials, unsigned* __restrict__ ticket,
                    double* __restrict__ scal, Slots5 slots)
 {
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // E mesh, E air, #inverted, ||g||^2, ||g_mesh||^2 (unscaled mesh term)
     double2* g2 = reinterpret_cast<double2*>(g);
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < G.nVtot; v += gridDim.x * kBlock) {
+    const int lane = threadIdx.x & (kGradLanes - 1);
+    const int groupBase = (threadIdx.x & 31) & ~(kGradLanes - 1);
+    const unsigned groupMask = ((1u << kGradLanes) - 1u) << groupBase;
+    const long nGroups = (long)gridDim.x * kBlock / kGradLanes;
+    for (long w = (blockIdx.x * (long)kBlock + threadIdx.x) / kGradLanes; w < G.nVtot; w += nGroups) {
+        const int v = (int)w;
         Vec2 gm = mk(0.0, 0.0), ga = mk(0.0, 0.0);
         int la = -1;
-        if (v < G.nV) {
-            gather_corners<false>(M, G.vcPtrM, G.vcIdxM, v, x, gm, acc[0], acc[2]);
-            if (A.n > 0) la = __ldg(G.g2l + v);
-        } else la = G.nBnd + (v - G.nV);
-        if (la >= 0) gather_corners<true>(A, G.vcPtrA, G.vcIdxA, la, x, ga, acc[1], acc[2]);
+        if (v < G.nV) { if (A.n > 0) la = __ldg(G.g2l + v); }
+        else la = G.nBnd + (v - G.nV);
+        gather_corners<false>(M, G.vcPtrM, G.vcIdxM, v < G.nV ? v : -1, x, lane, groupMask, groupBase, gm, acc[0], acc[2]);
+        gather_corners<true>(A, G.vcPtrA, G.vcIdxA, la, x, lane, groupMask, groupBase, ga, acc[1], acc[2]);
+        if (lane != 0) continue;
         const unsigned fx = fixedMask[v];
         // per-term masking like the reference: the mesh term zeroes the mesh's fixed vertices, the air term the air mesh's
         if (fx & 1u) gm = mk(0.0, 0.0);
@@ -365,81 +387,60 @@ hessian_elem_kernel(ElemView M, ElemView A, const double* __restrict__ x, double
     }
 }
 
-static constexpr int kRowBlock = 64;       // threads (= block rows) per CTA of the row gather
-static constexpr int kRowMaxB = 16;        // BSR blocks of a row accumulated in shared memory; longer rows go through global memory
+static constexpr int kRowLanes = 8;         // lanes per block row of the row gather (rows are ~7 blocks long)
 
-// adds row k of element e's block matrix into the accumulators of the BSR row [lo, lo + nb)
-template <bool IN_SMEM>
-__device__ __forceinline__ void row_add_elem(const double* __restrict__ hel, size_t nE, size_t e, int k, const int32_t* __restrict__ slot,
-                                             int nS, int t, int lo, double (*acc)[4][kRowBlock], double* __restrict__ val)
+// Pass 2, one group of 8 lanes per block row (= vertex): lane q owns the row's BSR blocks q, q + 8, ...  Every lane
+// walks ALL incident corners of the vertex in ascending element order (the group reads the same addresses: broadcasts)
+// and adds row k of an element's block matrix into its own block when the element's slot map says so -- a register
+// accumulator per owned block, contributions in the reference's triplet order, one 32-byte store per block.
+__device__ __forceinline__ void row_lane_add(const double* __restrict__ hel, size_t nE, size_t e, int k, const int32_t* __restrict__ slot,
+                                             int nS, int t, int myBlock, double (&acc)[4])
 {
-    const int bOf[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-        const int s = __ldg(slot + (size_t)(3 * k + l) * nS + t);
-        if (s < 0) continue;
-        // block (k,l): stored as is for k <= l, as the transpose of (l,k) otherwise
-        const int b = (k == 0) ? bOf[0][l] : ((k == 1) ? bOf[1][l] : bOf[2][l]);
-        const double2* src = reinterpret_cast<const double2*>(hel + 4 * ((size_t)b * nE + e));
-        const double2 r0 = __ldcg(src), r1 = __ldcg(src + 1);
-        const bool tr = k > l;
-        const double h00 = r0.x, h01 = tr ? r1.x : r0.y, h10 = tr ? r0.y : r1.x, h11 = r1.y;
-        if (IN_SMEM) {
-            const int j = s - lo, tid = threadIdx.x;
-            acc[j][0][tid] += h00; acc[j][1][tid] += h01; acc[j][2][tid] += h10; acc[j][3][tid] += h11;
-        } else {
-            double* o = val + 4 * (size_t)s;
-            o[0] += h00; o[1] += h01; o[2] += h10; o[3] += h11;
-        }
-    }
+    const int s0 = __ldg(slot + (size_t)(3 * k) * nS + t), s1 = __ldg(slot + (size_t)(3 * k + 1) * nS + t), s2 = __ldg(slot + (size_t)(3 * k + 2) * nS + t);
+    const int l = (s0 == myBlock) ? 0 : ((s1 == myBlock) ? 1 : ((s2 == myBlock) ? 2 : -1));
+    if (l < 0) return;
+    // block (k,l) of the element: stored as is for k <= l, as the transpose of (l,k) otherwise
+    const int lo = k < l ? k : l, hi = k < l ? l : k;
+    const int b = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);                 // (0,0)(0,1)(0,2)(1,1)(1,2)(2,2) -> 0..5
+    const double2* src = reinterpret_cast<const double2*>(hel + 4 * ((size_t)b * nE + e));
+    const double2 r0 = __ldcg(src), r1 = __ldcg(src + 1);
+    const bool tr = k > l;
+    acc[0] += r0.x; acc[1] += tr ? r1.x : r0.y; acc[2] += tr ? r0.y : r1.x; acc[3] += r1.y;
 }
 
-template <bool IN_SMEM>
-__device__ __forceinline__ void row_gather(const ElemView& M, const ElemView& A, const GatherView& G, int v, int la, const double* __restrict__ hel,
-                                           int lo, double (*acc)[4][kRowBlock], double* __restrict__ val)
-{
-    const size_t nE = (size_t)M.n + A.n;
-    if (v < G.nV)
-        for (int q = G.vcPtrM[v], qe = G.vcPtrM[v + 1]; q < qe; ++q) {
-            const int code = __ldg(G.vcIdxM + q);
-            row_add_elem<IN_SMEM>(hel, nE, (size_t)(code >> 2), code & 3, M.slot, M.n, code >> 2, lo, acc, val);
-        }
-    if (la >= 0)
-        for (int q = G.vcPtrA[la], qe = G.vcPtrA[la + 1]; q < qe; ++q) {
-            const int code = __ldg(G.vcIdxA + q);
-            row_add_elem<IN_SMEM>(hel, nE, (size_t)M.n + (code >> 2), code & 3, A.slot, A.n, code >> 2, lo, acc, val);
-        }
-}
-
-__global__ void __launch_bounds__(kRowBlock)
+__global__ void __launch_bounds__(kBlock)
 hessian_rows_kernel(ElemView M, ElemView A, GatherView G, const double* __restrict__ hel, const uint8_t* __restrict__ fixedMask,
                     const int32_t* __restrict__ rowOf, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx,
                     double* __restrict__ val)
 {
-    __shared__ double acc[kRowMaxB][4][kRowBlock];
-    const int tid = threadIdx.x;
-    for (int v = blockIdx.x * kRowBlock + tid; v < G.nVtot; v += gridDim.x * kRowBlock) {
+    const size_t nE = (size_t)M.n + A.n;
+    const int lane = threadIdx.x & (kRowLanes - 1);
+    for (long w = (blockIdx.x * (long)kBlock + threadIdx.x) / kRowLanes; w < G.nVtot; w += (long)gridDim.x * kBlock / kRowLanes) {
+        const int v = (int)w;
         const int r = rowOf[v], lo = rowPtr[r], nb = rowPtr[r + 1] - lo;
         const unsigned fx = fixedMask[v];
         if (fx) {
             // identity scaled like every other triplet of its term (mask bit 0: fixed by the mesh, bit 1: by the air mesh)
             const double dgn = ((fx & 1u) ? M.scale : 0.0) + ((fx & 2u) ? A.scale : 0.0);
-            for (int b = lo; b < lo + nb; ++b)
+            for (int b = lo + lane; b < lo + nb; b += kRowLanes)
                 if (colIdx[b] == r) { double2* o = reinterpret_cast<double2*>(val + 4 * (size_t)b); o[0] = make_double2(dgn, 0.0); o[1] = make_double2(0.0, dgn); }
             continue;
         }
         const int la = (v < G.nV) ? (A.n > 0 ? __ldg(G.g2l + v) : -1) : G.nBnd + (v - G.nV);
-        if (nb <= kRowMaxB) {
-            for (int j = 0; j < nb; ++j) { acc[j][0][tid] = 0.0; acc[j][1][tid] = 0.0; acc[j][2][tid] = 0.0; acc[j][3][tid] = 0.0; }
-            row_gather<true>(M, A, G, v, la, hel, lo, acc, val);
-            for (int j = 0; j < nb; ++j) {
-                double2* o = reinterpret_cast<double2*>(val + 4 * (size_t)(lo + j));
-                o[0] = make_double2(acc[j][0][tid], acc[j][1][tid]); o[1] = make_double2(acc[j][2][tid], acc[j][3][tid]);
+        const int qM0 = v < G.nV ? G.vcPtrM[v] : 0, qM1 = v < G.nV ? G.vcPtrM[v + 1] : 0;
+        const int qA0 = la >= 0 ? G.vcPtrA[la] : 0, qA1 = la >= 0 ? G.vcPtrA[la + 1] : 0;
+        for (int b = lo + lane; b < lo + nb; b += kRowLanes) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int q = qM0; q < qM1; ++q) {
+                const int code = __ldg(G.vcIdxM + q);
+                row_lane_add(hel, nE, (size_t)(code >> 2), code & 3, M.slot, M.n, code >> 2, b, acc);
             }
-        } else {
-            // long row (high-valence vertex): the owning thread accumulates straight in global memory, same order
-            for (int j = 0; j < 4 * nb; ++j) val[4 * (size_t)lo + j] = 0.0;
-            row_gather<false>(M, A, G, v, la, hel, lo, acc, val);
+            for (int q = qA0; q < qA1; ++q) {
+                const int code = __ldg(G.vcIdxA + q);
+                row_lane_add(hel, nE, (size_t)M.n + (code >> 2), code & 3, A.slot, A.n, code >> 2, b, acc);
+            }
+            double2* o = reinterpret_cast<double2*>(val + 4 * (size_t)b);
+            o[0] = make_double2(acc[0], acc[1]); o[1] = make_double2(acc[2], acc[3]);
         }
     }
 }
@@ -701,7 +702,7 @@ int launch_gradient(ocb_ctx* c, double p0)
 {
     ProfScope prof(c, K_GRADIENT);
     const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
-    const int grid = grid_for(c, c->nVtot, 8);
+    const int grid = grid_for(c, (long)c->nVtot * kGradLanes, 8);
     OCB_TRY(ensure_reduce_bufs(c, grid, 5));
     Slots5 sl; sl.s[0] = S_E_MESH; sl.s[1] = S_E_AIR; sl.s[2] = S_N_INVERTED; sl.s[3] = S_SQN_G; sl.s[4] = S_SQN_G_MESH;
     grad_gather_kernel<<<grid, kBlock, 0, c->stream>>>(M, A, gather_of(c), c->x.p, c->fixedMask.p, c->g.p, c->partials.p, c->sync.p, c->dScal, sl);
@@ -742,14 +743,16 @@ int launch_build_slots(ocb_ctx* c)
 
 int launch_hessian(ocb_ctx* c, double p0)
 {
-    ProfScope prof(c, K_HESSIAN);
     const ElemView M = view_of(c, c->mesh, false, p0, 0), A = view_of(c, c->air, true, c->wScafOverFa, 1);
     const size_t nE = (size_t)M.n + A.n;
     OCB_CUDA(c, c->hel.reserve(24 * nE + 4, c->stream));
-    hessian_elem_kernel<true><<<resident_grid<hessian_elem_kernel<true>>(c, (long)nE), kBlock, 0, c->stream>>>(M, A, c->x.p, c->hel.p, nullptr);
-    KCHECK(c);
-    const int grid = (int)std::min<long>(((long)c->nVtot + kRowBlock - 1) / kRowBlock, (long)c->numSMs * 16);
-    hessian_rows_kernel<<<grid < 1 ? 1 : grid, kRowBlock, 0, c->stream>>>(M, A, gather_of(c), c->hel.p, c->fixedMask.p, c->rowOf.p, c->rowPtr.p, c->colIdx.p, c->val.p);
+    {
+        ProfScope prof(c, K_HESSIAN);
+        hessian_elem_kernel<true><<<resident_grid<hessian_elem_kernel<true>>(c, (long)nE), kBlock, 0, c->stream>>>(M, A, c->x.p, c->hel.p, nullptr);
+        KCHECK(c);
+    }
+    ProfScope prof2(c, K_HESSIAN_ROWS);
+    hessian_rows_kernel<<<grid_for(c, (long)c->nVtot * kRowLanes, 8), kBlock, 0, c->stream>>>(M, A, gather_of(c), c->hel.p, c->fixedMask.p, c->rowOf.p, c->rowPtr.p, c->colIdx.p, c->val.p);
     KCHECK(c);
     return 0;
 }

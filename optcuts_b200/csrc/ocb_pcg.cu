@@ -34,6 +34,7 @@ struct PcgParams {
     double* partials;          // 2 x gridDim SyncSlots (64 B each), double buffered by epoch parity
     double* scal;              // device scalar block
     double relTol; int maxIt;
+    int scaledNorm;            // 1: converge in the block-Jacobi-scaled norm sqrt(r^T D^-1 r) (D = the 2x2 diagonal blocks); 0: plain 2-norm
     int maxBlkPerCta;          // SMEM mode: capacity of the per-CTA block arrays
     long long* dbg;            // optional: per-phase clock64 totals of CTA 0 (OCB_PCG_DEBUG=1)
     const int32_t* vertOf;     // solver row -> internal vertex (rhs gather / result scatter); nullptr = identity
@@ -529,14 +530,21 @@ pcg_kernel(PcgParams P)
     WAIT(2, red);
     double rz = red[0];
     const double bb = red[1];
+    // Convergence is measured in the norm the block-Jacobi part of the preconditioner induces, r^T D^-1 r against
+    // b^T D^-1 b (both ride on the all-reduce that exists anyway): every DOF converges relative to its OWN stiffness.
+    // The plain 2-norm is dominated by the stiff mesh rows; the scaffold's rows are 4-8 orders of magnitude softer
+    // (w_scaf / |F_air| against distorted mesh elements), so their part of the search direction stayed at 1e-3
+    // relative accuracy under ||r|| <= 1e-12 ||b|| -- and the line search's step bound comes from exactly those air
+    // triangles (torus, first iteration: E off by 2e-3; tests/test_gpu_runs.py).
+    const double bzb = red[0];
     if (MAS && bb > 0.0) {
         mas_down<MODE == 2 ? 9 : 5>(P.mas, MS, blockIdx.x);
         double lz[1] = {mas_finish()}, rzv[1];
         ALLREDUCE(1, lz, rzv);
         rz = rzv[0];
     }
-    const double tol2 = P.relTol * P.relTol * bb;
-    double rr = bb, beta = 0.0;
+    const double tol2 = P.relTol * P.relTol * (P.scaledNorm ? bzb : bb);
+    double rr = bb, rDr = bzb, beta = 0.0;
     int it = 0, status = 0, cur = 0;
     if (bb > 0.0 && !(rz > 0.0)) status = 3;
     if (bb > 0.0 && status == 0) {
@@ -590,10 +598,11 @@ pcg_kernel(PcgParams P)
             WAIT(2, red);
             if (P.dbg) u3 = clock64();
             double rzNew = red[0];
+            rDr = red[0];                     // r^T D^-1 r (the MAS part of r.z is added further down)
             rr = red[1];
             ++it;
             cur ^= 1;
-            if (rr <= tol2) { status = 0; break; }
+            if ((P.scaledNorm ? rDr : rr) <= tol2) { status = 0; break; }
             if (it >= P.maxIt) { status = 1; break; }
             if (MAS) {
                 long long st[2] = {0, 0};
@@ -624,7 +633,7 @@ pcg_kernel(PcgParams P)
     if (MODE == 2) cooperative_groups::this_cluster().sync();      // no CTA may exit while a peer still reads its shared memory
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.scal[S_PCG_ITERS] = (double)it;
-        P.scal[S_PCG_RELRES] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+        P.scal[S_PCG_RELRES] = bb > 0.0 ? (P.scaledNorm ? sqrt(rDr / bzb) : sqrt(rr / bb)) : 0.0;
         P.scal[S_PCG_STATUS] = (double)status;
         P.scal[S_PCG_BNORM] = sqrt(bb);
     }
@@ -667,7 +676,7 @@ static PcgParams make_params(ocb_ctx* c)
     P.nRows = c->nVtot; P.rowPtr = c->rowPtr.p; P.colIdx = c->colIdx.p; P.val = c->val.p; P.minv = c->minv.p;
     P.rhs = nullptr; P.negate = 0; P.x = c->px.p; P.xOut = c->p.p; P.vertOf = nullptr; P.masSmemOff = 0; P.mas = MasView(); P.mas.L = 0;
     P.r = c->pr.p; P.z = c->pz.p; P.d = c->pd.p; P.d2 = c->pd2.p; P.Ap = c->pAp.p;
-    P.partials = c->partials.p; P.scal = c->dScal; P.relTol = 1e-12; P.maxIt = 1; P.maxBlkPerCta = 0; P.dbg = nullptr;
+    P.partials = c->partials.p; P.scal = c->dScal; P.relTol = 1e-12; P.maxIt = 1; P.scaledNorm = 1; P.maxBlkPerCta = 0; P.dbg = nullptr;
     return P;
 }
 
@@ -821,6 +830,7 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     OCB_CUDA(c, c->partials.reserve(slotDoubles + 64, c->stream));
     PcgParams P = make_params(c);
     P.rhs = d_rhs; P.negate = negate_rhs ? 1 : 0; P.relTol = rel_tol; P.maxIt = max_it; P.maxBlkPerCta = pl.maxBlk;
+    P.scaledNorm = c->pcgPlainNorm ? 0 : 1;
     P.vertOf = c->vertOf.p;
     size_t smemBytes = pl.smem ? pl.smemBytes - mas_smem_estimate((c->nVtot + grid - 1) / grid, grid) : 0;     // the slice alone
     smemBytes = (smemBytes + 15) / 16 * 16;
