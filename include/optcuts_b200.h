@@ -60,9 +60,11 @@ const char* ocb_version(void);
 int  ocb_set_stream(ocb_ctx* ctx, void* cuda_stream);
 int  ocb_use_own_stream(ocb_ctx* ctx);
 int  ocb_synchronize(ocb_ctx* ctx);
-/* tuning switches: "pcg_plain_norm" (0 / 1): 1 = ocb_solve stops on ||r||_2 <= rel_tol ||b||_2; default 0 = on the
- * block-Jacobi-scaled norm sqrt(r^T D^-1 r) (D = the 2x2 diagonal blocks), in which the soft rows of the scaffold
- * converge relative to their own stiffness (needed for the line search's step bound to match the reference's LDL^T) */
+/* tuning switches: "pcg_scaled_norm" (0 / 1): 0 (default) = ocb_solve stops on ||r||_2 <= rel_tol ||b||_2; 1 = on the
+ * block-Jacobi-scaled norm sqrt(r^T D^-1 r) (D = the 2x2 diagonal blocks), in which soft rows (the scaffold's) converge
+ * relative to their own stiffness.  Measured against an LU of the same matrices (profiles/r2_pcg_norm.txt): no gain in
+ * the accuracy of the direction, ~3 % more iterations -- the differences to the reference's LDL^T on badly conditioned
+ * states (kappa ~ 1e12 at a Tutte start) are rounding, in both solvers, not the stopping test. */
 int  ocb_set_option(ocb_ctx* ctx, const char* key, double value);
 /* CUDA-event stopwatch on the context's stream (what bench.py times kernels with) */
 int  ocb_timer_start(ocb_ctx* ctx);
@@ -154,8 +156,8 @@ int ocb_multiply(ocb_ctx* ctx, const double* x, double* y);
  * a Hilbert curve through the UVs, affine coarse spaces, exact dense coarse inverse; 2x2 block-Jacobi when no geometry is
  * known).  rhs==NULL solves A x = -gradient
  * (Optimizer.cpp:557-563) with the gradient left on the device by ocb_gradient; the solution stays
- * on the device as the search direction; x_out may be NULL.  rel_tol <= 0 -> 1e-12 (relative residual in the D-scaled
- * norm, see ocb_set_option), max_it <= 0 -> 20*n; *rel_res returns the value reached in the same norm */
+ * on the device as the search direction; x_out may be NULL.  rel_tol <= 0 -> 1e-12 (relative residual
+ * ||r|| / ||b||; see ocb_set_option for the scaled variant), max_it <= 0 -> 20*n */
 int ocb_factorize(ocb_ctx* ctx);   /* builds the preconditioner (Galerkin products, group inverses, coarse inverse); OCB_ERR_BREAKDOWN if a diagonal 2x2 block is not SPD */
 int ocb_solve(ocb_ctx* ctx, const double* rhs, double* x_out, double rel_tol, int max_it,
               int* iters, double* rel_res);
@@ -244,6 +246,33 @@ typedef struct {
 int ocb_eval_stencils(ocb_ctx* ctx, const ocb_stencil_batch* batch, int maxIter, double relGL2Tol,
                       double* E_init, double* E_final, double* UV_out, int32_t* iters, double* score,
                       int32_t* status, int* argmax);
+
+/* ---- a16/a17 with bijectivity on: ONE Newton iteration of the nested Optimizer of every candidate in the batch.
+ * The nested Optimizer re-triangulates the candidate's local air mesh after every iteration (Optimizer.cpp:252-257 ->
+ * Scaffold.cpp:153-199, Triangle "qYQ"): Triangle stays with the host, so the caller advances all candidates in lock
+ * step -- triangulate the air region of every active candidate, pack local mesh + air mesh, call this, read the new UVs
+ * back (shim/CudaCandidates.cpp does exactly that inside TriMesh::querySplit / queryMerge).  A stencil's vertices are the
+ * local mesh's first, then the air mesh's own vertices (outer loop + Steiner points); its triangles the mesh's first
+ * (area weights), then the air mesh's (uniform weights, scaled by w_scaf / #air triangles; rest shape = the positions
+ * handed in, clamped by area_thres: TriMesh.cpp:373-383).  Per stencil: result = 0 step taken, 1 converged before a step
+ * (||g||^2 < target_gres, Optimizer.cpp:215-221), 2 step taken and the line search says stop (:635), -2 over the limits
+ * (128 vertices, 192 triangles, 32 free vertices), -4 inverted input; out6 = E_SD of the mesh at the returned UVs,
+ * E incl. scaffold, ||g||^2, accepted step, E before the step, lastEDec. */
+typedef struct {
+    int nStencil;
+    const int32_t* vert_ptr;     /* nStencil+1 */
+    const int32_t* tri_ptr;      /* nStencil+1 */
+    const int32_t* n_mesh_vert;  /* nStencil */
+    const int32_t* n_mesh_tri;   /* nStencil */
+    const double*  V_rest;       /* 3 per vertex (x y z interleaved; ignored for air vertices) */
+    const double*  UV;           /* 2 per vertex (interleaved) */
+    const int32_t* F;            /* 3 per triangle, LOCAL vertex ids */
+    const uint8_t* is_free;      /* per vertex: 1 = free DOF */
+    const double*  area_thres;   /* nStencil: areaThres_AM of the local air mesh (Scaffold.cpp:156,176) */
+    const double*  target_gres;  /* nStencil: Optimizer::updateTargetGRes of the local problem (Optimizer.cpp:675-678) */
+    double w_scaf;               /* 0.01 for the nested optimizers (Optimizer.cpp:87 with energyParams = {1}) */
+} ocb_stencil_step_batch;
+int ocb_stencil_newton_step(ocb_ctx* ctx, const ocb_stencil_step_batch* batch, double* UV_out, double* out6, int32_t* result);
 
 /* ---- a12 (solver set-up): the multilevel additive Schwarz preconditioner that replaces the numeric
  * factorisation (EigenLibSolver.cpp:80-93) is rebuilt by ocb_factorize; its hierarchy (row order along a Hilbert curve

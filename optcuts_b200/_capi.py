@@ -41,6 +41,11 @@ class NewtonResult(C.Structure):
                 ("alpha_init", C.c_double), ("E_last", C.c_double), ("ms_solve", C.c_double), ("ms_line_search", C.c_double)]
 
 
+class StencilStepBatch(C.Structure):
+    _fields_ = [("nStencil", C.c_int), ("vert_ptr", _i), ("tri_ptr", _i), ("n_mesh_vert", _i), ("n_mesh_tri", _i), ("V_rest", _d), ("UV", _d),
+                ("F", _i), ("is_free", _u8), ("area_thres", _d), ("target_gres", _d), ("w_scaf", C.c_double)]
+
+
 class StencilBatch(C.Structure):
     _fields_ = [("nStencil", C.c_int), ("vert_ptr", _i), ("tri_ptr", _i), ("V_rest", _d), ("UV", _d),
                 ("F", _i), ("is_free", _u8), ("score_scale", _d), ("score_offset", _d)]
@@ -99,6 +104,7 @@ _SIGS = [
     ("ocb_seam_energy", C.c_int, [C.c_void_p, C.c_int, _i, _d, _i, C.c_double, C.c_double, C.c_double, C.c_int, _d]),
     ("ocb_divgrad_scores", C.c_int, [C.c_void_p, _d]),
     ("ocb_eval_stencils", C.c_int, [C.c_void_p, C.POINTER(StencilBatch), C.c_int, C.c_double, _d, _d, _d, _i, _d, _i, C.POINTER(C.c_int)]),
+    ("ocb_stencil_newton_step", C.c_int, [C.c_void_p, C.POINTER(StencilStepBatch), _d, _d, _i]),
     ("ocb_precond_info", C.c_int, [C.c_void_p, _i]),
     ("ocb_set_coordinate_hint", C.c_int, [C.c_void_p, C.c_int, _d]),
     ("ocb_precond_hierarchy", C.c_int, [C.c_void_p, C.c_int, _d, C.c_int, _i, _i, _i, C.c_int]),
@@ -416,6 +422,23 @@ class Context:
         self._chk(self._L.ocb_eval_stencils(self._h, C.byref(b), int(maxIter), float(relGL2Tol), _pd(E0), _pd(E1), _pd(UVo), _pi(it),
                                             _pd(score), _pi(st), C.byref(arg)))
         return dict(E_init=E0, E_final=E1, UV=[UVo[vp[k]:vp[k + 1]] for k in range(nS)], iters=it, status=st, score=score, argmax=arg.value)
+
+    def stencil_newton_step(self, stencils, w_scaf=0.01):
+        """stencils: list of dicts {V_rest (nv,3), UV (nv,2), F (nt,3) local ids, is_free (nv,), n_mesh_vert, n_mesh_tri, area_thres,
+        target_gres}: ONE Newton iteration of every nested (bijective) optimizer.  Returns dict(UV=[...], out6, result)."""
+        nS = len(stencils)
+        vp = np.zeros(nS + 1, np.int32); tp = np.zeros(nS + 1, np.int32)
+        for k, s in enumerate(stencils):
+            vp[k + 1] = vp[k] + len(s["UV"]); tp[k + 1] = tp[k] + len(s["F"])
+        cat = lambda key, dt, w: np.ascontiguousarray(np.concatenate([np.asarray(s[key], dt).reshape(-1, w) for s in stencils]))
+        Vr, UV, F = cat("V_rest", np.float64, 3), cat("UV", np.float64, 2), cat("F", np.int32, 3)
+        fr = np.ascontiguousarray(np.concatenate([np.asarray(s["is_free"]).astype(np.uint8).ravel() for s in stencils]))
+        nvm = np.array([s["n_mesh_vert"] for s in stencils], np.int32); ntm = np.array([s["n_mesh_tri"] for s in stencils], np.int32)
+        th = np.array([s["area_thres"] for s in stencils], np.float64); tg = np.array([s["target_gres"] for s in stencils], np.float64)
+        b = StencilStepBatch(nS, _pi(vp), _pi(tp), _pi(nvm), _pi(ntm), _pd(Vr), _pd(UV), _pi(F), fr.ctypes.data_as(_u8), _pd(th), _pd(tg), float(w_scaf))
+        UVo, out6, res = np.zeros_like(UV), np.zeros((nS, 6)), np.zeros(nS, np.int32)
+        self._chk(self._L.ocb_stencil_newton_step(self._h, C.byref(b), _pd(UVo), _pd(out6), _pi(res)))
+        return dict(UV=[UVo[vp[k]:vp[k + 1]] for k in range(nS)], out6=out6, result=res)
 
     def divgrad_scores(self):
         out = np.zeros(self.sizes()["nV"])

@@ -239,7 +239,7 @@ int ocb_create(ocb_ctx** out, int device)
     ocb_ctx* c = new (std::nothrow) ocb_ctx();
     if (!c) return OCB_ERR_ARG;
     c->device = device;
-    { const char* e = getenv("OCB_PCG_PLAIN_NORM"); c->pcgPlainNorm = e && atoi(e); }
+    { const char* e = getenv("OCB_PCG_SCALED_NORM"); c->pcgPlainNorm = !(e && atoi(e)); }
     *out = c;
     return OCB_OK;
 }
@@ -295,7 +295,7 @@ int ocb_use_own_stream(ocb_ctx* c)
 int ocb_set_option(ocb_ctx* c, const char* key, double value)
 {
     if (!c || !key) return OCB_ERR_ARG;
-    if (!std::strcmp(key, "pcg_plain_norm")) { c->pcgPlainNorm = value != 0.0; return OCB_OK; }
+    if (!std::strcmp(key, "pcg_scaled_norm")) { c->pcgPlainNorm = value == 0.0; return OCB_OK; }
     return set_err(c, OCB_ERR_ARG, "ocb_set_option: unknown key");
 }
 int ocb_synchronize(ocb_ctx* c) { OCB_TRY(ensure_init(c)); OCB_CUDA(c, cudaStreamSynchronize(c->stream)); return OCB_OK; }
@@ -1329,6 +1329,41 @@ int ocb_eval_stencils(ocb_ctx* c, const ocb_stencil_batch* B, int maxIter, doubl
     OCB_CUDA(c, cudaMemcpyAsync(&hArg, dArg, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (argmax) *argmax = hArg;
+    return OCB_OK;
+}
+
+int ocb_stencil_newton_step(ocb_ctx* c, const ocb_stencil_step_batch* B, double* UV_out, double* out6, int32_t* result)
+{
+    if (!c || !B || B->nStencil < 0) return set_err(c, OCB_ERR_ARG, "ocb_stencil_newton_step: bad argument");
+    if (B->nStencil == 0) return OCB_OK;
+    if (!B->vert_ptr || !B->tri_ptr || !B->n_mesh_vert || !B->n_mesh_tri || !B->V_rest || !B->UV || !B->F || !B->is_free || !B->area_thres || !B->target_gres ||
+        !UV_out || !out6 || !result) return set_err(c, OCB_ERR_ARG, "ocb_stencil_newton_step: bad argument");
+    OCB_TRY(ensure_init(c));
+    const int nS = B->nStencil;
+    for (int s = 0; s < nS; ++s)
+        if (B->vert_ptr[s + 1] < B->vert_ptr[s] || B->tri_ptr[s + 1] < B->tri_ptr[s] || B->n_mesh_tri[s] > B->tri_ptr[s + 1] - B->tri_ptr[s] ||
+            B->n_mesh_vert[s] > B->vert_ptr[s + 1] - B->vert_ptr[s]) return set_err(c, OCB_ERR_ARG, "ocb_stencil_newton_step: inconsistent ranges");
+    const size_t nV = (size_t)B->vert_ptr[nS], nT = (size_t)B->tri_ptr[nS];
+    // one double arena and one int arena on the device: {V_rest, UV, areaThres, targetGRes | UV_out, out6} and {ptrs, counts, F, result, free flags}
+    OCB_CUDA(c, c->stD.reserve(3 * nV + 2 * nV + 2 * (size_t)nS + 2 * nV + 6 * (size_t)nS + 8, c->stream));
+    OCB_CUDA(c, c->stI.reserve(4 * ((size_t)nS + 1) + 3 * nT + (size_t)nS + (nV + 3) / 4 + 8, c->stream));
+    double* dVr = c->stD.p; double* dUV = dVr + 3 * nV; double* dTh = dUV + 2 * nV; double* dTg = dTh + nS; double* dUVo = dTg + nS; double* dOut = dUVo + 2 * nV;
+    int32_t* dVp = c->stI.p; int32_t* dTp = dVp + nS + 1; int32_t* dNv = dTp + nS + 1; int32_t* dNt = dNv + nS + 1; int32_t* dF = dNt + nS + 1;
+    int32_t* dRes = dF + 3 * nT; uint8_t* dFree = reinterpret_cast<uint8_t*>(dRes + nS);
+    OCB_TRY(upload_d(c, dVr, B->V_rest, 3 * nV)); OCB_TRY(upload_d(c, dUV, B->UV, 2 * nV));
+    OCB_TRY(upload_d(c, dTh, B->area_thres, (size_t)nS)); OCB_TRY(upload_d(c, dTg, B->target_gres, (size_t)nS));
+    OCB_TRY(upload_i(c, dVp, B->vert_ptr, (size_t)nS + 1)); OCB_TRY(upload_i(c, dTp, B->tri_ptr, (size_t)nS + 1));
+    OCB_TRY(upload_i(c, dNv, B->n_mesh_vert, (size_t)nS)); OCB_TRY(upload_i(c, dNt, B->n_mesh_tri, (size_t)nS));
+    OCB_TRY(upload_i(c, dF, B->F, 3 * nT));
+    OCB_CUDA(c, cudaMemcpyAsync(dFree, B->is_free, nV, cudaMemcpyHostToDevice, c->stream));
+    StencilStepHost h;
+    h.nStencil = nS; h.vertPtr = dVp; h.triPtr = dTp; h.nVm = dNv; h.nTm = dNt; h.Vrest = dVr; h.UV = dUV; h.F = dF; h.isFree = dFree;
+    h.areaThres = dTh; h.targetGRes = dTg; h.wScaf = B->w_scaf; h.UVout = dUVo; h.out6 = dOut; h.result = dRes;
+    OCB_TRY(launch_stencil_step(c, h));
+    OCB_CUDA(c, cudaMemcpyAsync(UV_out, dUVo, sizeof(double) * 2 * nV, cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaMemcpyAsync(out6, dOut, sizeof(double) * 6 * (size_t)nS, cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaMemcpyAsync(result, dRes, sizeof(int32_t) * (size_t)nS, cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     return OCB_OK;
 }
 

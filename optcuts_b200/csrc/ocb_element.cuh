@@ -35,6 +35,28 @@ __device__ __forceinline__ Vec2 ld2_step(const double* x0, const double* p, doub
     return mk(__dadd_rn(a.x, __dmul_rn(alpha, b.x)), __dadd_rn(a.y, __dmul_rn(alpha, b.y)));
 }
 
+// ---- rest-frame features of one triangle (TriMesh::computeFeatures arithmetic, TriMesh.cpp:355-398): out8 = area, areaSq,
+// |e0|^2, |e1|^2, e0.e1, and the three x / (2 A^2); triangles below `thres` (air-mesh degeneracy guard) get the
+// equilateral surrogate (:373-383).  a = P2 - P1, b = P3 - P1 (3-D; the air mesh has z = 0).  Returns the raw area.
+__device__ __forceinline__ double sd_rest_features(double ax, double ay, double az, double bx, double by, double bz, double thres, double out8[8])
+{
+    const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+    const double raw = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+    double area = raw, A2, e0, e1, d, k0, k1, kd;
+    if (area < thres) {
+        const double sqrt3 = sqrt(3.0);
+        area = thres; A2 = thres * thres;
+        e0 = e1 = 4.0 / sqrt3 * thres; d = e0 / 2.0;
+        k0 = k1 = 2.0 / sqrt3 / thres; kd = k0 / 2.0;
+    } else {
+        A2 = area * area;
+        e0 = ax * ax + ay * ay + az * az; e1 = bx * bx + by * by + bz * bz; d = ax * bx + ay * by + az * bz;
+        k0 = e0 / 2. / A2; k1 = e1 / 2. / A2; kd = d / 2. / A2;
+    }
+    out8[0] = area; out8[1] = A2; out8[2] = e0; out8[3] = e1; out8[4] = d; out8[5] = k0; out8[6] = k1; out8[7] = kd;
+    return raw;
+}
+
 // ---- value (division order as the reference's value/gradient functions) -----------------------
 __device__ __forceinline__ double sd_energy(Vec2 u, Vec2 v, double A2, double e0, double e1, double d,
                                             double w, double& dbArea)

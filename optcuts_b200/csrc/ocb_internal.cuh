@@ -140,7 +140,7 @@ struct ocb_ctx {
     int planGrid = 0;                        // persistent-CTA count the hierarchy was built for
     // what the last ocb_gradient / fused gradient pass left (ocb_newton_step_ex(OCB_STEP_REUSE_GRADIENT) continues from it)
     bool gradValid = false; double gradP0 = 0.0, gradSqn = 0.0, gradEMesh = 0.0, gradEAir = 0.0, gradSqnMesh = 0.0;
-    bool pcgPlainNorm = false;               // ocb_set_option("pcg_plain_norm"): stop on ||r|| / ||b|| instead of the D-scaled norm
+    bool pcgPlainNorm = true;                // false (ocb_set_option("pcg_scaled_norm", 1)): stop on the D-scaled norm instead of ||r|| / ||b||
     bool deferFactorCheck = false;           // ocb_newton_step: the block-Jacobi verdict is read together with the PCG status
     int64_t precondFallbacks = 0;            // solves repeated with block-Jacobi after the two-level preconditioner failed
     std::vector<int32_t> hStamp;             // scratch of the pattern builders
@@ -225,6 +225,12 @@ struct StencilHost {     // device pointers of one uploaded stencil batch
     double* Einit; double* Efinal; double* UVout; int32_t* iters; double* score; int32_t* status; int* argmax;
 };
 int launch_stencils(ocb_ctx* c, const StencilHost& h);
+struct StencilStepHost {  // device pointers of one uploaded batch of bijective stencils (one Newton iteration each)
+    int nStencil; const int32_t* vertPtr; const int32_t* triPtr; const int32_t* nVm; const int32_t* nTm; const double* Vrest; const double* UV;
+    const int32_t* F; const uint8_t* isFree; const double* areaThres; const double* targetGRes; double wScaf;
+    double* UVout; double* out6; int32_t* result;
+};
+int launch_stencil_step(ocb_ctx* c, const StencilStepHost& h);
 int launch_spmv(ocb_ctx* c, const double* dx, double* dy);
 int launch_jacobi_setup(ocb_ctx* c, bool check = true);   // check = false: no host round trip, the verdict stays in scal[S_JACOBI_BAD]
 int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it, bool allowMas = true);

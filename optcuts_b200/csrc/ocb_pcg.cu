@@ -530,12 +530,9 @@ pcg_kernel(PcgParams P)
     WAIT(2, red);
     double rz = red[0];
     const double bb = red[1];
-    // Convergence is measured in the norm the block-Jacobi part of the preconditioner induces, r^T D^-1 r against
-    // b^T D^-1 b (both ride on the all-reduce that exists anyway): every DOF converges relative to its OWN stiffness.
-    // The plain 2-norm is dominated by the stiff mesh rows; the scaffold's rows are 4-8 orders of magnitude softer
-    // (w_scaf / |F_air| against distorted mesh elements), so their part of the search direction stayed at 1e-3
-    // relative accuracy under ||r|| <= 1e-12 ||b|| -- and the line search's step bound comes from exactly those air
-    // triangles (torus, first iteration: E off by 2e-3; tests/test_gpu_runs.py).
+    // Optional (ocb_set_option "pcg_scaled_norm"): convergence in the norm the block-Jacobi part of the preconditioner
+    // induces, r^T D^-1 r against b^T D^-1 b (both ride on the all-reduce that exists anyway), so that every DOF converges
+    // relative to its own stiffness (the scaffold's rows are 4-8 orders of magnitude softer than a distorted mesh's).
     const double bzb = red[0];
     if (MAS && bb > 0.0) {
         mas_down<MODE == 2 ? 9 : 5>(P.mas, MS, blockIdx.x);

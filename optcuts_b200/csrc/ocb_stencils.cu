@@ -226,6 +226,248 @@ stencil_newton_kernel(StencilParams P)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bijective stencils: ONE Newton iteration per launch.
+//
+// With bijectivity on, the nested Optimizer of a candidate re-triangulates its local air mesh after EVERY Newton iteration
+// (Optimizer.cpp:252-257 -> Scaffold.cpp:153-199 -> Triangle "qYQ", Steiner points included), and Triangle stays with the
+// host.  So the candidates advance in lock step: the host triangulates the air region of every active candidate
+// (shim/CudaCandidates.cpp, all host threads), packs mesh + air mesh of all of them into one ragged batch, and this
+// kernel runs one iteration of Optimizer::solve's loop body for each (one CTA per candidate, everything in shared memory):
+//   air-mesh rest features from the current positions (TriMesh.cpp:355-398 incl. the degeneracy clamp),
+//   gradient of mesh term + w_scaf/|Fa| x uniform air term, convergence test ||g||^2 < targetGRes (Optimizer.cpp:209-221),
+//   projected element Hessians -> dense free-DOF system -> LDL^T -> search direction (:505-573, dense flavour),
+//   step bound over mesh and air triangles x 0.99, line search with both inversion guards, lastEDec without the scaffold's
+//   change, the relative-decrease stop (:575-652).
+// Free DOFs: the candidate's 1-4 free mesh vertices plus the Steiner points of its air mesh.
+static constexpr int kSV = 128, kST = 192, kSFree = 32;        // combined vertices, triangles, free vertices per stencil
+
+struct StepParams {
+    int nStencil;
+    const int32_t* vertPtr; const int32_t* triPtr; const int32_t* nVm; const int32_t* nTm;
+    const double* Vrest; const double* UV; const int32_t* F; const uint8_t* isFree;
+    const double* areaThres; const double* targetGRes; double wScaf;
+    double* UVout; double* out6; int32_t* result;
+};
+
+struct StepSmem {
+    double U[kSV][2], U0[kSV][2], Dir[kSV][2];
+    double Rest[8][kST];
+    double Ht[kST][21];
+    double Gt[kST][6];
+    double H[2 * kSFree][2 * kSFree + 1];
+    double G[2 * kSFree], P[2 * kSFree];
+    double Red[kStBlock / 32];
+    int F[kST][3];
+    int FreeIdx[kSV];
+    int FreeList[kSFree];
+    int nFree;
+};
+
+__global__ void __launch_bounds__(kStBlock)
+stencil_step_kernel(StepParams P)
+{
+    extern __shared__ __align__(16) unsigned char stepRaw[];
+    StepSmem& S = *reinterpret_cast<StepSmem*>(stepRaw);
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (s >= P.nStencil) return;
+    const int v0 = P.vertPtr[s], nV = P.vertPtr[s + 1] - v0, t0 = P.triPtr[s], nT = P.triPtr[s + 1] - t0;
+    const int nTm = P.nTm[s], nTa = nT - nTm;
+    double* out = P.out6 + 6 * (size_t)s;
+    auto fail = [&](int code) { if (tid == 0) { P.result[s] = code; for (int k = 0; k < 6; ++k) out[k] = 0.0; } };
+    if (nV > kSV || nT > kST || nV <= 0 || nTm <= 0 || nTa < 0) { fail(-2); return; }
+    for (int v = tid; v < nV; v += kStBlock) { S.U[v][0] = P.UV[2 * (size_t)(v0 + v)]; S.U[v][1] = P.UV[2 * (size_t)(v0 + v) + 1]; }
+    for (int t = tid; t < nT; t += kStBlock) for (int k = 0; k < 3; ++k) S.F[t][k] = P.F[3 * (size_t)(t0 + t) + k];
+    if (tid == 0) {
+        int nf = 0, all = 0;
+        for (int v = 0; v < nV; ++v) {
+            const bool fr = P.isFree[v0 + v] != 0;
+            all += fr ? 1 : 0;
+            if (fr && nf < kSFree) { S.FreeIdx[v] = nf; S.FreeList[nf] = v; ++nf; } else S.FreeIdx[v] = -1;
+        }
+        S.nFree = all > kSFree ? -1 : nf;
+    }
+    __syncthreads();
+    const int nFree = S.nFree;
+    if (nFree < 0) { fail(-2); return; }
+    bool badIndex = false;
+    for (int t = tid; t < nT; t += kStBlock) for (int k = 0; k < 3; ++k) if (S.F[t][k] < 0 || S.F[t][k] >= nV) badIndex = true;
+    if (__syncthreads_or(badIndex ? 1 : 0)) { fail(-2); return; }
+
+    // ---- rest features: the mesh's from V_rest, the air mesh's from its current positions (z = 0) with the clamp
+    double myArea = 0.0;
+    const double thres = P.areaThres[s];
+    for (int t = tid; t < nT; t += kStBlock) {
+        double f8[8];
+        const int a = S.F[t][0], b = S.F[t][1], c = S.F[t][2];
+        if (t < nTm) {
+            const double* p0 = P.Vrest + 3 * (size_t)(v0 + a); const double* p1 = P.Vrest + 3 * (size_t)(v0 + b); const double* p2 = P.Vrest + 3 * (size_t)(v0 + c);
+            myArea += sd_rest_features(p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2], p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2], 0.0, f8);
+        } else {
+            sd_rest_features(S.U[b][0] - S.U[a][0], S.U[b][1] - S.U[a][1], 0.0, S.U[c][0] - S.U[a][0], S.U[c][1] - S.U[a][1], 0.0, thres, f8);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) S.Rest[q][t] = f8[q];
+    }
+    const double surf = block_reduce<false>(myArea, S.Red);
+    const double wS = nTa > 0 ? P.wScaf / nTa : 0.0;
+
+    // energy of mesh (area weights) and air mesh (uniform weights) at the positions in S.U
+    auto energy_at = [&](double& Esd, double& Eair, bool& inverted) {
+        double em = 0.0, ea = 0.0, inv = 0.0;
+        for (int t = tid; t < nT; t += kStBlock) {
+            const int a = S.F[t][0], b = S.F[t][1], c = S.F[t][2];
+            const Vec2 U1 = mk(S.U[a][0], S.U[a][1]), U2 = mk(S.U[b][0], S.U[b][1]), U3 = mk(S.U[c][0], S.U[c][1]);
+            double db;
+            const double e = sd_energy(U2 - U1, U3 - U1, S.Rest[1][t], S.Rest[2][t], S.Rest[3][t], S.Rest[4][t], t < nTm ? S.Rest[0][t] / surf : 1.0, db);
+            if (t < nTm) em += e; else ea += e;
+            if (db < 0.0) inv += 1.0;
+        }
+        Esd = block_reduce<false>(em, S.Red);
+        Eair = block_reduce<false>(ea, S.Red);
+        inverted = block_reduce<false>(inv, S.Red) > 0.0;
+    };
+    double Esd, Eair; bool inv0;
+    energy_at(Esd, Eair, inv0);
+    if (inv0) { fail(-4); return; }
+    const double lastScaf = wS * Eair, Elast = Esd + lastScaf;
+    const int n = 2 * nFree;
+
+    // ---- element gradients + projected Hessians (the air mesh's scaled by w_scaf/|Fa| after the projection)
+    for (int t = tid; t < nT; t += kStBlock) {
+        const int a = S.F[t][0], b = S.F[t][1], c = S.F[t][2];
+        const Vec2 U1 = mk(S.U[a][0], S.U[a][1]), U2 = mk(S.U[b][0], S.U[b][1]), U3 = mk(S.U[c][0], S.U[c][1]);
+        const double w = t < nTm ? S.Rest[0][t] / surf : 1.0, sc = t < nTm ? 1.0 : wS;
+        Vec2 g[3];
+        sd_gradient(U1, U2, U3, S.Rest[1][t], S.Rest[2][t], S.Rest[3][t], S.Rest[4][t], w, g);
+        for (int k = 0; k < 3; ++k) { S.Gt[t][2 * k] = g[k].x; S.Gt[t][2 * k + 1] = g[k].y; }
+        double Hb[6][2][2];
+        sd_hessian(U1, U2, U3, S.Rest[1][t], S.Rest[5][t], S.Rest[6][t], S.Rest[7][t], w, Hb);
+        sd_project_psd(Hb);
+        const int bOf[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+        int q = 0;
+        for (int r = 0; r < 6; ++r) for (int cc = r; cc < 6; ++cc) S.Ht[t][q++] = sc * Hb[bOf[r >> 1][cc >> 1]][r & 1][cc & 1];
+    }
+    __syncthreads();
+    // gradient of the free DOFs: 1.0 * (mesh sum, triangle order) + w_scaf/|Fa| * (air sum, triangle order)
+    for (int r = tid; r < n; r += kStBlock) {
+        const int vr = S.FreeList[r >> 1];
+        double gm = 0.0, ga = 0.0;
+        for (int t = 0; t < nT; ++t) for (int k = 0; k < 3; ++k) if (S.F[t][k] == vr) { if (t < nTm) gm += S.Gt[t][2 * k + (r & 1)]; else ga += S.Gt[t][2 * k + (r & 1)]; }
+        S.G[r] = nTa > 0 ? gm + wS * ga : gm;
+    }
+    __syncthreads();
+    double sq = 0.0;
+    for (int r = 0; r < n; ++r) sq += S.G[r] * S.G[r];
+    if (sq < P.targetGRes[s] || nFree == 0) {            // converged: no step (Optimizer.cpp:215-221)
+        for (int v = tid; v < nV; v += kStBlock) { P.UVout[2 * (size_t)(v0 + v)] = S.U[v][0]; P.UVout[2 * (size_t)(v0 + v) + 1] = S.U[v][1]; }
+        if (tid == 0) { P.result[s] = 1; out[0] = Esd; out[1] = Elast; out[2] = sq; out[3] = 0.0; out[4] = Elast; out[5] = 0.0; }
+        return;
+    }
+    // ---- dense free-DOF system, contributions in triangle order
+    for (int e = tid; e < n * n; e += kStBlock) {
+        const int r = e / n, c = e % n;
+        if (c < r) continue;
+        const int vr = S.FreeList[r >> 1], vc = S.FreeList[c >> 1];
+        double acc = 0.0;
+        for (int t = 0; t < nT; ++t) {
+            int kr = -1, kc = -1;
+            for (int k = 0; k < 3; ++k) { if (S.F[t][k] == vr) kr = k; if (S.F[t][k] == vc) kc = k; }
+            if (kr < 0 || kc < 0) continue;
+            int rr = 2 * kr + (r & 1), cc = 2 * kc + (c & 1);
+            if (rr > cc) { const int tmp = rr; rr = cc; cc = tmp; }
+            acc += S.Ht[t][rr * 6 - rr * (rr - 1) / 2 + (cc - rr)];
+        }
+        S.H[r][c] = acc; S.H[c][r] = acc;
+    }
+    __syncthreads();
+    // ---- LDL^T (right-looking, the trailing update spread over the whole CTA) and the two triangular solves (one warp,
+    // column sweeps): H p = -g
+    for (int k = 0; k < n; ++k) {
+        __syncthreads();                                   // the trailing update of step k - 1 is complete
+        const double dk = S.H[k][k];
+        for (int i = k + 1 + tid; i < n; i += kStBlock) S.H[i][k] = S.H[i][k] / dk;              // L(i,k)
+        __syncthreads();
+        const int m = n - k - 1;
+        for (int e = tid; e < m * m; e += kStBlock) {
+            const int i = k + 1 + e / m, j = k + 1 + e % m;
+            if (j <= i) S.H[i][j] -= S.H[i][k] * dk * S.H[j][k];
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        for (int i = tid; i < n; i += 32) S.P[i] = -S.G[i];
+        __syncwarp();
+        for (int j = 0; j < n; ++j) {                      // forward: L y = -g
+            const double yj = S.P[j];
+            for (int i = j + 1 + tid; i < n; i += 32) S.P[i] -= S.H[i][j] * yj;
+            __syncwarp();
+        }
+        for (int i = tid; i < n; i += 32) S.P[i] /= S.H[i][i];
+        __syncwarp();
+        for (int j = n - 1; j >= 0; --j) {                 // backward: L^T p = D^-1 y
+            const double pj = S.P[j];
+            for (int i = tid; i < j; i += 32) S.P[i] -= S.H[j][i] * pj;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int v = tid; v < nV; v += kStBlock) {
+        const int f = S.FreeIdx[v];
+        S.Dir[v][0] = f >= 0 ? S.P[2 * f] : 0.0; S.Dir[v][1] = f >= 0 ? S.P[2 * f + 1] : 0.0;
+        S.U0[v][0] = S.U[v][0]; S.U0[v][1] = S.U[v][1];
+    }
+    __syncthreads();
+    // ---- step bound over mesh and air triangles, line search
+    double bound = 1.0;
+    for (int t = tid; t < nT; t += kStBlock) {
+        const int a = S.F[t][0], b = S.F[t][1], c = S.F[t][2];
+        bound = sd_step_bound(mk(S.U[a][0], S.U[a][1]), mk(S.U[b][0], S.U[b][1]), mk(S.U[c][0], S.U[c][1]),
+                              mk(S.Dir[a][0], S.Dir[a][1]), mk(S.Dir[b][0], S.Dir[b][1]), mk(S.Dir[c][0], S.Dir[c][1]), bound);
+    }
+    double alpha = block_reduce<true>(bound, S.Red) * 0.99;
+    bool inverted = false;
+    double EsdT = 0.0, EairT = 0.0, Etry = 0.0;
+    auto step_to = [&](double a) {
+        __syncthreads();
+        for (int v = tid; v < nV; v += kStBlock) {
+            S.U[v][0] = __dadd_rn(S.U0[v][0], __dmul_rn(a, S.Dir[v][0]));
+            S.U[v][1] = __dadd_rn(S.U0[v][1], __dmul_rn(a, S.Dir[v][1]));
+        }
+        __syncthreads();
+        energy_at(EsdT, EairT, inverted);
+        Etry = EsdT + wS * EairT;
+    };
+    step_to(alpha);
+    while (Etry > Elast && alpha > 0.0) { alpha /= 2.0; step_to(alpha); }          // plain decrease test (:597-610)
+    while (inverted && alpha > 0.0) { alpha /= 2.0; step_to(alpha); }              // inversion guards, mesh and air mesh (:615-629)
+    double eDec = Elast - Etry;
+    if (nTa > 0) eDec += (-lastScaf + wS * EairT);                                  // the scaffold's own change does not count (:631-634)
+    const bool stopped = (alpha == 0.0) || ((eDec / Elast < 1.0e-6 * alpha) && (alpha > 1.0e-3));
+    __syncthreads();
+    for (int v = tid; v < nV; v += kStBlock) { P.UVout[2 * (size_t)(v0 + v)] = S.U[v][0]; P.UVout[2 * (size_t)(v0 + v) + 1] = S.U[v][1]; }
+    if (tid == 0) { P.result[s] = stopped ? 2 : 0; out[0] = EsdT; out[1] = Etry; out[2] = sq; out[3] = alpha; out[4] = Elast; out[5] = eDec; }
+}
+
+int launch_stencil_step(ocb_ctx* c, const StencilStepHost& h)
+{
+    ProfScope prof(c, K_STENCILS);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(stencil_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
+        if (e != cudaSuccess) return cuda_fail(c, e, "stencil_step_kernel attribute");
+        attr = true;
+    }
+    StepParams P;
+    P.nStencil = h.nStencil; P.vertPtr = h.vertPtr; P.triPtr = h.triPtr; P.nVm = h.nVm; P.nTm = h.nTm; P.Vrest = h.Vrest; P.UV = h.UV; P.F = h.F;
+    P.isFree = h.isFree; P.areaThres = h.areaThres; P.targetGRes = h.targetGRes; P.wScaf = h.wScaf; P.UVout = h.UVout; P.out6 = h.out6; P.result = h.result;
+    stencil_step_kernel<<<h.nStencil, kStBlock, sizeof(StepSmem), c->stream>>>(P);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(c, e, "stencil_step_kernel");
+    return 0;
+}
+
 // block-reduce arg-max over the scores: first maximum wins (TriMesh.cpp:726-731)
 __global__ void __launch_bounds__(256)
 argmax_kernel(int n, const double* __restrict__ score, int* __restrict__ out)

@@ -49,3 +49,31 @@ def test_locality_order_is_a_permutation():
     a = np.sort(np.round(UV[F].reshape(len(F), -1), 12), axis=0)
     b = np.sort(np.round(Uv[Fn].reshape(len(F), -1), 12), axis=0)
     assert np.allclose(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the two-pass record / replay machinery of the candidate evaluation (shim/CudaCandidates.cpp) is decision-neutral
+import os
+import shutil
+import subprocess
+
+import pytest
+from conftest import GOLDEN, ROOT
+
+SELFCHECK = os.path.join(ROOT, "shim", "_build", "OptCuts_selfcheck_probe")
+
+
+@pytest.mark.parametrize("name,mesh,args", [("torus_cfg1", "torus.obj", ["0.999", "1", "0", "4.1", "1", "0"]),
+                                            ("bimba_cfg2", "bimba_i_f10000.obj", ["0.025", "1", "2", "4.1", "1", "0"])])
+def test_candidate_record_replay_is_decision_neutral(tmp_path, name, mesh, args):
+    """The reference host program with the patched TriMesh (querySplit / queryMerge run twice: record, then replay) and
+    OCB_CANDIDATES_SELFCHECK=1 (the recorded local problems are solved by the reference's own nested Optimizer): the
+    whole run must reproduce the reference's trace BIT FOR BIT -- same candidates, same keys, same decisions."""
+    if not os.path.exists(SELFCHECK):
+        pytest.skip("shim/_build/OptCuts_selfcheck_probe not built (make -C shim needs the reference headers)")
+    for f in os.listdir(os.path.join(GOLDEN, "inputs")):
+        shutil.copy(os.path.join(GOLDEN, "inputs", f), tmp_path)
+    env = dict(os.environ, ORACLE_TRACE=str(tmp_path / "trace.txt"), OCB_CANDIDATES_SELFCHECK="1")
+    r = subprocess.run([SELFCHECK, "100", str(tmp_path / mesh)] + args + ["t"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert open(tmp_path / "trace.txt").read() == open(os.path.join(GOLDEN, "traces", name + "_trace.txt")).read()

@@ -42,7 +42,7 @@ def main():
             nm = 2 * UV.shape[0]
             line = "%s it %d: n %d, diag range %.1e..%.1e" % (name, k, n, A.diagonal().min(), A.diagonal().max())
             for plain in (1, 0):
-                ctx.set_option("pcg_plain_norm", plain)
+                ctx.set_option("pcg_scaled_norm", 1 - plain)
                 ctx.factorize()
                 x, info = ctx.solve(None, 1e-12, 0)
                 em = np.linalg.norm(x[:nm] - ref[:nm]) / np.linalg.norm(ref[:nm])
