@@ -16,6 +16,14 @@ Workloads (config.workload):
 `e2e`    = the same through the C-ABI with HOST buffers: every step uploads the UVs (pinned host memory) and, with
            bijectivity on, the air mesh + rebuilds the sparsity pattern (as the host program must after every
            scaffold re-triangulation), runs the iteration and downloads the new UVs + the result scalars.
+The default line (no --workload) keeps bimba10k as `value` / `e2e` and adds, measured in the same run:
+  "workloads"     the same measurement (value, e2e, roofline, kernels, cpu_baseline) for bimba_x4 and bimba_x10,
+  "batch71"       BASELINE.json configs[3]: the reference's 71 benchmark meshes (tests/golden/inputs/benchmark71.tar.xz) through
+                  the reference's own host program with the GPU plugins (shim/_build/OptCuts_cuda_probe, one process per mesh,
+                  the per-mesh command line of batch.py:11-14), LPT-sharded over the ranks, every mesh bounded to
+                  --batch-iters Newton iterations: batch wall time (max over ranks), per-rank load, slowest mesh,
+  "host_program"  the WHOLE run of configs[1] (geometry + topology to convergence) in the host program: GPU plugins vs the
+                  unmodified reference on this box's host cores, with the reference's own info.txt timers of both.
 `--impl reference` times the reference's own CPU implementation of the same step
 (oracle/_ref/liboptcuts_ref.so = unmodified OptCuts::Optimizer with Eigen SimplicialLDLT, TBB shim on all
 host cores) from the same states: wall time of solve(1) minus the reference's own "scaffolding" timer.
@@ -136,23 +144,11 @@ def setup_context(ob, dev, s, p0, stream):
     return ctx
 
 
-def run_ours(args):
-    import torch
-    import optcuts_b200 as ob
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    states, p0 = load_states(args.workload)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)                # torch's current stream for the rest of the run: flush + events land on it
+def measure_workload(args, workload, K, W, torch, ob, local, world, stream, flush, with_cpu_baseline):
+    """value / e2e / roofline / kernels of one workload on this rank's GPU (max over ranks inside)"""
+    states, p0 = load_states(workload)
     ctxs = [setup_context(ob, local, s, p0, stream) for s in states]
     pcg_tol, pcg_max = args.pcg_tol, args.pcg_max_it
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
     def step_resident(i):
         c, s = ctxs[i % len(ctxs)], states[i % len(ctxs)]
@@ -210,7 +206,7 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         for i in range(K):
-            flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
+            flush.zero_()                      # L2 flush between timed iterations (outside the event pair, same stream)
             ev[i][0].record()
             res.append(fn(i))
             ev[i][1].record()
@@ -220,9 +216,6 @@ def run_ours(args):
         launches = sum(c.launch_count() for c in ctxs) - l0
         return ms, wall, launches, res
 
-    K, W = args.steps, max(args.warmup, 3)
-    sampler = ClockSampler(local)
-    sampler.start()
     ms, wall, launches, res = timed(step_resident, K, W, profile=True)
     prof = {}
     for c in ctxs:
@@ -231,7 +224,6 @@ def run_ours(args):
             a[0] += pms; a[1] += cnt
         c.profile_enable(False)
     ms_e2e, wall_e2e, _, res_e2e = timed(step_e2e, K, W)
-    clocks = sampler.stop()
 
     if world > 1:
         import torch.distributed as dist
@@ -270,7 +262,7 @@ def run_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+        traffic = json.load(open(tpath)).get(workload, {}).get(dom)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": d.get("achieved_gbs"), "peak": peak, "peak_source": peak_src,
                 "unit": "GB/s", "frac": d.get("frac"), "traffic": traffic,
                 "note": ("algorithmic bytes = (%.0f B/face [SpMV + vectors] + %.0f B/face [preconditioner levels] ) x faces + 4 x %d^2 [coarse inverse] "
@@ -285,51 +277,157 @@ def run_ours(args):
         return 0 if a is None else a["F"].nbytes + a["rest8"].nbytes + a["l2g"].nbytes + 16 * a["V"].shape[0]
     h2d = int(np.mean([16 * s["UV"].shape[0] + air_bytes(s) for s in states]))
     d2h = int(np.mean([16 * s["UV"].shape[0] for s in states])) + 16 * 8
-    line = {
-        "metric": "newton_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "wall_ms_per_step_incl_flush": 1e3 * wall / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "reference states of bimba_i_f10000 (recorded from the reference run, tests/golden)" if args.workload == "bimba10k"
+    out = {
+        "value": value, "unit": "it/s", "steps": K, "warmup": W, "ms_per_step": ms / K, "wall_ms_per_step_incl_flush": 1e3 * wall / K,
+        "data": "reference states of bimba_i_f10000 (recorded from the reference run, tests/golden)" if workload == "bimba10k"
                 else "synthetic: bimba Tutte state subdivided",
-        "config": {"workload": args.workload, "faces": int(states[0]["F"].shape[0]), "states": len(states),
+        "config": {"workload": workload, "faces": int(states[0]["F"].shape[0]), "states": len(states),
                    "air_faces": [int(s["air"]["F"].shape[0]) if s["air"] is not None else 0 for s in states],
                    "pcg_rel_tol": pcg_tol, "pcg_iters_mean": pcg_iters,
                    "preconditioner": ("two-level additive Schwarz: levels %s, exact coarse inverse of %d DOFs" % (pinfo[0]["nodes"], 6 * pinfo[0]["nodes"][-1]))
-                                     if pinfo[0]["enabled"] else "block-Jacobi", "l2": "flushed between timed iterations (256 MB memset)",
+                                     if pinfo[0]["enabled"] else "block-Jacobi", "l2": "flushed between timed iterations (256 MB memset on the timing stream)",
                    "parallelism": "independent meshes per GPU, no collective"},
-        "e2e": {"value": e2e_value, "unit": "it/s", "ms_per_step": ms_e2e / K, "wall_ms_per_step_incl_flush": 1e3 * wall_e2e / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "e2e": {"value": e2e_value, "unit": "it/s", "ms_per_step": ms_e2e / K, "wall_ms_per_step_incl_flush": 1e3 * wall_e2e / K,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
         "E_new": [res[i]["E_new"] for i in range(min(len(states), len(res)))],
     }
-    if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, budget_s=20.0)
-        print(json.dumps(line))
     for c in ctxs:
         c.close()
+    if with_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, workload, budget_s=20.0)
+    return out
+
+
+def run_ours(args):
+    import torch
+    import optcuts_b200 as ob
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)                # torch's current stream for the rest of the run: flush + events land on it
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    K, W = args.steps, max(args.warmup, 3)
+    full = args.workload is None                 # the default line: headline workload + the sub-objects
+    headline = args.workload or "bimba10k"
+    cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+    sampler = ClockSampler(local)
+    sampler.start()
+    main = measure_workload(args, headline, K, W, torch, ob, local, world, stream, flush, cpu)
+    clocks = sampler.stop()
+    line = {"metric": "newton_iters_per_s", "value": main["value"], "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64"}
+    line.update({k: v for k, v in main.items() if k not in line})
+    line["clocks"] = clocks
+    if full and not args.quick:
+        line["workloads"] = {}
+        for wl in ("bimba_x4", "bimba_x10"):
+            line["workloads"][wl] = measure_workload(args, wl, min(K, 6), 3, torch, ob, local, world, stream, flush, cpu)
+        del flush
+        torch.cuda.empty_cache()
+        line["batch71"] = batch71_ours(args, rank, world, local, torch)
+        if rank == 0 and world == 1:
+            line["host_program"] = host_program_run()
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------- batch + host program
+def batch71_ours(args, rank, world, local, torch):
+    """the 71 benchmark meshes through the host program with the GPU plugins, one process per mesh, this rank's LPT shard
+    on this rank's GPU; wall time = max over ranks (strong scaling: the batch is fixed)"""
+    from optcuts_b200 import batch
+    import tempfile
+    items = batch.benchmark71()
+    shards = batch.lpt_partition([batch.cost_model(it[1]) for it in items], world)
+    if not (os.path.exists(batch.CUDA_HOST) and os.path.exists(batch.ARCHIVE)):
+        return {"unavailable": "shim/_build/OptCuts_cuda_probe or the mesh archive is missing"}
+    rows = {}
+    with tempfile.TemporaryDirectory() as wd:
+        paths = batch.extract_benchmark(os.path.join(wd, "in"))
+        batch.run_mesh(batch.CUDA_HOST, paths[items[shards[rank][-1]][0]], os.path.join(wd, "warm"), 2, gpu=local)      # library load, CUDA context
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in shards[rank]:
+            rows[i] = batch.run_mesh(batch.CUDA_HOST, paths[items[i][0]], os.path.join(wd, "m%d" % i), args.batch_iters, gpu=local)
+        mine = time.perf_counter() - t0
+    its = sum(r["iters"] for r in rows.values())
+    bad = [items[i][0] for i, r in rows.items() if r["rc"] != 0]
+    slow = max(rows, key=lambda i: rows[i]["wall_s"])
+    per_rank = [mine]
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([mine, float(its), float(len(bad))], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [float(x[0]) for x in allt]
+        its = int(sum(float(x[1]) for x in allt))
+        nbad = int(sum(float(x[2]) for x in allt))
+    else:
+        nbad = len(bad)
+    wall = max(per_rank)
+    return {"meshes": len(items), "newton_iters_per_mesh_cap": args.batch_iters, "newton_iters": int(its), "wall_s": wall, "it_per_s": its / wall,
+            "per_rank_s": per_rank, "limiting_rank": int(np.argmax(per_rank)), "failed_meshes": nbad, "failed_on_rank0": bad,
+            "slowest_mesh_rank0": {"name": items[slow][0], "faces": items[slow][1], "wall_s": rows[slow]["wall_s"]},
+            "scaling": "strong", "note": "one host-program process per mesh (reference main + Optimizer hooks + device candidate evaluation), "
+                                         "config args %s, every mesh bounded to the cap; process start-up and CUDA context creation are inside" % " ".join(batch.MESH_ARGS)}
+
+
+def host_program_run():
+    """whole run of BASELINE.json configs[1] in the host program: GPU plugins vs the unmodified reference, this box"""
+    import subprocess
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "host_program_timing.py")], capture_output=True, text=True, errors="replace",
+                             timeout=900, env=dict(os.environ, OCB_TIMING_SKIP="cuda0")).stdout
+    except Exception as e:   # noqa: BLE001
+        return {"unavailable": str(e)}
+    res = {"config": "bimba_i_f10000.obj 0.025 1 2 4.1 1 0 (geometry + topology to convergence)", "cores": os.cpu_count()}
+    cur = None
+    for ln in out.split("\n"):
+        ln = ln.strip()
+        if ln.startswith("-- "):
+            cur = ln.split()[1]
+            res[cur] = {"wall_s": float(ln.split("wall")[1].split()[0])}
+        elif cur and ln.startswith("iterations:"):
+            res[cur]["newton_iters_topo_steps"] = ln.split(":", 1)[1].split()[:2]
+        elif cur and ln.startswith("timers:"):
+            res[cur]["info_txt_timers"] = ln.split(":", 1)[1].strip()
+        elif cur and ln.startswith("final"):
+            res[cur]["final_E_SD_E_se"] = ln.split(":", 1)[1].split()
+    if "cuda" in res and "ref" in res:
+        res["speedup_whole_run"] = res["ref"]["wall_s"] / res["cuda"]["wall_s"]
+    return res
+
+
 # ------------------------------------------------------------------------------------- reference arm
-def ref_step_times(args, n_steps, budget_s):
+def ref_step_times(workload, n_steps, budget_s):
     """Times Optimizer::solve(1) of the UNMODIFIED reference (oracle/_ref) from the workload's states."""
     from oracle import refapi
-    states, p0 = load_states(args.workload)
+    states, p0 = load_states(workload)
     kind = "reference"
     if not refapi.available():
         raise RuntimeError("oracle/_ref/liboptcuts_ref.so is missing (built by `make -C oracle ref` where /root/reference exists)")
     out_dir = tempfile.mkdtemp(prefix="ocb_ref_")
     refapi.set_output_folder(out_dir + "/")
     times, t_begin = [], time.perf_counter()
-    i = 0
     # the reference chats on stdout per iteration (Optimizer.cpp:212,582,612,642): keep the JSON line clean
     sys.stdout.flush()
     saved_fd = os.dup(1)
     devnull = os.open(os.devnull, os.O_WRONLY)
     os.dup2(devnull, 1)
     try:
-        return _ref_loop(refapi, states, p0, n_steps, budget_s, times, t_begin, i), kind
+        return _ref_loop(refapi, states, p0, n_steps, budget_s, times, t_begin, 0), kind
     finally:
         os.dup2(saved_fd, 1)
         os.close(saved_fd); os.close(devnull)
@@ -351,9 +449,28 @@ def _ref_loop(refapi, states, p0, n_steps, budget_s, times, t_begin, i):
     return times
 
 
-def cpu_baseline(args, budget_s):
+def cpu_baseline(args, workload, budget_s):
+    """bounded sample of the reference's CPU implementation of the same step, this box's host cores.  The 1M-face workload
+    runs in a child process under a time limit: one reference iteration there is minutes of sparse LDL^T."""
+    if workload == "bimba_x10":
+        import subprocess
+        limit = args.cpu_limit_x10
+        t0 = time.perf_counter()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0"],
+                               capture_output=True, text=True, errors="replace", timeout=limit)
+            ln = [x for x in r.stdout.split("\n") if x.startswith("{")]
+            d = json.loads(ln[-1])
+            if "cpu_baseline" in d:
+                return d["cpu_baseline"]
+            return {"unavailable": d.get("unavailable", "no result")}
+        except subprocess.TimeoutExpired:
+            return {"unavailable": "one reference Newton iteration (precompute + solve(1), Eigen SimplicialLDLT) did not finish within %d s on %d cores"
+                                   % (limit, os.cpu_count()), "lower_bound_s_per_step": time.perf_counter() - t0, "cores": os.cpu_count(), "kind": "reference"}
+        except Exception as e:   # noqa: BLE001
+            return {"unavailable": str(e)}
     try:
-        times, kind = ref_step_times(args, n_steps=64, budget_s=budget_s)
+        times, kind = ref_step_times(workload, n_steps=64, budget_s=budget_s)
     except Exception as e:   # noqa: BLE001
         return {"unavailable": str(e)}
     return {"value": len(times) / sum(times), "unit": "it/s", "cores": os.cpu_count(), "kind": kind,
@@ -362,130 +479,97 @@ def cpu_baseline(args, budget_s):
                       "from the same states; wall time minus the reference's own scaffolding timer" % len(times)}
 
 
+def reference_line(workload, K, W, budget):
+    times, kind = ref_step_times(workload, n_steps=K + W, budget_s=budget)
+    t = times[W:] if len(times) > W else times
+    v = len(t) / sum(t)
+    states, _ = load_states(workload)
+    return {"value": v, "unit": "it/s", "steps": len(t), "warmup": W, "ms_per_step": 1e3 * sum(t) / len(t),
+            "data": "same states as the GPU arm",
+            "config": {"workload": workload, "faces": int(states[0]["F"].shape[0]), "states": len(states)},
+            "cpu_baseline": {"value": v, "unit": "it/s", "cores": os.cpu_count(), "kind": kind,
+                             "sample": "%d timed Newton iterations (Optimizer::solve(1) minus its scaffolding timer), rank 0 only" % len(t)},
+            "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def batch71_reference(args, world):
+    """the reference arm of the batch: `world` concurrent CPU processes (one mesh each at a time), same meshes, same cap"""
+    from optcuts_b200 import batch
+    from concurrent.futures import ThreadPoolExecutor
+    items = batch.benchmark71()
+    if not (os.path.exists(batch.REF_HOST) and os.path.exists(batch.ARCHIVE)):
+        return {"unavailable": "oracle/_ref/OptCuts_probe or the mesh archive is missing"}
+    pick = list(range(len(items)))
+    if args.batch_ref_sample and args.batch_ref_sample < len(items):          # bounded sample: every k-th mesh by size
+        order = sorted(pick, key=lambda i: items[i][1])
+        pick = order[::max(1, len(order) // args.batch_ref_sample)][:args.batch_ref_sample]
+    with tempfile.TemporaryDirectory() as wd:
+        paths = batch.extract_benchmark(os.path.join(wd, "in"))
+        order = sorted(pick, key=lambda i: -items[i][1])
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=world) as ex:
+            rows = list(ex.map(lambda i: batch.run_mesh(batch.REF_HOST, paths[items[i][0]], os.path.join(wd, "m%d" % i), args.batch_iters), order))
+        wall = time.perf_counter() - t0
+    its = sum(r["iters"] for r in rows)
+    return {"meshes": len(pick), "of": len(items), "newton_iters_per_mesh_cap": args.batch_iters, "newton_iters": int(its), "wall_s": wall,
+            "it_per_s": its / wall, "concurrent_processes": world, "cores": os.cpu_count(), "failed_meshes": sum(1 for r in rows if r["rc"] != 0),
+            "note": "unmodified reference (oracle/_ref/OptCuts_probe), %d meshes at a time, largest first" % world}
+
+
 def run_reference(args):
-    rank = int(os.environ.get("RANK", 0))
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
     K, W = args.steps, max(args.warmup, 1)
-    per_step_budget = 150.0
+    headline = args.workload or "bimba10k"
     try:
-        times, kind = ref_step_times(args, n_steps=K + W, budget_s=per_step_budget)
+        main = reference_line(headline, K, W, 150.0)
     except Exception as e:   # noqa: BLE001
         print(json.dumps({"impl": "reference", "unavailable": str(e)}))
         return
-    t = times[W:] if len(times) > W else times
-    v = len(t) / sum(t)
-    states, _ = load_states(args.workload)
-    print(json.dumps({
-        "impl": "reference", "metric": "newton_iters_per_s", "value": v, "unit": "it/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
-        "steps": len(t), "warmup": W, "ms_per_step": 1e3 * sum(t) / len(t), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "same states as the GPU arm",
-        "config": {"workload": args.workload, "faces": int(states[0]["F"].shape[0]), "states": len(states)},
-        "cpu_baseline": {"value": v, "unit": "it/s", "cores": os.cpu_count(), "kind": kind,
-                         "sample": "%d timed Newton iterations (Optimizer::solve(1) minus its scaffolding timer), rank 0 only" % len(t)},
-        "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    line = {"impl": "reference", "metric": "newton_iters_per_s", "value": main["value"], "unit": "it/s", "n_gpus": world, "steps": main["steps"],
+            "warmup": W, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64"}
+    line.update({k: v for k, v in main.items() if k not in line})
+    if args.workload is None and not args.quick:
+        line["workloads"] = {}
+        try:
+            line["workloads"]["bimba_x4"] = reference_line("bimba_x4", 2, 0, 30.0)
+        except Exception as e:   # noqa: BLE001
+            line["workloads"]["bimba_x4"] = {"unavailable": str(e)}
+        line["batch71"] = batch71_reference(args, world)
+    print(json.dumps(line))
 
 
-# ------------------------------------------------------------------------------------------ batch leg
 def run_batch(args):
-    """BASELINE.json configs[3]: the 71-mesh benchmark sharded as independent meshes over the ranks (LPT on the
-    face count, no collective on the data path).  The benchmark OBJs cannot travel, so every mesh is a synthetic
-    disk with the benchmark mesh's face count; each gets `--batch-iters` free-running Newton iterations.
-    One "step" = the whole batch; value = Newton iterations of all meshes / max-over-ranks time (strong scaling)."""
-    import torch
-    from optcuts_b200 import batch
+    """--workload batch71: the batch alone (both arms)"""
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    items = batch.benchmark71()
-    shards = batch.lpt_partition([batch.cost_model(it[1]) for it in items], world)
     if args.impl == "reference":
         if rank != 0:
             return
-        from oracle import refapi
-        import ctypes
-        t_tot, n_it, done = 0.0, 0, 0
-        sys.stdout.flush(); saved = os.dup(1); dn = os.open(os.devnull, os.O_WRONLY); os.dup2(dn, 1)
-        try:
-            for k in sorted(range(len(items)), key=lambda i: items[i][1])[::7][:10]:       # bounded sample: 10 meshes across the size range
-                V_rest, F, UV = batch.synthetic_disk(items[k][1], seed=k)
-                m = refapi.RefMesh(V_rest, F, UV)
-                opt = refapi.RefOptimizer(m, 0.975, scaffolding=False, mute=True)
-                t0 = time.perf_counter()
-                for _ in range(args.batch_iters):
-                    if opt.solve(1):
-                        break
-                    n_it += 1
-                t_tot += time.perf_counter() - t0
-                done += 1
-                opt.close(); m.close()
-        finally:
-            os.dup2(saved, 1); os.close(saved); os.close(dn)
-        v = n_it / t_tot
+        b = batch71_reference(args, world)
+        v = b.get("it_per_s")
         print(json.dumps({"impl": "reference", "metric": "newton_iters_per_s", "value": v, "unit": "it/s", "n_gpus": world, "steps": 1, "warmup": 0,
-                          "ms_per_step": 1e3 * t_tot, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                          "data": "synthetic disks with the benchmark face counts", "config": {"workload": "batch71", "sampled_meshes": done},
-                          "cpu_baseline": {"value": v, "unit": "it/s", "cores": os.cpu_count(), "kind": "reference",
-                                           "sample": "%d of the 71 meshes (every 7th by size), %d Newton iterations each, one mesh at a time" % (done, args.batch_iters)},
+                          "ms_per_step": 1e3 * b.get("wall_s", 0.0), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "the reference's 71 benchmark meshes", "config": {"workload": "batch71"}, "batch71": b,
+                          "cpu_baseline": {"value": v, "unit": "it/s", "cores": os.cpu_count(), "kind": "reference", "sample": b.get("note")},
                           "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
-    import optcuts_b200 as ob
+    import torch
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    meshes = {k: batch.synthetic_disk(items[k][1], seed=k) for k in shards[rank]}
-
-    def one_pass():
-        n_it, h2d, d2h, launches = 0, 0, 0, 0
-        for k, (V_rest, F, UV) in meshes.items():
-            ctx = ob.Context(local)
-            mesh = ob.TriMesh(V_rest, F, UV, ctx=ctx)
-            opt = ob.Optimizer(mesh, energyParams=(0.975,), ctx=ctx)
-            opt.precompute()
-            for _ in range(args.batch_iters):
-                if opt.solve(1):
-                    break
-                n_it += 1
-            res = opt.getResult()
-            h2d += V_rest.nbytes + F.nbytes + UV.nbytes
-            d2h += res.V.nbytes
-            launches += ctx.launch_count()
-            ctx.close()
-        return n_it, h2d, d2h, launches
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier(); torch.cuda.synchronize()
-    one_pass()                                   # warm-up (library load, allocator)
     sampler = ClockSampler(local); sampler.start()
-    K = max(1, min(args.steps, 3))
-    barrier(); t0 = time.perf_counter()
-    tot = [one_pass() for _ in range(K)]
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    barrier()
+    b = batch71_ours(args, rank, world, local, torch)
     clocks = sampler.stop()
-    n_it = sum(t[0] for t in tot) / K
-    vals = torch.tensor([dt / K, float(n_it)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        import torch.distributed as dist
-        tmax = vals[:1].clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        nsum = vals[1:].clone(); dist.all_reduce(nsum, op=dist.ReduceOp.SUM)
-        tstep, ntot = float(tmax[0]), float(nsum[0])
-    else:
-        tstep, ntot = float(vals[0]), float(vals[1])
     if rank == 0:
-        v = ntot / tstep
-        print(json.dumps({"metric": "newton_iters_per_s", "value": v, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": 1,
-                          "ms_per_step": 1e3 * tstep, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                          "data": "synthetic disks with the face counts of the reference's 71 benchmark meshes",
-                          "config": {"workload": "batch71", "meshes": 71, "newton_iters_per_mesh": args.batch_iters, "total_newton_iters": ntot,
-                                     "parallelism": "LPT shard of independent meshes per GPU, no collective", "l2": "inputs re-uploaded per mesh",
-                                     "timing": "wall clock around the whole batch (host work included), max over ranks"},
-                          "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": tot[0][1], "d2h_bytes_per_step": tot[0][2]},
-                          "gpu_launches": int(sum(t[3] for t in tot)), "clocks": clocks,
-                          "batch_wall_s": tstep}))
+        v = b.get("it_per_s")
+        print(json.dumps({"metric": "newton_iters_per_s", "value": v, "unit": "it/s", "n_gpus": world, "steps": 1, "warmup": 1,
+                          "ms_per_step": 1e3 * b.get("wall_s", 0.0), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "the reference's 71 benchmark meshes (tests/golden/inputs/benchmark71.tar.xz)",
+                          "config": {"workload": "batch71", "parallelism": "LPT shard of independent meshes per GPU, no collective"},
+                          "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None}, "batch71": b, "clocks": clocks}))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -497,8 +581,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bimba10k", choices=["bimba10k", "bimba_x4", "bimba_x10", "batch71"])
-    ap.add_argument("--batch-iters", type=int, default=25, help="batch71: Newton iterations per mesh")
+    ap.add_argument("--workload", default=None, choices=["bimba10k", "bimba_x4", "bimba_x10", "batch71"],
+                    help="default: bimba10k as the headline + bimba_x4 / bimba_x10 / batch71 / host_program sub-objects")
+    ap.add_argument("--quick", action="store_true", help="headline workload only (no sub-objects)")
+    ap.add_argument("--batch-iters", type=int, default=15, help="batch71: cap of Newton iterations per mesh")
+    ap.add_argument("--batch-ref-sample", type=int, default=24, help="reference arm of batch71: number of meshes sampled across the size range (0 = all 71)")
+    ap.add_argument("--cpu-limit-x10", type=int, default=45, help="time limit (s) of the reference's iteration at 1M faces")
     ap.add_argument("--pcg-tol", type=float, default=1e-12)
     ap.add_argument("--pcg-max-it", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

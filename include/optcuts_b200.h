@@ -256,7 +256,7 @@ int ocb_eval_stencils(ocb_ctx* ctx, const ocb_stencil_batch* batch, int maxIter,
  * (area weights), then the air mesh's (uniform weights, scaled by w_scaf / #air triangles; rest shape = the positions
  * handed in, clamped by area_thres: TriMesh.cpp:373-383).  Per stencil: result = 0 step taken, 1 converged before a step
  * (||g||^2 < target_gres, Optimizer.cpp:215-221), 2 step taken and the line search says stop (:635), -2 over the limits
- * (128 vertices, 192 triangles, 32 free vertices), -4 inverted input; out6 = E_SD of the mesh at the returned UVs,
+ * (128 vertices, 192 triangles, 32 free vertices), -4 inverted input, -5 non-finite result; out6 = E_SD of the mesh at the returned UVs,
  * E incl. scaffold, ||g||^2, accepted step, E before the step, lastEDec. */
 typedef struct {
     int nStencil;

@@ -54,6 +54,48 @@ def run_sharded(items, work, rank, world, gather=None):
     return merged, shards
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# the real batch: the reference's 71 benchmark meshes through the reference's own host program (one process per mesh,
+# the per-mesh command line of batch.py:11-14 in headless mode 100) with the GPU plugins dropped in
+ARCHIVE = os.path.join(os.path.dirname(_HERE), "tests", "golden", "inputs", "benchmark71.tar.xz")
+CUDA_HOST = os.path.join(os.path.dirname(_HERE), "shim", "_build", "OptCuts_cuda_probe")
+REF_HOST = os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "OptCuts_probe")
+MESH_ARGS = ["0.999", "1", "0", "4.1", "1", "0"]          # BASELINE.json configs[0] / batch.py: lambda_init 0.999, OptCuts, b_d 4.1, bijective
+
+
+def extract_benchmark(dst):
+    """unpacks the 71 OBJ files (5 MB archive, a data fixture) into dst; returns {name: path}"""
+    import tarfile
+    with tarfile.open(ARCHIVE) as t:
+        t.extractall(dst)
+    return {f: os.path.join(dst, f) for f in sorted(os.listdir(dst)) if f.endswith(".obj")}
+
+
+def run_mesh(exe, mesh_path, workdir, max_iters, gpu=None, timeout=1800):
+    """one mesh through a host program (probe build: ORACLE_MAX_ITERS bounds the run).  Returns dict(rc, wall_s, iters)."""
+    import subprocess
+    import time
+    os.makedirs(workdir, exist_ok=True)
+    env = dict(os.environ, ORACLE_TRACE=os.path.join(workdir, "trace.txt"))
+    if max_iters:
+        env["ORACLE_MAX_ITERS"] = str(int(max_iters))
+    if gpu is not None:
+        env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+    t0 = time.perf_counter()
+    try:
+        r = subprocess.run([exe, "100", mesh_path] + MESH_ARGS + ["b"], cwd=workdir, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout)
+        rc = r.returncode
+    except subprocess.TimeoutExpired:
+        rc = -999
+    dt = time.perf_counter() - t0
+    n = 0
+    try:
+        n = sum(1 for _ in open(os.path.join(workdir, "trace.txt")))
+    except OSError:
+        pass
+    return dict(rc=rc, wall_s=dt, iters=n)
+
+
 def synthetic_disk(faces, seed=0):
     """A synthetic open triangle mesh with ~`faces` triangles: a jittered grid lifted onto a bumpy surface, with
     a distorted but inversion-free initial UV (stands in for the benchmark meshes, which cannot travel)."""

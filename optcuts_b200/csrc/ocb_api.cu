@@ -56,7 +56,7 @@ static void prof_collect(ocb_ctx* c)
 
 static bool host_timing_on() { static const bool on = []() { const char* e = getenv("OCB_HOST_TIMING"); return e && atoi(e); }(); return on; }
 struct HostTimingRec { const char* name; double total; long count; };
-static std::vector<HostTimingRec>& host_timing_table() { static std::vector<HostTimingRec> t; return t; }
+static std::vector<HostTimingRec>& host_timing_table() { static std::vector<HostTimingRec>* t = new std::vector<HostTimingRec>(); return *t; }   // never destroyed: the report runs from atexit
 static double wall_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 HostTimer::HostTimer(const char* n) : name(n), t0(host_timing_on() ? wall_now() : 0.0)
 {
@@ -106,7 +106,7 @@ ElemView view_of(const ocb_ctx* c, const ElemSet& s, bool isAir, double scale, i
     const double* r = s.rest.p;
     v.area = r; v.areaSq = r + n; v.e0 = r + 2 * n; v.e1 = r + 3 * n; v.d = r + 4 * n;
     v.k0 = r + 5 * n; v.k1 = r + 6 * n; v.kd = r + 7 * n;
-    v.slot = s.slot.p;
+    v.slot = s.slot.p; v.rec = s.rec.p; v.vcSlot = s.vcSlot.p;
     v.surfaceArea = isAir ? 1.0 : c->surfaceArea;
     v.uniform = uniform;
     v.scale = scale;
@@ -251,7 +251,7 @@ void ocb_destroy(ocb_ctx* c)
     if (c->inited) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
-        c->mesh.v.release(); c->mesh.rest.release(); c->mesh.slot.release();
+        c->mesh.v.release(); c->mesh.rest.release(); c->mesh.slot.release(); c->mesh.rec.release(); c->mesh.vcSlot.release(); c->air.rec.release(); c->air.vcSlot.release();
         c->air.v.release(); c->air.rest.release(); c->air.slot.release();
         c->l2g.release(); c->vcPtrM.release(); c->vcIdxM.release(); c->vcPtrA.release(); c->vcIdxA.release(); c->g2l.release(); c->hel.release(); c->fixedMask.release(); c->perm.release(); c->scratchV.release(); c->stD.release(); c->stI.release();
         c->x.release(); c->x0.release(); c->g.release(); c->p.release();
@@ -366,6 +366,16 @@ static int upload_elems(ocb_ctx* c, ElemSet& S, std::vector<int32_t>& hostCopy, 
         hostCopy.assign(F_global_soa, F_global_soa + (size_t)3 * n);
         OCB_TRY(upload_i(c, S.v.p, hostCopy.data(), (size_t)3 * n));
         OCB_TRY(upload_d(c, S.rest.p, rest8, (size_t)8 * n));
+        // the same data once more as one 64-byte record per triangle (vertex-gather kernels)
+        OCB_CUDA(c, S.rec.reserve((size_t)8 * n + 8, c->stream));
+        std::vector<double> rec((size_t)8 * n, 0.0);
+        for (int t = 0; t < n; ++t) {
+            double* r = rec.data() + 8 * (size_t)t;
+            int32_t iv[4] = {F_global_soa[t], F_global_soa[(size_t)n + t], F_global_soa[2 * (size_t)n + t], 0};
+            std::memcpy(r, iv, 16);
+            for (int q = 0; q < 5; ++q) r[2 + q] = rest8[(size_t)q * n + t];
+        }
+        OCB_TRY(upload_d(c, S.rec.p, rec.data(), (size_t)8 * n));
     } else hostCopy.clear();
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;

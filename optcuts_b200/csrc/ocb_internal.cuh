@@ -44,6 +44,9 @@ struct ElemSet {
     DevBuf<int32_t> v;      // 3 x n  (v0 | v1 | v2), stride = n
     DevBuf<double> rest;    // 8 x n  (TriMesh.hpp:44-52 order, see optcuts_b200.h), stride = n
     DevBuf<int32_t> slot;   // 9 x n  BSR block slot of (k,l), -1 if either vertex is fixed
+    DevBuf<double> rec;     // 8 x n  one 64-byte record per triangle {v0 v1 v2 - | area areaSq e0 e1 d -} for the vertex-gather
+                            //        kernels, which visit triangles in no particular order (2 sectors instead of 8)
+    DevBuf<int32_t> vcSlot; // 4 x 3n per corner of the vertex->corner list: {element << 2 | corner, slot(k,0), slot(k,1), slot(k,2)}
 };
 
 // kernel-side view of an ElemSet
@@ -53,6 +56,8 @@ struct ElemView {
     const double* area; const double* areaSq; const double* e0; const double* e1; const double* d;
     const double* k0; const double* k1; const double* kd;
     const int32_t* slot;     // 9 x n or nullptr
+    const double* rec;       // 8 x n records (see ElemSet)
+    const int32_t* vcSlot;   // 4 per corner (see ElemSet)
     double surfaceArea;      // normaliser; weight = uniform ? 1 : area / surfaceArea
     int uniform;
     double scale;            // energyParam0 (mesh) or w_scaf/|Fa| (air): applied after projection

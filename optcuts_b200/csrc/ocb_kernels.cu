@@ -196,6 +196,17 @@ struct GatherView {
 };
 struct Slots5 { int s[5]; };
 
+// one triangle's 64-byte record: four 16-byte loads, two sectors (the SoA arrays cost eight sectors per visit)
+struct ElemRecord { int i0, i1, i2; double area, A2, e0, e1, d; };
+__device__ __forceinline__ ElemRecord load_record(const double* __restrict__ rec, int t)
+{
+    const int4 iv = __ldg(reinterpret_cast<const int4*>(rec) + 4 * (size_t)t);
+    const double2 a = __ldg(reinterpret_cast<const double2*>(rec) + 4 * (size_t)t + 1), b = __ldg(reinterpret_cast<const double2*>(rec) + 4 * (size_t)t + 2);
+    const double2 cc = __ldg(reinterpret_cast<const double2*>(rec) + 4 * (size_t)t + 3);
+    ElemRecord R; R.i0 = iv.x; R.i1 = iv.y; R.i2 = iv.z; R.area = a.x; R.A2 = a.y; R.e0 = b.x; R.e1 = b.y; R.d = cc.x;
+    return R;
+}
+
 static constexpr int kGradLanes = 4;        // lanes per vertex: the corner evaluations (7 fp64 divisions each) of a vertex run side by side
 
 // The kGradLanes lanes of a vertex evaluate its corners round-robin (corner j on lane j % kGradLanes); the sum is then
@@ -214,11 +225,10 @@ __device__ __forceinline__ void gather_corners(const ElemView& S, const int32_t*
         Vec2 gk = mk(0.0, 0.0);
         if (q < q1) {
             const int code = __ldg(idx + q), t = code >> 2, k = code & 3;
-            const int i0 = __ldg(S.v0 + t), i1 = __ldg(S.v1 + t), i2 = __ldg(S.v2 + t);
-            const double area = __ldg(S.area + t), A2 = __ldg(S.areaSq + t), e0 = __ldg(S.e0 + t), e1 = __ldg(S.e1 + t), d = __ldg(S.d + t);
-            const double w = AIR_SET ? 1.0 : area / S.surfaceArea;
+            const ElemRecord R = load_record(S.rec, t);
+            const double w = AIR_SET ? 1.0 : R.area / S.surfaceArea;
             double E, dbArea;
-            sd_corner(ld2(x, i0), ld2(x, i1), ld2(x, i2), A2, e0, e1, d, w, k, gk, E, dbArea);
+            sd_corner(ld2(x, R.i0), ld2(x, R.i1), ld2(x, R.i2), R.A2, R.e0, R.e1, R.d, w, k, gk, E, dbArea);
             if (k == 0) { Esum += E; if (dbArea < 0.0) nInv += 1.0; }
         }
 #pragma unroll
@@ -393,19 +403,29 @@ static constexpr int kRowLanes = 8;         // lanes per block row of the row ga
 // walks ALL incident corners of the vertex in ascending element order (the group reads the same addresses: broadcasts)
 // and adds row k of an element's block matrix into its own block when the element's slot map says so -- a register
 // accumulator per owned block, contributions in the reference's triplet order, one 32-byte store per block.
-__device__ __forceinline__ void row_lane_add(const double* __restrict__ hel, size_t nE, size_t e, int k, const int32_t* __restrict__ slot,
-                                             int nS, int t, int myBlock, double (&acc)[4])
+__device__ __forceinline__ void row_lane_add(const double* __restrict__ hel, size_t nE, size_t eBase, const int4 cs, int myBlock, double (&acc)[4])
 {
-    const int s0 = __ldg(slot + (size_t)(3 * k) * nS + t), s1 = __ldg(slot + (size_t)(3 * k + 1) * nS + t), s2 = __ldg(slot + (size_t)(3 * k + 2) * nS + t);
-    const int l = (s0 == myBlock) ? 0 : ((s1 == myBlock) ? 1 : ((s2 == myBlock) ? 2 : -1));
+    // cs = {element << 2 | corner, slot(k,0), slot(k,1), slot(k,2)}: one 16-byte load per corner, read front to back
+    const int k = cs.x & 3;
+    const int l = (cs.y == myBlock) ? 0 : ((cs.z == myBlock) ? 1 : ((cs.w == myBlock) ? 2 : -1));
     if (l < 0) return;
     // block (k,l) of the element: stored as is for k <= l, as the transpose of (l,k) otherwise
     const int lo = k < l ? k : l, hi = k < l ? l : k;
     const int b = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);                 // (0,0)(0,1)(0,2)(1,1)(1,2)(2,2) -> 0..5
-    const double2* src = reinterpret_cast<const double2*>(hel + 4 * ((size_t)b * nE + e));
+    const double2* src = reinterpret_cast<const double2*>(hel + 4 * ((size_t)b * nE + eBase + (size_t)(cs.x >> 2)));
     const double2 r0 = __ldcg(src), r1 = __ldcg(src + 1);
     const bool tr = k > l;
     acc[0] += r0.x; acc[1] += tr ? r1.x : r0.y; acc[2] += tr ? r0.y : r1.x; acc[3] += r1.y;
+}
+
+// per corner of the vertex->corner list: the corner code and the three BSR slots of its row of the element block matrix
+__global__ void __launch_bounds__(kBlock)
+build_vcslot_kernel(int nCorners, int n, const int32_t* __restrict__ vcIdx, const int32_t* __restrict__ slot, int32_t* __restrict__ vcSlot)
+{
+    for (int q = blockIdx.x * kBlock + threadIdx.x; q < nCorners; q += gridDim.x * kBlock) {
+        const int code = vcIdx[q], t = code >> 2, k = code & 3;
+        reinterpret_cast<int4*>(vcSlot)[q] = make_int4(code, slot[(size_t)(3 * k) * n + t], slot[(size_t)(3 * k + 1) * n + t], slot[(size_t)(3 * k + 2) * n + t]);
+    }
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -431,14 +451,8 @@ hessian_rows_kernel(ElemView M, ElemView A, GatherView G, const double* __restri
         const int qA0 = la >= 0 ? G.vcPtrA[la] : 0, qA1 = la >= 0 ? G.vcPtrA[la + 1] : 0;
         for (int b = lo + lane; b < lo + nb; b += kRowLanes) {
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int q = qM0; q < qM1; ++q) {
-                const int code = __ldg(G.vcIdxM + q);
-                row_lane_add(hel, nE, (size_t)(code >> 2), code & 3, M.slot, M.n, code >> 2, b, acc);
-            }
-            for (int q = qA0; q < qA1; ++q) {
-                const int code = __ldg(G.vcIdxA + q);
-                row_lane_add(hel, nE, (size_t)M.n + (code >> 2), code & 3, A.slot, A.n, code >> 2, b, acc);
-            }
+            for (int q = qM0; q < qM1; ++q) row_lane_add(hel, nE, 0, __ldg(reinterpret_cast<const int4*>(M.vcSlot) + q), b, acc);
+            for (int q = qA0; q < qA1; ++q) row_lane_add(hel, nE, (size_t)M.n, __ldg(reinterpret_cast<const int4*>(A.vcSlot) + q), b, acc);
             double2* o = reinterpret_cast<double2*>(val + 4 * (size_t)b);
             o[0] = make_double2(acc[0], acc[1]); o[1] = make_double2(acc[2], acc[3]);
         }
@@ -622,9 +636,10 @@ divgrad_gather_kernel(ElemView M, GatherView G, const double* __restrict__ x, do
         for (int pass = 0; pass < 2; ++pass) {
             for (int q = q0; q < q1; ++q) {
                 const int code = __ldg(G.vcIdxM + q), t = code >> 2, k = code & 3;
-                const double w = M.area[t] / M.surfaceArea;
+                const ElemRecord R = load_record(M.rec, t);
+                const double w = R.area / M.surfaceArea;
                 Vec2 gk; double E, dbArea;
-                sd_corner(ld2(x, M.v0[t]), ld2(x, M.v1[t]), ld2(x, M.v2[t]), M.areaSq[t], M.e0[t], M.e1[t], M.d[t], w, k, gk, E, dbArea);
+                sd_corner(ld2(x, R.i0), ld2(x, R.i1), ld2(x, R.i2), R.A2, R.e0, R.e1, R.d, w, k, gk, E, dbArea);
                 if (pass == 0) { mx += gk.x; my += gk.y; }
                 else { const double dx = gk.x - mx, dy = gk.y - my; dev += dx * dx + dy * dy; }
             }
@@ -731,6 +746,9 @@ int launch_build_slots(ocb_ctx* c)
         OCB_CUDA(c, S.slot.reserve((size_t)9 * S.n, c->stream));
         build_slots_kernel<<<grid_for(c, S.n), kBlock, 0, c->stream>>>(S.n, S.v.p, S.v.p + S.n, S.v.p + 2 * (size_t)S.n,
                                                                       c->fixedMask.p, c->rowPtr.p, c->colIdx.p, S.slot.p, missing, c->rowOf.p);
+        KCHECK(c);
+        OCB_CUDA(c, S.vcSlot.reserve((size_t)12 * S.n + 4, c->stream));
+        build_vcslot_kernel<<<grid_for(c, 3L * S.n), kBlock, 0, c->stream>>>(3 * S.n, S.n, which ? c->vcIdxA.p : c->vcIdxM.p, S.slot.p, S.vcSlot.p);
         KCHECK(c);
     }
     int hMissing = 0;

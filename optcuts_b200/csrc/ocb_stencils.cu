@@ -386,7 +386,10 @@ stencil_step_kernel(StepParams P)
     for (int k = 0; k < n; ++k) {
         __syncthreads();                                   // the trailing update of step k - 1 is complete
         const double dk = S.H[k][k];
-        for (int i = k + 1 + tid; i < n; i += kStBlock) S.H[i][k] = S.H[i][k] / dk;              // L(i,k)
+        // a vanished pivot (the projected element Hessians are only semi-definite) is skipped like Eigen::LDLT::solve does:
+        // zero column, zero component of the solution
+        const bool zeroPivot = !(fabs(dk) > 0.0);
+        for (int i = k + 1 + tid; i < n; i += kStBlock) S.H[i][k] = zeroPivot ? 0.0 : S.H[i][k] / dk;              // L(i,k)
         __syncthreads();
         const int m = n - k - 1;
         for (int e = tid; e < m * m; e += kStBlock) {
@@ -403,7 +406,7 @@ stencil_step_kernel(StepParams P)
             for (int i = j + 1 + tid; i < n; i += 32) S.P[i] -= S.H[i][j] * yj;
             __syncwarp();
         }
-        for (int i = tid; i < n; i += 32) S.P[i] /= S.H[i][i];
+        for (int i = tid; i < n; i += 32) S.P[i] = (fabs(S.H[i][i]) > 0.0) ? S.P[i] / S.H[i][i] : 0.0;
         __syncwarp();
         for (int j = n - 1; j >= 0; --j) {                 // backward: L^T p = D^-1 y
             const double pj = S.P[j];
@@ -445,6 +448,9 @@ stencil_step_kernel(StepParams P)
     if (nTa > 0) eDec += (-lastScaf + wS * EairT);                                  // the scaffold's own change does not count (:631-634)
     const bool stopped = (alpha == 0.0) || ((eDec / Elast < 1.0e-6 * alpha) && (alpha > 1.0e-3));
     __syncthreads();
+    bool bad = false;
+    for (int v = tid; v < nV; v += kStBlock) if (!isfinite(S.U[v][0]) || !isfinite(S.U[v][1])) bad = true;
+    if (__syncthreads_or(bad ? 1 : 0)) { fail(-5); return; }       // non-finite result: the caller evaluates this stencil itself
     for (int v = tid; v < nV; v += kStBlock) { P.UVout[2 * (size_t)(v0 + v)] = S.U[v][0]; P.UVout[2 * (size_t)(v0 + v) + 1] = S.U[v][1]; }
     if (tid == 0) { P.result[s] = stopped ? 2 : 0; out[0] = EsdT; out[1] = Etry; out[2] = sq; out[3] = alpha; out[4] = Elast; out[5] = eDec; }
 }

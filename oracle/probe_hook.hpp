@@ -17,6 +17,21 @@
 #include <cstring>
 #include <set>
 #include <string>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
+// a crash in a test run leaves a backtrace on stderr (the probe binaries are linked -rdynamic)
+static void oracle_segv_handler(int sig)
+{
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "\n[oracle probe] fatal signal, backtrace:\n";
+    if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+static const bool oracle_segv_installed = []() { signal(SIGSEGV, oracle_segv_handler); signal(SIGABRT, oracle_segv_handler); return true; }();
 
 static void oracle_write_rec(FILE* f, const char* name, char type, long rows, long cols, const void* data)
 {

@@ -92,6 +92,13 @@ static Solver* bind(OcbOptView& v)
     return S;
 }
 
+bool ocbDeviceResident(LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* solver)
+{
+    if (!enabled()) return false;
+    Solver* S = dynamic_cast<Solver*>(solver);
+    return S && S->newton.deviceResident;
+}
+
 bool ocbHookEnergy(OcbOptView& v, double& energyVal, bool excludeScaffold)
 {
     Solver* S = bind(v);

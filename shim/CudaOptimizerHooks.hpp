@@ -40,6 +40,7 @@ bool ocbHookEnergy(OcbOptView& v, double& energyVal, bool excludeScaffold);
 bool ocbHookGradient(OcbOptView& v, Eigen::VectorXd& gradient, bool excludeScaffold);
 bool ocbHookHessian(OcbOptView& v);
 bool ocbHookStep(OcbOptView& v, bool& stopped);
+bool ocbDeviceResident(LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* solver);      // the hooks drive this optimizer's solver
 
 }  // namespace OptCuts
 
@@ -51,4 +52,7 @@ bool ocbHookStep(OcbOptView& v, bool& stopped);
 #define OCB_HOOK_STEP     if (!useDense) { OCB_OPT_VIEW(this->gradient); bool ocbStopped_ = false; \
                               if (OptCuts::ocbHookStep(ocbV_, ocbStopped_)) { fractureInitiated = false; \
                                   if (!mute && !ocbStopped_) writeEnergyValToFile(false); return ocbStopped_; } }
+// Scaffold::mergeVNeighbor only feeds LinSysSolver::set_pattern (Optimizer.cpp:174, 358, 524), which the device-resident solver
+// ignores: the 5 000 std::set copies per Newton iteration are skipped while the hooks are active
+#define OCB_MERGE_VNEIGHBOR if (useDense || !OptCuts::ocbDeviceResident(linSysSolver)) scaffold.mergeVNeighbor(result.vNeighbor, vNeighbor_withScaf);
 #endif

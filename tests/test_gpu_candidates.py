@@ -23,7 +23,7 @@ def _run(tmp_path, mesh, args, max_iters=None):
     env = dict(os.environ, ORACLE_TRACE=str(tmp_path / "trace.txt"), OCB_CANDIDATES_VERIFY=str(tmp_path / "verify.txt"), OCB_HOST_TIMING="1")
     if max_iters:
         env["ORACLE_MAX_ITERS"] = str(max_iters)
-    r = subprocess.run([CUDA_PROBE, "100", str(tmp_path / mesh)] + args + ["t"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=3000)
+    r = subprocess.run([CUDA_PROBE, "100", str(tmp_path / mesh)] + args + ["t"], cwd=tmp_path, env=env, capture_output=True, text=True, errors="replace", timeout=3000)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     rows = [dict(kv.split("=") for kv in ln.split()) for ln in open(tmp_path / "verify.txt")]
     stats = [ln for ln in r.stderr.split("\n") if "ocb candidates" in ln]

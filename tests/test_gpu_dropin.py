@@ -38,7 +38,7 @@ def test_newton_iterations_inside_reference_host(obj, tmp_path, device_newton):
         pytest.skip("shim/_build/OptCuts_cuda_probe not built (make -C shim needs the reference headers)")
     n = 10
     env = dict(os.environ, ORACLE_TRACE=str(tmp_path / "trace.txt"), ORACLE_MAX_ITERS=str(n), OCB_DEVICE_NEWTON=device_newton)
-    r = subprocess.run([CUDA_PROBE, "100", obj] + ARGS, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([CUDA_PROBE, "100", obj] + ARGS, cwd=tmp_path, env=env, capture_output=True, text=True, errors="replace", timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     got = parse_trace(tmp_path / "trace.txt")
     # the fixture is the reference's state after iteration 1: iteration k here == iteration k+1 of the golden trace
@@ -67,7 +67,7 @@ def test_whole_run_matches_reference(obj, tmp_path):
     for name, exe in (("cuda", CUDA_BIN), ("ref", REF_BIN)):
         d = tmp_path / name
         d.mkdir()
-        r = subprocess.run([exe, "100", obj] + ARGS, cwd=d, capture_output=True, text=True, timeout=1500)
+        r = subprocess.run([exe, "100", obj] + ARGS, cwd=d, capture_output=True, text=True, errors="replace", timeout=1500)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         folder = os.listdir(d / "output")[0]
         info = open(d / "output" / folder / "info.txt").read().split("\n")

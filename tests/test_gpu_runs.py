@@ -40,7 +40,7 @@ def run_cuda(name, tmp_path, extra_env=None):
         shutil.copy(os.path.join(INPUTS, f), tmp_path)
     env = dict(os.environ, ORACLE_TRACE=str(tmp_path / "trace.txt"))
     env.update(extra_env or {})
-    r = subprocess.run([CUDA_PROBE, "100", str(tmp_path / mesh)] + args + ["t"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=3000)
+    r = subprocess.run([CUDA_PROBE, "100", str(tmp_path / mesh)] + args + ["t"], cwd=tmp_path, env=env, capture_output=True, text=True, errors="replace", timeout=3000)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     folder = os.listdir(tmp_path / "output")[0]
     info = open(tmp_path / "output" / folder / "info.txt").read().split("\n")

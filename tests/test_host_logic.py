@@ -74,6 +74,6 @@ def test_candidate_record_replay_is_decision_neutral(tmp_path, name, mesh, args)
     for f in os.listdir(os.path.join(GOLDEN, "inputs")):
         shutil.copy(os.path.join(GOLDEN, "inputs", f), tmp_path)
     env = dict(os.environ, ORACLE_TRACE=str(tmp_path / "trace.txt"), OCB_CANDIDATES_SELFCHECK="1")
-    r = subprocess.run([SELFCHECK, "100", str(tmp_path / mesh)] + args + ["t"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    r = subprocess.run([SELFCHECK, "100", str(tmp_path / mesh)] + args + ["t"], cwd=tmp_path, env=env, capture_output=True, text=True, errors="replace", timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert open(tmp_path / "trace.txt").read() == open(os.path.join(GOLDEN, "traces", name + "_trace.txt")).read()
