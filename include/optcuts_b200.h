@@ -117,6 +117,8 @@ int ocb_get_sizes(const ocb_ctx* ctx, int64_t* sizes8);
 int ocb_energy(ocb_ctx* ctx, double energyParam0, double* E_total, double* E_sd, double* E_scaf);
 /* per-element values of the mesh term, w = triArea/surfaceArea or 1 (uniformWeight) */
 int ocb_energy_per_elem(ocb_ctx* ctx, int uniformWeight, double* out_nF);
+/* a3: SymDirichletEnergy::getEnergyValByElemID (:48-68): the value of triangle triI alone */
+int ocb_energy_by_elem(ocb_ctx* ctx, int triI, int uniformWeight, double* E);
 
 /* ---- a4/a13: gradient — SymDirichletEnergy::computeGradient (:258-304), Optimizer::computeGradient
  * (Optimizer.cpp:783-797), Scaffold::augmentGradient (Scaffold.cpp:210-229).  Result (nSys,
@@ -144,6 +146,10 @@ int ocb_hessian_assemble(ocb_ctx* ctx, double energyParam0);
 int ocb_hessian_triplets(ocb_ctx* ctx, int uniformWeight, double* V, int32_t* I, int32_t* J, int64_t* n);
 /* projected 6x6 element blocks of the mesh term (row-major 36 per triangle, w applied, unscaled) */
 int ocb_hessian_blocks(ocb_ctx* ctx, int uniformWeight, double* out_nFx36);
+/* a6: Energy::computeHessian(data, MatrixXd&, uniformWeight) of the MESH term, the dense flavour of the nested optimizers
+ * (SymDirichletEnergy.cpp:306-427): H_out is 2nV x 2nV (symmetric; fixed vertices: zero row / column, unit diagonal),
+ * element blocks added in triangle order.  For local stencils: nV <= 4096. */
+int ocb_hessian_dense(ocb_ctx* ctx, int uniformWeight, double* H_out);
 /* mirrors LinSysSolver::update_a(I,J,S): zero, then accumulate triplets with i<=j */
 int ocb_update_values_triplets(ocb_ctx* ctx, int64_t nT, const int32_t* I, const int32_t* J, const double* S);
 /* reference layout read-back: 1-based upper-triangular CSR (LinSysSolver.hpp:27-29, get_ia/ja/a) */

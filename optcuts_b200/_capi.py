@@ -82,6 +82,8 @@ _SIGS = [
     ("ocb_get_sizes", C.c_int, [C.c_void_p, _i64]),
     ("ocb_energy", C.c_int, [C.c_void_p, C.c_double, _d, _d, _d]),
     ("ocb_energy_per_elem", C.c_int, [C.c_void_p, C.c_int, _d]),
+    ("ocb_energy_by_elem", C.c_int, [C.c_void_p, C.c_int, C.c_int, _d]),
+    ("ocb_hessian_dense", C.c_int, [C.c_void_p, C.c_int, _d]),
     ("ocb_gradient", C.c_int, [C.c_void_p, C.c_double, _d, _d]),
     ("ocb_set_pattern", C.c_int, [C.c_void_p, C.c_int, _i, _i, _i, C.c_int]),
     ("ocb_set_pattern_from_elements", C.c_int, [C.c_void_p]),
@@ -291,6 +293,17 @@ class Context:
         out = np.zeros(self.sizes()["nF"])
         self._chk(self._L.ocb_energy_per_elem(self._h, int(uniformWeight), _pd(out)))
         return out
+
+    def energy_by_elem(self, triI, uniformWeight=False):
+        e = C.c_double()
+        self._chk(self._L.ocb_energy_by_elem(self._h, int(triI), int(uniformWeight), C.byref(e)))
+        return e.value
+
+    def hessian_dense(self, uniformWeight=False):
+        n = 2 * self.sizes()["nV"]
+        H = np.zeros((n, n))
+        self._chk(self._L.ocb_hessian_dense(self._h, int(uniformWeight), _pd(H)))
+        return H
 
     def gradient(self, energyParam0=1.0, download=True):
         g = np.zeros(self.sizes()["nSys"]) if download else None

@@ -584,6 +584,21 @@ int ocb_energy_per_elem(ocb_ctx* c, int uniform, double* out)
     return OCB_OK;
 }
 
+// a3: SymDirichletEnergy::getEnergyValByElemID (:48-68): the value of ONE triangle (used by the local-stencil code for its
+// initial energy, TriMesh.cpp:2306, 2474, 2563)
+int ocb_energy_by_elem(ocb_ctx* c, int triI, int uniform, double* E)
+{
+    if (!c || !E) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));
+    OCB_TRY(need(c, c->haveUV, "ocb_energy_by_elem: no UV"));
+    if (triI < 0 || triI >= c->nF) return set_err(c, OCB_ERR_ARG, "ocb_energy_by_elem: triangle index out of range");
+    OCB_CUDA(c, c->scratchD.reserve(2, c->stream));
+    OCB_TRY(launch_energy_one_elem(c, triI, uniform, c->scratchD.p));
+    OCB_CUDA(c, cudaMemcpyAsync(E, c->scratchD.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OCB_OK;
+}
+
 int ocb_gradient(ocb_ctx* c, double p0, double* g_out, double* sqnorm)
 {
     HostTimer _ht("gradient");
@@ -855,6 +870,27 @@ int ocb_hessian_blocks(ocb_ctx* c, int uniform, double* out)
     OCB_CUDA(c, c->scratchD.reserve(36 * (size_t)c->nF, c->stream));
     OCB_TRY(launch_hessian_blocks(c, uniform, c->scratchD.p));
     OCB_CUDA(c, cudaMemcpyAsync(out, c->scratchD.p, sizeof(double) * 36 * (size_t)c->nF, cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OCB_OK;
+}
+
+// a6: Energy::computeHessian(data, MatrixXd&, uniformWeight) -- the dense flavour the nested optimizers use (SymDirichletEnergy.cpp:306-427)
+int ocb_hessian_dense(ocb_ctx* c, int uniform, double* H_out)
+{
+    HostTimer _ht("hessian_dense");
+    if (!c || !H_out) return OCB_ERR_ARG;
+    OCB_TRY(ensure_init(c));
+    OCB_TRY(need(c, c->haveUV, "ocb_hessian_dense: no UV"));
+    if (c->nV > 4096) return set_err(c, OCB_ERR_ARG, "ocb_hessian_dense: more than 4096 vertices (a dense 2n x 2n matrix is for local stencils)");
+    const size_t n = 2 * (size_t)c->nV;
+    OCB_CUDA(c, c->scratchD.reserve(36 * (size_t)c->nF + n * n + 4, c->stream));
+    OCB_CUDA(c, c->scratchI.reserve((size_t)c->nV + 2, c->stream));
+    double* dB = c->scratchD.p; double* dH = dB + 36 * (size_t)c->nF;
+    OCB_TRY(upload_i(c, c->scratchI.p, c->hInv.data(), (size_t)c->nV));
+    OCB_TRY(launch_hessian_blocks(c, uniform, dB));
+    OCB_CUDA(c, cudaMemsetAsync(dH, 0, sizeof(double) * n * n, c->stream));
+    OCB_TRY(launch_dense_hessian(c, dB, c->scratchI.p, dH));
+    OCB_CUDA(c, cudaMemcpyAsync(H_out, dH, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
     return OCB_OK;
 }

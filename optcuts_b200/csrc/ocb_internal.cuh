@@ -208,12 +208,14 @@ int fetch_scalars(ocb_ctx* c);   // D2H of the scalar block + stream sync
 // launchers implemented in ocb_kernels.cu / ocb_pcg.cu
 int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha, bool alphaFromStepBound = false);   // alphaFromStepBound: alpha * scal[S_STEP_BOUND], read on the device
 int launch_energy_per_elem(ocb_ctx* c, int uniform, double* d_out);
+int launch_energy_one_elem(ocb_ctx* c, int t, int uniform, double* d_out);
 int launch_gradient(ocb_ctx* c, double p0);
 int launch_sqnorm(ocb_ctx* c, const double* v, int n, int slot);
 int launch_g2l(ocb_ctx* c);                          // mesh-vertex -> air-local alias table after a new air mesh
 int launch_build_slots(ocb_ctx* c);
 int launch_hessian(ocb_ctx* c, double p0);
 int launch_hessian_blocks(ocb_ctx* c, int uniform, double* d_out36);
+int launch_dense_hessian(ocb_ctx* c, const double* d_blocks36, const int32_t* d_inv, double* d_out);
 int launch_step_bound(ocb_ctx* c, const double* d_dir, double alpha0);
 int launch_step_forward(ocb_ctx* c, double alpha);
 int launch_triplet_scatter(ocb_ctx* c, int64_t nT, const int32_t* dI, const int32_t* dJ, const double* dS);

@@ -649,6 +649,32 @@ divgrad_gather_kernel(ElemView M, GatherView G, const double* __restrict__ x, do
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a6: dense Hessian of the mesh term (SymDirichletEnergy::computeHessian, dense flavour, :306-427): the thread of vertex v adds
+// row k of every incident element's projected block matrix into dense rows 2v, 2v + 1 in ascending triangle order (the
+// order of the reference's serial addBlockToMatrix loop); fixed vertices: zero row / column, unit diagonal.  `out` is
+// pre-zeroed, n = 2 nV, indexed by the CALLER's vertex ids (inv: internal -> caller).
+__global__ void __launch_bounds__(kBlock)
+dense_hessian_kernel(ElemView M, GatherView G, const double* __restrict__ blocks36, const uint8_t* __restrict__ fixedMask,
+                     const int32_t* __restrict__ inv, double* __restrict__ out)
+{
+    const size_t n = 2 * (size_t)G.nV;
+    for (int v = blockIdx.x * kBlock + threadIdx.x; v < G.nV; v += gridDim.x * kBlock) {
+        const size_t r = 2 * (size_t)inv[v];
+        if (fixedMask[v]) { out[r * n + r] = 1.0; out[(r + 1) * n + r + 1] = 1.0; continue; }
+        for (int q = G.vcPtrM[v]; q < G.vcPtrM[v + 1]; ++q) {
+            const int code = G.vcIdxM[q], t = code >> 2, k = code & 3;
+            const int idx[3] = {M.v0[t], M.v1[t], M.v2[t]};
+            const double* B = blocks36 + 36 * (size_t)t;
+            for (int l = 0; l < 3; ++l) {
+                if (fixedMask[idx[l]]) continue;
+                const size_t c = 2 * (size_t)inv[idx[l]];
+                for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) out[(r + i) * n + c + j] += B[(2 * k + i) * 6 + 2 * l + j];
+            }
+        }
+    }
+}
+
 // =============================================================================================
 // launchers
 #define KCHECK(c) do { (c)->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return cuda_fail((c), _e, __func__); } while (0)
@@ -680,6 +706,16 @@ int launch_energy(ocb_ctx* c, double p0, bool stepped, double alpha, bool alphaF
     Slots3 sl; sl.s[0] = S_E_MESH; sl.s[1] = S_E_AIR; sl.s[2] = S_N_INVERTED;
     if (stepped) energy_kernel<true><<<grid, kBlock, 0, c->stream>>>(M, A, c->x0.p, c->p.p, alpha, c->partials.p, c->sync.p, c->dScal, sl, alphaFromStepBound ? 1 : 0);
     else energy_kernel<false><<<grid, kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, 0.0, c->partials.p, c->sync.p, c->dScal, sl, 0);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_energy_one_elem(ocb_ctx* c, int t, int uniform, double* d_out)
+{
+    ProfScope prof(c, K_ENERGY);
+    ElemView M = view_of(c, c->mesh, false, 1.0, uniform);
+    M.v0 += t; M.v1 += t; M.v2 += t; M.area += t; M.areaSq += t; M.e0 += t; M.e1 += t; M.d += t; M.n = 1;     // a one-triangle view
+    energy_per_elem_kernel<<<1, kBlock, 0, c->stream>>>(M, c->x.p, d_out);
     KCHECK(c);
     return 0;
 }
@@ -781,6 +817,15 @@ int launch_hessian_blocks(ocb_ctx* c, int uniform, double* d_out36)
     const ElemView M = view_of(c, c->mesh, false, 1.0, uniform);
     ElemView A = M; A.n = 0;
     hessian_elem_kernel<false><<<resident_grid<hessian_elem_kernel<false>>(c, M.n), kBlock, 0, c->stream>>>(M, A, c->x.p, nullptr, d_out36);
+    KCHECK(c);
+    return 0;
+}
+
+int launch_dense_hessian(ocb_ctx* c, const double* d_blocks36, const int32_t* d_inv, double* d_out)
+{
+    ProfScope prof(c, K_HESSIAN_ROWS);
+    const ElemView M = view_of(c, c->mesh, false, 1.0, 0);
+    dense_hessian_kernel<<<grid_for(c, c->nV, 8), kBlock, 0, c->stream>>>(M, gather_of(c), d_blocks36, c->fixedMask.p, d_inv, d_out);
     KCHECK(c);
     return 0;
 }

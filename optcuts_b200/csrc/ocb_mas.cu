@@ -378,29 +378,44 @@ __device__ __forceinline__ int find_col(const int32_t* __restrict__ colIdx, int 
     return -1;
 }
 
-// A_1 = P_1^T A P_1 on the leaf adjacency, as a GATHER: 8 lanes per leaf row, lane q owns the leaf blocks q, q + 8, ...
-// of that row and sums, over the leaf's fine rows in ascending order and their blocks in stored order, the contributions
-// that fall into its block.  36 register accumulators, one plain store: no atomics and no memset, so the preconditioner
-// (and with it the CG iteration count and the search direction) is reproducible to the bit.
+// sum of one value over the 8 lanes of a group in LANE ORDER (every lane gets the same, order-exact sum)
+__device__ __forceinline__ double group8_sum(double v, unsigned mask, int base)
+{
+    double acc = __shfl_sync(mask, v, base);
+#pragma unroll
+    for (int l = 1; l < 8; ++l) acc += __shfl_sync(mask, v, base + l);
+    return acc;
+}
+
+// A_1 = P_1^T A P_1 on the leaf adjacency, as a GATHER: 8 lanes per leaf row, lane = one fine row of the leaf (leaves hold
+// <= 8 rows).  For every leaf block of the row, each lane sums the contributions of ITS fine row's blocks that fall into it
+// (stored order), then the 8 partial 6x6 blocks are added in lane order = ascending fine row: no atomics, no memset, a
+// fixed order -- the preconditioner (and with it the CG iteration count and the search direction) is reproducible to the
+// bit -- and all the loads of a leaf are in flight at once (a serial walk of the 8 rows cost 80 us at 10k faces).
 __global__ void __launch_bounds__(256)
 mas_galerkin_fine_kernel(int nLeaves, const int32_t* __restrict__ childBeg, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx,
                          const double* __restrict__ val, const float4* __restrict__ vinfo, const int32_t* __restrict__ rowPtr1,
                          const int32_t* __restrict__ colIdx1, double* __restrict__ val1)
 {
     const float* vleaf = reinterpret_cast<const float*>(vinfo);
-    for (long w = blockIdx.x * 256L + threadIdx.x; w < 8L * nLeaves; w += gridDim.x * 256L) {
-        const int a = (int)(w >> 3), k8 = (int)(w & 7);
-        const int r0 = childBeg[a], r1 = childBeg[a + 1];
-        for (int s = rowPtr1[a] + k8; s < rowPtr1[a + 1]; s += 8) {
+    const int lane8 = threadIdx.x & 7, base = (threadIdx.x & 31) & ~7;
+    const unsigned mask = 0xffu << base;
+    for (long w = (blockIdx.x * 256L + threadIdx.x) >> 3; w < nLeaves; w += (gridDim.x * 256L) >> 3) {
+        const int a = (int)w;
+        const int i = childBeg[a] + lane8;
+        const bool have = i < childBeg[a + 1];
+        float4 vi = make_float4(0.f, 0.f, 0.f, 0.f);
+        int b0 = 0, b1 = 0;
+        if (have) { vi = vinfo[i]; b0 = rowPtr[i]; b1 = rowPtr[i + 1]; }
+        const bool live = have && vi.x != 0.0f;
+        const double fi[3] = {mas_unpack(vi.x), mas_unpack(vi.y), mas_unpack(vi.z)};
+        for (int s = rowPtr1[a]; s < rowPtr1[a + 1]; ++s) {
             const int a2 = colIdx1[s];
             double acc[36];
 #pragma unroll
             for (int q = 0; q < 36; ++q) acc[q] = 0.0;
-            for (int i = r0; i < r1; ++i) {
-                const float4 vi = vinfo[i];
-                if (vi.x == 0.0f) continue;
-                const double fi[3] = {mas_unpack(vi.x), mas_unpack(vi.y), mas_unpack(vi.z)};
-                for (int b = rowPtr[i], be = rowPtr[i + 1]; b < be; ++b) {
+            if (live)
+                for (int b = b0; b < b1; ++b) {
                     const int j = colIdx[b];
                     if (__float_as_int(vleaf[4 * (size_t)j + 3]) != a2) continue;
                     const float4 vj = vinfo[j];
@@ -418,68 +433,80 @@ mas_galerkin_fine_kernel(int nLeaves, const int32_t* __restrict__ childBeg, cons
                                 for (int qj = 0; qj < 3; ++qj)
                                     acc[(ci * 3 + qi) * 6 + cj * 3 + qj] += fi[qi] * A[ci][cj] * fj[qj];
                 }
-            }
-            double2* o = reinterpret_cast<double2*>(val1 + 36 * (size_t)s);
+            double* o = val1 + 36 * (size_t)s;
 #pragma unroll
-            for (int q = 0; q < 18; ++q) o[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
+            for (int q = 0; q < 36; ++q) {
+                const double t = group8_sum(acc[q], mask, base);
+                if ((q & 7) == lane8) o[q] = t;                 // the 36 stores spread over the 8 lanes
+            }
         }
     }
 }
 
-// A_{l+1} = R A_l R^T, gathered the same way: 8 lanes per node row of level l + 1, lane q owns the blocks q, q + 8, ... and
-// sums R_a S R_b^T over the children a of its row (ascending) and their blocks (stored order) whose column's parent is its column
+// A_{l+1} = R A_l R^T, gathered the same way: 8 lanes per node row of level l + 1, lane = one child of the node (groups hold
+// <= 8 nodes); per block of the row each lane sums R_a S R_b^T over its child's blocks (stored order) whose column's parent
+// is the block's column, then the partial blocks are added in lane order = ascending child
 __global__ void __launch_bounds__(128)
 mas_coarsen_kernel(int nUp, const int32_t* __restrict__ groupBeg, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx,
                    const double* __restrict__ val, const int32_t* __restrict__ parent, const double4* __restrict__ geom,
                    const double4* __restrict__ geomUp, const int32_t* __restrict__ rowPtrUp, const int32_t* __restrict__ colIdxUp,
                    double* __restrict__ valUp)
 {
-    for (long w = blockIdx.x * 128L + threadIdx.x; w < 8L * nUp; w += gridDim.x * 128L) {
-        const int pa = (int)(w >> 3), k8 = (int)(w & 7);
-        const int c0 = groupBeg[pa], c1 = groupBeg[pa + 1];
+    const int lane8 = threadIdx.x & 7, base = (threadIdx.x & 31) & ~7;
+    const unsigned mask = 0xffu << base;
+    for (long w = (blockIdx.x * 128L + threadIdx.x) >> 3; w < nUp; w += (gridDim.x * 128L) >> 3) {
+        const int pa = (int)w;
+        const int a = groupBeg[pa] + lane8;
+        const bool live = a < groupBeg[pa + 1];
         const double4 gpa = geomUp[pa];
         const double isa = 1.0 / gpa.z;
-        for (int s = rowPtrUp[pa] + k8; s < rowPtrUp[pa + 1]; s += 8) {
+        double Ra10 = 0.0, Ra11 = 0.0, Ra20 = 0.0, Ra22 = 0.0;
+        int k0 = 0, k1 = 0;
+        if (live) {
+            const double4 ga = geom[a];
+            Ra10 = (ga.x - gpa.x) * isa; Ra11 = ga.z * isa; Ra20 = (ga.y - gpa.y) * isa; Ra22 = ga.z * isa;
+            k0 = rowPtr[a]; k1 = rowPtr[a + 1];
+        }
+        for (int s = rowPtrUp[pa]; s < rowPtrUp[pa + 1]; ++s) {
             const int pb = colIdxUp[s];
             const double4 gpb = geomUp[pb];
             const double isb = 1.0 / gpb.z;
             double acc[36];
 #pragma unroll
             for (int q = 0; q < 36; ++q) acc[q] = 0.0;
-            for (int a = c0; a < c1; ++a) {
-                const double4 ga = geom[a];
-                const double Ra10 = (ga.x - gpa.x) * isa, Ra11 = ga.z * isa, Ra20 = (ga.y - gpa.y) * isa, Ra22 = ga.z * isa;
-                for (int blk = rowPtr[a], be = rowPtr[a + 1]; blk < be; ++blk) {
-                    const int b = colIdx[blk];
-                    if (parent[b] != pb) continue;
-                    const double4 gb = geom[b];
-                    const double Rb10 = (gb.x - gpb.x) * isb, Rb11 = gb.z * isb, Rb20 = (gb.y - gpb.y) * isb, Rb22 = gb.z * isb;
-                    const double* M = val + 36 * (size_t)blk;
+            for (int blk = k0; blk < k1; ++blk) {
+                const int b = colIdx[blk];
+                if (parent[b] != pb) continue;
+                const double4 gb = geom[b];
+                const double Rb10 = (gb.x - gpb.x) * isb, Rb11 = gb.z * isb, Rb20 = (gb.y - gpb.y) * isb, Rb22 = gb.z * isb;
+                const double* M = val + 36 * (size_t)blk;
 #pragma unroll
-                    for (int ci = 0; ci < 2; ++ci)
+                for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
-                        for (int cj = 0; cj < 2; ++cj) {
-                            double T[3][3];
-                            // T = S Rb^T
+                    for (int cj = 0; cj < 2; ++cj) {
+                        double T[3][3];
+                        // T = S Rb^T
 #pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                const double S0 = M[(ci * 3 + i) * 6 + cj * 3], S1 = M[(ci * 3 + i) * 6 + cj * 3 + 1], S2 = M[(ci * 3 + i) * 6 + cj * 3 + 2];
-                                T[i][0] = S0;
-                                T[i][1] = S0 * Rb10 + S1 * Rb11;
-                                T[i][2] = S0 * Rb20 + S2 * Rb22;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 3; ++j) {
-                                acc[(ci * 3 + 0) * 6 + cj * 3 + j] += T[0][j];
-                                acc[(ci * 3 + 1) * 6 + cj * 3 + j] += Ra10 * T[0][j] + Ra11 * T[1][j];
-                                acc[(ci * 3 + 2) * 6 + cj * 3 + j] += Ra20 * T[0][j] + Ra22 * T[2][j];
-                            }
+                        for (int i = 0; i < 3; ++i) {
+                            const double S0 = M[(ci * 3 + i) * 6 + cj * 3], S1 = M[(ci * 3 + i) * 6 + cj * 3 + 1], S2 = M[(ci * 3 + i) * 6 + cj * 3 + 2];
+                            T[i][0] = S0;
+                            T[i][1] = S0 * Rb10 + S1 * Rb11;
+                            T[i][2] = S0 * Rb20 + S2 * Rb22;
                         }
-                }
-            }
-            double2* o = reinterpret_cast<double2*>(valUp + 36 * (size_t)s);
 #pragma unroll
-            for (int q = 0; q < 18; ++q) o[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
+                        for (int j = 0; j < 3; ++j) {
+                            acc[(ci * 3 + 0) * 6 + cj * 3 + j] += T[0][j];
+                            acc[(ci * 3 + 1) * 6 + cj * 3 + j] += Ra10 * T[0][j] + Ra11 * T[1][j];
+                            acc[(ci * 3 + 2) * 6 + cj * 3 + j] += Ra20 * T[0][j] + Ra22 * T[2][j];
+                        }
+                    }
+            }
+            double* o = valUp + 36 * (size_t)s;
+#pragma unroll
+            for (int q = 0; q < 36; ++q) {
+                const double t = group8_sum(acc[q], mask, base);
+                if ((q & 7) == lane8) o[q] = t;
+            }
         }
     }
 }

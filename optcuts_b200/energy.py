@@ -40,8 +40,15 @@ class SymDirichletEnergy:
         self._bind(data, uniformWeight)
         return self.ctx.energy_per_elem(False)
 
+    # SymDirichletEnergy::getEnergyValByElemID (:48-68)
     def getEnergyValByElemID(self, data, elemI, uniformWeight=False):
-        return float(self.getEnergyValPerElem(data, uniformWeight)[elemI])
+        self._bind(data, uniformWeight)
+        return self.ctx.energy_by_elem(int(elemI), False)
+
+    # SymDirichletEnergy::computeHessian, dense flavour (:306-427)
+    def computeHessianDense(self, data, uniformWeight=False):
+        self._bind(data, uniformWeight)
+        return self.ctx.hessian_dense(False)
 
     # SymDirichletEnergy::computeGradient (:258-304)
     def computeGradient(self, data, uniformWeight=False):

@@ -64,6 +64,21 @@ void CudaSymDirichletEnergy::getEnergyValPerElem(const TriMesh& data, Eigen::Vec
     check(ocb_energy_per_elem(ctx, 0, e.data()), "ocb_energy_per_elem");
 }
 
+void CudaSymDirichletEnergy::getEnergyValByElemID(const TriMesh& data, int elemI, double& energyVal, bool uniformWeight) const
+{
+    if (!bind(data, uniformWeight)) { SymDirichletEnergy::getEnergyValByElemID(data, elemI, energyVal, uniformWeight); return; }
+    check(ocb_energy_by_elem(ctx, elemI, 0, &energyVal), "ocb_energy_by_elem");
+}
+
+void CudaSymDirichletEnergy::computeHessian(const TriMesh& data, Eigen::MatrixXd& Hessian, bool uniformWeight) const
+{
+    // dense flavour (SymDirichletEnergy.cpp:306-427): only sensible for small meshes; the device path takes meshes the plugin is
+    // bound to (>= minFaces) that still fit a dense matrix
+    if (data.V.rows() > 4096 || !bind(data, uniformWeight)) { SymDirichletEnergy::computeHessian(data, Hessian, uniformWeight); return; }
+    Hessian.resize(data.V.rows() * 2, data.V.rows() * 2);
+    check(ocb_hessian_dense(ctx, 0, Hessian.data()), "ocb_hessian_dense");       // symmetric: row- and column-major coincide
+}
+
 void CudaSymDirichletEnergy::computeGradient(const TriMesh& data, Eigen::VectorXd& gradient, bool uniformWeight) const
 {
     if (!bind(data, uniformWeight)) { SymDirichletEnergy::computeGradient(data, gradient, uniformWeight); return; }

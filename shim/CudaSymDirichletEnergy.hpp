@@ -27,9 +27,8 @@ public:
     virtual void computeGradient(const TriMesh& data, Eigen::VectorXd& gradient, bool uniformWeight = false) const;
     virtual void computeHessian(const TriMesh& data, Eigen::VectorXd* V,
                                 Eigen::VectorXi* I = NULL, Eigen::VectorXi* J = NULL, bool uniformWeight = false) const;
-    virtual void computeHessian(const TriMesh& data, Eigen::MatrixXd& Hessian, bool uniformWeight = false) const {
-        SymDirichletEnergy::computeHessian(data, Hessian, uniformWeight);        // dense flavour: local stencils only
-    }
+    virtual void getEnergyValByElemID(const TriMesh& data, int elemI, double& energyVal, bool uniformWeight = false) const;
+    virtual void computeHessian(const TriMesh& data, Eigen::MatrixXd& Hessian, bool uniformWeight = false) const;   // dense flavour
     virtual void initStepSize(const TriMesh& data, const Eigen::VectorXd& searchDir, double& stepSize) const;
     virtual void computeDivGradPerVert(const TriMesh& data, Eigen::VectorXd& divGradPerVert) const;
 

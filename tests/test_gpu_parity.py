@@ -43,6 +43,37 @@ def test_energy(ctx, port, state):
     assert abs(et - float(state.r("E_last"))) <= 1e-13 * et
 
 
+def test_energy_by_elem_id(ctx, port, state100):
+    """a3: SymDirichletEnergy::getEnergyValByElemID == the per-element vector's entry, bit for bit"""
+    s = state100
+    s.upload(ctx, with_air=False)
+    per = port.energy_per_elem(s.F, s.UV, s.rest8, s.surfaceArea)
+    for t in (0, 1, 17, s.nF // 2, s.nF - 1):
+        assert ctx.energy_by_elem(t) == per[t]
+    import optcuts_b200 as ob
+    with pytest.raises(ob.OcbError):
+        ctx.energy_by_elem(s.nF)
+
+
+def test_hessian_dense_matches_reference(ctx, ref):
+    """a6: the dense flavour of computeHessian (nested optimizers) against the reference's own, on a local-stencil sized mesh
+    with a fixed vertex: same element blocks, added in triangle order"""
+    from test_oracle_vs_reference import random_mesh
+    V_rest, F, UV = random_mesh(3, n=7)
+    r8, sc = ctx.rest_features(V_rest, F)
+    fixed = np.array([0], np.int32)                 # what TriMesh::computeFeatures(resetFixedV) pins (TriMesh.cpp:325-328)
+    ctx.set_mesh(UV.shape[0], F, r8, sc["surfaceArea"], fixed)
+    ctx.set_uv(UV)
+    H = ctx.hessian_dense()
+    m = ref.RefMesh(V_rest, F, UV)
+    Hr = m.hessian_dense()
+    m.close()
+    assert H.shape == Hr.shape and np.array_equal(H, H.T)
+    assert np.max(np.abs(H - Hr)) <= 1e-12 * np.max(np.abs(Hr))
+    for v in fixed:
+        assert H[2 * v, 2 * v] == 1.0 and np.count_nonzero(H[2 * v]) == 1
+
+
 def test_energy_is_deterministic(ctx, state1):
     state1.upload(ctx)
     vals = {ctx.energy(state1.p0) for _ in range(5)}
