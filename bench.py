@@ -354,7 +354,7 @@ def batch71_ours(args, rank, world, local, torch):
     rows = {}
     with tempfile.TemporaryDirectory() as wd:
         paths = batch.extract_benchmark(os.path.join(wd, "in"))
-        batch.run_mesh(batch.CUDA_HOST, paths[items[shards[rank][-1]][0]], os.path.join(wd, "warm"), 2, gpu=local)      # library load, CUDA context
+        warm = batch.run_mesh(batch.CUDA_HOST, paths[items[shards[rank][-1]][0]], os.path.join(wd, "warm"), 1, gpu=local)   # smallest mesh of the shard, 1 iteration
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
@@ -380,7 +380,9 @@ def batch71_ours(args, rank, world, local, torch):
     return {"meshes": len(items), "newton_iters_per_mesh_cap": args.batch_iters, "newton_iters": int(its), "wall_s": wall, "it_per_s": its / wall,
             "per_rank_s": per_rank, "limiting_rank": int(np.argmax(per_rank)), "failed_meshes": nbad, "failed_on_rank0": bad,
             "slowest_mesh_rank0": {"name": items[slow][0], "faces": items[slow][1], "wall_s": rows[slow]["wall_s"]},
-            "scaling": "strong", "note": "one host-program process per mesh (reference main + Optimizer hooks + device candidate evaluation), "
+            "one_iteration_process_wall_s": warm["wall_s"],
+            "scaling": "strong", "note": "one_iteration_process_wall_s = the fixed cost of a process (CUDA context creation on a box without a persistence "
+                                         "daemon: 2.7-3.4 s cold, profiles/r2_process_init.txt); one host-program process per mesh (reference main + Optimizer hooks + device candidate evaluation), "
                                          "config args %s, every mesh bounded to the cap; process start-up and CUDA context creation are inside" % " ".join(batch.MESH_ARGS)}
 
 
@@ -584,7 +586,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=["bimba10k", "bimba_x4", "bimba_x10", "batch71"],
                     help="default: bimba10k as the headline + bimba_x4 / bimba_x10 / batch71 / host_program sub-objects")
     ap.add_argument("--quick", action="store_true", help="headline workload only (no sub-objects)")
-    ap.add_argument("--batch-iters", type=int, default=15, help="batch71: cap of Newton iterations per mesh")
+    ap.add_argument("--batch-iters", type=int, default=40, help="batch71: cap of Newton iterations per mesh")
     ap.add_argument("--batch-ref-sample", type=int, default=24, help="reference arm of batch71: number of meshes sampled across the size range (0 = all 71)")
     ap.add_argument("--cpu-limit-x10", type=int, default=45, help="time limit (s) of the reference's iteration at 1M faces")
     ap.add_argument("--pcg-tol", type=float, default=1e-12)

@@ -208,6 +208,7 @@ typedef struct {
     double sqn_g, targetGRes, alpha, E_new, E_scaf_new, E_sd_new, lastEDec, pcg_rel_res;
     int converged, stopped, n_halvings, pcg_iters;
     double alpha_init, E_last, ms_solve, ms_line_search;
+    int pcg_status, reserved;    /* 0, OCB_ERR_NOT_CONVERGED (max_it) or OCB_ERR_BREAKDOWN (truncated CG: d.Ad <= 0, the iterate reached so far was used) */
 } ocb_newton_result;
 int ocb_newton_step(ocb_ctx* ctx, double energyParam0, double targetGRes, double pcg_rel_tol,
                     int pcg_max_it, int allowEDecRelTol, ocb_newton_result* out);

@@ -38,7 +38,8 @@ class NewtonResult(C.Structure):
                 ("E_scaf_new", C.c_double), ("E_sd_new", C.c_double), ("lastEDec", C.c_double),
                 ("pcg_rel_res", C.c_double), ("converged", C.c_int), ("stopped", C.c_int),
                 ("n_halvings", C.c_int), ("pcg_iters", C.c_int),
-                ("alpha_init", C.c_double), ("E_last", C.c_double), ("ms_solve", C.c_double), ("ms_line_search", C.c_double)]
+                ("alpha_init", C.c_double), ("E_last", C.c_double), ("ms_solve", C.c_double), ("ms_line_search", C.c_double),
+                ("pcg_status", C.c_int), ("reserved", C.c_int)]
 
 
 class StencilStepBatch(C.Structure):

@@ -1039,7 +1039,7 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
     }
     OCB_TRY(launch_pcg(c, dRhs, negate, rel_tol, max_it));
     OCB_TRY(fetch_scalars(c));
-    if (c->hScal[S_JACOBI_BAD] != 0.0) {       // verdict of a set-up whose host check was deferred (ocb_newton_step)
+    if (c->hScal[S_JACOBI_BAD] != 0.0 && !c->tolerateIndefinite) {       // verdict of a set-up whose host check was deferred
         c->precondValid = false;
         return set_err(c, OCB_ERR_BREAKDOWN, "a diagonal 2x2 block of the matrix is not positive definite");
     }
@@ -1171,7 +1171,7 @@ static int line_search_core(ocb_ctx* c, double p0, double E_last, double lastSca
         Escaf = scaf ? c->wScafOverFa * c->hScal[S_E_AIR] : 0.0;
         E = p0 * Esd + Escaf;
         // plain decrease test (:597); the inversion guard (:615-629) follows the loop
-        if (E > E_last) {
+        if (!(E <= E_last)) {                  // also catches a non-finite trial energy
             alpha /= 2.0; ++halvings;
             if (alpha == 0.0) { stopped = 1; break; }
             continue;
@@ -1254,9 +1254,15 @@ int ocb_newton_step_ex(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_
     c->deferFactorCheck = false;
     if (rf < 0) return rf;
     int its = 0; double rr = 0.0;
+    // Inside a Newton iteration a matrix that is SPD only up to rounding is not an error: non-PD diagonal blocks fall back to
+    // the identity in the preconditioner, a CG breakdown returns the truncated iterate (see pcg_kernel), and the line search
+    // decides -- what the reference gets from an LDL^T that never checks definiteness (EigenLibSolver.cpp:80-107).
+    c->tolerateIndefinite = true;
     int rs = ocb_solve(c, nullptr, nullptr, pcg_rel_tol, pcg_max_it, &its, &rr);
+    c->tolerateIndefinite = false;
     out->pcg_iters = its; out->pcg_rel_res = rr;
-    if (rs < 0 && rs != OCB_ERR_NOT_CONVERGED) return rs;
+    out->pcg_status = rs;
+    if (rs < 0 && rs != OCB_ERR_NOT_CONVERGED && rs != OCB_ERR_BREAKDOWN) return rs;
     const double tB = wall_now();
     // step bound, then the first trial at 0.99 * bound (Optimizer.cpp:580) chained on the device
     OCB_CUDA(c, cudaMemcpyAsync(c->x0.p, c->x.p, sizeof(double) * c->nSys(), cudaMemcpyDeviceToDevice, c->stream));
@@ -1272,7 +1278,7 @@ int ocb_newton_step_ex(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_
     out->lastEDec = ls.lastEDec; out->n_halvings = ls.n_halvings; out->stopped = ls.stopped;
     out->E_last = E_last;
     out->ms_solve = 1e3 * (tB - tA); out->ms_line_search = 1e3 * (wall_now() - tB);
-    return rs == OCB_ERR_NOT_CONVERGED ? rs : OCB_OK;
+    return (rs == OCB_ERR_NOT_CONVERGED || rs == OCB_ERR_BREAKDOWN) ? OCB_ERR_NOT_CONVERGED : OCB_OK;
 }
 
 int ocb_newton_step(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_tol, int pcg_max_it,

@@ -146,6 +146,7 @@ struct ocb_ctx {
     // what the last ocb_gradient / fused gradient pass left (ocb_newton_step_ex(OCB_STEP_REUSE_GRADIENT) continues from it)
     bool gradValid = false; double gradP0 = 0.0, gradSqn = 0.0, gradEMesh = 0.0, gradEAir = 0.0, gradSqnMesh = 0.0;
     bool pcgPlainNorm = true;                // false (ocb_set_option("pcg_scaled_norm", 1)): stop on the D-scaled norm instead of ||r|| / ||b||
+    bool tolerateIndefinite = false;         // ocb_newton_step_ex: a matrix that is SPD only up to rounding is handled, not reported
     bool deferFactorCheck = false;           // ocb_newton_step: the block-Jacobi verdict is read together with the PCG status
     int64_t precondFallbacks = 0;            // solves repeated with block-Jacobi after the two-level preconditioner failed
     std::vector<int32_t> hStamp;             // scratch of the pattern builders

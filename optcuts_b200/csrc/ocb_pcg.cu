@@ -622,9 +622,19 @@ pcg_kernel(PcgParams P)
         }
     }
     __syncthreads();
+    // Truncated CG (Steihaug): when a direction of non-positive curvature shows up (d.Ad <= 0: the projected Hessian of an
+    // extremely distorted start, entries spanning 60 orders of magnitude, is only PSD up to rounding) the iterate reached so
+    // far is returned -- still a descent direction -- and, if that happens on the very first direction, the preconditioned
+    // steepest-descent direction z = M^-1 b; the line search takes it from there, like it does behind the reference's LDL^T.
+    const bool steepest = (status == 2 && it == 0);
     for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kBlk) {
         const size_t dst = P.vertOf ? (size_t)P.vertOf[row] : (size_t)row;
-        reinterpret_cast<double2*>(P.xOut)[dst] = (bb > 0.0) ? (SMEM ? S.x[row - rowBeg] : reinterpret_cast<const double2*>(P.x)[row]) : make_double2(0.0, 0.0);
+        double2 xo = make_double2(0.0, 0.0);
+        if (bb > 0.0) {
+            if (steepest) xo = SMEM ? S.z[row - rowBeg] : reinterpret_cast<const double2*>(P.z)[row];
+            else xo = SMEM ? S.x[row - rowBeg] : reinterpret_cast<const double2*>(P.x)[row];
+        }
+        reinterpret_cast<double2*>(P.xOut)[dst] = xo;
     }
 
     if (MODE == 2) cooperative_groups::this_cluster().sync();      // no CTA may exit while a peer still reads its shared memory
