@@ -199,6 +199,7 @@ int ocb_step_forward(ocb_ctx* ctx, double alpha);
  *   OCB_STEP_REUSE_MATRIX          ocb_hessian_assemble ran at this x (fractureInitiated: the topology step assembled
  *                                  the matrix for the Newton step that follows it, Optimizer.cpp:428, 512-514, 567)
  *   OCB_STEP_SKIP_CONVERGENCE_TEST the caller has tested ||g||^2 < targetGRes already
+ * pcg_max_it <= 0: max(2000, 12 sqrt(n)) iterations, then the current iterate is used (inexact Newton).
  * ms_solve / ms_line_search: host wall clock of {assembly, set-up, PCG} and {step bound, line search} (the reference's
  * timer_step activities 0-4 and 5). */
 #define OCB_STEP_REUSE_GRADIENT 1
@@ -208,7 +209,8 @@ typedef struct {
     double sqn_g, targetGRes, alpha, E_new, E_scaf_new, E_sd_new, lastEDec, pcg_rel_res;
     int converged, stopped, n_halvings, pcg_iters;
     double alpha_init, E_last, ms_solve, ms_line_search;
-    int pcg_status, reserved;    /* 0, OCB_ERR_NOT_CONVERGED (max_it) or OCB_ERR_BREAKDOWN (truncated CG: d.Ad <= 0, the iterate reached so far was used) */
+    int pcg_status, reserved;    /* pcg_status: 0, OCB_ERR_NOT_CONVERGED (max_it) or OCB_ERR_BREAKDOWN (truncated CG: d.Ad <= 0, the iterate reached
+                                  * so far was used); reserved: how often the diagonal was lifted after a breakdown (0 on healthy systems) */
 } ocb_newton_result;
 int ocb_newton_step(ocb_ctx* ctx, double energyParam0, double targetGRes, double pcg_rel_tol,
                     int pcg_max_it, int allowEDecRelTol, ocb_newton_result* out);

@@ -1262,7 +1262,29 @@ int ocb_newton_step_ex(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_
     // the identity in the preconditioner, a CG breakdown returns the truncated iterate (see pcg_kernel), and the line search
     // decides -- what the reference gets from an LDL^T that never checks definiteness (EigenLibSolver.cpp:80-107).
     c->tolerateIndefinite = true;
+    // iteration cap of the inexact-Newton safety net: ~20x what a healthy system of this size needs (126 / 286 / 600 CG iterations
+    // at 10k / 160k / 1M faces, i.e. ~0.6 sqrt(n)); a system that has not converged by then (kappa beyond 1e16 at an extremely
+    // distorted start) hands its current iterate -- a descent direction -- to the line search instead of burning 20 n iterations
+    if (pcg_max_it <= 0) pcg_max_it = std::max(2000, (int)(12.0 * std::sqrt((double)c->nSys())));
     int rs = ocb_solve(c, nullptr, nullptr, pcg_rel_tol, pcg_max_it, &its, &rr);
+    // A breakdown means the ASSEMBLED matrix is indefinite: at an extremely distorted start (benchmark meshes male_2, cat_noUV,
+    // horse ...: ||g||^2 up to 1e51) the rounding of entries of size 1e50 exceeds the soft eigenvalues by 30 orders of magnitude.
+    // The reference's LDL^T never notices; CG does.  Only then the diagonal is lifted RELATIVELY, A_ii *= (1 + delta) with delta
+    // escalating 1e-8 -> 1e-5 -> 1e-2, which covers rounding noise proportional to each row's own size and leaves soft rows alone,
+    // and the solve is repeated.  Healthy systems never come here, so parity with the reference is untouched.
+    for (int esc = 0; esc < 3 && rs == OCB_ERR_BREAKDOWN; ++esc) {
+        static const double deltas[3] = {1.0e-8, 1.0e-5, 1.0e-2};
+        OCB_TRY(launch_diag_shift(c, deltas[esc]));
+        c->precondValid = false;
+        c->deferFactorCheck = true;
+        const int rf2 = ocb_factorize(c);
+        c->deferFactorCheck = false;
+        if (rf2 < 0) return rf2;
+        int its2 = 0;
+        rs = ocb_solve(c, nullptr, nullptr, pcg_rel_tol, pcg_max_it, &its2, &rr);
+        its += its2;
+        out->reserved = esc + 1;                                 // how many times the diagonal was lifted
+    }
     c->tolerateIndefinite = false;
     out->pcg_iters = its; out->pcg_rel_res = rr;
     out->pcg_status = rs;

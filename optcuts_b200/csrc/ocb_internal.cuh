@@ -146,7 +146,7 @@ struct ocb_ctx {
     // what the last ocb_gradient / fused gradient pass left (ocb_newton_step_ex(OCB_STEP_REUSE_GRADIENT) continues from it)
     bool gradValid = false; double gradP0 = 0.0, gradSqn = 0.0, gradEMesh = 0.0, gradEAir = 0.0, gradSqnMesh = 0.0;
     bool pcgPlainNorm = true;                // false (ocb_set_option("pcg_scaled_norm", 1)): stop on the D-scaled norm instead of ||r|| / ||b||
-    bool scaleSystem = true;                 // ocb_newton_step_ex scales the assembled system symmetrically (option "scale_system")
+    bool scaleSystem = false;                // ocb_newton_step_ex scales the assembled system symmetrically (option "scale_system")
     bool systemScaled = false;               // c->val currently holds S A S (only between the assembly and the end of ocb_newton_step_ex)
     ocb::DevBuf<double> rowScale;            // S: 2 per solver row
     bool tolerateIndefinite = false;         // ocb_newton_step_ex: a matrix that is SPD only up to rounding is handled, not reported
@@ -244,6 +244,7 @@ struct StencilStepHost {  // device pointers of one uploaded batch of bijective 
 };
 int launch_stencil_step(ocb_ctx* c, const StencilStepHost& h);
 int launch_spmv(ocb_ctx* c, const double* dx, double* dy);
+int launch_diag_shift(ocb_ctx* c, double delta);          // diagonal entries *= (1 + delta)
 int launch_scale_system(ocb_ctx* c);                       // val <- S val S, S = diag^-1/2; sets c->systemScaled
 int launch_jacobi_setup(ocb_ctx* c, bool check = true);   // check = false: no host round trip, the verdict stays in scal[S_JACOBI_BAD]
 int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol, int max_it, bool allowMas = true);

@@ -838,6 +838,23 @@ int launch_spmv(ocb_ctx* c, const double* dx, double* dy)
     return 0;
 }
 
+// relative diagonal regularisation A_ii *= (1 + delta): used ONLY after a CG breakdown (see ocb_newton_step_ex)
+__global__ void __launch_bounds__(256)
+diag_shift_kernel(int nRows, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, double* __restrict__ val, double factor)
+{
+    for (int row = blockIdx.x * 256 + threadIdx.x; row < nRows; row += gridDim.x * 256)
+        for (int b = rowPtr[row]; b < rowPtr[row + 1]; ++b)
+            if (colIdx[b] == row) { val[4 * (size_t)b] *= factor; val[4 * (size_t)b + 3] *= factor; }
+}
+int launch_diag_shift(ocb_ctx* c, double delta)
+{
+    ProfScope prof(c, K_JACOBI_SETUP);
+    int grid = (c->nVtot + 255) / 256; if (grid > c->numSMs * 8) grid = c->numSMs * 8; if (grid < 1) grid = 1;
+    diag_shift_kernel<<<grid, 256, 0, c->stream>>>(c->nVtot, c->rowPtr.p, c->colIdx.p, c->val.p, 1.0 + delta);
+    KCHECK(c);
+    return 0;
+}
+
 int launch_scale_system(ocb_ctx* c)
 {
     ProfScope prof(c, K_JACOBI_SETUP);

@@ -159,7 +159,9 @@ bool ocbHookStep(OcbOptView& v, bool& stopped)
     v.energyVal_scaffold = r.E_scaf_new;
     v.energyVal_ET[0] = r.E_sd_new;
     st.lastIters = r.pcg_iters; st.totalIters += r.pcg_iters; st.steps++;
-    if (!v.mute) std::printf("stepSize: %g -> %g (device: %d CG iterations, rel. residual %.2e)\n", r.alpha_init, r.alpha, r.pcg_iters, r.pcg_rel_res);
+    if (!v.mute) std::printf("stepSize: %g -> %g (device: %d CG iterations, rel. residual %.2e%s%s)\n", r.alpha_init, r.alpha, r.pcg_iters, r.pcg_rel_res,
+                             r.pcg_status == OCB_ERR_BREAKDOWN ? ", truncated at non-positive curvature" : (r.pcg_status == OCB_ERR_NOT_CONVERGED ? ", iteration cap" : ""),
+                             r.reserved ? ", diagonal lifted after a breakdown" : "");
     stopped = r.stopped != 0;
     return true;
 }
