@@ -358,9 +358,14 @@ def batch71_ours(args, rank, world, local, torch):
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
+        # `procs` host-program processes at a time on this rank's GPU (largest mesh first): a process spends most of its life in
+        # host code (CUDA context creation 2.7-3.4 s, OBJ parsing, Triangle, mesh edits), so the GPU is shared by time slicing
+        from concurrent.futures import ThreadPoolExecutor
+        procs = max(1, min(args.batch_procs, (os.cpu_count() or 1) // max(1, world)))
         t0 = time.perf_counter()
-        for i in shards[rank]:
-            rows[i] = batch.run_mesh(batch.CUDA_HOST, paths[items[i][0]], os.path.join(wd, "m%d" % i), args.batch_iters, gpu=local)
+        with ThreadPoolExecutor(max_workers=procs) as ex:
+            res = list(ex.map(lambda i: batch.run_mesh(batch.CUDA_HOST, paths[items[i][0]], os.path.join(wd, "m%d" % i), args.batch_iters, gpu=local), shards[rank]))
+        rows = dict(zip(shards[rank], res))
         mine = time.perf_counter() - t0
     its = sum(r["iters"] for r in rows.values())
     bad = [items[i][0] for i, r in rows.items() if r["rc"] != 0]
@@ -380,7 +385,7 @@ def batch71_ours(args, rank, world, local, torch):
     return {"meshes": len(items), "newton_iters_per_mesh_cap": args.batch_iters, "newton_iters": int(its), "wall_s": wall, "it_per_s": its / wall,
             "per_rank_s": per_rank, "limiting_rank": int(np.argmax(per_rank)), "failed_meshes": nbad, "failed_on_rank0": bad,
             "slowest_mesh_rank0": {"name": items[slow][0], "faces": items[slow][1], "wall_s": rows[slow]["wall_s"]},
-            "one_iteration_process_wall_s": warm["wall_s"],
+            "one_iteration_process_wall_s": warm["wall_s"], "concurrent_processes_per_gpu": procs,
             "scaling": "strong", "note": "one_iteration_process_wall_s = the fixed cost of a process (CUDA context creation on a box without a persistence "
                                          "daemon: 2.7-3.4 s cold, profiles/r2_process_init.txt); one host-program process per mesh (reference main + Optimizer hooks + device candidate evaluation), "
                                          "config args %s, every mesh bounded to the cap; process start-up and CUDA context creation are inside" % " ".join(batch.MESH_ARGS)}
@@ -407,8 +412,25 @@ def host_program_run():
             res[cur]["info_txt_timers"] = ln.split(":", 1)[1].strip()
         elif cur and ln.startswith("final"):
             res[cur]["final_E_SD_E_se"] = ln.split(":", 1)[1].split()
+        elif cur and ln.startswith("[ocb candidates]"):
+            w = ln.split()
+            res[cur]["candidates"] = {"queries": int(w[2]), "local_problems": int(w[4]), "lock_step_rounds": int(w[11]), "total_s": float(w[19]),
+                                      "triangle_s": float(w[22]), "device_and_packing_s": float(w[27])}
     if "cuda" in res and "ref" in res:
         res["speedup_whole_run"] = res["ref"]["wall_s"] / res["cuda"]["wall_s"]
+
+        def tm(d, key):      # one entry of the reference's own info.txt timer line ("topo1.29 desc0.47 ... bSplit0.10 iSplit0.08 cMerge0.0003")
+            return next((float(t[len(key):]) for t in d.get("info_txt_timers", "").split() if t.startswith(key)), None)
+        try:                 # kernel (6): nested local solves of querySplit / queryMerge (timer_step boundarySplit + interiorSplit + cornerMerge)
+            ours, ref = (sum(tm(res[k], t) for t in ("bSplit", "iSplit", "cMerge")) for k in ("cuda", "ref"))
+            n = res["cuda"].get("candidates", {}).get("local_problems")
+            res["speedup_in_process_timers"] = tm(res["ref"], "topo") and (sum(tm(res["ref"], t) for t in ("topo", "desc", "scaf")) / sum(tm(res["cuda"], t) for t in ("topo", "desc", "scaf")))
+            if n:
+                res["candidate_evaluation"] = {"local_problems": n, "ours_s": ours, "reference_s": ref, "ours_candidates_per_s": n / ours,
+                                               "reference_candidates_per_s": n / ref, "ratio": ref / ours,
+                                               "note": "same local problems in both arms when the op sequences agree; seconds = the reference's timer_step boundarySplit + interiorSplit + cornerMerge of info.txt in each arm"}
+        except Exception:    # noqa: BLE001
+            pass
     return res
 
 
@@ -509,13 +531,14 @@ def batch71_reference(args, world):
         paths = batch.extract_benchmark(os.path.join(wd, "in"))
         order = sorted(pick, key=lambda i: -items[i][1])
         t0 = time.perf_counter()
-        with ThreadPoolExecutor(max_workers=world) as ex:
+        conc = max(1, min(world * args.batch_procs, os.cpu_count() or 1))      # as many host processes at a time as the GPU arm runs
+        with ThreadPoolExecutor(max_workers=conc) as ex:
             rows = list(ex.map(lambda i: batch.run_mesh(batch.REF_HOST, paths[items[i][0]], os.path.join(wd, "m%d" % i), args.batch_iters), order))
         wall = time.perf_counter() - t0
     its = sum(r["iters"] for r in rows)
     return {"meshes": len(pick), "of": len(items), "newton_iters_per_mesh_cap": args.batch_iters, "newton_iters": int(its), "wall_s": wall,
-            "it_per_s": its / wall, "concurrent_processes": world, "cores": os.cpu_count(), "failed_meshes": sum(1 for r in rows if r["rc"] != 0),
-            "note": "unmodified reference (oracle/_ref/OptCuts_probe), %d meshes at a time, largest first" % world}
+            "it_per_s": its / wall, "concurrent_processes": conc, "cores": os.cpu_count(), "failed_meshes": sum(1 for r in rows if r["rc"] != 0),
+            "note": "unmodified reference (oracle/_ref/OptCuts_probe), %d meshes at a time, largest first" % conc}
 
 
 def run_reference(args):
@@ -587,6 +610,7 @@ def main():
                     help="default: bimba10k as the headline + bimba_x4 / bimba_x10 / batch71 / host_program sub-objects")
     ap.add_argument("--quick", action="store_true", help="headline workload only (no sub-objects)")
     ap.add_argument("--batch-iters", type=int, default=40, help="batch71: cap of Newton iterations per mesh")
+    ap.add_argument("--batch-procs", type=int, default=3, help="batch71: host-program processes at a time per GPU (the reference arm runs gpus x this many CPU processes)")
     ap.add_argument("--batch-ref-sample", type=int, default=24, help="reference arm of batch71: number of meshes sampled across the size range (0 = all 71)")
     ap.add_argument("--cpu-limit-x10", type=int, default=45, help="time limit (s) of the reference's iteration at 1M faces")
     ap.add_argument("--pcg-tol", type=float, default=1e-12)

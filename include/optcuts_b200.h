@@ -199,7 +199,7 @@ int ocb_step_forward(ocb_ctx* ctx, double alpha);
  *   OCB_STEP_REUSE_MATRIX          ocb_hessian_assemble ran at this x (fractureInitiated: the topology step assembled
  *                                  the matrix for the Newton step that follows it, Optimizer.cpp:428, 512-514, 567)
  *   OCB_STEP_SKIP_CONVERGENCE_TEST the caller has tested ||g||^2 < targetGRes already
- * pcg_max_it <= 0: max(2000, 12 sqrt(n)) iterations, then the current iterate is used (inexact Newton).
+ * pcg_max_it <= 0: max(10000, 40 sqrt(n)) iterations, then the current iterate is used (inexact Newton).
  * ms_solve / ms_line_search: host wall clock of {assembly, set-up, PCG} and {step bound, line search} (the reference's
  * timer_step activities 0-4 and 5). */
 #define OCB_STEP_REUSE_GRADIENT 1

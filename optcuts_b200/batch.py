@@ -79,8 +79,9 @@ def run_mesh(exe, mesh_path, workdir, max_iters, gpu=None, timeout=1800):
     env = dict(os.environ, ORACLE_TRACE=os.path.join(workdir, "trace.txt"))
     if max_iters:
         env["ORACLE_MAX_ITERS"] = str(int(max_iters))
-    if gpu is not None:
-        env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+    if gpu is not None:                       # the gpu-th VISIBLE device (a launcher may have restricted / renumbered them already)
+        vis = [d for d in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if d.strip()]
+        env["CUDA_VISIBLE_DEVICES"] = vis[gpu] if gpu < len(vis) else str(gpu)
     t0 = time.perf_counter()
     try:
         r = subprocess.run([exe, "100", mesh_path] + MESH_ARGS + ["b"], cwd=workdir, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout)

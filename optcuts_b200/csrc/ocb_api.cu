@@ -259,7 +259,7 @@ void ocb_destroy(ocb_ctx* c)
         c->pr.release(); c->pz.release(); c->pd.release(); c->pd2.release(); c->pAp.release(); c->pb.release(); c->minv.release();
         c->rowPtr.release(); c->colIdx.release(); c->val.release();
         c->partials.release(); c->sync.release(); c->scratchD.release(); c->scratchI.release();
-        c->xSaved.release(); c->rowScale.release(); c->px.release(); c->rowOf.release(); c->vertOf.release(); c->userRow.release();
+        c->xSaved.release(); c->rowScale.release(); c->pcgHalo.release(); c->px.release(); c->rowOf.release(); c->vertOf.release(); c->userRow.release();
         c->masD.ints.release(); c->masD.geom.release(); c->masD.val.release(); c->masD.rcCta.release(); c->masD.inv.release(); c->masD.vinfo.release();
         prof_collect(c);
         for (auto e : c->profPool) cudaEventDestroy(e);
@@ -401,6 +401,7 @@ int ocb_set_mesh(ocb_ctx* c, int nV, int nF, const int32_t* F, const double* res
     c->nVa = c->nFa = c->nBnd = 0; c->air.n = 0; c->hFa.clear(); c->hL2G.clear(); c->wScafOverFa = 0.0;
     c->nVtot = nV;
     c->hFuser.assign(F, F + (size_t)3 * nF);
+    c->meshAdjValid = false;
     compute_order(c, nV, nF, F);
     OCB_TRY(upload_perm(c));
     {
@@ -619,7 +620,7 @@ int ocb_gradient(ocb_ctx* c, double p0, double* g_out, double* sqnorm)
 }
 
 // ------------------------------------------------------------------------------------------ pattern
-// The solver's own row order: recursive coordinate bisection of the current UVs when they are known (plus the
+// The solver's own row order: the Hilbert-curve order of the current UVs when they are known (plus the
 // preconditioner hierarchy on top of it, see ocb_mas.cu), identity otherwise.
 static int choose_order(ocb_ctx* c)
 {
@@ -792,33 +793,52 @@ int ocb_set_pattern_from_elements(ocb_ctx* c)
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(need(c, c->nV > 0, "ocb_set_pattern_from_elements before ocb_set_mesh"));
     OCB_TRY(ensure_init(c));
-    const int nVtot = c->nVtot;
+    const int nVtot = c->nVtot, nV = c->nV;
     c->hFixed.resize((size_t)nVtot, 0);
-    // degree upper bound (with duplicates), fill, then sort + unique every short row
     HostTimer* _ta = new HostTimer("  adjacency");
-    std::vector<int32_t> cnt((size_t)nVtot + 1, 0);
-    auto count = [&](const std::vector<int32_t>& F, int n) {
+    // The MESH part of the adjacency changes only with ocb_set_mesh: its de-duplicated neighbour lists are built once and kept
+    // (f2, first half: with bijectivity on the pattern is rebuilt after every Newton iteration because the AIR mesh changed).
+    if (!c->meshAdjValid) {
+        std::vector<int32_t> cnt((size_t)nV + 1, 0);
+        const std::vector<int32_t>& F = c->hF; const int n = c->nF;
         for (int t = 0; t < n; ++t) for (int k = 0; k < 3; ++k) cnt[(size_t)F[(size_t)k * n + t] + 1] += 2;
-    };
-    count(c->hF, c->nF); count(c->hFa, c->nFa);
-    for (int v = 0; v < nVtot; ++v) cnt[v + 1] += cnt[v] + 1;       // +1: the diagonal
-    std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1), buf((size_t)cnt[nVtot]);
-    for (int v = 0; v < nVtot; ++v) buf[fill[v]++] = v;
-    auto scatter = [&](const std::vector<int32_t>& F, int n) {
+        for (int v = 0; v < nV; ++v) cnt[v + 1] += cnt[v];
+        std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1), buf((size_t)cnt[nV]);
         for (int t = 0; t < n; ++t) {
             const int a = F[t], b = F[(size_t)n + t], d = F[2 * (size_t)n + t];
             buf[fill[a]++] = b; buf[fill[a]++] = d; buf[fill[b]++] = a; buf[fill[b]++] = d; buf[fill[d]++] = a; buf[fill[d]++] = b;
         }
-    };
-    scatter(c->hF, c->nF); scatter(c->hFa, c->nFa);
+        c->hMeshAdjPtr.assign((size_t)nV + 1, 0);
+        c->hMeshAdj.clear(); c->hMeshAdj.reserve(buf.size() / 2 + 16);
+        std::vector<int32_t> stamp((size_t)nV, -1);
+        for (int v = 0; v < nV; ++v) {
+            for (int q = cnt[v]; q < fill[v]; ++q) { const int u = buf[q]; if (stamp[u] != v) { stamp[u] = v; c->hMeshAdj.push_back(u); } }
+            c->hMeshAdjPtr[v + 1] = (int32_t)c->hMeshAdj.size();
+        }
+        c->meshAdjValid = true;
+    }
+    // air mesh: buckets with duplicates (small), de-duplicated while the rows are written
+    std::vector<int32_t> acnt((size_t)nVtot + 1, 0);
+    {
+        const std::vector<int32_t>& F = c->hFa; const int n = c->nFa;
+        for (int t = 0; t < n; ++t) for (int k = 0; k < 3; ++k) acnt[(size_t)F[(size_t)k * n + t] + 1] += 2;
+    }
+    for (int v = 0; v < nVtot; ++v) acnt[v + 1] += acnt[v];
+    std::vector<int32_t> afill(acnt.begin(), acnt.end() - 1), abuf((size_t)acnt[nVtot]);
+    {
+        const std::vector<int32_t>& F = c->hFa; const int n = c->nFa;
+        for (int t = 0; t < n; ++t) {
+            const int a = F[t], b = F[(size_t)n + t], d = F[2 * (size_t)n + t];
+            abuf[afill[a]++] = b; abuf[afill[a]++] = d; abuf[afill[b]++] = a; abuf[afill[b]++] = d; abuf[afill[d]++] = a; abuf[afill[d]++] = b;
+        }
+    }
     delete _ta;
-    // the solver's row order first (it needs only the UVs), then the pattern directly in that order: rows de-duplicated
-    // with a stamp and insertion-sorted (they are ~7 entries long)
+    // the solver's row order first (it needs only the UVs), then the pattern directly in that order
     { HostTimer _tb("  choose_order (incl. UV download)"); OCB_TRY(choose_order(c)); }
     HostTimer* _tc = new HostTimer("  pattern rows");
     c->hRowPtr.clear(); c->hColIdx.clear();
     c->hSRowPtr.resize((size_t)nVtot + 1);
-    c->hSColIdx.resize(buf.size());                        // upper bound (duplicates included), trimmed below
+    c->hSColIdx.resize(c->hMeshAdj.size() + abuf.size() + (size_t)nVtot);      // upper bound, trimmed below
     c->hStamp.assign((size_t)nVtot, -1);
     {
         int32_t* out = c->hSColIdx.data();
@@ -826,19 +846,19 @@ int ocb_set_pattern_from_elements(ocb_ctx* c)
         int32_t* stamp = c->hStamp.data();
         const int32_t* vertOf = c->hVertOf.data(); const int32_t* rowOf = c->hRowOf.data();
         const uint8_t* fixed = c->hFixed.data();
-        const int32_t* bufp = buf.data();
+        const int32_t* mp = c->hMeshAdjPtr.data(); const int32_t* ma = c->hMeshAdj.data();
         int w = 0;
         rowPtr[0] = 0;
         for (int r = 0; r < nVtot; ++r) {
             const int v = vertOf[r];
             if (fixed[v]) out[w++] = r;
             else {
-                for (const int32_t* q = bufp + cnt[v], *qe = bufp + fill[v]; q < qe; ++q) {
-                    const int u = *q;
-                    if (stamp[u] == v) continue;
-                    stamp[u] = v;
-                    if (u != v && fixed[u]) continue;
-                    out[w++] = rowOf[u];                   // rows stay unsorted: every look-up (host and device) is a linear scan
+                out[w++] = r;                                  // the diagonal block; rows stay unsorted (every look-up is a linear scan)
+                const bool hasAir = acnt[v] < afill[v];
+                if (v < nV) for (int q = mp[v]; q < mp[v + 1]; ++q) { const int u = ma[q]; if (hasAir) stamp[u] = v; if (!fixed[u]) out[w++] = rowOf[u]; }
+                if (hasAir) {
+                    stamp[v] = v;
+                    for (int q = acnt[v]; q < afill[v]; ++q) { const int u = abuf[q]; if (stamp[u] == v) continue; stamp[u] = v; if (!fixed[u]) out[w++] = rowOf[u]; }
                 }
             }
             rowPtr[r + 1] = w;
@@ -1262,10 +1282,12 @@ int ocb_newton_step_ex(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_
     // the identity in the preconditioner, a CG breakdown returns the truncated iterate (see pcg_kernel), and the line search
     // decides -- what the reference gets from an LDL^T that never checks definiteness (EigenLibSolver.cpp:80-107).
     c->tolerateIndefinite = true;
-    // iteration cap of the inexact-Newton safety net: ~20x what a healthy system of this size needs (126 / 286 / 600 CG iterations
-    // at 10k / 160k / 1M faces, i.e. ~0.6 sqrt(n)); a system that has not converged by then (kappa beyond 1e16 at an extremely
-    // distorted start) hands its current iterate -- a descent direction -- to the line search instead of burning 20 n iterations
-    if (pcg_max_it <= 0) pcg_max_it = std::max(2000, (int)(12.0 * std::sqrt((double)c->nSys())));
+    // iteration cap of the inexact-Newton safety net.  A healthy system needs ~0.6 sqrt(n) CG iterations (126 / 286 / 600 at 10k /
+    // 160k / 1M faces), but ONE nearly degenerate triangle can raise that 30-fold on an otherwise ordinary state (bimba configs[1],
+    // iteration 10: diagonal 3e-3 .. 1e10, 4 813 iterations to 1e-12 -- and a direction truncated at 2 000 moved the step bound by
+    // 22 %, profiles/r2_direction_accuracy.txt), so the cap sits well above that; a system that has not converged by then (kappa
+    // beyond 1e16 at an extremely distorted start) hands its current iterate -- a descent direction -- to the line search.
+    if (pcg_max_it <= 0) pcg_max_it = std::max(10000, (int)(40.0 * std::sqrt((double)c->nSys())));
     int rs = ocb_solve(c, nullptr, nullptr, pcg_rel_tol, pcg_max_it, &its, &rr);
     // A breakdown means the ASSEMBLED matrix is indefinite: at an extremely distorted start (benchmark meshes male_2, cat_noUV,
     // horse ...: ||g||^2 up to 1e51) the rounding of entries of size 1e50 exceeds the soft eigenvalues by 30 orders of magnitude.

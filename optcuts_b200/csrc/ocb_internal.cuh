@@ -135,7 +135,7 @@ struct ocb_ctx {
     // BSR(2x2), full symmetric storage
     int nnzb = 0;
     std::vector<int32_t> hRowPtr, hColIdx;   // pattern in INTERNAL vertex order (host only: download_csr, nnz)
-    // the solver's own row order (recursive coordinate bisection, ocb_mas.cu): the device BSR, the PCG vectors and
+    // the solver's own row order (Hilbert-curve order of the UVs, ocb_mas.cu): the device BSR, the PCG vectors and
     // the preconditioner live in it; identity when no UV was known at pattern time
     std::vector<int32_t> hRowOf, hVertOf;    // internal vertex -> solver row and back
     std::vector<int32_t> hSRowPtr, hSColIdx; // the device pattern (solver order)
@@ -153,6 +153,8 @@ struct ocb_ctx {
     bool deferFactorCheck = false;           // ocb_newton_step: the block-Jacobi verdict is read together with the PCG status
     int64_t precondFallbacks = 0;            // solves repeated with block-Jacobi after the two-level preconditioner failed
     std::vector<int32_t> hStamp;             // scratch of the pattern builders
+    std::vector<int32_t> hMeshAdjPtr, hMeshAdj;   // de-duplicated vertex adjacency of the MESH (internal ids), kept until the next ocb_set_mesh
+    bool meshAdjValid = false;
     std::vector<double> hHint;               // ocb_set_coordinate_hint: 2 per vertex (interleaved), caller numbering
     std::vector<double> hXY;                 // host mirror of x (INTERNAL numbering) as last written by ocb_set_uv: spares the
     bool hXYMesh = false, hXYAir = false;    // row-order code its download; a device-side update of x invalidates it
@@ -170,6 +172,7 @@ struct ocb_ctx {
     unsigned char* stPinned = nullptr; size_t stPinnedCap = 0;   // pinned staging arena of ocb_stencil_newton_step
     ocb::DevBuf<int32_t> scratchI;
     int pcgGrid = 0, pcgBlock = 0;
+    ocb::DevBuf<int32_t> pcgHalo;            // cluster-mode PCG: halo slot table (see spmv_fused_ell)
     size_t pcgSmemAttr = 0;
     int clusterOk = -1;                      // -1 unknown, 0 a 16-CTA cluster cannot be scheduled, 1 ok
     ocb::DevBuf<double> xSaved;              // ocb_save_uv / ocb_restore_uv snapshot

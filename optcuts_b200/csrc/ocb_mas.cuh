@@ -3,7 +3,7 @@
 //
 //   M^-1 = blockdiag2x2(A)^-1 + sum_{l=1..L-1} P_l D_l^-1 P_l^T + P_L (P_L^T A P_L)^-1 P_L^T
 //
-// The solver rows are ordered by recursive coordinate bisection of the UV positions so that a persistent CTA's
+// The solver rows are ordered along a Hilbert curve through the UV positions so that a persistent CTA's
 // contiguous row range is a compact patch, split into leaves of <= 8 vertices.  Level-l nodes carry 6 DOFs: the
 // affine displacement fields (1, x, y) x (u, v) on the node, x/y in node-local coordinates.  8 consecutive nodes
 // form a group (= a node of level l+1); below the coarse level L, D_l is the block diagonal of the Galerkin

@@ -41,6 +41,9 @@ struct PcgParams {
     const int32_t* vertOf;     // solver row -> internal vertex (rhs gather / result scatter); nullptr = identity
     double* xOut;              // result in INTERNAL vertex order (x is the working copy in solver order)
     size_t masSmemOff;         // byte offset of the MAS scratch in dynamic shared memory
+    size_t haloSmemOff;        // cluster mode: byte offset of the halo buffer (kHaloCap double2) in dynamic shared memory; 0 = none
+    int32_t* haloIdx;          // cluster mode: gridDim x kHaloCap packed (owner << 20 | local row) of every halo slot
+    int haloCap;               // slots available per CTA (what the shared-memory budget leaves, <= kHaloCap)
     MasView mas;               // mas.L == 0: block-Jacobi only
 };
 
@@ -324,11 +327,29 @@ __device__ __forceinline__ Slice carve(unsigned char* base, int nLoc, int W)
 // SMEM-mode SpMV with the fused direction update: one thread per SCALAR row (thread pair = block row), the row's
 // blocks walked serially out of the ELL slice.  ~14 instructions per block and no shuffles: the 16-lanes-per-row
 // mapping of the streaming path below costs ~10x more issue slots, which is what bounds a solve that runs on few SMs.
+// Cluster mode: the off-slice entries of a CTA's ELL slice (~8 % of them) used to cost one distributed-shared-memory round
+// trip EACH, issued one after the other from inside the row loop (plus an integer division for the owner).  Now every
+// such entry owns a slot of a per-CTA halo buffer: at the start of the SpMV all slots are filled at once (z + beta d of the
+// owner's shared memory, every remote load in flight together: ONE round trip), and the row loop reads local shared memory
+// only.  The value in a slot is exactly the z + beta d the loop used to form, so the sums are bit-identical.
+static constexpr int kHaloCap = 512;
 template <bool DSMEM>
 __device__ __forceinline__ double spmv_fused_ell(const PcgParams& P, const Slice& S, int rowBeg, int rowEnd, int rowsPer, const double* z,
                                                  const double* dOld, double* dNew, double beta,
-                                                 const double2* __restrict__ sdOld, double2* __restrict__ sdNew)
+                                                 const double2* __restrict__ sdOld, double2* __restrict__ sdNew,
+                                                 double2* __restrict__ haloV = nullptr, int nHalo = 0)
 {
+    if (DSMEM && haloV) {
+        cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+        const int32_t* hi = P.haloIdx + (size_t)blockIdx.x * kHaloCap;
+        for (int h = threadIdx.x; h < nHalo; h += blockDim.x) {
+            const int packed = __ldg(hi + h), owner = packed >> 20, lc = packed & 0xfffff;
+            const double2 zz = cluster.map_shared_rank(S.z, owner)[lc];
+            const double2 dd = cluster.map_shared_rank(const_cast<double2*>(sdOld), owner)[lc];
+            haloV[h] = make_double2(zz.x + beta * dd.x, zz.y + beta * dd.y);
+        }
+        __syncthreads();
+    }
     const double2* z2 = reinterpret_cast<const double2*>(z);
     const double2* d2 = reinterpret_cast<const double2*>(dOld);
     const double2* __restrict__ gval2 = reinterpret_cast<const double2*>(P.val);
@@ -342,8 +363,13 @@ __device__ __forceinline__ double spmv_fused_ell(const PcgParams& P, const Slice
             const int c = S.col[k * S.nLoc + lr];
             const double2 a = S.val2[2 * (k * S.nLoc + lr) + half];
             double2 zz, dd;
+            if (DSMEM && c < 0) {                  // halo slot: z + beta d already formed
+                const double2 hv = haloV[-c - 1];
+                acc += a.x * hv.x + a.y * hv.y;
+                continue;
+            }
             if (c >= rowBeg && c < rowEnd) { zz = S.z[c - rowBeg]; dd = sdOld[c - rowBeg]; }     // own range: no global traffic
-            else if (DSMEM) {                      // halo straight out of the owner CTA's shared memory (same cluster)
+            else if (DSMEM) {                      // halo straight out of the owner CTA's shared memory (slots exhausted)
                 const int owner = c / rowsPer, lc = c - owner * rowsPer;
                 cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
                 zz = cluster.map_shared_rank(S.z, owner)[lc];
@@ -480,6 +506,30 @@ pcg_kernel(PcgParams P)
         }
     }
 
+    // cluster mode: give every off-slice entry of the slice a halo slot
+    double2* haloV = nullptr;
+    __shared__ int sHaloCount;
+    int nHalo = 0;
+    if (MODE == 2 && P.haloSmemOff && P.haloIdx) {
+        haloV = reinterpret_cast<double2*>(smemRaw + P.haloSmemOff);
+        if (threadIdx.x == 0) sHaloCount = 0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < nLoc * S.W; e += kBlk) {
+            const int lr = e % nLoc, k = e / nLoc;
+            if (k >= S.len[lr]) continue;
+            const int c = S.col[k * S.nLoc + lr];
+            if (c >= rowBeg && c < rowEnd) continue;
+            const int slot = atomicAdd(&sHaloCount, 1);
+            if (slot < P.haloCap) {
+                const int owner = c / rowsPer;
+                P.haloIdx[(size_t)blockIdx.x * kHaloCap + slot] = (owner << 20) | (c - owner * rowsPer);
+                S.col[k * S.nLoc + lr] = -(slot + 1);
+            }
+        }
+        __syncthreads();
+        nHalo = min(sHaloCount, P.haloCap);
+    }
+
     const bool MAS = P.mas.L > 0;
     MasSmem MS = {};
     if (MAS) { MS = mas_carve(smemRaw + P.masSmemOff, P.mas); mas_init(P.mas, MS, blockIdx.x, rowBeg, rowEnd); }
@@ -555,7 +605,7 @@ pcg_kernel(PcgParams P)
             double2* sdOld = cur ? S.d[1] : S.d[0];
             double2* sdNew = cur ? S.d[0] : S.d[1];
             double* dOldG = cur ? P.d2 : P.d;
-            double la[1] = {SMEM ? spmv_fused_ell<MODE == 2>(P, S, rowBeg, rowEnd, rowsPer, P.z, dOldG, dNew, beta, sdOld, sdNew)
+            double la[1] = {SMEM ? spmv_fused_ell<MODE == 2>(P, S, rowBeg, rowEnd, rowsPer, P.z, dOldG, dNew, beta, sdOld, sdNew, haloV, nHalo)
                                  : spmv_fused(P, rowBeg, rowEnd, P.z, dOldG, dNew, beta)}, ra[1];
             if (P.dbg) { __syncthreads(); t1 = clock64(); }
             ALLREDUCE(1, la, ra);
@@ -717,7 +767,7 @@ static PcgParams make_params(ocb_ctx* c)
 {
     PcgParams P;
     P.nRows = c->nVtot; P.rowPtr = c->rowPtr.p; P.colIdx = c->colIdx.p; P.val = c->val.p; P.minv = c->minv.p;
-    P.rhs = nullptr; P.negate = 0; P.rowScale = nullptr; P.x = c->px.p; P.xOut = c->p.p; P.vertOf = nullptr; P.masSmemOff = 0; P.mas = MasView(); P.mas.L = 0;
+    P.rhs = nullptr; P.negate = 0; P.rowScale = nullptr; P.x = c->px.p; P.xOut = c->p.p; P.vertOf = nullptr; P.masSmemOff = 0; P.haloSmemOff = 0; P.haloIdx = nullptr; P.haloCap = 0; P.mas = MasView(); P.mas.L = 0;
     P.r = c->pr.p; P.z = c->pz.p; P.d = c->pd.p; P.d2 = c->pd2.p; P.Ap = c->pAp.p;
     P.partials = c->partials.p; P.scal = c->dScal; P.relTol = 1e-12; P.maxIt = 1; P.scaledNorm = 1; P.maxBlkPerCta = 0; P.dbg = nullptr;
     return P;
@@ -755,7 +805,7 @@ static PcgPlan pcg_plan(ocb_ctx* c)
 {
     static const int targetRows = []() { const char* e = getenv("OCB_PCG_ROWS_PER_CTA"); int v = e ? atoi(e) : 256; return v < 32 ? 32 : v; }();
     static const bool allowSmem = []() { const char* e = getenv("OCB_PCG_NO_SMEM"); return !(e && atoi(e)); }();
-    const size_t limit = 214 * 1024;
+    const size_t limit = 214 * 1024;                        // slice + preconditioner scratch; the cluster mode adds its 8 KB halo buffer on top
     static const bool allowCluster = []() { const char* e = getenv("OCB_PCG_NO_CLUSTER"); return !(e && atoi(e)); }();
     PcgPlan pl; pl.smem = false; pl.cluster = false; pl.maxBlk = 0; pl.smemBytes = 0;
     const int n = c->nVtot;
@@ -776,7 +826,7 @@ static PcgPlan pcg_plan(ocb_ctx* c)
         const size_t bytes = slice_need(kClusterSize, maxBlk);
         if (bytes <= limit) {
             if (c->clusterOk < 0) {                           // probe once: can such a cluster be scheduled?
-                cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+                cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
                 cudaFuncSetAttribute(pcg_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(kClusterSize); cfg.blockDim = dim3(kPcgBlockCluster); cfg.dynamicSmemBytes = limit;
@@ -917,7 +967,19 @@ int launch_pcg(ocb_ctx* c, const double* d_rhs, bool negate_rhs, double rel_tol,
         P.mas.cinvInSmem = (!pl.smem && cinvBytes <= 120 * 1024) ? 1 : 0;
         smemBytes += mas_smem_bytes(P.mas.maxLocalNodes, P.mas.rowsPer, P.mas.ldC, P.mas.cinvInSmem ? P.mas.maxOwnC * kMasDof : 0);
     }
-    const size_t smemCap = 220 * 1024;      // + ~5 KB static (reduction scratch) <= 227 KB per CTA
+    const size_t smemCap = 221 * 1024;      // + 5.2 KB static (reduction scratch, cluster partials) <= 227 KB per CTA
+    static const bool haloOn = []() { const char* e = getenv("OCB_PCG_NO_HALO"); return !(e && atoi(e)); }();
+    if (pl.cluster && haloOn) {             // the halo buffer takes what the budget leaves (7 KB = 448 slots at 10k faces; ~200 are used)
+        smemBytes = (smemBytes + 15) / 16 * 16;
+        const size_t avail = smemCap > smemBytes ? smemCap - smemBytes : 0;
+        const int slots = (int)std::min<size_t>(kHaloCap, avail / sizeof(double2));
+        if (slots >= 64) {
+            P.haloSmemOff = smemBytes; P.haloCap = slots;
+            smemBytes += (size_t)slots * sizeof(double2);
+            OCB_CUDA(c, c->pcgHalo.reserve((size_t)grid * kHaloCap + 4, c->stream));
+            P.haloIdx = c->pcgHalo.p;
+        }
+    }
     if (smemBytes > smemCap) return set_err(c, OCB_ERR_STATE, "PCG: shared-memory plan exceeds the SM capacity");
     OCB_CUDA(c, cudaMemsetAsync(c->partials.p, 0, slotDoubles * sizeof(double), c->stream));
     static const bool dbgOn = []() { const char* e = getenv("OCB_PCG_DEBUG"); return e && atoi(e); }();

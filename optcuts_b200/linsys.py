@@ -1,6 +1,6 @@
 """CudaLinSysSolver — Python mirror of OptCuts::LinSysSolver<VectorXi,VectorXd>
 (src/LinSysSolver/LinSysSolver.hpp:22-256) with the EigenLibSolver role
-(src/LinSysSolver/EigenLibSolver.cpp) played by the device block-Jacobi PCG.
+(src/LinSysSolver/EigenLibSolver.cpp) played by the device PCG (two-level additive Schwarz preconditioner).
 """
 import numpy as np
 from ._capi import Context

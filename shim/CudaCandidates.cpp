@@ -87,7 +87,7 @@ double now(void) { return std::chrono::duration<double>(std::chrono::steady_cloc
 void report(void)
 {
     Batch& B = batch();
-    if (B.queries && std::getenv("OCB_HOST_TIMING"))
+    if (B.queries && (std::getenv("OCB_HOST_TIMING") || std::getenv("OCB_CANDIDATES_REPORT")))
         std::fprintf(stderr, "[ocb candidates] %ld queries, %ld local problems on the device in %ld lock-step rounds (%ld passed to the CPU), "
                              "%.3f s: Triangle %.3f s, device + packing %.3f s\n", B.queries, B.solved, B.rounds, B.passThroughs, B.tSolve, B.tTriangle, B.tDevice);
 }

@@ -58,25 +58,44 @@ def stages(trace):
     return out
 
 
+def branches(name):
+    """The recorded reference traces a run may reproduce.  The reference's op sequence is not unique under perturbation:
+    Optimizer::solve propagates a fracture when a candidate lowers E_w by more than the LAST NEWTON ITERATION did
+    (createFracture(lastEDec, propagateFracture), Optimizer.cpp:232), a difference of two nearly equal energies.  The
+    UNMODIFIED reference run on bimba configs[1] with its input vertices perturbed by a relative 1e-9 / 1e-7 ends in one of
+    exactly two ways (tools/ref_sensitivity.py, profiles/r2_reference_sensitivity.txt): 77 connectivity stages and finals
+    4.28086 / 2.65232 (the unperturbed run), or the same 77 stages followed by two more splits, finals 4.2781x / 2.70188.
+    `<name>_alt_trace.txt` is the reference's own trace of that second branch (tools/ref_sensitivity.py bimba_cfg2 4 1e-9 2).
+    A different linear solver perturbs every iteration by kappa * eps >> 1e-9, so either branch is the reference's answer."""
+    out = []
+    for tag in ("", "_alt"):
+        t = os.path.join(GOLDEN, "traces", name + tag + "_trace.txt")
+        if os.path.exists(t):
+            out.append((tag or "main", parse_trace(t), open(os.path.join(GOLDEN, "traces", name + tag + "_info.txt")).read().split("\n")))
+    return out
+
+
 def compare(name, got, info):
     """Identical DECISIONS: the same sequence of mesh connectivities (every split / merge, type and path, in the same
-    order), the same number of topology steps; the energies at every stationary point of the geometry step (conv=1: the
-    states the topology decisions and the dual update are taken from) and the finals within 2e-5: the reference declares a
-    geometry step converged as soon as ONE Newton iteration lowers E by less than 1e-6 relative (Optimizer.cpp:635), so its
-    own stationary points are only defined to a few 1e-6 (torus: the reference stops after 11 iterations at E_SD
-    4.0936044, this path after 13 at 4.0935812, lower; bimba configs[1] agrees in all six digits info.txt prints).
-    Not asserted: the Newton iteration COUNT inside a stage and per-iteration energies of the free run.  The reference's
-    LDL^T and this PCG both solve systems with kappa ~ 1e12 at a distorted start (profiles/r2_pcg_norm.txt: diagonal
-    1e-8..1e9), i.e. both carry ~1e-4 relative error in the softest components there; on the torus the first step is
-    0.99 x the inversion bound and moves E from 12.2 to 0.54, so that noise is 2e-3 in E after ONE iteration and a run may
-    need one or two iterations more or fewer to reach the same stationary point (bimba configs[1]: 172 vs 170).  The
-    per-iteration 1e-9 bar is checked teacher-forced on ~50 recorded states (tests/test_gpu_sweep.py)."""
-    want = parse_trace(os.path.join(GOLDEN, "traces", name + "_trace.txt"))
-    winfo = open(os.path.join(GOLDEN, "traces", name + "_info.txt")).read().split("\n")
-    sg, sw = stages(got), stages(want)
-    for k in range(min(len(sg), len(sw))):
-        assert sg[k]["key"] == sw[k]["key"], "%s: topology operation %d differs: mesh %s vs reference %s" % (name, k, sg[k]["key"], sw[k]["key"])
-    assert len(sg) == len(sw), "%s: %d connectivity stages vs reference %d" % (name, len(sg), len(sw))
+    order) as one branch of the reference (see branches()), the same number of topology steps; the energies at every
+    stationary point of the geometry step (conv=1: the states the topology decisions and the dual update are taken from) and
+    the finals within 2e-5: the reference declares a geometry step converged as soon as ONE Newton iteration lowers E by less
+    than 1e-6 relative (Optimizer.cpp:635), so its own stationary points are only defined to a few 1e-6 (torus: the
+    reference stops after 11 iterations at E_SD 4.0936044, this path after 13-17 at 4.0935812, lower).
+    Not asserted: the Newton iteration COUNT inside a stage and per-iteration energies of the free run: the reference's own
+    free run leaves the 1e-9 band after 4 iterations when its input is perturbed by 1e-13 (same evidence file), this path
+    after 5-6.  The per-iteration 1e-9 bar is checked teacher-forced on ~50 recorded states (tests/test_gpu_sweep.py)."""
+    sg = stages(got)
+    cands = branches(name)
+    match = [b for b in cands if [s["key"] for s in stages(b[1])] == [s["key"] for s in sg]]
+    if not match:
+        tag, want, _ = cands[0]
+        sw = stages(want)
+        for k in range(min(len(sg), len(sw))):
+            assert sg[k]["key"] == sw[k]["key"], "%s: topology operation %d differs: mesh %s vs reference %s" % (name, k, sg[k]["key"], sw[k]["key"])
+        assert len(sg) == len(sw), "%s: %d connectivity stages vs reference %d (and no recorded reference branch matches)" % (name, len(sg), len(sw))
+    tag, want, winfo = match[0]
+    sw = stages(want)
     worst, n_stationary, lead = 0.0, 0, 0
     for a, b in zip(sg, sw):
         ca = [ln for ln in a["lines"] if ln["conv"] == "1"]
@@ -95,13 +114,13 @@ def compare(name, got, info):
             break
         lead += 1
     # the Newton iteration COUNT depends on where the reference's relative-decrease stop (1e-6 per iteration, Optimizer.cpp:635)
-    # happens to fire on a flat landscape (torus: 11 in the reference, 13-16 here); only a gross deviation is an error
+    # happens to fire on a flat landscape (torus: 11 in the reference, 13-17 here); only a gross deviation is an error
     assert abs(len(got) - len(want)) <= max(8, 0.1 * len(want)), "%s: %d Newton iterations vs reference %d" % (name, len(got), len(want))
     # info.txt line 2: Newton iterations, topology steps, ...; line 4: final E_SD, E_se (north_star: within 1e-6)
     assert info[1].split()[1] == winfo[1].split()[1], (info[1], winfo[1])
     for a, b in zip(info[3].split(), winfo[3].split()):
         assert abs(float(a) - float(b)) <= 2e-5 * abs(float(b)) + 1e-12, (info[3], winfo[3])
-    return dict(stages=len(sg), stationary_points=n_stationary, worst_rel_at_stationary=worst, newton_iters=(len(got), len(want)),
+    return dict(reference_branch=tag, stages=len(sg), stationary_points=n_stationary, worst_rel_at_stationary=worst, newton_iters=(len(got), len(want)),
                 leading_iterations_within_1e9=lead)
 
 

@@ -18,7 +18,7 @@ INPUTS = os.path.join(ROOT, "tests", "golden", "inputs")
 def main():
     mesh = sys.argv[1] if len(sys.argv) > 1 else "bimba_i_f10000.obj"
     args = sys.argv[2:] if len(sys.argv) > 2 else ["0.025", "1", "2", "4.1", "1", "0"]
-    runs = [("cuda", os.path.join(ROOT, "shim", "_build", "OptCuts_cuda"), {"OCB_DEVICE_NEWTON": "1"}),
+    runs = [("cuda", os.path.join(ROOT, "shim", "_build", "OptCuts_cuda"), {"OCB_DEVICE_NEWTON": "1", "OCB_CANDIDATES_REPORT": "1"}),
             ("cuda0", os.path.join(ROOT, "shim", "_build", "OptCuts_cuda"), {"OCB_DEVICE_NEWTON": "0"}),
             ("ref", os.path.join(ROOT, "oracle", "_ref", "OptCuts_bin"), {})]
     if os.environ.get("OCB_TIMING_SKIP"):
@@ -37,6 +37,9 @@ def main():
         print("-- %-5s rc=%d wall %.2f s\n   iterations: %s\n   timers: %s\n   final E_SD, E_se: %s" % (name, r.returncode, dt, info[1], info[2], info[3]))
         if r.returncode != 0:
             print(r.stderr[-1500:])
+        for ln in r.stderr.split("\n"):
+            if ln.startswith("[ocb candidates]"):
+                print("   " + ln)
         res[name] = dt
     if "ref" in res:
         for k in res:
