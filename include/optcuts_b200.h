@@ -154,6 +154,9 @@ int ocb_hessian_dense(ocb_ctx* ctx, int uniformWeight, double* H_out);
 int ocb_update_values_triplets(ocb_ctx* ctx, int64_t nT, const int32_t* I, const int32_t* J, const double* S);
 /* reference layout read-back: 1-based upper-triangular CSR (LinSysSolver.hpp:27-29, get_ia/ja/a) */
 int ocb_download_csr(ocb_ctx* ctx, int32_t* ia, int32_t* ja, double* a);
+/* change counter of the device matrix (pattern or values): lets a caller keep its read-back copy (LinSysSolver::coeffMtr,
+ * LinSysSolver.hpp:183-196, asks entry by entry) until the next assembly; -1 for a null context */
+long long ocb_matrix_version(const ocb_ctx* ctx);
 /* y = A x with the device matrix (fixes the reference's broken LinSysSolver::multiply, :172-187) */
 int ocb_multiply(ocb_ctx* ctx, const double* x, double* y);
 

@@ -93,6 +93,7 @@ _SIGS = [
     ("ocb_hessian_blocks", C.c_int, [C.c_void_p, C.c_int, _d]),
     ("ocb_update_values_triplets", C.c_int, [C.c_void_p, C.c_int64, _i, _i, _d]),
     ("ocb_download_csr", C.c_int, [C.c_void_p, _i, _i, _d]),
+    ("ocb_matrix_version", C.c_longlong, [C.c_void_p]),
     ("ocb_multiply", C.c_int, [C.c_void_p, _d, _d]),
     ("ocb_factorize", C.c_int, [C.c_void_p]),
     ("ocb_solve", C.c_int, [C.c_void_p, _d, _d, C.c_double, C.c_int, C.POINTER(C.c_int), _d]),

@@ -4,6 +4,10 @@
 // reference counterpart in the header.
 #include "ocb_internal.cuh"
 #include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <unistd.h>
 #include <algorithm>
 #include <cmath>
 #include <new>
@@ -70,9 +74,24 @@ HostTimer::~HostTimer()
     for (auto& r : host_timing_table()) if (r.name == name) { r.total += dt; r.count++; return; }
     host_timing_table().push_back(HostTimingRec{name, dt, 1});
 }
+// seconds since this process started (Linux: field 22 of /proc/self/stat against the boot-time clock)
+static double process_age_s()
+{
+    FILE* f = fopen("/proc/self/stat", "r");
+    if (!f) return -1.0;
+    char buf[2048]; const size_t n = fread(buf, 1, sizeof(buf) - 1, f); fclose(f); buf[n] = 0;
+    const char* p = strrchr(buf, ')');                        // the command name may contain spaces
+    if (!p) return -1.0;
+    unsigned long long start = 0; int field = 2;
+    for (p += 2; *p && field < 21; ++p) if (*p == ' ') ++field;
+    sscanf(p, "%llu", &start);
+    struct timespec ts; clock_gettime(CLOCK_BOOTTIME, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec - (double)start / (double)sysconf(_SC_CLK_TCK);
+}
 void host_timing_report()
 {
     if (!host_timing_on()) return;
+    fprintf(stderr, "[ocb host] process age at the report: %.3f s\n", process_age_s());
     for (auto& r : host_timing_table()) fprintf(stderr, "[ocb host] %-28s %8ld calls  %10.3f ms total  %8.3f us/call\n", r.name, r.count, 1e3 * r.total, 1e6 * r.total / (r.count ? r.count : 1));
     host_timing_table().clear();
 }
@@ -80,7 +99,10 @@ void host_timing_report()
 int ensure_init(ocb_ctx* c)
 {
     if (c->inited) { cudaSetDevice(c->device); return 0; }
+    HostTimer _hc("cuda context + stream (first call)");
+    if (host_timing_on()) fprintf(stderr, "[ocb host] process age at the first CUDA call: %.3f s\n", process_age_s());
     OCB_CUDA(c, cudaSetDevice(c->device));
+    OCB_CUDA(c, cudaFree(0));                                // creates the primary context here (timed above), not in the first allocation
     if (!c->streamGiven) { OCB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     OCB_CUDA(c, cudaEventCreate(&c->ev0));
     OCB_CUDA(c, cudaEventCreate(&c->ev1));
@@ -671,7 +693,7 @@ static int finish_install(ocb_ctx* c)
     OCB_CUDA(c, cudaMemcpyAsync(c->fixedMask.p, c->hFixed.data(), (size_t)c->nVtot, cudaMemcpyHostToDevice, c->stream));
     // (pageable sources: cudaMemcpyAsync returns once the data is staged, so the local vectors may go out of scope)
     { HostTimer _h3("  mas_install"); OCB_TRY(mas_install(c)); }
-    c->patternValid = true; c->matrixValid = c->precondValid = false;
+    c->patternValid = true; c->matrixValid = c->precondValid = false; ++c->matrixVersion;
     HostTimer _h4("  build_slots");
     return launch_build_slots(c);
 }
@@ -880,6 +902,7 @@ int ocb_hessian_assemble(ocb_ctx* c, double p0)
     if (!c->patternValid && c->nV > 0) OCB_TRY(ocb_set_pattern_from_elements(c));     // no pattern handed over: the element lists define it
     OCB_TRY(need(c, c->patternValid && c->slotsValid, "ocb_hessian_assemble: no sparsity pattern (ocb_set_pattern)"));
     OCB_TRY(launch_hessian(c, p0));
+    ++c->matrixVersion;
     c->matrixValid = true; c->precondValid = false; c->systemScaled = false;
     return OCB_OK;
 }
@@ -971,9 +994,12 @@ int ocb_update_values_triplets(ocb_ctx* c, int64_t nT, const int32_t* I, const i
         OCB_TRY(upload_d(c, c->scratchD.p, S, (size_t)nT));
     }
     OCB_TRY(launch_triplet_scatter(c, nT, c->scratchI.p, c->scratchI.p + nT, c->scratchD.p));
+    ++c->matrixVersion;
     c->matrixValid = true; c->precondValid = false; c->systemScaled = false;
     return OCB_OK;
 }
+
+long long ocb_matrix_version(const ocb_ctx* c) { return c ? c->matrixVersion : -1; }
 
 int ocb_download_csr(ocb_ctx* c, int32_t* ia, int32_t* ja, double* a)
 {
@@ -1272,7 +1298,7 @@ int ocb_newton_step_ex(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_
     if (!(flags & OCB_STEP_SKIP_CONVERGENCE_TEST) && sqn < targetGRes) { out->converged = 1; return OCB_OK; }
     if (!c->patternValid) OCB_TRY(ocb_set_pattern_from_elements(c));
     if (!((flags & OCB_STEP_REUSE_MATRIX) && c->matrixValid)) OCB_TRY(ocb_hessian_assemble(c, p0));
-    if (c->scaleSystem && !c->systemScaled) { OCB_TRY(launch_scale_system(c)); c->precondValid = false; }
+    if (c->scaleSystem && !c->systemScaled) { OCB_TRY(launch_scale_system(c)); c->precondValid = false; ++c->matrixVersion; }
     c->deferFactorCheck = true;
     const int rf = c->precondValid ? 0 : ocb_factorize(c);
     c->deferFactorCheck = false;
@@ -1297,6 +1323,7 @@ int ocb_newton_step_ex(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_
     for (int esc = 0; esc < 3 && rs == OCB_ERR_BREAKDOWN; ++esc) {
         static const double deltas[3] = {1.0e-8, 1.0e-5, 1.0e-2};
         OCB_TRY(launch_diag_shift(c, deltas[esc]));
+        ++c->matrixVersion;
         c->precondValid = false;
         c->deferFactorCheck = true;
         const int rf2 = ocb_factorize(c);

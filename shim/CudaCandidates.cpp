@@ -8,11 +8,14 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
 
 namespace OptCuts {
 
@@ -31,6 +34,67 @@ struct Hasher {
         for (size_t i = 0; i < bytes; ++i) { a ^= p[i]; a *= 1099511628211ull; b = (b ^ p[i]) * 0xff51afd7ed558ccdull + 0x2545f4914f6cdd1dull; }
     }
     template <typename T> void pod(const T& v) { add(&v, sizeof(T)); }
+};
+
+// Host threads of the lock-step solve: one persistent pool for the whole run.  A round triangulates ~100 small air regions
+// (~20 us each) and there are ~40 rounds per query, so the threads must not be created per round (a parallel_for that spawns
+// its workers, like the TBB stand-in of the oracle build, costs more than the triangulations themselves).  Workers sleep on a
+// condition variable between rounds; the calling thread takes part in the work.
+class Pool {
+public:
+    static Pool& get(void) { static Pool* p = new Pool(); return *p; }     // never destroyed: the host program leaves through exit()
+    void run(int n, const std::function<void(int)>& f)
+    {
+        if (n <= 0) return;
+        if (n < 4 || workers.empty()) { for (int i = 0; i < n; ++i) f(i); return; }
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            fn = &f; total = n; next.store(0); pending.store(n); ++generation;
+        }
+        cv.notify_all();
+        work();
+        while (pending.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+        { std::lock_guard<std::mutex> lock(mu); fn = NULL; }                    // workers that wake up from now on skip this job
+        while (inside.load(std::memory_order_acquire) > 0) std::this_thread::yield();   // ... and those already in have left before the next job is posted
+    }
+private:
+    Pool(void)
+    {
+        const char* e = std::getenv("OCB_HOST_THREADS");
+        int nt = e ? std::atoi(e) : static_cast<int>(std::thread::hardware_concurrency());
+        if (nt > 32) nt = 32;
+        for (int t = 1; t < nt; ++t) workers.emplace_back([this]() { loop(); });
+        for (auto& w : workers) w.detach();
+    }
+    void work(void)
+    {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= total) break;
+            (*fn)(i);
+            pending.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    void loop(void)
+    {
+        unsigned long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lock(mu);
+                cv.wait(lock, [&]() { return generation != seen; });
+                seen = generation;
+                if (!fn) continue;
+                inside.fetch_add(1);
+            }
+            work();
+            inside.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::vector<std::thread> workers;
+    std::mutex mu; std::condition_variable cv;
+    const std::function<void(int)>* fn = NULL;
+    int total = 0; unsigned long generation = 0;
+    std::atomic<int> next{0}, pending{0}, inside{0};
 };
 
 struct Problem {
@@ -56,7 +120,7 @@ struct Batch {
     ocb_ctx* ctx = NULL;
     // statistics
     long queries = 0, solved = 0, rounds = 0, passThroughs = 0;
-    double tSolve = 0.0, tTriangle = 0.0, tDevice = 0.0;
+    double tSolve = 0.0, tTriangle = 0.0, tDevice = 0.0, tPass1 = 0.0, tPass2 = 0.0, tMark = 0.0, tKey = 0.0, tCopy = 0.0;
 };
 Batch& batch(void) { static Batch B; return B; }
 
@@ -89,7 +153,8 @@ void report(void)
     Batch& B = batch();
     if (B.queries && (std::getenv("OCB_HOST_TIMING") || std::getenv("OCB_CANDIDATES_REPORT")))
         std::fprintf(stderr, "[ocb candidates] %ld queries, %ld local problems on the device in %ld lock-step rounds (%ld passed to the CPU), "
-                             "%.3f s: Triangle %.3f s, device + packing %.3f s\n", B.queries, B.solved, B.rounds, B.passThroughs, B.tSolve, B.tTriangle, B.tDevice);
+                             "%.3f s: Triangle %.3f s, device + packing %.3f s; the reference's query code around it: recording pass %.3f s, replay pass %.3f s\n",
+                     B.queries, B.solved, B.rounds, B.passThroughs, B.tSolve, B.tTriangle, B.tDevice, B.tPass1, B.tPass2);
 }
 
 Key keyOf(const TriMesh& m, bool bij, const Eigen::MatrixXd& UV_bnds, const Eigen::MatrixXi& E, const Eigen::VectorXi& bnd, double tol, int maxIter)
@@ -154,7 +219,7 @@ void solveAll(Batch& B)
     for (int round = 0; !active.empty(); ++round) {
         // ---- host: this round's air meshes (Triangle), all threads
         const double t1 = now();
-        tbb::parallel_for(0, static_cast<int>(active.size()), 1, [&](int k) { Problem& p = P[active[k]]; if (p.bij) buildAir(p); });
+        Pool::get().run(static_cast<int>(active.size()), [&](int k) { Problem& p = P[active[k]]; if (p.bij) buildAir(p); });
         const double t2 = now();
         B.tTriangle += t2 - t1;
         // ---- pack: per problem the mesh's vertices, then the air mesh's own; the mesh's triangles, then the air mesh's
@@ -314,19 +379,23 @@ OcbBatchScope::OcbBatchScope(void) : outer(false)
         outer = true;
         B.index.clear(); B.problems.clear();
         B.mode.store(RECORD);
+        B.tMark = now();
     }
 }
 void OcbBatchScope::solve(void)
 {
     Batch& B = batch();
     B.queries++;
+    B.tPass1 += now() - B.tMark;
     solveAll(B);
     B.mode.store(REPLAY);
+    B.tMark = now();
 }
 OcbBatchScope::~OcbBatchScope(void)
 {
     if (outer) {
         Batch& B = batch();
+        B.tPass2 += now() - B.tMark;
         B.mode.store(OFF);
         B.index.clear(); B.problems.clear();
     }

@@ -45,6 +45,7 @@ protected:
     double relTol;
     int maxIter, lastIters;
     double lastRelRes;
+    long long downloadedVersion = -1;
 
     void check(int rc, const char* what) const {
         if (rc == OCB_ERR_NOT_CONVERGED) return;      // the solution is still written; Optimizer's line search decides
@@ -85,8 +86,27 @@ public:
         }
         check(ocb_set_pattern(ctx, nV, ptr.data(), idx.data(), fixed.data(), static_cast<int>(fixed.size())), "ocb_set_pattern");
     }
-    void set_pattern(const Eigen::SparseMatrix<double>& mtr) {     // only used by the dense/SparseLU side paths of the reference
-        throw std::runtime_error("CudaLinSysSolver::set_pattern(SparseMatrix) is not on the hot path");
+    // EigenLibSolver::set_pattern(const SparseMatrix&) (EigenLibSolver.cpp:46-69): the matrix itself is handed over (pattern AND
+    // values, SPD, no fixed vertices known).  No call site in the reference; implemented for the completeness of the plugin surface:
+    // the vertex adjacency is read off the block structure (vertex = index / DIM), the upper-triangular entries go through the
+    // same triplet route as update_a.
+    void set_pattern(const Eigen::SparseMatrix<double>& mtr) {
+        if (mtr.rows() != mtr.cols() || mtr.rows() % DIM) throw std::runtime_error("CudaLinSysSolver::set_pattern(SparseMatrix): not a square matrix of DIM x DIM blocks");
+        const int nV = static_cast<int>(mtr.rows() / DIM);
+        Base::numRows = nV * DIM;
+        std::vector<std::set<int>> nb(nV);
+        std::vector<int32_t> I, J; std::vector<double> S;
+        for (int k = 0; k < mtr.outerSize(); ++k)
+            for (Eigen::SparseMatrix<double>::InnerIterator it(mtr, k); it; ++it) {
+                const int r = static_cast<int>(it.row()), c = static_cast<int>(it.col());
+                if (r / DIM != c / DIM) { nb[r / DIM].insert(c / DIM); nb[c / DIM].insert(r / DIM); }
+                if (r <= c) { I.push_back(r); J.push_back(c); S.push_back(it.value()); }
+            }
+        const bool wasResident = newton.deviceResident;
+        newton.deviceResident = false;
+        set_pattern(nb, std::set<int>());
+        newton.deviceResident = wasResident;
+        check(ocb_update_values_triplets(ctx, static_cast<int64_t>(S.size()), I.data(), J.data(), S.data()), "ocb_update_values_triplets");
     }
 
     // LinSysSolver::update_a (LinSysSolver.hpp:138-159): zero, accumulate triplets with i <= j
@@ -121,9 +141,13 @@ public:
         Base::ia.resize(sz[5] + 1); Base::ja.resize(sz[6]); Base::a.resize(sz[6]);
         check(ocb_download_csr(ctx, Base::ia.data(), Base::ja.data(), Base::a.data()), "ocb_download_csr");
     }
+    // LinSysSolver::coeffMtr (LinSysSolver.hpp:183-196): one entry of the upper-triangular CSR.  The device matrix is read back
+    // once per assembly (a 64-bit change counter of the context tells whether the host copy is current), not once per call.
     double coeffMtr(int rowI, int colI) const {
         if (rowI > colI) std::swap(rowI, colI);
-        const_cast<CudaLinSysSolver*>(this)->download();
+        CudaLinSysSolver* self = const_cast<CudaLinSysSolver*>(this);
+        const long long ver = ocb_matrix_version(ctx);
+        if (ver != self->downloadedVersion || Base::ia.size() == 0) { self->download(); self->downloadedVersion = ver; }
         for (int k = Base::ia[rowI] - 1; k < Base::ia[rowI + 1] - 1; ++k) if (Base::ja[k] - 1 == colI) return Base::a[k];
         return 0.0;
     }

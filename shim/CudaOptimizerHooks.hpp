@@ -54,5 +54,10 @@ bool ocbDeviceResident(LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* solver); 
                                   if (!mute && !ocbStopped_) writeEnergyValToFile(false); return ocbStopped_; } }
 // Scaffold::mergeVNeighbor only feeds LinSysSolver::set_pattern (Optimizer.cpp:174, 358, 524), which the device-resident solver
 // ignores: the 5 000 std::set copies per Newton iteration are skipped while the hooks are active
+// `data_findExtrema = result` (Optimizer.cpp:381, 452: "potentially time-consuming", a whole-TriMesh copy with its std::map / std::set
+// members, ~5 ms at 10k faces, once per createFracture call, i.e. once per Newton iteration while a fracture propagates) only feeds
+// the viewer's "find extrema" channel (main.cpp:81, 1577): nothing reads it in headless runs.  OCB_KEEP_FIND_EXTREMA=1 keeps the copy.
+namespace OptCuts { inline bool ocbKeepFindExtrema(void) { static const bool on = []() { const char* e = std::getenv("OCB_KEEP_FIND_EXTREMA"); return e && std::atoi(e) != 0; }(); return on; } }
+#define OCB_COPY_FIND_EXTREMA if (useDense || OptCuts::ocbKeepFindExtrema() || !OptCuts::ocbDeviceResident(linSysSolver)) data_findExtrema = result;
 #define OCB_MERGE_VNEIGHBOR if (useDense || !OptCuts::ocbDeviceResident(linSysSolver)) scaffold.mergeVNeighbor(result.vNeighbor, vNeighbor_withScaf);
 #endif

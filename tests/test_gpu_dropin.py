@@ -78,3 +78,15 @@ def test_whole_run_matches_reference(obj, tmp_path):
     assert abs(out["cuda"]["iters"][0] - out["ref"]["iters"][0]) <= 0.05 * out["ref"]["iters"][0]
     for a, b in zip(out["cuda"]["E"], out["ref"]["E"]):
         assert abs(a - b) <= 2e-6 * abs(b)
+
+
+def test_linsys_solver_virtual_surface():
+    """Every virtual of OptCuts::LinSysSolver on shim/CudaLinSysSolver.hpp (C++ program shim/test_linsys_surface.cpp): the
+    Optimizer's set_pattern(vNeighbor) + update_a + factorize + solve sequence, set_pattern(SparseMatrix), multiply, coeffMtr and
+    getNumNonzeros against Eigen::SimplicialLDLT on the same matrix (solution 1e-9, products and entries 1e-12)."""
+    exe = os.path.join(ROOT, "shim", "_build", "linsys_surface_test")
+    if not os.path.exists(exe):
+        pytest.skip("shim/_build/linsys_surface_test not built (make -C shim needs the reference headers)")
+    r = subprocess.run([exe], capture_output=True, text=True, errors="replace", timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0 and "linsys surface: ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
