@@ -352,9 +352,10 @@ def batch71_ours(args, rank, world, local, torch):
     if not (os.path.exists(batch.CUDA_HOST) and os.path.exists(batch.ARCHIVE)):
         return {"unavailable": "shim/_build/OptCuts_cuda_probe or the mesh archive is missing"}
     rows = {}
-    with tempfile.TemporaryDirectory() as wd:
+    with tempfile.TemporaryDirectory() as wd, batch.MpsDaemon(local) as mps:
         paths = batch.extract_benchmark(os.path.join(wd, "in"))
-        warm = batch.run_mesh(batch.CUDA_HOST, paths[items[shards[rank][-1]][0]], os.path.join(wd, "warm"), 1, gpu=local)   # smallest mesh of the shard, 1 iteration
+        cenv = mps.child_env()
+        warm = batch.run_mesh(batch.CUDA_HOST, paths[items[shards[rank][-1]][0]], os.path.join(wd, "warm"), 1, extra_env=cenv)   # smallest mesh of the shard, 1 iteration
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
@@ -364,9 +365,10 @@ def batch71_ours(args, rank, world, local, torch):
         procs = max(1, min(args.batch_procs, (os.cpu_count() or 1) // max(1, world)))
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=procs) as ex:
-            res = list(ex.map(lambda i: batch.run_mesh(batch.CUDA_HOST, paths[items[i][0]], os.path.join(wd, "m%d" % i), args.batch_iters, gpu=local), shards[rank]))
+            res = list(ex.map(lambda i: batch.run_mesh(batch.CUDA_HOST, paths[items[i][0]], os.path.join(wd, "m%d" % i), args.batch_iters, extra_env=cenv), shards[rank]))
         rows = dict(zip(shards[rank], res))
         mine = time.perf_counter() - t0
+        mps_up = mps.up
     its = sum(r["iters"] for r in rows.values())
     bad = [items[i][0] for i, r in rows.items() if r["rc"] != 0]
     slow = max(rows, key=lambda i: rows[i]["wall_s"])
@@ -385,10 +387,12 @@ def batch71_ours(args, rank, world, local, torch):
     return {"meshes": len(items), "newton_iters_per_mesh_cap": args.batch_iters, "newton_iters": int(its), "wall_s": wall, "it_per_s": its / wall,
             "per_rank_s": per_rank, "limiting_rank": int(np.argmax(per_rank)), "failed_meshes": nbad, "failed_on_rank0": bad,
             "slowest_mesh_rank0": {"name": items[slow][0], "faces": items[slow][1], "wall_s": rows[slow]["wall_s"]},
-            "one_iteration_process_wall_s": warm["wall_s"], "concurrent_processes_per_gpu": procs,
-            "scaling": "strong", "note": "one_iteration_process_wall_s = the fixed cost of a process (CUDA context creation on a box without a persistence "
-                                         "daemon: 2.7-3.4 s cold, profiles/r2_process_init.txt); one host-program process per mesh (reference main + Optimizer hooks + device candidate evaluation), "
-                                         "config args %s, every mesh bounded to the cap; process start-up and CUDA context creation are inside" % " ".join(batch.MESH_ARGS)}
+            "one_iteration_process_wall_s": warm["wall_s"], "concurrent_processes_per_gpu": procs, "mps": bool(mps_up),
+            "scaling": "strong",
+            "note": "one host-program process per mesh (reference main + Optimizer hooks + device candidate evaluation), config args %s, every mesh "
+                    "bounded to the cap, process start-up inside; mps = the per-mesh processes attach to an NVIDIA MPS daemon started for the batch "
+                    "(own CUDA context creation costs 1.7-4.7 s per process on this pool's boxes, 0.2-0.6 s through MPS: profiles/r2_mps_process_start.txt); "
+                    "one_iteration_process_wall_s = the fixed cost of one process" % " ".join(batch.MESH_ARGS)}
 
 
 def host_program_run():
@@ -609,7 +613,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=["bimba10k", "bimba_x4", "bimba_x10", "batch71"],
                     help="default: bimba10k as the headline + bimba_x4 / bimba_x10 / batch71 / host_program sub-objects")
     ap.add_argument("--quick", action="store_true", help="headline workload only (no sub-objects)")
-    ap.add_argument("--batch-iters", type=int, default=40, help="batch71: cap of Newton iterations per mesh")
+    ap.add_argument("--batch-iters", type=int, default=150, help="batch71: cap of Newton iterations per mesh (both arms)")
     ap.add_argument("--batch-procs", type=int, default=3, help="batch71: host-program processes at a time per GPU (the reference arm runs gpus x this many CPU processes)")
     ap.add_argument("--batch-ref-sample", type=int, default=24, help="reference arm of batch71: number of meshes sampled across the size range (0 = all 71)")
     ap.add_argument("--cpu-limit-x10", type=int, default=45, help="time limit (s) of the reference's iteration at 1M faces")

@@ -71,7 +71,60 @@ def extract_benchmark(dst):
     return {f: os.path.join(dst, f) for f in sorted(os.listdir(dst)) if f.endswith(".obj")}
 
 
-def run_mesh(exe, mesh_path, workdir, max_iters, gpu=None, timeout=1800):
+def visible_device(gpu):
+    """the gpu-th VISIBLE device as CUDA_VISIBLE_DEVICES names it (a launcher may have restricted / renumbered the devices already)"""
+    vis = [d for d in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if d.strip()]
+    return vis[gpu] if gpu < len(vis) else str(gpu)
+
+
+class MpsDaemon:
+    """NVIDIA MPS control daemon for ONE GPU, for the life of a batch: the per-mesh host processes attach to the server's GPU
+    context instead of creating their own (1.7-4.7 s per process on this pool's boxes, erratic -> 0.2-0.6 s; profiles/
+    r2_mps_process_start.txt) and their kernels run side by side instead of time-sliced.  A batch of one short process per mesh
+    (batch.py:11-14) is what MPS is for.  Own pipe / log directory per GPU, so every rank of a multi-GPU batch runs its own daemon;
+    nothing is started when the binary is missing, OCB_BATCH_MPS=0, or the daemon does not come up -- the batch then runs as before.
+    Use as a context manager; child_env() is what the per-mesh processes need."""
+
+    def __init__(self, gpu):
+        self.gpu, self.dev, self.dir, self.up = gpu, visible_device(gpu), None, False
+
+    def __enter__(self):
+        import shutil
+        import subprocess
+        import tempfile
+        if os.environ.get("OCB_BATCH_MPS", "1") == "0" or not shutil.which("nvidia-cuda-mps-control"):
+            return self
+        self.dir = tempfile.mkdtemp(prefix="ocb_mps_%d_" % self.gpu)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=self.dev, CUDA_MPS_PIPE_DIRECTORY=os.path.join(self.dir, "pipe"), CUDA_MPS_LOG_DIRECTORY=os.path.join(self.dir, "log"))
+        os.makedirs(env["CUDA_MPS_PIPE_DIRECTORY"]); os.makedirs(env["CUDA_MPS_LOG_DIRECTORY"])
+        try:
+            self.up = subprocess.run(["nvidia-cuda-mps-control", "-d"], env=env, timeout=30, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 0
+        except Exception:   # noqa: BLE001
+            self.up = False
+        self._env = env
+        return self
+
+    def child_env(self):
+        if not self.up:
+            return {"CUDA_VISIBLE_DEVICES": self.dev}
+        # the server sees exactly one device (index 0 of ITS list)
+        return {"CUDA_VISIBLE_DEVICES": "0", "CUDA_MPS_PIPE_DIRECTORY": self._env["CUDA_MPS_PIPE_DIRECTORY"], "CUDA_MPS_LOG_DIRECTORY": self._env["CUDA_MPS_LOG_DIRECTORY"]}
+
+    def __exit__(self, *exc):
+        import shutil
+        import subprocess
+        if self.up:
+            try:
+                subprocess.run(["nvidia-cuda-mps-control"], input="quit\n", text=True, env=self._env, timeout=60, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            except Exception:   # noqa: BLE001
+                pass
+            self.up = False
+        if self.dir:
+            shutil.rmtree(self.dir, ignore_errors=True)
+        return False
+
+
+def run_mesh(exe, mesh_path, workdir, max_iters, gpu=None, timeout=1800, extra_env=None):
     """one mesh through a host program (probe build: ORACLE_MAX_ITERS bounds the run).  Returns dict(rc, wall_s, iters)."""
     import subprocess
     import time
@@ -79,9 +132,9 @@ def run_mesh(exe, mesh_path, workdir, max_iters, gpu=None, timeout=1800):
     env = dict(os.environ, ORACLE_TRACE=os.path.join(workdir, "trace.txt"))
     if max_iters:
         env["ORACLE_MAX_ITERS"] = str(int(max_iters))
-    if gpu is not None:                       # the gpu-th VISIBLE device (a launcher may have restricted / renumbered them already)
-        vis = [d for d in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if d.strip()]
-        env["CUDA_VISIBLE_DEVICES"] = vis[gpu] if gpu < len(vis) else str(gpu)
+    if gpu is not None:
+        env["CUDA_VISIBLE_DEVICES"] = visible_device(gpu)
+    env.update(extra_env or {})
     t0 = time.perf_counter()
     try:
         r = subprocess.run([exe, "100", mesh_path] + MESH_ARGS + ["b"], cwd=workdir, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout)

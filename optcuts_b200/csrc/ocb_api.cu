@@ -263,6 +263,7 @@ int ocb_create(ocb_ctx** out, int device)
     c->device = device;
     { const char* e = getenv("OCB_PCG_SCALED_NORM"); c->pcgPlainNorm = !(e && atoi(e)); }
     { const char* e = getenv("OCB_SCALE_SYSTEM"); if (e) c->scaleSystem = atoi(e) != 0; }
+    { const char* e = getenv("OCB_MAS_EQUILIBRATE"); if (e) c->masEquilibrate = atoi(e) != 0; }
     *out = c;
     return OCB_OK;
 }
@@ -321,6 +322,7 @@ int ocb_set_option(ocb_ctx* c, const char* key, double value)
     if (!c || !key) return OCB_ERR_ARG;
     if (!std::strcmp(key, "pcg_scaled_norm")) { c->pcgPlainNorm = value == 0.0; return OCB_OK; }
     if (!std::strcmp(key, "scale_system")) { c->scaleSystem = value != 0.0; return OCB_OK; }
+    if (!std::strcmp(key, "mas_equilibrate")) { c->masEquilibrate = value != 0.0; c->precondValid = false; return OCB_OK; }
     return set_err(c, OCB_ERR_ARG, "ocb_set_option: unknown key");
 }
 int ocb_synchronize(ocb_ctx* c) { OCB_TRY(ensure_init(c)); OCB_CUDA(c, cudaStreamSynchronize(c->stream)); return OCB_OK; }
@@ -1097,6 +1099,11 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
         // safety net: the two-level preconditioner came out indefinite (r.M^-1 r <= 0, detected on the device): repeat the
         // solve with block-Jacobi only, which cannot fail on an SPD matrix
         c->precondFallbacks++;
+        {
+            static const bool dbg = []() { const char* e = getenv("OCB_PCG_DEBUG"); return e && atoi(e); }();
+            if (dbg) fprintf(stderr, "[ocb pcg] two-level preconditioner rejected at CG iteration %d: r.M^-1 r = %.6e (previous %.6e); repeating with block-Jacobi\n",
+                             (int)c->hScal[S_PCG_ITERS], c->hScal[S_MISC0], c->hScal[S_MISC1]);
+        }
         OCB_TRY(launch_pcg(c, dRhs, negate, rel_tol, max_it, false));
         OCB_TRY(fetch_scalars(c));
         itersTotal += (int)c->hScal[S_PCG_ITERS];

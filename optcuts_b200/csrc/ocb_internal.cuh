@@ -155,6 +155,7 @@ struct ocb_ctx {
     std::vector<int32_t> hStamp;             // scratch of the pattern builders
     std::vector<int32_t> hMeshAdjPtr, hMeshAdj;   // de-duplicated vertex adjacency of the MESH (internal ids), kept until the next ocb_set_mesh
     bool meshAdjValid = false;
+    bool masEquilibrate = false;              // option mas_equilibrate: diagonal equilibration inside the group / coarse inversions
     long long matrixVersion = 0;              // bumped whenever the device matrix (pattern or values) changes: ocb_matrix_version
     std::vector<double> hHint;               // ocb_set_coordinate_hint: 2 per vertex (interleaved), caller numbering
     std::vector<double> hXY;                 // host mirror of x (INTERNAL numbering) as last written by ocb_set_uv: spares the

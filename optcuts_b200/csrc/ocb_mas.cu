@@ -349,7 +349,7 @@ int mas_install(ocb_ctx* c)
     const int ldC = (nC + kMasCoarseBlk - 1) / kMasCoarseBlk * kMasCoarseBlk;
     OCB_CUDA(c, D.tabI.reserve(tI.size() + 4, c->stream));
     OCB_CUDA(c, D.tabD.reserve(tD.size() + 4, c->stream));
-    OCB_CUDA(c, D.dense.reserve(2 * (size_t)ldC * ldC + (size_t)ldC + 2 * kMasCoarseBlk * kMasCoarseBlk + 8 + kMasCoarseMax / kMasCoarseBlk, c->stream));
+    OCB_CUDA(c, D.dense.reserve(2 * (size_t)ldC * ldC + 2 * (size_t)ldC + 2 * kMasCoarseBlk * kMasCoarseBlk + 16 + kMasCoarseMax / kMasCoarseBlk, c->stream));
     OCB_CUDA(c, D.cinv.reserve((size_t)ldC * ldC + 8, c->stream));
     OCB_CUDA(c, D.rcCta.reserve((size_t)ldC + 8, c->stream));
     OCB_CUDA(c, cudaMemcpyAsync(D.tabI.p, tI.data(), tI.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -513,15 +513,34 @@ mas_coarsen_kernel(int nUp, const int32_t* __restrict__ groupBeg, const int32_t*
 
 // ------------------------------------------------------------------------------------------------
 // coarse level: dense Galerkin matrix and its exact inverse
+// Diagonal equilibration of the coarse matrix (option mas_equilibrate): scale[k] = 1 / sqrt(A_kk) (1 where A_kk <= 0: a node of fixed
+// vertices only).  The Gauss-Jordan elimination below has no pivoting; on a badly scaled Galerkin matrix (a nearly degenerate
+// triangle puts 1e10 next to 1e-3 on the diagonal) it loses the soft part to rounding and the inverse comes out indefinite; the
+// equilibrated matrix has a unit diagonal and the elimination error is relative to each DOF's own stiffness.
+__global__ void __launch_bounds__(256)
+mas_dense_scale_kernel(int nNodes, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, const double* __restrict__ val, int ld, double* __restrict__ scale)
+{
+    for (int k = blockIdx.x * 256 + threadIdx.x; k < ld; k += gridDim.x * 256) {
+        double d = 1.0;
+        if (k < nNodes * kMasDof) {
+            const int a = k / kMasDof, i = k % kMasDof;
+            d = 0.0;
+            for (int blk = rowPtr[a]; blk < rowPtr[a + 1]; ++blk) if (colIdx[blk] == a) d = val[36 * (size_t)blk + 7 * i];
+        }
+        scale[k] = d > 0.0 ? 1.0 / sqrt(d) : 1.0;
+    }
+}
 __global__ void __launch_bounds__(256)
 mas_dense_fill_kernel(int nNodes, const int32_t* __restrict__ rowPtr, const int32_t* __restrict__ colIdx, const double* __restrict__ val,
-                      int ld, int nC, double* __restrict__ X)
+                      int ld, int nC, double* __restrict__ X, const double* __restrict__ scale)
 {
     const int total = nNodes * 36;
     for (int w = blockIdx.x * 256 + threadIdx.x; w < total; w += gridDim.x * 256) {
         const int a = w / 36, ij = w % 36, i = ij / 6, j = ij % 6;
-        for (int blk = rowPtr[a]; blk < rowPtr[a + 1]; ++blk)
-            X[(size_t)(kMasDof * a + i) * ld + kMasDof * colIdx[blk] + j] = val[36 * (size_t)blk + ij];
+        for (int blk = rowPtr[a]; blk < rowPtr[a + 1]; ++blk) {
+            const int r = kMasDof * a + i, cc = kMasDof * colIdx[blk] + j;
+            X[(size_t)r * ld + cc] = scale ? val[36 * (size_t)blk + ij] * (scale[r] * scale[cc]) : val[36 * (size_t)blk + ij];
+        }
     }
     for (int k = nC + blockIdx.x * 256 + threadIdx.x; k < ld; k += gridDim.x * 256) X[(size_t)k * ld + k] = 1.0;     // padding
 }
@@ -542,7 +561,7 @@ static constexpr double kMasPivotTol = 1e-6;
 // wavefronts per load instead of 4 with 50, by the bank arithmetic); not yet measured on the GPU, so 50 stays.
 static constexpr int kCB = kMasCoarseBlk, kCBs = kMasCoarseBlk + 2;
 static constexpr int kDenseThreads = 576;                                // 18 warps: warp w owns the 8x8 sub-tiles 2w and 2w+1 (6x6 grid)
-struct DenseInvArgs { int nb, ld, nC; double* X; double* Y; double* P; double* diag0; float* out; long long* dbg; int* ticket; };
+struct DenseInvArgs { int nb, ld, nC; double* X; double* Y; double* P; double* diag0; float* out; long long* dbg; int* ticket; const double* scale; };
 
 // The tile products run on the FP64 tensor cores (mma.sync m8n8k4: the only tensor path for doubles; nothing else on
 // this path is a dense contraction).  A thread owns 4 elements of a 48x48 tile, in the accumulator-fragment layout:
@@ -775,7 +794,8 @@ mas_dense_invert_kernel(DenseInvArgs A)
     const size_t total = (size_t)ld * ld;
     for (size_t e = (size_t)blockIdx.x * kDenseThreads + tid; e < total; e += (size_t)gridDim.x * kDenseThreads) {
         const int i = (int)(e / ld), j = (int)(e % ld);
-        A.out[e] = (i < A.nC && j < A.nC) ? mas_pack(0.5 * (__ldcg(X + e) + __ldcg(X + (size_t)j * ld + i))) : 0.0f;
+        const double sij = A.scale ? A.scale[i] * A.scale[j] : 1.0;         // equilibrated inversion: the inverse of S A S is S^-1 A^-1 S^-1
+        A.out[e] = (i < A.nC && j < A.nC) ? mas_pack(0.5 * (__ldcg(X + e) + __ldcg(X + (size_t)j * ld + i)) * sij) : 0.0f;
     }
 }
 
@@ -787,6 +807,7 @@ struct MasInvertArgs {
     int groupPre[kMasMaxLevels + 1];
     const int32_t* rowPtr[kMasMaxLevels]; const int32_t* colIdx[kMasMaxLevels]; const double* val[kMasMaxLevels];
     const int32_t* parent[kMasMaxLevels]; const int32_t* groupBeg[kMasMaxLevels]; float* inv[kMasMaxLevels];
+    int equilibrate;
 };
 __global__ void __launch_bounds__(kDenseThreads)
 mas_invert_kernel(MasInvertArgs P)
@@ -819,13 +840,23 @@ mas_invert_kernel(MasInvertArgs P)
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) if (tile_col(m, e) == m.r) d0s[m.r] = d[e];
+    __shared__ double sc[kCB];
+    if (P.equilibrate) {                           // see mas_dense_scale_kernel: invert S D S with S = diag^-1/2, store S (S D S)^-1 S
+        __syncthreads();
+        if (threadIdx.x < kCB) { const double dd = d0s[threadIdx.x]; sc[threadIdx.x] = dd > 0.0 ? 1.0 / sqrt(dd) : 1.0; }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] *= sc[m.r] * sc[tile_col(m, e)];
+        if (threadIdx.x < kCB && d0s[threadIdx.x] > 0.0) d0s[threadIdx.x] = 1.0;
+    }
     tile_store_smem(T, d, m);
     tile_invert_smem(T, ibuf, d0s);
     float* out = P.inv[l] + (size_t)g * kMasBlk * kMasBlk;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int j = tile_col(m, e);
-        out[m.r * kMasBlk + j] = (m.r < nd && j < nd) ? mas_pack(0.5 * (T[m.r][j] + T[j][m.r])) : 0.0f;
+        const double sij = P.equilibrate ? sc[m.r] * sc[j] : 1.0;
+        out[m.r * kMasBlk + j] = (m.r < nd && j < nd) ? mas_pack(0.5 * (T[m.r][j] + T[j][m.r]) * sij) : 0.0f;
     }
 }
 
@@ -860,6 +891,7 @@ int launch_mas_setup(ocb_ctx* c)
             A.rowPtr[l - 1] = D.lvRowPtr[l - 1]; A.colIdx[l - 1] = D.lvColIdx[l - 1]; A.val[l - 1] = D.lvVal[l - 1];
             A.parent[l - 1] = V.parent; A.groupBeg[l - 1] = V.groupBeg; A.inv[l - 1] = V.inv;
         }
+        A.equilibrate = c->masEquilibrate ? 1 : 0;
         mas_invert_kernel<<<A.groupPre[H.L - 1], kDenseThreads, 0, c->stream>>>(A);
         KCHECK(c);
     }
@@ -871,10 +903,13 @@ int launch_mas_setup(ocb_ctx* c)
         A.nb = W.ldC / kCB; A.ld = W.ldC; A.nC = W.nC;
         A.X = D.dense.p; A.Y = A.X + ld * ld; A.diag0 = A.Y + ld * ld; A.P = A.diag0 + ld; A.out = D.cinv.p;
         A.ticket = reinterpret_cast<int*>(A.P + 2 * kCB * kCB);
+        double* scale = A.P + 2 * kCB * kCB + 8 + kMasCoarseMax / kMasCoarseBlk;
+        A.scale = c->masEquilibrate ? scale : nullptr;
         OCB_CUDA(c, cudaMemsetAsync(A.ticket, 0, sizeof(int) * (size_t)(A.nb + 1), c->stream));
         OCB_CUDA(c, cudaMemsetAsync(A.X, 0, ld * ld * sizeof(double), c->stream));
         int g = (V.nNodes * 36 + 255) / 256; if (g > c->numSMs * 8) g = c->numSMs * 8; if (g < 1) g = 1;
-        mas_dense_fill_kernel<<<g, 256, 0, c->stream>>>(V.nNodes, D.lvRowPtr[H.L - 1], D.lvColIdx[H.L - 1], D.lvVal[H.L - 1], W.ldC, W.nC, A.X);
+        if (A.scale) { mas_dense_scale_kernel<<<(W.ldC + 255) / 256, 256, 0, c->stream>>>(V.nNodes, D.lvRowPtr[H.L - 1], D.lvColIdx[H.L - 1], D.lvVal[H.L - 1], W.ldC, scale); KCHECK(c); }
+        mas_dense_fill_kernel<<<g, 256, 0, c->stream>>>(V.nNodes, D.lvRowPtr[H.L - 1], D.lvColIdx[H.L - 1], D.lvVal[H.L - 1], W.ldC, W.nC, A.X, A.scale);
         KCHECK(c);
         const size_t smem = 4 * (size_t)kCB * kCBs * sizeof(double) + 5 * kCB * sizeof(double);
         if (!D.denseAttr) {

@@ -595,7 +595,8 @@ pcg_kernel(PcgParams P)
     const double tol2 = P.relTol * P.relTol * (P.scaledNorm ? bzb : bb);
     double rr = bb, rDr = bzb, beta = 0.0;
     int it = 0, status = 0, cur = 0;
-    if (bb > 0.0 && !(rz > 0.0)) status = 3;
+    double rzFail = 0.0;                          // diagnostics of a rejected preconditioner (status 3): the offending r.M^-1 r
+    if (bb > 0.0 && !(rz > 0.0)) { status = 3; rzFail = rz; }
     if (bb > 0.0 && status == 0) {
         for (;;) {
             // ---- phase A: d_new = z + beta d_old (fused) ; Ap = A d_new ; pAp
@@ -668,7 +669,7 @@ pcg_kernel(PcgParams P)
                 P.dbg[5] += u0 - t2; P.dbg[6] += t3 - u0; P.dbg[7] += u1 - t3; P.dbg[8] += u2 - u1; P.dbg[9] += u3 - u2;
                 P.dbg[10] += u4 - u3; P.dbg[11] += u5 - u4; P.dbg[12] += clock64() - u5;
             }
-            if (!(rzNew > 0.0)) { status = 3; break; }        // r.M^-1 r <= 0 (or NaN): the preconditioner is not SPD; the host retries with block-Jacobi
+            if (!(rzNew > 0.0)) { status = 3; rzFail = rzNew; break; }        // r.M^-1 r <= 0 (or NaN): the preconditioner is not SPD; the host retries with block-Jacobi
             beta = rzNew / rz;
             rz = rzNew;
         }
@@ -696,6 +697,7 @@ pcg_kernel(PcgParams P)
         P.scal[S_PCG_RELRES] = bb > 0.0 ? (P.scaledNorm ? sqrt(rDr / bzb) : sqrt(rr / bb)) : 0.0;
         P.scal[S_PCG_STATUS] = (double)status;
         P.scal[S_PCG_BNORM] = sqrt(bb);
+        if (status == 3) { P.scal[S_MISC0] = rzFail; P.scal[S_MISC1] = rz; }
     }
 #undef ALLREDUCE
 #undef ARRIVE

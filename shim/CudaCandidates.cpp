@@ -1,5 +1,6 @@
 // Lock-step evaluation of the topology step's local problems on the GPU (see shim/CudaCandidates.hpp).
 #include "CudaCandidates.hpp"
+#include "OcbThreadPool.hpp"
 #include "SymDirichletEnergy.hpp"
 #include "optcuts_b200.h"
 
@@ -34,67 +35,6 @@ struct Hasher {
         for (size_t i = 0; i < bytes; ++i) { a ^= p[i]; a *= 1099511628211ull; b = (b ^ p[i]) * 0xff51afd7ed558ccdull + 0x2545f4914f6cdd1dull; }
     }
     template <typename T> void pod(const T& v) { add(&v, sizeof(T)); }
-};
-
-// Host threads of the lock-step solve: one persistent pool for the whole run.  A round triangulates ~100 small air regions
-// (~20 us each) and there are ~40 rounds per query, so the threads must not be created per round (a parallel_for that spawns
-// its workers, like the TBB stand-in of the oracle build, costs more than the triangulations themselves).  Workers sleep on a
-// condition variable between rounds; the calling thread takes part in the work.
-class Pool {
-public:
-    static Pool& get(void) { static Pool* p = new Pool(); return *p; }     // never destroyed: the host program leaves through exit()
-    void run(int n, const std::function<void(int)>& f)
-    {
-        if (n <= 0) return;
-        if (n < 4 || workers.empty()) { for (int i = 0; i < n; ++i) f(i); return; }
-        {
-            std::lock_guard<std::mutex> lock(mu);
-            fn = &f; total = n; next.store(0); pending.store(n); ++generation;
-        }
-        cv.notify_all();
-        work();
-        while (pending.load(std::memory_order_acquire) > 0) std::this_thread::yield();
-        { std::lock_guard<std::mutex> lock(mu); fn = NULL; }                    // workers that wake up from now on skip this job
-        while (inside.load(std::memory_order_acquire) > 0) std::this_thread::yield();   // ... and those already in have left before the next job is posted
-    }
-private:
-    Pool(void)
-    {
-        const char* e = std::getenv("OCB_HOST_THREADS");
-        int nt = e ? std::atoi(e) : static_cast<int>(std::thread::hardware_concurrency());
-        if (nt > 32) nt = 32;
-        for (int t = 1; t < nt; ++t) workers.emplace_back([this]() { loop(); });
-        for (auto& w : workers) w.detach();
-    }
-    void work(void)
-    {
-        for (;;) {
-            const int i = next.fetch_add(1);
-            if (i >= total) break;
-            (*fn)(i);
-            pending.fetch_sub(1, std::memory_order_release);
-        }
-    }
-    void loop(void)
-    {
-        unsigned long seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lock(mu);
-                cv.wait(lock, [&]() { return generation != seen; });
-                seen = generation;
-                if (!fn) continue;
-                inside.fetch_add(1);
-            }
-            work();
-            inside.fetch_sub(1, std::memory_order_release);
-        }
-    }
-    std::vector<std::thread> workers;
-    std::mutex mu; std::condition_variable cv;
-    const std::function<void(int)>* fn = NULL;
-    int total = 0; unsigned long generation = 0;
-    std::atomic<int> next{0}, pending{0}, inside{0};
 };
 
 struct Problem {
@@ -219,7 +159,7 @@ void solveAll(Batch& B)
     for (int round = 0; !active.empty(); ++round) {
         // ---- host: this round's air meshes (Triangle), all threads
         const double t1 = now();
-        Pool::get().run(static_cast<int>(active.size()), [&](int k) { Problem& p = P[active[k]]; if (p.bij) buildAir(p); });
+        OcbThreadPool::get().run(static_cast<int>(active.size()), [&](int k) { Problem& p = P[active[k]]; if (p.bij) buildAir(p); });
         const double t2 = now();
         B.tTriangle += t2 - t1;
         // ---- pack: per problem the mesh's vertices, then the air mesh's own; the mesh's triangles, then the air mesh's

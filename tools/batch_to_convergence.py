@@ -22,11 +22,12 @@ from optcuts_b200 import batch  # noqa: E402
 EXE = {"ref": os.path.join(ROOT, "oracle", "_ref", "OptCuts_bin"), "cuda": os.path.join(ROOT, "shim", "_build", "OptCuts_cuda")}
 
 
-def run_one(exe, mesh_path, wd, timeout):
+def run_one(exe, mesh_path, wd, timeout, extra_env=None):
     os.makedirs(wd, exist_ok=True)
     t0 = time.perf_counter()
     try:
-        r = subprocess.run([exe, "100", mesh_path] + batch.MESH_ARGS + ["b"], cwd=wd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=timeout, text=True, errors="replace")
+        r = subprocess.run([exe, "100", mesh_path] + batch.MESH_ARGS + ["b"], cwd=wd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=timeout, text=True, errors="replace",
+                           env=dict(os.environ, **(extra_env or {})))
         rc, err = r.returncode, r.stderr[-300:]
     except subprocess.TimeoutExpired:
         rc, err = -999, "timeout"
@@ -46,13 +47,15 @@ def run_one(exe, mesh_path, wd, timeout):
 def run(kind, out_path, procs, timeout, first_n):
     items = batch.benchmark71()
     order = sorted(range(len(items)), key=lambda i: -items[i][1])[:first_n]           # largest first
-    with tempfile.TemporaryDirectory() as wd:
+    import contextlib
+    with tempfile.TemporaryDirectory() as wd, (batch.MpsDaemon(0) if kind == "cuda" else contextlib.nullcontext()) as mps:
         paths = batch.extract_benchmark(os.path.join(wd, "in"))
+        cenv = mps.child_env() if kind == "cuda" else None
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=procs) as ex:
-            rows = list(ex.map(lambda i: run_one(EXE[kind], paths[items[i][0]], os.path.join(wd, "m%d" % i), timeout), order))
+            rows = list(ex.map(lambda i: run_one(EXE[kind], paths[items[i][0]], os.path.join(wd, "m%d" % i), timeout, cenv), order))
         wall = time.perf_counter() - t0
-    res = {"kind": kind, "procs": procs, "cores": os.cpu_count(), "timeout_s": timeout, "batch_wall_s": wall,
+    res = {"kind": kind, "mps": bool(kind == "cuda" and mps.up), "procs": procs, "cores": os.cpu_count(), "timeout_s": timeout, "batch_wall_s": wall,
            "meshes": {items[i][0]: dict(rows[k], faces=items[i][1]) for k, i in enumerate(order)}}
     with open(out_path, "w") as f:
         json.dump(res, f, indent=1, sort_keys=True)
