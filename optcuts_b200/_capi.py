@@ -368,7 +368,7 @@ class Context:
         self._chk(self._L.ocb_precond_info(self._h, _pi(info)))
         L = int(info[1])
         return dict(enabled=bool(info[0]), levels=L, local_levels=int(info[2]), grid=int(info[3]), nodes=[int(v) for v in info[4:4 + L]],
-                    fallbacks=int(info[15]))
+                    fallbacks=int(info[15]), direct_solves=int(info[14]))
 
     def solve(self, rhs=None, rel_tol=1e-12, max_it=0, download=True, allow_not_converged=False):
         rhs = None if rhs is None else _f64(np.asarray(rhs).ravel())

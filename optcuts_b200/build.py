@@ -23,6 +23,7 @@ UNITS = [
     ("ocb_pcg.cu", []),
     ("ocb_mas.cu", []),
     ("ocb_stencils.cu", ["-fmad=false"]),
+    ("ocb_direct.cu", []),
 ]
 
 
@@ -55,7 +56,7 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError("nvcc failed on %s" % src)
     if force or _newer(LIB, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

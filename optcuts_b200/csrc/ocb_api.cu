@@ -282,6 +282,7 @@ void ocb_destroy(ocb_ctx* c)
         c->pr.release(); c->pz.release(); c->pd.release(); c->pd2.release(); c->pAp.release(); c->pb.release(); c->minv.release();
         c->rowPtr.release(); c->colIdx.release(); c->val.release();
         c->partials.release(); c->sync.release(); c->scratchD.release(); c->scratchI.release();
+        direct_release(c);
         c->xSaved.release(); c->rowScale.release(); c->pcgHalo.release(); c->px.release(); c->rowOf.release(); c->vertOf.release(); c->userRow.release();
         c->masD.ints.release(); c->masD.geom.release(); c->masD.val.release(); c->masD.rcCta.release(); c->masD.inv.release(); c->masD.vinfo.release();
         prof_collect(c);
@@ -1095,15 +1096,31 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
         return set_err(c, OCB_ERR_BREAKDOWN, "a diagonal 2x2 block of the matrix is not positive definite");
     }
     int itersTotal = (int)c->hScal[S_PCG_ITERS];
-    if ((int)c->hScal[S_PCG_STATUS] == 3) {
-        // safety net: the two-level preconditioner came out indefinite (r.M^-1 r <= 0, detected on the device): repeat the
-        // solve with block-Jacobi only, which cannot fail on an SPD matrix
-        c->precondFallbacks++;
-        {
-            static const bool dbg = []() { const char* e = getenv("OCB_PCG_DEBUG"); return e && atoi(e); }();
-            if (dbg) fprintf(stderr, "[ocb pcg] two-level preconditioner rejected at CG iteration %d: r.M^-1 r = %.6e (previous %.6e); repeating with block-Jacobi\n",
-                             (int)c->hScal[S_PCG_ITERS], c->hScal[S_MISC0], c->hScal[S_MISC1]);
+    static const bool dbg = []() { const char* e = getenv("OCB_PCG_DEBUG"); return e && atoi(e); }();
+    {
+        // Safety net (ocb_direct.cu): a system CG cannot handle -- the two-level preconditioner came out indefinite (status 3), the
+        // assembled matrix is indefinite by rounding (2), or, inside a Newton iteration, the iteration cap was reached (1) -- is
+        // solved by a dense Cholesky when it is small enough.  Healthy systems never come here.
+        const int st0 = (int)c->hScal[S_PCG_STATUS];
+        if ((st0 == 3 || ((st0 == 2 || st0 == 1) && c->tolerateIndefinite)) && direct_solver_available(c)) {
+            if (dbg) fprintf(stderr, "[ocb pcg] CG gave up (status %d after %d iterations, r.M^-1 r = %.3e): dense Cholesky of %d unknowns\n",
+                             st0, itersTotal, st0 == 3 ? c->hScal[S_MISC0] : 0.0, (int)n);
+            int lifts = 0;
+            const int rd = launch_direct_solve(c, dRhs, negate, &lifts);
+            if (rd < 0) return rd;
+            if (rd == 0) {
+                c->hScal[S_PCG_STATUS] = 0.0; c->hScal[S_PCG_RELRES] = 0.0;
+                c->lastDirectLifts = lifts;
+                if (st0 == 3) c->precondFallbacks++;
+            }
         }
+    }
+    if ((int)c->hScal[S_PCG_STATUS] == 3) {
+        // the two-level preconditioner came out indefinite (r.M^-1 r <= 0, detected on the device) and the dense safety net is
+        // not available: repeat the solve with block-Jacobi only, which cannot fail on an SPD matrix
+        c->precondFallbacks++;
+        if (dbg) fprintf(stderr, "[ocb pcg] two-level preconditioner rejected at CG iteration %d: r.M^-1 r = %.6e (previous %.6e); repeating with block-Jacobi\n",
+                         (int)c->hScal[S_PCG_ITERS], c->hScal[S_MISC0], c->hScal[S_MISC1]);
         OCB_TRY(launch_pcg(c, dRhs, negate, rel_tol, max_it, false));
         OCB_TRY(fetch_scalars(c));
         itersTotal += (int)c->hScal[S_PCG_ITERS];
@@ -1148,6 +1165,7 @@ int ocb_precond_info(const ocb_ctx* c, int32_t* info)
     if (!c || !info) return OCB_ERR_ARG;
     fill_precond_info(c->masH, info);
     info[15] = (int32_t)c->precondFallbacks;
+    info[14] = (int32_t)c->directSolves;
     return OCB_OK;
 }
 int ocb_set_coordinate_hint(ocb_ctx* c, int n, const double* xy)

@@ -155,7 +155,11 @@ struct ocb_ctx {
     std::vector<int32_t> hStamp;             // scratch of the pattern builders
     std::vector<int32_t> hMeshAdjPtr, hMeshAdj;   // de-duplicated vertex adjacency of the MESH (internal ids), kept until the next ocb_set_mesh
     bool meshAdjValid = false;
-    bool masEquilibrate = false;              // option mas_equilibrate: diagonal equilibration inside the group / coarse inversions
+    void* directHandle = nullptr;             // cuSOLVER handle of the dense safety net (ocb_direct.cu), created at first use
+    ocb::DevBuf<double> directA, directB, directWork; ocb::DevBuf<int> directInfo;
+    int lastDirectLifts = 0;
+    long long directSolves = 0;               // solves that went through the dense Cholesky
+    bool masEquilibrate = true;               // option mas_equilibrate (OCB_MAS_EQUILIBRATE=0 turns it off): diagonal equilibration inside the group / coarse inversions
     long long matrixVersion = 0;              // bumped whenever the device matrix (pattern or values) changes: ocb_matrix_version
     std::vector<double> hHint;               // ocb_set_coordinate_hint: 2 per vertex (interleaved), caller numbering
     std::vector<double> hXY;                 // host mirror of x (INTERNAL numbering) as last written by ocb_set_uv: spares the
@@ -249,6 +253,10 @@ struct StencilStepHost {  // device pointers of one uploaded batch of bijective 
 };
 int launch_stencil_step(ocb_ctx* c, const StencilStepHost& h);
 int launch_spmv(ocb_ctx* c, const double* dx, double* dy);
+static constexpr int kDirectMaxDof = 40000;               // largest system (scalar unknowns) the dense safety net takes: 12.8 GB of fp64
+bool direct_solver_available(const ocb_ctx* c);
+int launch_direct_solve(ocb_ctx* c, const double* d_rhs, bool negate, int* liftsUsed);   // 0 solved, 1 not available / not factorisable, < 0 error
+void direct_release(ocb_ctx* c);
 int launch_diag_shift(ocb_ctx* c, double delta);          // diagonal entries *= (1 + delta)
 int launch_scale_system(ocb_ctx* c);                       // val <- S val S, S = diag^-1/2; sets c->systemScaled
 int launch_jacobi_setup(ocb_ctx* c, bool check = true);   // check = false: no host round trip, the verdict stays in scal[S_JACOBI_BAD]
