@@ -323,6 +323,7 @@ int ocb_set_option(ocb_ctx* c, const char* key, double value)
     if (!c || !key) return OCB_ERR_ARG;
     if (!std::strcmp(key, "pcg_scaled_norm")) { c->pcgPlainNorm = value == 0.0; return OCB_OK; }
     if (!std::strcmp(key, "scale_system")) { c->scaleSystem = value != 0.0; return OCB_OK; }
+    if (!std::strcmp(key, "force_direct")) { c->forceDirect = value != 0.0; return OCB_OK; }
     if (!std::strcmp(key, "mas_equilibrate")) { c->masEquilibrate = value != 0.0; c->precondValid = false; return OCB_OK; }
     return set_err(c, OCB_ERR_ARG, "ocb_set_option: unknown key");
 }
@@ -1089,6 +1090,18 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
         OCB_TRY(vec_to_device(c, c->pb.p, rhs));
         dRhs = c->pb.p; negate = false;
     }
+    if (c->forceDirect && direct_solver_available(c)) {          // option force_direct (tests): the safety net instead of CG
+        int lifts = 0;
+        const int rd = launch_direct_solve(c, dRhs, negate, &lifts);
+        if (rd < 0) return rd;
+        if (rd == 0) {
+            if (x_out) OCB_TRY(vec_to_host(c, x_out, c->p.p));
+            OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+            if (iters) *iters = 0;
+            if (rel_res) *rel_res = 0.0;
+            return OCB_OK;
+        }
+    }
     OCB_TRY(launch_pcg(c, dRhs, negate, rel_tol, max_it));
     OCB_TRY(fetch_scalars(c));
     if (c->hScal[S_JACOBI_BAD] != 0.0 && !c->tolerateIndefinite) {       // verdict of a set-up whose host check was deferred
@@ -1103,7 +1116,7 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
         // solved by a dense Cholesky when it is small enough.  Healthy systems never come here.
         const int st0 = (int)c->hScal[S_PCG_STATUS];
         if ((st0 == 3 || ((st0 == 2 || st0 == 1) && c->tolerateIndefinite)) && direct_solver_available(c)) {
-            if (dbg) fprintf(stderr, "[ocb pcg] CG gave up (status %d after %d iterations, r.M^-1 r = %.3e): dense Cholesky of %d unknowns\n",
+            if (dbg) fprintf(stderr, "[ocb pcg] CG gave up (status %d after %d iterations, r.M^-1 r = %.3e): direct solve of %d unknowns\n",
                              st0, itersTotal, st0 == 3 ? c->hScal[S_MISC0] : 0.0, (int)n);
             int lifts = 0;
             const int rd = launch_direct_solve(c, dRhs, negate, &lifts);

@@ -156,8 +156,10 @@ struct ocb_ctx {
     std::vector<int32_t> hMeshAdjPtr, hMeshAdj;   // de-duplicated vertex adjacency of the MESH (internal ids), kept until the next ocb_set_mesh
     bool meshAdjValid = false;
     void* directHandle = nullptr;             // cuSOLVER handle of the dense safety net (ocb_direct.cu), created at first use
-    ocb::DevBuf<double> directA, directB, directWork; ocb::DevBuf<int> directInfo;
+    void* directBlas = nullptr;               // cuBLAS handle of the block-tridiagonal path
+    ocb::DevBuf<double> directA, directB, directWork; ocb::DevBuf<int> directInfo; ocb::DevBuf<int32_t> directI; ocb::DevBuf<long long> directL;
     int lastDirectLifts = 0;
+    bool forceDirect = false;                 // option force_direct: ocb_solve uses the direct safety net instead of CG (tests)
     long long directSolves = 0;               // solves that went through the dense Cholesky
     bool masEquilibrate = true;               // option mas_equilibrate (OCB_MAS_EQUILIBRATE=0 turns it off): diagonal equilibration inside the group / coarse inversions
     long long matrixVersion = 0;              // bumped whenever the device matrix (pattern or values) changes: ocb_matrix_version

@@ -141,3 +141,32 @@ def test_bare_solver_with_coordinate_hint(ctx, state1):
         assert it["iters"] < 260, it
     finally:
         c2.close()
+
+
+@pytest.mark.parametrize("dense", [0, 1], ids=["block-tridiagonal", "dense"])
+def test_direct_safety_net_matches_pcg(state1, monkeypatch, dense):
+    """The direct safety net of the solve (csrc/ocb_direct.cu: block-tridiagonal Cholesky over breadth-first levels, or one dense
+    potrf of the whole matrix) on the golden state: the reference's LDL^T direction to 1e-8 (the bar of the PCG comparison),
+    true residual at rounding level, and it really ran (cuSOLVER / cuBLAS found)."""
+    import optcuts_b200 as ob
+    if dense:
+        monkeypatch.setenv("OCB_DIRECT_DENSE", "1")
+    c = ob.Context(0)
+    try:
+        _newton_system(c, state1)
+        x_cg, info = c.solve(None, 1e-12, 0)
+        d0 = c.precond_info()["direct_solves"]
+        c.set_option("force_direct", 1)
+        x_d, _ = c.solve(None, 1e-12, 0)
+        c.set_option("force_direct", 0)
+        assert c.precond_info()["direct_solves"] == d0 + 1, "the direct path did not run (cuSOLVER / cuBLAS not found?)"
+        g, _ = c.gradient(state1.p0)
+        res = np.linalg.norm(c.multiply(x_d) + g) / np.linalg.norm(g)
+        ref = state1.r("searchDir")
+        err_ref = np.linalg.norm(x_d - ref) / np.linalg.norm(ref)
+        err_cg = np.linalg.norm(x_d - x_cg) / np.linalg.norm(x_cg)
+        print("direct (%s): true residual %.2e, vs the reference's LDL^T direction %.2e, vs the PCG direction %.2e (%d CG iterations)"
+              % ("dense" if dense else "block-tridiagonal", res, err_ref, err_cg, info["iters"]))
+        assert res < 1e-10 and err_ref < 1e-8 and err_cg < 1e-8
+    finally:
+        c.close()
