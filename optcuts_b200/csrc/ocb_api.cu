@@ -1073,13 +1073,22 @@ int ocb_factorize(ocb_ctx* c)
     return OCB_OK;
 }
 
+// Experimental (OCB_DIRECT_FIRST=1, off by default): after a Newton system CG could not handle, the next 4, 8, ... 32 systems go to the
+// direct safety net without trying CG first.  Measured (150 iterations, profiles/r2_direct_first_experiment.txt): male_2 9.2 -> 6.2 s,
+// but torusOnPlane 4.2 -> 8.0 s and cat_noUV 12.0 -> 48 s: the hard and the healthy systems of such a run are interleaved, and a
+// direct solve costs 20x a healthy CG solve.  CG first, every time, is the default.
+static bool direct_first(ocb_ctx* c)
+{
+    static const bool on = []() { const char* e = getenv("OCB_DIRECT_FIRST"); return e && atoi(e); }();
+    return on && c->tolerateIndefinite && c->directSkip > 0 && direct_solver_available(c);
+}
+
 int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int max_it, int* iters, double* rel_res)
 {
     HostTimer _ht("solve");
     if (!c) return OCB_ERR_ARG;
     OCB_TRY(ensure_init(c));                             // selects the context's device (two contexts on two GPUs in one thread)
     OCB_TRY(need(c, c->patternValid && c->matrixValid, "ocb_solve: no matrix"));
-    if (!c->precondValid) OCB_TRY(ocb_factorize(c));
     const size_t n = c->nSys();
     if (rel_tol <= 0.0) rel_tol = 1e-12;
     if (max_it <= 0) max_it = (int)std::min<size_t>(20 * n, 2000000);
@@ -1090,18 +1099,25 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
         OCB_TRY(vec_to_device(c, c->pb.p, rhs));
         dRhs = c->pb.p; negate = false;
     }
-    if (c->forceDirect && direct_solver_available(c)) {          // option force_direct (tests): the safety net instead of CG
+    // The safety net FIRST: option force_direct (tests), or a Newton iteration right after one whose system CG could not handle
+    // (direct_first(): a hard phase lasts for dozens of iterations; the failed CG attempt and the preconditioner set-up of each
+    // are skipped, and CG gets another try after 4, 8, ... 32 iterations)
+    const bool directFirst = direct_first(c);
+    if ((c->forceDirect || directFirst) && direct_solver_available(c)) {
         int lifts = 0;
         const int rd = launch_direct_solve(c, dRhs, negate, &lifts);
         if (rd < 0) return rd;
         if (rd == 0) {
+            if (directFirst) c->directSkip--;
+            c->hScal[S_PCG_ITERS] = 0.0; c->hScal[S_PCG_STATUS] = 0.0; c->hScal[S_PCG_RELRES] = 0.0;
             if (x_out) OCB_TRY(vec_to_host(c, x_out, c->p.p));
-            OCB_CUDA(c, cudaStreamSynchronize(c->stream));
+            if (x_out) OCB_CUDA(c, cudaStreamSynchronize(c->stream));
             if (iters) *iters = 0;
             if (rel_res) *rel_res = 0.0;
             return OCB_OK;
         }
     }
+    if (!c->precondValid) OCB_TRY(ocb_factorize(c));
     OCB_TRY(launch_pcg(c, dRhs, negate, rel_tol, max_it));
     OCB_TRY(fetch_scalars(c));
     if (c->hScal[S_JACOBI_BAD] != 0.0 && !c->tolerateIndefinite) {       // verdict of a set-up whose host check was deferred
@@ -1115,6 +1131,7 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
         // assembled matrix is indefinite by rounding (2), or, inside a Newton iteration, the iteration cap was reached (1) -- is
         // solved by a dense Cholesky when it is small enough.  Healthy systems never come here.
         const int st0 = (int)c->hScal[S_PCG_STATUS];
+        if (st0 == 0 && c->tolerateIndefinite) c->directBackoff = 0;          // CG handled this Newton system: the hard phase is over
         if ((st0 == 3 || ((st0 == 2 || st0 == 1) && c->tolerateIndefinite)) && direct_solver_available(c)) {
             if (dbg) fprintf(stderr, "[ocb pcg] CG gave up (status %d after %d iterations, r.M^-1 r = %.3e): direct solve of %d unknowns\n",
                              st0, itersTotal, st0 == 3 ? c->hScal[S_MISC0] : 0.0, (int)n);
@@ -1122,6 +1139,7 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
             const int rd = launch_direct_solve(c, dRhs, negate, &lifts);
             if (rd < 0) return rd;
             if (rd == 0) {
+                if (c->tolerateIndefinite) { c->directBackoff = std::min(std::max(2 * c->directBackoff, 4), 32); c->directSkip = c->directBackoff; }
                 c->hScal[S_PCG_STATUS] = 0.0; c->hScal[S_PCG_RELRES] = 0.0;
                 c->lastDirectLifts = lifts;
                 if (st0 == 3) c->precondFallbacks++;
@@ -1338,9 +1356,10 @@ int ocb_newton_step_ex(ocb_ctx* c, double p0, double targetGRes, double pcg_rel_
     if (!((flags & OCB_STEP_REUSE_MATRIX) && c->matrixValid)) OCB_TRY(ocb_hessian_assemble(c, p0));
     if (c->scaleSystem && !c->systemScaled) { OCB_TRY(launch_scale_system(c)); c->precondValid = false; ++c->matrixVersion; }
     c->deferFactorCheck = true;
-    const int rf = c->precondValid ? 0 : ocb_factorize(c);
+    c->tolerateIndefinite = true;                              // (see below; set here because direct_first() looks at it)
+    const int rf = (c->precondValid || direct_first(c)) ? 0 : ocb_factorize(c);     // (the set-up is skipped when this solve goes to the direct safety net first)
     c->deferFactorCheck = false;
-    if (rf < 0) return rf;
+    if (rf < 0) { c->tolerateIndefinite = false; return rf; }
     int its = 0; double rr = 0.0;
     // Inside a Newton iteration a matrix that is SPD only up to rounding is not an error: non-PD diagonal blocks fall back to
     // the identity in the preconditioner, a CG breakdown returns the truncated iterate (see pcg_kernel), and the line search

@@ -159,6 +159,7 @@ struct ocb_ctx {
     void* directBlas = nullptr;               // cuBLAS handle of the block-tridiagonal path
     ocb::DevBuf<double> directA, directB, directWork; ocb::DevBuf<int> directInfo; ocb::DevBuf<int32_t> directI; ocb::DevBuf<long long> directL;
     int lastDirectLifts = 0;
+    int directSkip = 0, directBackoff = 0;    // Newton solves that still go to the safety net first / length of the current back-off
     bool forceDirect = false;                 // option force_direct: ocb_solve uses the direct safety net instead of CG (tests)
     long long directSolves = 0;               // solves that went through the dense Cholesky
     bool masEquilibrate = true;               // option mas_equilibrate (OCB_MAS_EQUILIBRATE=0 turns it off): diagonal equilibration inside the group / coarse inversions

@@ -1,7 +1,7 @@
 """The reference's 71 benchmark meshes TO CONVERGENCE through a host program, one process per mesh with the reference's own
 command line (batch.py:11-14, headless mode 100, lambda_init 0.999, OptCuts, b_d 4.1, bijective), several processes at a time.
 
-    python tools/batch_to_convergence.py ref  out.json [procs] [timeout_s] [first_n]     the unmodified reference (oracle/_ref/OptCuts_bin)
+    python tools/batch_to_convergence.py ref  out.json [procs] [timeout_s] [first_n]     the unmodified reference (oracle/_ref/OptCuts_bin); first_n < 0: a sample spread over the sizes
     python tools/batch_to_convergence.py cuda out.json [procs] [timeout_s] [first_n]     the host program with the GPU plugins (shim/_build/OptCuts_cuda)
     python tools/batch_to_convergence.py compare ref.json cuda.json                      per-mesh table + summary
 
@@ -46,7 +46,8 @@ def run_one(exe, mesh_path, wd, timeout, extra_env=None):
 
 def run(kind, out_path, procs, timeout, first_n):
     items = batch.benchmark71()
-    order = sorted(range(len(items)), key=lambda i: -items[i][1])[:first_n]           # largest first
+    order = sorted(range(len(items)), key=lambda i: -items[i][1])                     # largest first
+    order = order[:first_n] if first_n > 0 else order[::max(1, len(order) // -first_n)][:-first_n]      # first_n < 0: that many meshes spread over the size range
     import contextlib
     with tempfile.TemporaryDirectory() as wd, (batch.MpsDaemon(0) if kind == "cuda" else contextlib.nullcontext()) as mps:
         paths = batch.extract_benchmark(os.path.join(wd, "in"))

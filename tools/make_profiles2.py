@@ -11,12 +11,13 @@ import collections, csv, io, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1]
-PFX = "f2_"
+PFX = sys.argv[2] if len(sys.argv) > 2 else "f3_"
 
-for f in ("bench", "bench_ref"):
-    src = os.path.join(OUT, PFX + f + ".json")
-    if os.path.exists(src) and os.path.getsize(src):
-        shutil.copy(src, os.path.join(PROF, "%s_%s.json" % (tag, f)))
+for f in ("bench", "bench_ref", "bench_wall"):
+    for ext in (".json", ".txt"):
+        src = os.path.join(OUT, PFX + f + ext)
+        if os.path.exists(src) and os.path.getsize(src):
+            shutil.copy(src, os.path.join(PROF, "%s_%s%s" % (tag, f, ext)))
 for f, dst in (("pcg_phase_cycles.txt", "pcg_phase_cycles.txt"), ("host_timing.txt", "host_timing_bimba10k.txt"), ("mas_dense_phases.txt", "mas_dense_phases.txt"),
                ("host_program.txt", "host_program.txt"), ("smoke.log", "smoke.log"), ("sanitizer_memcheck.log", "sanitizer_memcheck.log"),
                ("sanitizer_racecheck.log", "sanitizer_racecheck.log"), ("sanitizer_initcheck.log", "sanitizer_initcheck.log"), ("sanitizer_synccheck.log", "sanitizer_synccheck.log")):

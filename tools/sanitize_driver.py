@@ -36,6 +36,10 @@ def small(ctx, quick):
     ia, ja, a = ctx.download_csr()
     ctx.factorize()
     p, info = ctx.solve(None, 1e-12, 0)
+    ctx.set_option("force_direct", 1)                   # the direct safety net (csrc/ocb_direct.cu: block-tridiagonal Cholesky, cuSOLVER / cuBLAS blocks)
+    pd, _ = ctx.solve(None, 1e-12, 0)
+    ctx.set_option("force_direct", 0)
+    assert np.linalg.norm(pd - p) <= 1e-7 * np.linalg.norm(p), "direct solve differs from PCG"
     ctx.multiply(p)
     al = ctx.step_bound(None, 1.0)
     ctx.save_uv()
