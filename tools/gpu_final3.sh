@@ -21,3 +21,5 @@ for tool in memcheck racecheck initcheck synccheck; do
 done
 OCB_HOST_TIMING=1 python tools/host_program_timing.py > gpurun_out/f3_host_program.txt 2>&1; tail -12 gpurun_out/f3_host_program.txt
 ls -la gpurun_out | grep f3_
+python tools/batch_to_convergence.py ref gpurun_out/f3_b71_ref_sample.json 3 900 -8 2>&1 | tail -2
+bash tools/gpu_round2r.sh > /dev/null 2>&1; cp gpurun_out/r2r_host_program.txt gpurun_out/f3_host_program_cfg0_cfg1.txt; cut -c1-300 gpurun_out/f3_host_program_cfg0_cfg1.txt | grep -v "ocb host"
