@@ -363,6 +363,11 @@ def batch71_ours(args, rank, world, local, torch):
         # host code (CUDA context creation 2.7-3.4 s, OBJ parsing, Triangle, mesh edits), so the GPU is shared by time slicing
         from concurrent.futures import ThreadPoolExecutor
         procs = max(1, min(args.batch_procs, (os.cpu_count() or 1) // max(1, world)))
+        # torchrun exports OMP_NUM_THREADS=1 to its ranks and the per-mesh processes would inherit it: the direct safety net's library
+        # calls (cuSOLVER potrf) then run their host part on one thread -- male_2 took 70-93 s of a 2-GPU batch instead of 11 s
+        # (profiles/r2_bench_n2_before_omp.json).  Every host process gets its share of the cores instead.
+        threads = max(4, (os.cpu_count() or 1) // (procs * max(1, world)))
+        cenv = dict(cenv, OMP_NUM_THREADS=str(threads))
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=procs) as ex:
             res = list(ex.map(lambda i: batch.run_mesh(batch.CUDA_HOST, paths[items[i][0]], os.path.join(wd, "m%d" % i), args.batch_iters, extra_env=cenv), shards[rank]))
@@ -387,7 +392,7 @@ def batch71_ours(args, rank, world, local, torch):
     return {"meshes": len(items), "newton_iters_per_mesh_cap": args.batch_iters, "newton_iters": int(its), "wall_s": wall, "it_per_s": its / wall,
             "per_rank_s": per_rank, "limiting_rank": int(np.argmax(per_rank)), "failed_meshes": nbad, "failed_on_rank0": bad,
             "slowest_mesh_rank0": {"name": items[slow][0], "faces": items[slow][1], "wall_s": rows[slow]["wall_s"]},
-            "one_iteration_process_wall_s": warm["wall_s"], "concurrent_processes_per_gpu": procs, "mps": bool(mps_up),
+            "one_iteration_process_wall_s": warm["wall_s"], "concurrent_processes_per_gpu": procs, "omp_threads_per_process": threads, "mps": bool(mps_up),
             "scaling": "strong",
             "note": "one host-program process per mesh (reference main + Optimizer hooks + device candidate evaluation), config args %s, every mesh "
                     "bounded to the cap, process start-up inside; mps = the per-mesh processes attach to an NVIDIA MPS daemon started for the batch "
