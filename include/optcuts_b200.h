@@ -64,7 +64,11 @@ int  ocb_synchronize(ocb_ctx* ctx);
  * block-Jacobi-scaled norm sqrt(r^T D^-1 r) (D = the 2x2 diagonal blocks), in which soft rows (the scaffold's) converge
  * relative to their own stiffness.  Measured against an LU of the same matrices (profiles/r2_pcg_norm.txt): no gain in
  * the accuracy of the direction, ~3 % more iterations -- the differences to the reference's LDL^T on badly conditioned
- * states (kappa ~ 1e12 at a Tutte start) are rounding, in both solvers, not the stopping test. */
+ * states (kappa ~ 1e12 at a Tutte start) are rounding, in both solvers, not the stopping test.
+ * "mas_equilibrate" (default 1): the preconditioner's group / coarse inversions work on the diagonally equilibrated blocks (keeps the
+ * preconditioner positive definite on badly scaled systems: one degenerate triangle, diagonal 3e-3 .. 1e10).
+ * "scale_system" (default 0): symmetric diagonal scaling of the whole Newton system (measured: 7-17x more CG iterations).
+ * "force_direct" (default 0, tests): ocb_solve goes to the direct safety net (block-tridiagonal Cholesky, see ocb_solve) instead of CG. */
 int  ocb_set_option(ocb_ctx* ctx, const char* key, double value);
 /* CUDA-event stopwatch on the context's stream (what bench.py times kernels with) */
 int  ocb_timer_start(ocb_ctx* ctx);
@@ -166,7 +170,12 @@ int ocb_multiply(ocb_ctx* ctx, const double* x, double* y);
  * known).  rhs==NULL solves A x = -gradient
  * (Optimizer.cpp:557-563) with the gradient left on the device by ocb_gradient; the solution stays
  * on the device as the search direction; x_out may be NULL.  rel_tol <= 0 -> 1e-12 (relative residual
- * ||r|| / ||b||; see ocb_set_option for the scaled variant), max_it <= 0 -> 20*n */
+ * ||r|| / ||b||; see ocb_set_option for the scaled variant), max_it <= 0 -> 20*n.
+ * Safety net: when CG cannot handle a system of <= 40 000 unknowns (the two-level preconditioner comes out indefinite; inside
+ * ocb_newton_step also a breakdown d.Ad <= 0 or the iteration cap) the system is solved directly, by a block-tridiagonal Cholesky
+ * over the breadth-first levels of the matrix graph whose block steps are cuSOLVER / cuBLAS calls (opened with dlopen at first use;
+ * without the libraries the solve is repeated with block-Jacobi CG).  ocb_precond_info()[14] counts those solves, [15] the rejected
+ * preconditioners.  The libraries' host part uses OpenMP: a process started with OMP_NUM_THREADS=1 pays ~7x for such a solve. */
 int ocb_factorize(ocb_ctx* ctx);   /* builds the preconditioner (Galerkin products, group inverses, coarse inverse); OCB_ERR_BREAKDOWN if a diagonal 2x2 block is not SPD */
 int ocb_solve(ocb_ctx* ctx, const double* rhs, double* x_out, double rel_tol, int max_it,
               int* iters, double* rel_res);

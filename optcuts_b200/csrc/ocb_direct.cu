@@ -15,6 +15,8 @@
 // Both libraries are loaded with dlopen at first use, so this library has no link-time dependency on them; when they are missing,
 // or the system is larger, the block-Jacobi retry stays the fallback.  A matrix that is indefinite by rounding makes potrf fail:
 // the diagonal is then lifted relatively (1e-8, 1e-5, 1e-2) as after a CG breakdown.
+// The libraries' host side uses OpenMP: under OMP_NUM_THREADS=1 (what torchrun exports to its ranks) a solve costs ~7x
+// (male_2: 70-93 s for 150 Newton iterations instead of 12 s, profiles/r2_bench_n2_before_omp.json).
 #include "ocb_internal.cuh"
 #include <dlfcn.h>
 #include <algorithm>
@@ -196,15 +198,13 @@ direct_gather_rhs_kernel(int nRows, const int32_t* __restrict__ vertOf, const do
     }
 }
 __global__ void __launch_bounds__(256)
-direct_scatter_x_kernel(int nRows, const int32_t* __restrict__ vertOf, const double* __restrict__ x, double* __restrict__ xOut, double* __restrict__ scal, int devInfo0,
-                        const int* __restrict__ devInfo)
+direct_scatter_x_kernel(int nRows, const int32_t* __restrict__ vertOf, const double* __restrict__ x, double* __restrict__ xOut, const int* __restrict__ devInfo)
 {
-    const bool ok = devInfo[0] == 0 && devInfo[1] == 0;
+    const bool ok = devInfo[0] == 0 && devInfo[1] == 0;       // potrf and potrs both went through
     for (int row = blockIdx.x * 256 + threadIdx.x; row < nRows; row += gridDim.x * 256) {
         const size_t dst = vertOf ? (size_t)vertOf[row] : (size_t)row;
         if (ok) { xOut[2 * dst] = x[2 * (size_t)row]; xOut[2 * dst + 1] = x[2 * (size_t)row + 1]; }
     }
-    (void)scal; (void)devInfo0;
 }
 
 }  // namespace
@@ -346,7 +346,7 @@ int launch_direct_solve(ocb_ctx* c, const double* d_rhs, bool negate, int* lifts
         OCB_CUDA(c, cudaStreamSynchronize(c->stream));
         if (hInfo[0] != 0) continue;                          // not positive definite to working precision: lift the diagonal and repeat
         if (S.potrs(c->directHandle, kFillLower, n, 1, c->directA.p, n, c->directB.p, n, c->directInfo.p + 1) != 0) return 1;
-        direct_scatter_x_kernel<<<grid, 256, 0, c->stream>>>(nRows, c->vertOf.p, c->directB.p, c->p.p, c->dScal, 0, c->directInfo.p);
+        direct_scatter_x_kernel<<<grid, 256, 0, c->stream>>>(nRows, c->vertOf.p, c->directB.p, c->p.p, c->directInfo.p);
         KCHECK(c);
         if (liftsUsed) *liftsUsed = t;
         c->directSolves++;
