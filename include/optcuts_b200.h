@@ -179,6 +179,12 @@ int ocb_multiply(ocb_ctx* ctx, const double* x, double* y);
 int ocb_factorize(ocb_ctx* ctx);   /* builds the preconditioner (Galerkin products, group inverses, coarse inverse); OCB_ERR_BREAKDOWN if a diagonal 2x2 block is not SPD */
 int ocb_solve(ocb_ctx* ctx, const double* rhs, double* x_out, double rel_tol, int max_it,
               int* iters, double* rel_res);
+/* host only, no CUDA call (tests): the breadth-first level order and the blocks the direct safety net's block-tridiagonal Cholesky
+ * would use for a SYMMETRIC vertex pattern in CSR form (unsorted rows and diagonal entries allowed).  pos[v] = position of v in the
+ * level order, blkOf[v] = its block, blkBeg[k] = first position of block k (up to n + 1 entries).  Every coupling joins equal or
+ * adjacent blocks.  Returns the number of blocks (> 0) or an OCB_ERR_* code. */
+int ocb_direct_level_blocks(int n, const int32_t* rowPtr, const int32_t* colIdx, int target_vertices_per_block,
+                            int32_t* pos, int32_t* blkOf, int32_t* blkBeg);
 int ocb_get_search_dir(ocb_ctx* ctx, double* p_out);
 int ocb_set_search_dir(ocb_ctx* ctx, const double* p);
 

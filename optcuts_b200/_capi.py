@@ -97,6 +97,7 @@ _SIGS = [
     ("ocb_multiply", C.c_int, [C.c_void_p, _d, _d]),
     ("ocb_factorize", C.c_int, [C.c_void_p]),
     ("ocb_solve", C.c_int, [C.c_void_p, _d, _d, C.c_double, C.c_int, C.POINTER(C.c_int), _d]),
+    ("ocb_direct_level_blocks", C.c_int, [C.c_int, _i, _i, C.c_int, _i, _i, _i]),
     ("ocb_get_search_dir", C.c_int, [C.c_void_p, _d]),
     ("ocb_set_search_dir", C.c_int, [C.c_void_p, _d]),
     ("ocb_step_bound", C.c_int, [C.c_void_p, _d, _d]),
@@ -140,6 +141,18 @@ def precond_hierarchy(xy, grid):
         return vert_of, levels, int(info[2])
     finally:
         L.ocb_destroy(h)
+
+
+def direct_level_blocks(row_ptr, col_idx, target=192):
+    """Host-only: level order and blocks of the direct safety net for a symmetric vertex pattern (CSR).  Returns (pos, blk_of, blk_beg)."""
+    L = load_library()
+    row_ptr, col_idx = _i32(np.asarray(row_ptr), "C"), _i32(np.asarray(col_idx), "C")
+    n = len(row_ptr) - 1
+    pos, blk_of, blk_beg = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n + 1, np.int32)
+    nb = L.ocb_direct_level_blocks(n, _pi(row_ptr), _pi(col_idx), int(target), _pi(pos), _pi(blk_of), _pi(blk_beg))
+    if nb < 0:
+        raise OcbError(nb, "ocb_direct_level_blocks")
+    return pos, blk_of, blk_beg[:nb + 1].copy()
 
 
 def load_library():

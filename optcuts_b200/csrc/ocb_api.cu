@@ -1167,6 +1167,14 @@ int ocb_solve(ocb_ctx* c, const double* rhs, double* x_out, double rel_tol, int 
     return OCB_OK;
 }
 
+int ocb_direct_level_blocks(int n, const int32_t* rowPtr, const int32_t* colIdx, int target, int32_t* pos, int32_t* blkOf, int32_t* blkBeg)
+{
+    if (n <= 0 || !rowPtr || !colIdx || !pos || !blkOf || !blkBeg || target < 1) return OCB_ERR_ARG;
+    for (int v = 0; v < n; ++v) if (rowPtr[v + 1] < rowPtr[v]) return OCB_ERR_ARG;
+    for (int q = 0; q < rowPtr[n]; ++q) if (colIdx[q] < 0 || colIdx[q] >= n) return OCB_ERR_ARG;
+    return direct_level_blocks_host(n, rowPtr, colIdx, target, pos, blkOf, blkBeg);
+}
+
 int ocb_get_search_dir(ocb_ctx* c, double* p)
 {
     if (!c || !p) return OCB_ERR_ARG;

@@ -42,10 +42,10 @@ struct Cusolver {
     void* lib = nullptr;
     fnCreate create = nullptr; fnSetStream setStream = nullptr; fnPotrfBuf potrfBuf = nullptr; fnPotrf potrf = nullptr; fnPotrs potrs = nullptr;
 };
-Cusolver& cusolver()
+typedef int (*fnDestroy)(void*);
+Cusolver load_cusolver()
 {
-    static Cusolver S;
-    if (S.tried) return S;
+    Cusolver S;
     S.tried = true;
     const char* off = getenv("OCB_NO_DIRECT");
     if (off && atoi(off)) return S;
@@ -58,6 +58,7 @@ Cusolver& cusolver()
     S.ok = S.create && S.setStream && S.potrfBuf && S.potrf && S.potrs;
     return S;
 }
+Cusolver& cusolver() { static Cusolver S = load_cusolver(); return S; }      // (thread-safe: initialised once, on first use)
 constexpr int kFillLower = 0;                 // CUBLAS_FILL_MODE_LOWER
 constexpr int kOpN = 0, kOpT = 1, kSideRight = 1, kDiagNonUnit = 0;
 
@@ -73,10 +74,9 @@ struct Cublas {
     void* lib = nullptr;
     fnBCreate create = nullptr; fnBSetStream setStream = nullptr; fnSyrk syrk = nullptr; fnTrsm trsm = nullptr; fnGemv gemv = nullptr; fnTrsv trsv = nullptr;
 };
-Cublas& cublas()
+Cublas load_cublas()
 {
-    static Cublas S;
-    if (S.tried) return S;
+    Cublas S;
     S.tried = true;
     const char* names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so.13", "libcublas.so"};
     for (const char* nme : names) { S.lib = dlopen(nme, RTLD_NOW | RTLD_LOCAL); if (S.lib) break; }
@@ -87,6 +87,7 @@ Cublas& cublas()
     S.ok = S.create && S.setStream && S.syrk && S.trsm && S.gemv && S.trsv;
     return S;
 }
+Cublas& cublas() { static Cublas S = load_cublas(); return S; }
 
 // block-tridiagonal layout: row (solver order) -> position in the level order; per block its first position and the offsets of
 // D_k (n_k x n_k, column-major) and B_k (n_{k+1} x n_k: rows of block k+1, columns of block k) in one buffer
@@ -208,6 +209,16 @@ direct_scatter_x_kernel(int nRows, const int32_t* __restrict__ vertOf, const dou
 }
 
 }  // namespace
+
+// host only (tests): the level order and blocks the block-tridiagonal path would use for a vertex pattern given as CSR (rows may be
+// unsorted, the diagonal may be present).  pos / blkOf: n entries each; blkBeg: up to n + 1 entries.  Returns the number of blocks.
+int direct_level_blocks_host(int n, const int32_t* rowPtr, const int32_t* colIdx, int target, int32_t* pos, int32_t* blkOf, int32_t* blkBeg)
+{
+    std::vector<int32_t> rp(rowPtr, rowPtr + n + 1), ci(colIdx, colIdx + rowPtr[n]), p, b, bb;
+    level_blocks(rp, ci, n, target, p, b, bb);
+    std::copy(p.begin(), p.end(), pos); std::copy(b.begin(), b.end(), blkOf); std::copy(bb.begin(), bb.end(), blkBeg);
+    return (int)bb.size() - 1;
+}
 
 bool direct_solver_available(const ocb_ctx* c)
 {
@@ -358,7 +369,10 @@ int launch_direct_solve(ocb_ctx* c, const double* d_rhs, bool negate, int* lifts
 void direct_release(ocb_ctx* c)
 {
     c->directA.release(); c->directB.release(); c->directWork.release(); c->directInfo.release(); c->directI.release(); c->directL.release();
-    // the cuSOLVER handle is left to process teardown (destroying it needs the library, which may already be unloading)
+    // the library handles (the libraries are never dlclose()d, so their entry points are still there)
+    if (c->directHandle && cusolver().lib) { fnDestroy d = (fnDestroy)dlsym(cusolver().lib, "cusolverDnDestroy"); if (d) d(c->directHandle); }
+    if (c->directBlas && cublas().lib) { fnDestroy d = (fnDestroy)dlsym(cublas().lib, "cublasDestroy_v2"); if (d) d(c->directBlas); }
+    c->directHandle = nullptr; c->directBlas = nullptr;
 }
 
 }  // namespace ocb

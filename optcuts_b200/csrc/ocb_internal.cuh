@@ -260,6 +260,7 @@ static constexpr int kDirectMaxDof = 40000;               // largest system (sca
 bool direct_solver_available(const ocb_ctx* c);
 int launch_direct_solve(ocb_ctx* c, const double* d_rhs, bool negate, int* liftsUsed);   // 0 solved, 1 not available / not factorisable, < 0 error
 void direct_release(ocb_ctx* c);
+int direct_level_blocks_host(int n, const int32_t* rowPtr, const int32_t* colIdx, int target, int32_t* pos, int32_t* blkOf, int32_t* blkBeg);
 int launch_diag_shift(ocb_ctx* c, double delta);          // diagonal entries *= (1 + delta)
 int launch_scale_system(ocb_ctx* c);                       // val <- S val S, S = diag^-1/2; sets c->systemScaled
 int launch_jacobi_setup(ocb_ctx* c, bool check = true);   // check = false: no host round trip, the verdict stays in scal[S_JACOBI_BAD]

@@ -73,3 +73,16 @@ def test_synthetic_disk_is_valid(port):
         assert rc == 0
         u, v = UV[F[:, 1]] - UV[F[:, 0]], UV[F[:, 2]] - UV[F[:, 0]]
         assert np.all(u[:, 0] * v[:, 1] - u[:, 1] * v[:, 0] > 0)             # inversion-free start
+
+
+def test_visible_device_and_mps_fallback(monkeypatch):
+    """the per-mesh processes of a batch: the gpu-th VISIBLE device under a launcher's CUDA_VISIBLE_DEVICES, and an MpsDaemon that
+    was told not to start (OCB_BATCH_MPS=0) hands out plain child environments and leaves nothing behind"""
+    from optcuts_b200 import batch
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "3,5")
+    assert batch.visible_device(0) == "3" and batch.visible_device(1) == "5" and batch.visible_device(2) == "2"
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES")
+    assert batch.visible_device(1) == "1"
+    monkeypatch.setenv("OCB_BATCH_MPS", "0")
+    with batch.MpsDaemon(1) as mps:
+        assert not mps.up and mps.child_env() == {"CUDA_VISIBLE_DEVICES": "1"} and mps.dir is None
