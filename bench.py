@@ -21,7 +21,8 @@ The default line (no --workload) keeps bimba10k as `value` / `e2e` and adds, mea
   "batch71"       BASELINE.json configs[3]: the reference's 71 benchmark meshes (tests/golden/inputs/benchmark71.tar.xz) through
                   the reference's own host program with the GPU plugins (shim/_build/OptCuts_cuda_probe, one process per mesh,
                   the per-mesh command line of batch.py:11-14), LPT-sharded over the ranks, every mesh bounded to
-                  --batch-iters Newton iterations: batch wall time (max over ranks), per-rank load, slowest mesh,
+                  --batch-iters Newton iterations (150), --batch-procs processes at a time per GPU (3) attached to an MPS daemon
+                  started for the batch: batch wall time (max over ranks), per-rank load, slowest mesh,
   "host_program"  the WHOLE run of configs[1] (geometry + topology to convergence) in the host program: GPU plugins vs the
                   unmodified reference on this box's host cores, with the reference's own info.txt timers of both.
 `--impl reference` times the reference's own CPU implementation of the same step
@@ -360,7 +361,7 @@ def batch71_ours(args, rank, world, local, torch):
             import torch.distributed as dist
             dist.barrier()
         # `procs` host-program processes at a time on this rank's GPU (largest mesh first): a process spends most of its life in
-        # host code (CUDA context creation 2.7-3.4 s, OBJ parsing, Triangle, mesh edits), so the GPU is shared by time slicing
+        # host code (OBJ parsing, Triangle, mesh edits, the reference's query code), so the GPU is shared (side by side under MPS)
         from concurrent.futures import ThreadPoolExecutor
         procs = max(1, min(args.batch_procs, (os.cpu_count() or 1) // max(1, world)))
         # torchrun exports OMP_NUM_THREADS=1 to its ranks and the per-mesh processes would inherit it: the direct safety net's library
