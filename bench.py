@@ -366,8 +366,10 @@ def batch71_ours(args, rank, world, local, torch):
         procs = max(1, min(args.batch_procs, (os.cpu_count() or 1) // max(1, world)))
         # torchrun exports OMP_NUM_THREADS=1 to its ranks and the per-mesh processes would inherit it: the direct safety net's library
         # calls (cuSOLVER potrf) then run their host part on one thread -- male_2 took 70-93 s of a 2-GPU batch instead of 11 s
-        # (profiles/r2_bench_n2_before_omp.json).  Every host process gets its share of the cores instead.
-        threads = max(4, (os.cpu_count() or 1) // (procs * max(1, world)))
+        # (profiles/r2_bench_n2_before_omp.json).  Every rank's processes get the rank's share of the cores instead (1 GPU: all cores,
+        # which is what an unset OMP_NUM_THREADS means; a third of that per process cost the 1-GPU batch 25 %:
+        # profiles/r2_bench_batch71_omp5.json, 126 s against 101 s).
+        threads = max(4, (os.cpu_count() or 1) // max(1, world))
         cenv = dict(cenv, OMP_NUM_THREADS=str(threads))
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=procs) as ex:
